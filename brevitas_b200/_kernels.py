@@ -1,0 +1,310 @@
+"""Tensor-level wrappers over the C-ABI: pointer/size marshalling, output allocation, no autograd.
+
+Every function requires CUDA tensors and launches on the current stream of the tensor's device.  CPU
+tensors are rejected (there is no CPU implementation behind the C-ABI by design).
+"""
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call
+
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+# launch counter: bench.py reports how many of OUR kernels' C-ABI calls ran inside the timed region
+launch_count = 0
+
+
+def dtype_tag(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"brevitas_b200: unsupported dtype {t.dtype} (supported: float32, bfloat16, float16)")
+
+
+def _check_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "brevitas_b200: expected a CUDA tensor, got a tensor on '%s'. The B200 fake-quant path has no "
+                "CPU fallback." % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"brevitas_b200: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _launch(dev, name, *args):
+    global launch_count
+    launch_count += 1
+    if torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            return call(name, *args)
+    return call(name, *args)
+
+
+def broadcast_pattern(x_shape, s_shape) -> Tuple[int, int]:
+    """(inner, count) such that element i of x uses scale[(i // inner) % count].
+
+    Supports any scale whose non-singleton dims form one contiguous block of x's dims: scalar, ``[O,1]`` /
+    ``[O,1,1,1]`` (per output channel), ``[1,C,1,1]`` (per dim-1 channel), ``[B,T,1]`` (per token), same shape.
+    """
+    x_shape = tuple(x_shape)
+    s_shape = tuple(s_shape)
+    numel = 1
+    for d in s_shape:
+        numel *= d
+    if numel == 1:
+        return 1, 1
+    if len(s_shape) > len(x_shape):
+        raise RuntimeError(f"scale of shape {s_shape} is not broadcastable to {x_shape}")
+    s_shape = (1,) * (len(x_shape) - len(s_shape)) + s_shape
+    nz = [i for i, d in enumerate(s_shape) if d != 1]
+    for i in nz:
+        if s_shape[i] != x_shape[i]:
+            raise RuntimeError(f"scale of shape {s_shape} is not broadcastable to {x_shape}")
+    a, b = nz[0], nz[-1] + 1
+    for i in range(a, b):
+        if s_shape[i] != x_shape[i]:
+            raise RuntimeError(
+                f"brevitas_b200: unsupported scale broadcast {s_shape} -> {x_shape} (non-contiguous channel dims)")
+    count = 1
+    for d in x_shape[a:b]:
+        count *= d
+    inner = 1
+    for d in x_shape[b:]:
+        inner *= d
+    return inner, count
+
+
+def _scale_args(x, scale):
+    inner, count = broadcast_pattern(x.shape, scale.shape)
+    sdt = dtype_tag(scale)
+    if scale.dtype != x.dtype and not (scale.dtype == torch.float32 and count == 1):
+        raise RuntimeError(
+            f"brevitas_b200: scale dtype {scale.dtype} with input dtype {x.dtype} is only supported for a "
+            "one-element fp32 scale")
+    return inner, count, sdt
+
+
+# ---- the 12 STE primitives ---------------------------------------------------------------------------------
+
+def unary(name: str, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _check_cuda(x)
+    x = _c(x)
+    y = torch.empty_like(x) if out is None else out
+    _launch(dev, name, x.data_ptr(), y.data_ptr(), x.numel(), dtype_tag(x), _stream(dev))
+    return y
+
+
+def abs_binary_sign_grad_bwd(x, gy):
+    dev = _check_cuda(x, gy)
+    x, gy = _c(x), _c(gy)
+    gx = torch.empty_like(gy)
+    _launch(dev, "bvb_abs_binary_sign_grad_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), x.numel(),
+            dtype_tag(x), _stream(dev))
+    return gx
+
+
+def tensor_clamp(x, min_val, max_val, inplace=False):
+    dev = _check_cuda(x, min_val, max_val)
+    if inplace:
+        if not x.is_contiguous():
+            raise RuntimeError("tensor_clamp_ste_impl_: in-place clamp needs a contiguous tensor")
+        xc = x
+    else:
+        xc = _c(x)
+    mn = _c(min_val).to(x.dtype)       # .type_as(x) of the reference (function/ops.py:98-99)
+    mx = _c(max_val).to(x.dtype)
+    mn_inner, mn_count = broadcast_pattern(x.shape, mn.shape)
+    mx_inner, mx_count = broadcast_pattern(x.shape, mx.shape)
+    y = xc if inplace else torch.empty_like(xc)
+    _launch(dev, "bvb_tensor_clamp_ste_impl", xc.data_ptr(), mn.data_ptr(), mx.data_ptr(), y.data_ptr(), xc.numel(),
+            mn_inner, mn_count, mx_inner, mx_count, 1 if inplace else 0, dtype_tag(x), _stream(dev))
+    return y
+
+
+def scalar_clamp(x, min_val: float, max_val: float):
+    dev = _check_cuda(x)
+    x = _c(x)
+    y = torch.empty_like(x)
+    _launch(dev, "bvb_scalar_clamp_ste_impl", x.data_ptr(), y.data_ptr(), x.numel(), float(min_val), float(max_val),
+            dtype_tag(x), _stream(dev))
+    return y
+
+
+def scalar_clamp_min(x, min_val: float):
+    dev = _check_cuda(x)
+    x = _c(x)
+    y = torch.empty_like(x)
+    _launch(dev, "bvb_scalar_clamp_min_ste_impl", x.data_ptr(), y.data_ptr(), x.numel(), float(min_val),
+            dtype_tag(x), _stream(dev))
+    return y
+
+
+# ---- IntQuant with a provided scale ------------------------------------------------------------------------
+
+def int_quant_fwd(x, scale, zero_point: float, qmin: float, qmax: float, round_mode: int, want_codes=False):
+    dev = _check_cuda(x, scale)
+    x, scale = _c(x), _c(scale)
+    inner, count, sdt = _scale_args(x, scale)
+    y = torch.empty_like(x)
+    codes = torch.empty_like(x) if want_codes else None
+    _launch(dev, "bvb_int_quant_fwd", x.data_ptr(), scale.data_ptr(), y.data_ptr(), _ptr(codes), x.numel(), inner,
+            count, sdt, zero_point, qmin, qmax, round_mode, dtype_tag(x), _stream(dev))
+    return (y, codes) if want_codes else y
+
+
+def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, want_gscale):
+    dev = _check_cuda(gy, x, scale)
+    gy, x, scale = _c(gy), _c(x), _c(scale)
+    inner, count, sdt = _scale_args(x, scale)
+    gx = torch.empty_like(x)
+    gs = torch.empty(count, dtype=torch.float32, device=dev) if want_gscale else None
+    _launch(dev, "bvb_int_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), gx.data_ptr(), _ptr(gs),
+            x.numel(), inner, count, sdt, zero_point, qmin, qmax, round_mode, clamp_mode, dtype_tag(x), _stream(dev))
+    return gx, gs
+
+
+# ---- fused abs-max + quant --------------------------------------------------------------------------------
+
+def rows_absmax_int_quant_fwd(x, rows, cols, scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode,
+                              want_absmax=False):
+    dev = _check_cuda(x)
+    x = _c(x)
+    assert rows * cols == x.numel()
+    y = torch.empty_like(x)
+    scale = torch.empty(rows, dtype=x.dtype, device=dev)
+    absmax = torch.empty(rows, dtype=x.dtype, device=dev) if want_absmax else None
+    _launch(dev, "bvb_rows_absmax_int_quant_fwd", x.data_ptr(), y.data_ptr(), scale.data_ptr(), _ptr(absmax), rows,
+            cols, scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode, dtype_tag(x), _stream(dev))
+    return y, scale, absmax
+
+
+def rows_absmax_int_quant_bwd(gy, x, scale, gscale, rows, cols, int_threshold, zero_point, qmin, qmax, round_mode,
+                              clamp_mode):
+    dev = _check_cuda(gy, x, scale, gscale)
+    gy, x, scale = _c(gy), _c(x), _c(scale)
+    if gscale is not None:
+        gscale = _c(gscale)
+    gx = torch.empty_like(x)
+    _launch(dev, "bvb_rows_absmax_int_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), _ptr(gscale),
+            gx.data_ptr(), rows, cols, int_threshold, zero_point, qmin, qmax, round_mode, clamp_mode, dtype_tag(x),
+            _stream(dev))
+    return gx
+
+
+def _workspace(dev):
+    return torch.empty(_lib.load().bvb_workspace_bytes(), dtype=torch.uint8, device=dev)
+
+
+def tensor_absmax_int_quant_fwd(x, scale_dtype, scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode):
+    dev = _check_cuda(x)
+    x = _c(x)
+    y = torch.empty_like(x)
+    scale = torch.empty((), dtype=scale_dtype, device=dev)
+    absmax = torch.empty((), dtype=x.dtype, device=dev)
+    ws = _workspace(dev)
+    _launch(dev, "bvb_tensor_absmax_int_quant_fwd", x.data_ptr(), y.data_ptr(), scale.data_ptr(), absmax.data_ptr(),
+            x.numel(), _DTYPES[scale_dtype], scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode,
+            dtype_tag(x), ws.data_ptr(), _stream(dev))
+    return y, scale, absmax
+
+
+def tensor_absmax_int_quant_bwd(gy, x, scale, absmax, gscale, int_threshold, zero_point, qmin, qmax, round_mode,
+                                clamp_mode):
+    dev = _check_cuda(gy, x, scale, absmax, gscale)
+    gy, x = _c(gy), _c(x)
+    gx = torch.empty_like(x)
+    ws = _workspace(dev)
+    _launch(dev, "bvb_tensor_absmax_int_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), absmax.data_ptr(),
+            _ptr(gscale), gx.data_ptr(), x.numel(), dtype_tag(scale), int_threshold, zero_point, qmin, qmax,
+            round_mode, clamp_mode, dtype_tag(x), ws.data_ptr(), _stream(dev))
+    return gx
+
+
+# ---- binary ------------------------------------------------------------------------------------------------
+
+def binary_quant_fwd(x, scale, clamped: bool):
+    dev = _check_cuda(x, scale)
+    x, scale = _c(x), _c(scale)
+    inner, count, sdt = _scale_args(x, scale)
+    y = torch.empty_like(x)
+    _launch(dev, "bvb_binary_quant_fwd", x.data_ptr(), scale.data_ptr(), y.data_ptr(), x.numel(), inner, count, sdt,
+            1 if clamped else 0, dtype_tag(x), _stream(dev))
+    return y
+
+
+def binary_quant_bwd(gy, x, scale, clamped: bool, want_gscale: bool):
+    dev = _check_cuda(gy, x, scale)
+    gy, x, scale = _c(gy), _c(x), _c(scale)
+    inner, count, sdt = _scale_args(x, scale)
+    gx = torch.empty_like(x)
+    gs = torch.empty(count, dtype=torch.float32, device=dev) if want_gscale else None
+    _launch(dev, "bvb_binary_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), gx.data_ptr(), _ptr(gs),
+            x.numel(), inner, count, sdt, 1 if clamped else 0, dtype_tag(x), _stream(dev))
+    return gx, gs
+
+
+# ---- statistics --------------------------------------------------------------------------------------------
+
+def absmax_rows(x, rows, cols):
+    dev = _check_cuda(x)
+    x = _c(x)
+    out = torch.empty(rows, dtype=x.dtype, device=dev)
+    _launch(dev, "bvb_absmax_rows", x.data_ptr(), out.data_ptr(), rows, cols, dtype_tag(x), _stream(dev))
+    return out
+
+
+def absmax_tensor(x):
+    dev = _check_cuda(x)
+    x = _c(x)
+    out = torch.empty((), dtype=x.dtype, device=dev)
+    ws = _workspace(dev)
+    _launch(dev, "bvb_absmax_tensor", x.data_ptr(), out.data_ptr(), x.numel(), dtype_tag(x), ws.data_ptr(),
+            _stream(dev))
+    return out
+
+
+def abs_kth_value_rows(x, rows, cols, k, want_index=False):
+    dev = _check_cuda(x)
+    x = _c(x)
+    out = torch.empty(rows, dtype=x.dtype, device=dev)
+    idx = torch.empty(rows, dtype=torch.int64, device=dev) if want_index else None
+    ws = torch.empty(_lib.load().bvb_kth_workspace_bytes(rows), dtype=torch.uint8, device=dev)
+    _launch(dev, "bvb_abs_kth_value_rows", x.data_ptr(), out.data_ptr(), _ptr(idx), rows, cols, k, dtype_tag(x),
+            ws.data_ptr(), _stream(dev))
+    return out, idx
+
+
+def percentile_k(q: float, n: int) -> int:
+    """k of AbsPercentile (src/brevitas/core/stats/stats_op.py:55, 61): floor(.01 * q * n + 0.5), 1-indexed."""
+    return int(math.floor(.01 * q * n + 0.5))
+
+
+def running_stats_update(running, stat, momentum: float, first: bool):
+    dev = _check_cuda(running, stat)
+    if running.dtype != torch.float32 or not running.is_contiguous():
+        raise RuntimeError("running_stats_update: running buffer must be contiguous float32")
+    stat = _c(stat)
+    _launch(dev, "bvb_running_stats_update", running.data_ptr(), stat.data_ptr(), running.numel(), float(momentum),
+            float(1 - momentum), 1 if first else 0, dtype_tag(stat), _stream(dev))
+    return running

@@ -1,0 +1,266 @@
+"""Mirror of ``brevitas.core.quant`` -- the ``tensor_quant`` modules -- on fused sm_100a kernels.
+
+Reference: src/brevitas/core/quant/int_base.py:15-97 (IntQuant), int.py:94-163 (RescalingIntQuant),
+binary.py:19-64 (BinaryQuant), :67-125 (ClampedBinaryQuant), delay.py:43-54 (DelayWrapper).
+
+Same constructor arguments, same sub-module names (``int_quant``, ``scaling_impl``, ``int_scaling_impl``,
+``zero_point_impl``, ``msb_clamp_bit_width_impl`` ...), same ``forward`` contract
+``x -> (y, scale, zero_point, bit_width)``, hence state-dict compatible with the reference.  What changes is how
+``forward`` executes: where the reference issues ~9-20 ATen kernels, these modules launch ONE kernel
+(statistic + scale + quant-dequant) or one kernel after a few tiny scale ops, selected from the types of the
+injected sub-modules (rounding mode, clamp-gradient mode, statistic, view).  Configurations the fused kernels do
+not cover (tensor-valued zero-point, learned bit-width, exotic injected modules) run the literal reference
+sequence on the STE kernels (op-level drop-in).
+"""
+from functools import lru_cache
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .. import _lib
+from .. import ops as _ops  # noqa: F401
+from ..function.ops import max_int, min_int
+from ..function.ops_ste import binary_sign_ste
+from .bit_width import BitWidthConst
+from .function_wrapper import CLAMP_MODE_OF, ROUND_MODE_OF, RoundSte, TensorClamp
+from .scaling import IntScaling, PowerOfTwoIntScaling
+from .utils import StatelessBuffer
+from .zero_point import ZeroZeroPoint
+
+
+# ---- delay (core/quant/delay.py) ----------------------------------------------------------------------------
+class _NoDelay(nn.Module):
+    def forward(self, x: Tensor, y: Tensor) -> Tensor:
+        return y
+
+
+class _DelayQuant(nn.Module):
+    def __init__(self, quant_delay_steps):
+        super().__init__()
+        self.quant_delay_steps: int = quant_delay_steps
+
+    def forward(self, x: Tensor, y: Tensor) -> Tensor:
+        if self.quant_delay_steps > 0:
+            self.quant_delay_steps = self.quant_delay_steps - 1
+            return x
+        return y
+
+
+class DelayWrapper(nn.Module):
+    """Returns the un-quantized input for the first ``quant_delay_steps`` calls (delay.py:43-54)."""
+
+    def __init__(self, quant_delay_steps: Optional[int]):
+        super().__init__()
+        if quant_delay_steps is None or quant_delay_steps <= 0:
+            self.delay_impl = _NoDelay()
+        else:
+            self.delay_impl = _DelayQuant(quant_delay_steps)
+
+    def forward(self, x: Tensor, y: Tensor) -> Tensor:
+        return self.delay_impl(x, y)
+
+
+# ---- host copies of the 0-dim range tensors ------------------------------------------------------------------
+@lru_cache(maxsize=None)
+def int_range(signed: bool, narrow_range: bool, bit_width: int, dtype: torch.dtype) -> Tuple[float, float]:
+    """(min_int, max_int) as the reference computes them from a 0-dim ``bit_width`` tensor of ``dtype``
+    (function/ops.py:133-191), evaluated once on the host so the fused kernels need no device read-back."""
+    bw = torch.tensor(float(bit_width), dtype=dtype)
+    return float(min_int(signed, narrow_range, bw)), float(max_int(signed, narrow_range, bw))
+
+
+@lru_cache(maxsize=None)
+def _int_threshold(kind: str, signed: bool, narrow_range: bool, bit_width: int, dtype: torch.dtype) -> float:
+    bw = torch.tensor(float(bit_width), dtype=dtype)
+    if kind == 'int':
+        impl = IntScaling(signed, narrow_range)
+    else:
+        impl = PowerOfTwoIntScaling(signed)
+    return float(impl(bw))
+
+
+class IntQuant(nn.Module):
+    """Scaled, shifted, uniform integer quantization, output in dequantized format (int_base.py:15-97).
+
+    ``y = (clamp(round(x / scale + zero_point), min_int, max_int) - zero_point) * scale``, one kernel.
+    """
+
+    def __init__(self, narrow_range: bool, signed: bool, float_to_int_impl: Optional[nn.Module] = None,
+                 tensor_clamp_impl: Optional[nn.Module] = None, quant_delay_steps: int = 0):
+        super().__init__()
+        self.float_to_int_impl = float_to_int_impl if float_to_int_impl is not None else RoundSte()
+        self.tensor_clamp_impl = tensor_clamp_impl if tensor_clamp_impl is not None else TensorClamp()
+        self.signed = signed
+        self.narrow_range = narrow_range
+        self.delay_wrapper = DelayWrapper(quant_delay_steps)
+
+    # -- kernel mode selection
+    def kernel_modes(self) -> Optional[Tuple[int, int]]:
+        rm = ROUND_MODE_OF.get(type(self.float_to_int_impl))
+        cm = CLAMP_MODE_OF.get(type(self.tensor_clamp_impl))
+        if rm is None or cm is None:
+            return None
+        return rm, cm
+
+    def min_int(self, bit_width):
+        return min_int(self.signed, self.narrow_range, bit_width)
+
+    def max_int(self, bit_width):
+        return max_int(self.signed, self.narrow_range, bit_width)
+
+    def to_int(self, scale: Tensor, zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
+        """Integer codes as floats (int_base.py:64-76), literal op sequence on the STE kernels."""
+        y = x / scale
+        y = y + zero_point
+        min_int_val = self.min_int(bit_width)
+        max_int_val = self.max_int(bit_width)
+        y = self.float_to_int_impl(y)
+        y = self.tensor_clamp_impl(y, min_val=min_int_val, max_val=max_int_val)
+        return y
+
+    def forward_fused(self, scale: Tensor, zero_point: float, qmin: float, qmax: float, x: Tensor) -> Optional[Tensor]:
+        """One-kernel path given host copies of zero-point and integer range; None if not applicable."""
+        modes = self.kernel_modes()
+        if modes is None:
+            return None
+        if scale.dtype != x.dtype and not (scale.numel() == 1 and scale.dtype == torch.float32):
+            return None
+        y = torch.ops.brevitas_b200.int_quant(x, scale, zero_point, qmin, qmax, modes[0], modes[1])
+        return self.delay_wrapper(x, y)
+
+    def forward(self, scale: Tensor, zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
+        if (x.is_cuda and zero_point.numel() == 1 and bit_width.numel() == 1 and not zero_point.requires_grad
+                and not bit_width.requires_grad and not torch.cuda.is_current_stream_capturing()):
+            # direct call with tensor arguments: one read-back of the two 0-dim tensors, then the fused kernel
+            qmin = float(self.min_int(bit_width))
+            qmax = float(self.max_int(bit_width))
+            y = self.forward_fused(scale, float(zero_point), qmin, qmax, x)
+            if y is not None:
+                return y
+        y_int = self.to_int(scale, zero_point, bit_width, x)
+        y = y_int - zero_point
+        y = y * scale
+        return self.delay_wrapper(x, y)
+
+
+class RescalingIntQuant(nn.Module):
+    """Gets scale, zero-point and bit-width from their implementations and quantizes (int.py:94-163).
+
+    ``scale = scaling_impl(x) / int_scaling_impl(bit_width)``; returns ``(y, scale, zero_point, bit_width)``.
+    """
+
+    def __init__(self, int_quant: nn.Module, scaling_impl: nn.Module, int_scaling_impl: nn.Module,
+                 zero_point_impl: nn.Module, bit_width_impl: nn.Module):
+        super().__init__()
+        self.int_quant = int_quant
+        self.scaling_impl = scaling_impl
+        self.int_scaling_impl = int_scaling_impl
+        self.zero_point_impl = zero_point_impl
+        self.msb_clamp_bit_width_impl = bit_width_impl
+
+    def _host_config(self, bw_dtype: torch.dtype):
+        """(zero_point, qmin, qmax, round_mode, clamp_mode, int_threshold or None) when every range input is a
+        construction-time constant; None otherwise (-> literal reference sequence)."""
+        iq = self.int_quant
+        if type(iq) is not IntQuant or type(self.zero_point_impl) is not ZeroZeroPoint \
+                or type(self.msb_clamp_bit_width_impl) is not BitWidthConst:
+            return None
+        modes = iq.kernel_modes()
+        if modes is None:
+            return None
+        bw = self.msb_clamp_bit_width_impl.bit_width_value
+        qmin, qmax = int_range(iq.signed, iq.narrow_range, bw, bw_dtype)
+        isi = self.int_scaling_impl
+        if type(isi) is IntScaling:
+            thr = _int_threshold('int', isi.signed, isi.narrow_range, bw, bw_dtype)
+        elif type(isi) is PowerOfTwoIntScaling:
+            thr = _int_threshold('po2', isi.signed, False, bw, bw_dtype)
+        else:
+            thr = None
+        return 0.0, qmin, qmax, modes[0], modes[1], thr
+
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        bit_width = self.msb_clamp_bit_width_impl()
+        cfg = self._host_config(bit_width.dtype) if x.is_cuda else None
+        if cfg is None:
+            if not x.is_cuda:
+                raise RuntimeError("brevitas_b200.RescalingIntQuant: CPU tensors are not supported (no CPU fallback)")
+            threshold = self.scaling_impl(x)
+            int_threshold = self.int_scaling_impl(bit_width)
+            scale = threshold / int_threshold
+            zero_point = self.zero_point_impl(x, scale, bit_width)
+            y = self.int_quant(scale, zero_point, bit_width, x)
+            return y, scale, zero_point, bit_width
+        zp, qmin, qmax, rm, cm, int_thr = cfg
+        plan_fn = getattr(self.scaling_impl, 'fused_stats_plan', None)
+        plan = plan_fn(x) if (plan_fn is not None and int_thr is not None) else None
+        if plan is not None:
+            g = plan.geom
+            if g.kind == 'rows':
+                y, scale, absmax = torch.ops.brevitas_b200.rows_absmax_int_quant(
+                    x, g.rows, g.cols, plan.scaling_min_val, int_thr, zp, qmin, qmax, rm, cm)
+            else:
+                scale_dtype = torch.promote_types(x.dtype, bit_width.dtype)
+                y, scale, absmax = torch.ops.brevitas_b200.tensor_absmax_int_quant(
+                    x, scale_dtype, plan.scaling_min_val, int_thr, zp, qmin, qmax, rm, cm)
+            scale = scale.view(plan.out_shape)
+            if plan.on_absmax is not None:
+                plan.on_absmax(absmax.view(plan.out_shape))
+            zero_point = self.zero_point_impl(x, scale, bit_width)
+            return self.int_quant.delay_wrapper(x, y), scale, zero_point, bit_width
+        threshold = self.scaling_impl(x)
+        int_threshold = self.int_scaling_impl(bit_width)
+        scale = threshold / int_threshold
+        zero_point = self.zero_point_impl(x, scale, bit_width)
+        if scale.dtype != x.dtype and scale.numel() != 1:
+            x = x.to(torch.promote_types(x.dtype, scale.dtype))      # what ATen's type promotion would do
+        y = self.int_quant.forward_fused(scale, zp, qmin, qmax, x)
+        if y is None:
+            y = self.int_quant(scale, zero_point, bit_width, x)
+        return y, scale, zero_point, bit_width
+
+
+class BinaryQuant(nn.Module):
+    """``y = binary_sign_ste(x) * scale``; zero-point 0, bit-width 1 (binary.py:19-64)."""
+
+    def __init__(self, scaling_impl: nn.Module, quant_delay_steps: int = 0):
+        super().__init__()
+        self.scaling_impl = scaling_impl
+        self.bit_width = BitWidthConst(1)
+        self.zero_point = StatelessBuffer(torch.tensor(0.0))
+        self.delay_wrapper = DelayWrapper(quant_delay_steps)
+
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        scale = self.scaling_impl(x)
+        if scale.dtype == x.dtype or (scale.numel() == 1 and scale.dtype == torch.float32):
+            y = torch.ops.brevitas_b200.binary_quant(x, scale, False)
+        else:
+            y = binary_sign_ste(x) * scale
+        y = self.delay_wrapper(x, y)
+        return y, scale, self.zero_point(), self.bit_width()
+
+
+class ClampedBinaryQuant(nn.Module):
+    """``y = binary_sign_ste(clamp(x, -scale, scale)) * scale``: the clamp shapes the gradient (binary.py:67-125)."""
+
+    def __init__(self, scaling_impl: nn.Module, tensor_clamp_impl: Optional[nn.Module] = None,
+                 quant_delay_steps: int = 0):
+        super().__init__()
+        self.scaling_impl = scaling_impl
+        self.bit_width = BitWidthConst(1)
+        self.zero_point = StatelessBuffer(torch.tensor(0.0))
+        self.delay_wrapper = DelayWrapper(quant_delay_steps)
+        self.tensor_clamp_impl = tensor_clamp_impl if tensor_clamp_impl is not None else TensorClamp()
+
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        scale = self.scaling_impl(x)
+        fusable = type(self.tensor_clamp_impl) is TensorClamp and (
+            scale.dtype == x.dtype or (scale.numel() == 1 and scale.dtype == torch.float32))
+        if fusable:
+            y = torch.ops.brevitas_b200.binary_quant(x, scale, True)
+        else:
+            y = self.tensor_clamp_impl(x, - scale, scale)
+            y = binary_sign_ste(y) * scale
+        y = self.delay_wrapper(x, y)
+        return y, scale, self.zero_point(), self.bit_width()

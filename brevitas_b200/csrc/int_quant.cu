@@ -1,0 +1,893 @@
+// brevitas_b200 :: integer fake-quantization, forward and STE backward.
+//
+// Replaces the ATen op chains issued by
+//   IntQuant.to_int / IntQuant.forward          src/brevitas/core/quant/int_base.py:64-97
+//   RescalingIntQuant.forward                   src/brevitas/core/quant/int.py:156-163
+//   StatsFromParameterScaling / RuntimeStatsScaling + AbsMax
+//                                               src/brevitas/core/scaling/runtime.py:19-102,
+//                                               src/brevitas/core/stats/stats_op.py:129-141
+// and the autograd graph PyTorch builds behind them.
+//
+// Kernels
+//   int_quant_fwd_kernel          provided scale, pure streaming, 1R+1W
+//   int_quant_bwd_kernel          provided scale, 2R+1W, optional d(scale) reduction
+//   rows_fwd_tma_kernel           per-row abs-max + quant-dequant in ONE HBM pass: each row is staged
+//                                 in shared memory by a TMA bulk copy (ring of mbarrier-tracked stages),
+//                                 reduced with redux/shuffle, then quantised from shared memory
+//   rows_fwd_generic_kernel       same contract for ragged / unaligned / oversized rows (two reads)
+//   rows_bwd_kernel               per-row streaming backward incl. gradient through the abs-max
+//   absmax_tensor_kernel (+finalise), tensor_bwd_fixup_kernel: whole-tensor statistic
+#include "common.cuh"
+#include "host.cuh"
+
+namespace bvb {
+
+constexpr int ST_THREADS = 256;   // streaming kernels
+constexpr int ST_UNROLL = 4;
+
+// A one-element scale may be an fp32 0-dim tensor while x is bf16/fp16 (fp32 quantizer modules fed
+// low-precision activations): ATen's mul/div kernels then use the fp32 value in opmath, un-rounded.
+template <typename T>
+__device__ __forceinline__ float load_scale0(const T* scale, int scale_f32) {
+    return scale_f32 ? reinterpret_cast<const float*>(scale)[0] : DT<T>::to_f(scale[0]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// provided-scale forward
+// smode 0: one scale for the whole tensor; 1: scale index constant within a 16-byte vector
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int RM>
+__global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
+        const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ y, T* __restrict__ codes,
+        int64_t nvec, int64_t inner_v, int64_t count, int smode, int scale_f32, int reverse, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    uint4* yv = reinterpret_cast<uint4*>(y);
+    uint4* cv = reinterpret_cast<uint4*>(codes);
+    const int64_t chunk = ST_THREADS * ST_UNROLL;
+    const int64_t nchunks = (nvec + chunk - 1) / chunk;
+    float s0 = 0.f;
+    if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t cc = reverse ? (nchunks - 1 - c) : c;
+        const int64_t base = cc * chunk + threadIdx.x;
+        uint4 q[ST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            int64_t v = base + (int64_t)u * ST_THREADS;
+            if (v < nvec) q[u] = ldg_stream(xv + v);
+        }
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            int64_t v = base + (int64_t)u * ST_THREADS;
+            if (v < nvec) {
+                float s = s0;
+                if (smode != 0) s = DT<T>::to_f(scale[(v / inner_v) % count]);
+                float e[V], k[V];
+                DT<T>::unpack(q[u], e);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    float t1, t3, t5;
+                    to_int_chain<T, RM>(e[i], s, p, t1, t3, t5);
+                    k[i] = t5;
+                    float t6 = fsub(t5, p.zp);
+                    if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
+                    e[i] = fmul(t6, s);
+                }
+                stg_stream(yv + v, DT<T>::pack(e));
+                if (codes) stg_stream(cv + v, DT<T>::pack(k));
+            }
+        }
+    }
+}
+
+// element-wise fallback for [start, n): any broadcast pattern, any alignment
+template <typename T, int RM>
+__global__ void int_quant_fwd_scalar_kernel(const T* x, const T* scale, T* y, T* codes, int64_t start, int64_t n,
+                                            int64_t inner, int64_t count, int scale_f32, QParams p) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float s = count == 1 ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[(i / inner) % count]);
+        float t1, t3, t5;
+        to_int_chain<T, RM>(DT<T>::to_f(x[i]), s, p, t1, t3, t5);
+        float t6 = fsub(t5, p.zp);
+        if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
+        y[i] = DT<T>::from_f(fmul(t6, s));
+        if (codes) codes[i] = DT<T>::from_f(t5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one element of the backward
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int RM>
+__device__ __forceinline__ float bwd_elem(float g, float x, float s, float inv_s, const QParams& p, int masked,
+                                          bool want_gs, float& gs_acc) {
+    float gsv = DT<T>::rnd(fmul(g, s));                  // d y / d t6 : grad * scale
+    float d = gsv;
+    if (masked || want_gs) {
+        float t1, t3, t5;
+        to_int_chain<T, RM>(x, s, p, t1, t3, t5);
+        if (masked) {
+            bool m = !(t3 > p.qmax) && !(t3 < p.qmin);   // torch.where backward of both clamp stages
+            d = m ? gsv : 0.f;
+        }
+        if (want_gs) {
+            float t6 = fsub(t5, p.zp);
+            // d(scale) = g * t6  -  d * ((x / s) / s); order-dependent sum => fp32 accumulation,
+            // reciprocal for the second division is within the documented tolerance
+            gs_acc += g * t6 - d * (t1 * inv_s);
+        }
+    }
+    return fdiv(d, s);                                   // d t1 / d x : grad / scale (rounded at store)
+}
+
+// provided-scale backward; gscale_out (nullable) accumulated with float atomics
+template <typename T, int RM>
+__global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
+        const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ gx,
+        float* gscale_out, int64_t nvec, int64_t inner_v, int64_t count, int smode, int scale_f32, int masked, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ float red[32];
+    const uint4* gv = reinterpret_cast<const uint4*>(gy);
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    uint4* ov = reinterpret_cast<uint4*>(gx);
+    const bool want_gs = gscale_out != nullptr;
+    const int64_t chunk = ST_THREADS * ST_UNROLL;
+    const int64_t nchunks = (nvec + chunk - 1) / chunk;
+    float s0 = 0.f, inv0 = 0.f;
+    if (smode == 0) { s0 = load_scale0<T>(scale, scale_f32); inv0 = 1.f / s0; }
+    float acc = 0.f;          // smode 0: block-wide; smode 1: run of equal scale indices
+    int64_t acc_idx = -1;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t base = c * chunk + threadIdx.x;
+        uint4 qg[ST_UNROLL], qx[ST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            int64_t v = base + (int64_t)u * ST_THREADS;
+            if (v < nvec) { qg[u] = ldg_stream(gv + v); qx[u] = ldg_stream(xv + v); }
+        }
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            int64_t v = base + (int64_t)u * ST_THREADS;
+            if (v < nvec) {
+                float s = s0, inv_s = inv0;
+                if (smode != 0) {
+                    int64_t idx = (v / inner_v) % count;
+                    s = DT<T>::to_f(scale[idx]);
+                    inv_s = 1.f / s;
+                    if (want_gs && idx != acc_idx) {
+                        if (acc_idx >= 0) atomicAdd(gscale_out + acc_idx, acc);
+                        acc = 0.f;
+                        acc_idx = idx;
+                    }
+                }
+                float eg[V], ex[V];
+                DT<T>::unpack(qg[u], eg);
+                DT<T>::unpack(qx[u], ex);
+#pragma unroll
+                for (int i = 0; i < V; ++i) eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, want_gs, acc);
+                stg_stream(ov + v, DT<T>::pack(eg));
+            }
+        }
+    }
+    if (want_gs) {
+        if (smode == 0) {
+            float t = block_sum_f(acc, red);
+            if (threadIdx.x == 0) atomicAdd(gscale_out, t);
+        } else if (acc_idx >= 0) {
+            atomicAdd(gscale_out + acc_idx, acc);
+        }
+    }
+}
+
+template <typename T, int RM>
+__global__ void int_quant_bwd_scalar_kernel(const T* gy, const T* x, const T* scale, T* gx, float* gscale_out,
+                                            int64_t start, int64_t n, int64_t inner, int64_t count, int scale_f32,
+                                            int masked, QParams p) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool want_gs = gscale_out != nullptr;
+    for (int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int64_t idx = count == 1 ? 0 : (i / inner) % count;
+        float s = count == 1 ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[idx]);
+        float acc = 0.f;
+        float r = bwd_elem<T, RM>(DT<T>::to_f(gy[i]), DT<T>::to_f(x[i]), s, 1.f / s, p, masked, want_gs, acc);
+        gx[i] = DT<T>::from_f(r);
+        if (want_gs) atomicAdd(gscale_out + idx, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fused per-row abs-max + quant-dequant, TMA-staged (the C2 / C3 headline kernel)
+// dynamic smem: [0,64) mbarriers | [64,192) reduction scratch | [256, ...) `stages` row buffers
+// ------------------------------------------------------------------------------------------------------
+constexpr int ROWS_MAX_STAGES = 8;
+constexpr int ROWS_SMEM_HEADER = 256;
+
+template <typename T>
+__device__ __forceinline__ float finalize_scale(float amax, float min_val, int has_min, float int_thr, int scale_f32 = 0) {
+    // _StatsScaling: ScalarClampMinSte(scaling_min_val) (core/restrict_val.py:22-42), then
+    // RescalingIntQuant: scale = threshold / int_threshold (core/quant/int.py:160), both rounded to T
+    // (0-dim T threshold / 0-dim fp32 int_threshold promotes to an fp32 scale: scale_f32)
+    float thr = has_min ? clamp_min_nan(amax, min_val) : amax;
+    float s = fdiv(thr, int_thr);
+    return scale_f32 ? s : DT<T>::rnd(s);
+}
+
+template <typename T, int RM>
+__global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ scale_out,
+                                    T* __restrict__ absmax_out, int rows, int cols, int stages, uint32_t stage_stride,
+                                    float min_val, int has_min, float int_thr, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint32_t* red = reinterpret_cast<uint32_t*>(smem + 64);
+    unsigned char* bufs = smem + ROWS_SMEM_HEADER;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t)cols * (uint32_t)sizeof(T);
+    const int nvec = (int)(row_bytes >> 4);
+    const int first = blockIdx.x, step = gridDim.x;
+    const int my_rows = (rows - first + step - 1) / step;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int pre = my_rows < stages ? my_rows : stages;
+        for (int s = 0; s < pre; ++s) {
+            mbar_arrive_expect_tx(&bars[s], row_bytes);
+            bulk_g2s(bufs + (size_t)s * stage_stride, x + (size_t)(first + s * step) * cols, row_bytes, &bars[s]);
+        }
+    }
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (int it = 0; it < my_rows; ++it) {
+        const int row = first + it * step;
+        mbar_wait(&bars[s], parity);
+        const uint4* buf = reinterpret_cast<const uint4*>(bufs + (size_t)s * stage_stride);
+
+        // pass 1 (shared memory): max |x| as raw bits
+        uint32_t m = 0;
+#pragma unroll 4
+        for (int v = tid; v < nvec; v += blockDim.x) m = DT<T>::absmax_acc(m, buf[v]);
+        m = warp_max_u32(DT<T>::absmax_fold(m));
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        m = warp_max_u32(lane < nw ? red[lane] : 0u);
+
+        const float amax = DT<T>::bits_to_f(m);
+        const float sc = finalize_scale<T>(amax, min_val, has_min, int_thr);
+        if (tid == 0) {
+            scale_out[row] = DT<T>::from_f(sc);
+            if (absmax_out) absmax_out[row] = DT<T>::from_f(amax);
+        }
+
+        // pass 2 (shared memory -> HBM): quant-dequant, 128-bit stores
+        uint4* yrow = reinterpret_cast<uint4*>(y + (size_t)row * cols);
+#pragma unroll 2
+        for (int v = tid; v < nvec; v += blockDim.x) {
+            uint4 q = buf[v];
+            float e[V];
+            DT<T>::unpack(q, e);
+#pragma unroll
+            for (int i = 0; i < V; ++i) e[i] = quant_dequant<T, RM>(e[i], sc, p);
+            stg_stream(yrow + v, DT<T>::pack(e));
+        }
+        __syncthreads();      // everyone is done with buf[s] and red[]
+        if (tid == 0 && it + stages < my_rows) {
+            mbar_arrive_expect_tx(&bars[s], row_bytes);
+            bulk_g2s(bufs + (size_t)s * stage_stride, x + (size_t)(row + stages * step) * cols, row_bytes, &bars[s]);
+        }
+        if (++s == stages) { s = 0; parity ^= 1u; }
+    }
+}
+
+// generic rows forward: one CTA per row, element loads, any cols / alignment (second read hits L1/L2)
+template <typename T, int RM>
+__global__ void rows_fwd_generic_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ scale_out,
+                                        T* __restrict__ absmax_out, int64_t rows, int64_t cols,
+                                        float min_val, int has_min, float int_thr, int quantize, QParams p) {
+    __shared__ uint32_t red[32];
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const T* xr = x + row * cols;
+        uint32_t m = 0;
+        for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+            uint32_t b = __float_as_uint(DT<T>::to_f(xr[j])) & 0x7fffffffu;
+            m = max(m, b);
+        }
+        m = block_max_u32(m, red);
+        const float amax = __uint_as_float(m);       // exact: came from a T value widened to fp32
+        const float sc = finalize_scale<T>(amax, min_val, has_min, int_thr);
+        if (threadIdx.x == 0) {
+            if (scale_out) scale_out[row] = DT<T>::from_f(sc);
+            if (absmax_out) absmax_out[row] = DT<T>::from_f(amax);
+        }
+        if (quantize) {
+            T* yr = y + row * cols;
+            for (int64_t j = threadIdx.x; j < cols; j += blockDim.x)
+                yr[j] = DT<T>::from_f(quant_dequant<T, RM>(DT<T>::to_f(xr[j]), sc, p));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-row backward with gradient through the abs-max (streaming: 2R + 1W, then a one-element fix-up)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t canon_abs_bits(float v) {
+    uint32_t b = __float_as_uint(v) & 0x7fffffffu;
+    return b > 0x7f800000u ? 0x7f800001u : b;        // all NaNs tie, like torch.max
+}
+
+template <typename T, int RM, bool VECTOR>
+__global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale,
+                                const T* __restrict__ gscale, T* __restrict__ gx, int64_t rows, int64_t cols,
+                                float int_thr, int masked, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ uint32_t red_u[32];
+    __shared__ float red_f[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float s = DT<T>::to_f(scale[row]);
+        const float inv_s = 1.f / s;
+        const T* gr = gy + row * cols;
+        const T* xr = x + row * cols;
+        T* outr = gx + row * cols;
+        float acc = 0.f;
+        uint32_t best = 0, best_idx = 0xffffffffu;
+        if (VECTOR) {
+            const int nvec = (int)(cols / V);
+            const uint4* gv = reinterpret_cast<const uint4*>(gr);
+            const uint4* xv = reinterpret_cast<const uint4*>(xr);
+            uint4* ov = reinterpret_cast<uint4*>(outr);
+            for (int v0 = tid; v0 < nvec; v0 += blockDim.x * 2) {
+                const int v1 = v0 + blockDim.x;
+                uint4 qg0 = ldg_stream(gv + v0), qx0 = ldg_stream(xv + v0);
+                uint4 qg1 = make_uint4(0, 0, 0, 0), qx1 = make_uint4(0, 0, 0, 0);
+                if (v1 < nvec) { qg1 = ldg_stream(gv + v1); qx1 = ldg_stream(xv + v1); }
+                float eg[V], ex[V];
+                DT<T>::unpack(qg0, eg);
+                DT<T>::unpack(qx0, ex);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    uint32_t b = canon_abs_bits(ex[i]);
+                    if (b > best) { best = b; best_idx = (uint32_t)(v0 * V + i); }
+                    eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, true, acc);
+                }
+                stg_stream(ov + v0, DT<T>::pack(eg));
+                if (v1 < nvec) {
+                    DT<T>::unpack(qg1, eg);
+                    DT<T>::unpack(qx1, ex);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        uint32_t b = canon_abs_bits(ex[i]);
+                        if (b > best) { best = b; best_idx = (uint32_t)(v1 * V + i); }
+                        eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, true, acc);
+                    }
+                    stg_stream(ov + v1, DT<T>::pack(eg));
+                }
+            }
+        } else {
+            for (int64_t j = tid; j < cols; j += blockDim.x) {
+                float xe = DT<T>::to_f(xr[j]);
+                uint32_t b = canon_abs_bits(xe);
+                if (b > best) { best = b; best_idx = (uint32_t)j; }
+                outr[j] = DT<T>::from_f(bwd_elem<T, RM>(DT<T>::to_f(gr[j]), xe, s, inv_s, p, masked, true, acc));
+            }
+        }
+        // row reductions: max bits, sum, then the smallest index attaining the max
+        uint32_t wm = warp_max_u32(best);
+        float ws = warp_sum_f(acc);
+        if (lane == 0) { red_u[warp] = wm; red_f[warp] = ws; }
+        __syncthreads();
+        const uint32_t rmax = warp_max_u32(lane < nw ? red_u[lane] : 0u);
+        const float rsum = warp_sum_f(lane < nw ? red_f[lane] : 0.f);
+        __syncthreads();
+        uint32_t cand = (best == rmax) ? best_idx : 0xffffffffu;
+        cand = warp_min_u32(cand);
+        if (lane == 0) red_u[warp] = cand;
+        __syncthreads();      // also orders this block's gx stores before the fix-up read below
+        if (tid == 0) {
+            uint32_t amin = 0xffffffffu;
+            for (int w = 0; w < nw; ++w) amin = min(amin, red_u[w]);
+            if (amin != 0xffffffffu) {     // cols > 0
+                float gsc = rsum + (gscale ? DT<T>::to_f(gscale[row]) : 0.f);
+                // scale = thr / int_thr  =>  d thr = d scale / int_thr; clamp_min_ste and view are identity;
+                // max(dim) routes it to the arg-max, abs multiplies by sgn(x)
+                float dthr = DT<T>::rnd(fdiv(DT<T>::rnd(gsc), int_thr));
+                float xe = DT<T>::to_f(xr[amin]);
+                float contrib = fmul(dthr, sign3(xe));
+                float cur = DT<T>::to_f(outr[amin]);
+                outr[amin] = DT<T>::from_f(fadd(cur, contrib));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// whole-tensor abs-max: phase 1 block maxima -> atomicMax, last block finalises the scale
+// workspace words: [0] max bits  [1] ticket  [2] Gs (float)  [3] tie count  [4..] tie indices (int64)
+// ------------------------------------------------------------------------------------------------------
+constexpr int WS_MAXBITS = 0, WS_TICKET = 1, WS_GS = 2, WS_TIES = 3, WS_LIST = 4;
+constexpr int TIE_CAP = 4096;
+
+template <typename T>
+__global__ void __launch_bounds__(ST_THREADS) absmax_tensor_kernel(
+        const T* __restrict__ x, int64_t n, int vec_ok, uint32_t* ws, T* scale_out, T* absmax_out,
+        float min_val, int has_min, float int_thr, int scale_f32) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ uint32_t red[32];
+    const int64_t nvec = vec_ok ? n / V : 0;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const int64_t chunk = ST_THREADS * ST_UNROLL;
+    const int64_t nchunks = (nvec + chunk - 1) / chunk;
+    uint32_t m = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t base = c * chunk + threadIdx.x;
+        uint4 q[ST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            int64_t v = base + (int64_t)u * ST_THREADS;
+            q[u] = (v < nvec) ? ldg_stream(xv + v) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) m = DT<T>::absmax_acc(m, q[u]);
+    }
+    m = DT<T>::absmax_fold(m);
+    // widen to fp32 bit ordering so that all dtypes share the same workspace encoding
+    uint32_t mf = __float_as_uint(DT<T>::bits_to_f(m));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        mf = max(mf, __float_as_uint(DT<T>::to_f(x[i])) & 0x7fffffffu);
+    mf = block_max_u32(mf, red);
+    if (threadIdx.x == 0) {
+        atomicMax(ws + WS_MAXBITS, mf);
+        __threadfence();
+        uint32_t ticket = atomicAdd(ws + WS_TICKET, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            uint32_t all = atomicMax(ws + WS_MAXBITS, 0u);
+            float amax = __uint_as_float(all);
+            if (absmax_out) absmax_out[0] = DT<T>::from_f(amax);
+            if (scale_out) {
+                float sc = finalize_scale<T>(amax, min_val, has_min, int_thr, scale_f32);
+                if (scale_f32) reinterpret_cast<float*>(scale_out)[0] = sc;
+                else scale_out[0] = DT<T>::from_f(sc);
+            }
+        }
+    }
+}
+
+// provided-scale backward for the whole-tensor statistic: additionally collects the positions of the tied maxima
+template <typename T, int RM>
+__global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
+        const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, const T* __restrict__ absmax,
+        T* __restrict__ gx, int64_t n, int vec_ok, uint32_t* ws, int scale_f32, int masked, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ float red[32];
+    const float s = load_scale0<T>(scale, scale_f32);
+    const float inv_s = 1.f / s;
+    const uint32_t mbits = canon_abs_bits(DT<T>::to_f(absmax[0]));
+    long long* list = reinterpret_cast<long long*>(ws + WS_LIST);
+    float acc = 0.f;
+    const int64_t nvec = vec_ok ? n / V : 0;
+    const uint4* gv = reinterpret_cast<const uint4*>(gy);
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    uint4* ov = reinterpret_cast<uint4*>(gx);
+    const int64_t chunk = ST_THREADS * ST_UNROLL;
+    const int64_t nchunks = (nvec + chunk - 1) / chunk;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t base = c * chunk + threadIdx.x;
+        uint4 qg[ST_UNROLL], qx[ST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            int64_t v = base + (int64_t)u * ST_THREADS;
+            if (v < nvec) { qg[u] = ldg_stream(gv + v); qx[u] = ldg_stream(xv + v); }
+        }
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            int64_t v = base + (int64_t)u * ST_THREADS;
+            if (v < nvec) {
+                float eg[V], ex[V];
+                DT<T>::unpack(qg[u], eg);
+                DT<T>::unpack(qx[u], ex);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    if (canon_abs_bits(ex[i]) == mbits) {
+                        uint32_t slot = atomicAdd(ws + WS_TIES, 1u);
+                        if (slot < TIE_CAP) list[slot] = v * V + i;
+                    }
+                    eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, true, acc);
+                }
+                stg_stream(ov + v, DT<T>::pack(eg));
+            }
+        }
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float xe = DT<T>::to_f(x[i]);
+        if (canon_abs_bits(xe) == mbits) {
+            uint32_t slot = atomicAdd(ws + WS_TIES, 1u);
+            if (slot < TIE_CAP) list[slot] = i;
+        }
+        gx[i] = DT<T>::from_f(bwd_elem<T, RM>(DT<T>::to_f(gy[i]), xe, s, inv_s, p, masked, true, acc));
+    }
+    float t = block_sum_f(acc, red);
+    if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(ws + WS_GS), t);
+}
+
+// torch.max() backward: grad / (#ties) to every tied maximum (evenly_distribute_backward), times sgn(x)
+template <typename T>
+__global__ void tensor_bwd_fixup_kernel(const T* __restrict__ x, const T* __restrict__ absmax, const T* __restrict__ gscale,
+                                        T* __restrict__ gx, int64_t n, const uint32_t* ws, float int_thr, int scale_f32) {
+    const uint32_t ties = ws[WS_TIES];
+    if (ties == 0) return;
+    const float gsc = *reinterpret_cast<const float*>(ws + WS_GS) + (gscale ? load_scale0<T>(gscale, scale_f32) : 0.f);
+    const float dthr = DT<T>::rnd(fdiv(DT<T>::rnd(gsc), int_thr));
+    const float share = DT<T>::rnd(fdiv(dthr, (float)ties));
+    const long long* list = reinterpret_cast<const long long*>(ws + WS_LIST);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (ties <= TIE_CAP) {
+        for (int64_t k = tid; k < ties; k += stride) {
+            int64_t i = list[k];
+            float xe = DT<T>::to_f(x[i]);
+            gx[i] = DT<T>::from_f(fadd(DT<T>::to_f(gx[i]), fmul(share, sign3(xe))));
+        }
+    } else {       // pathological tie count: rescan
+        const uint32_t mbits = canon_abs_bits(DT<T>::to_f(absmax[0]));
+        for (int64_t i = tid; i < n; i += stride) {
+            float xe = DT<T>::to_f(x[i]);
+            if (canon_abs_bits(xe) == mbits)
+                gx[i] = DT<T>::from_f(fadd(DT<T>::to_f(gx[i]), fmul(share, sign3(xe))));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-side launch logic
+// ------------------------------------------------------------------------------------------------------
+static inline QParams make_qparams(float zero_point, float qmin, float qmax, int dtype) {
+    QParams p;
+    p.qmin = round_to_dtype(qmin, dtype);
+    p.qmax = round_to_dtype(qmax, dtype);
+    p.zp = round_to_dtype(zero_point, dtype);
+    p.zp_nonzero = (zero_point != 0.f) ? 1 : 0;
+    return p;
+}
+
+static inline unsigned stream_grid(int64_t nvec_or_n, int per_block) {
+    int64_t b = (nvec_or_n + per_block - 1) / per_block;
+    int per_sm = tuning().stream_ctas_per_sm > 0 ? tuning().stream_ctas_per_sm : 16;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+template <typename T, int RM>
+static int launch_int_quant_fwd(const void* x, const void* scale, void* y, void* codes, int64_t n,
+                                int64_t inner, int64_t count, int scale_f32, const QParams& p, int reverse,
+                                cudaStream_t st) {
+    constexpr int V = DT<T>::VEC;
+    int64_t nvec = 0;
+    int smode = (count == 1) ? 0 : 1;
+    bool vec_ok = aligned16(x) && aligned16(y) && (!codes || aligned16(codes));
+    if (smode == 1 && (inner % V) != 0) vec_ok = false;
+    if (vec_ok) nvec = n / V;
+    if (nvec > 0) {
+        unsigned grid = stream_grid(nvec, ST_THREADS * ST_UNROLL);
+        int_quant_fwd_kernel<T, RM><<<grid, ST_THREADS, 0, st>>>((const T*)x, (const T*)scale, (T*)y, (T*)codes, nvec,
+                                                                 smode ? inner / V : 1, count, smode, scale_f32, reverse, p);
+    }
+    int64_t done = nvec * V;
+    if (done < n) {
+        unsigned grid = stream_grid(n - done, 256);
+        int_quant_fwd_scalar_kernel<T, RM><<<grid, 256, 0, st>>>((const T*)x, (const T*)scale, (T*)y, (T*)codes,
+                                                                 done, n, inner, count, scale_f32, p);
+    }
+    return check_launch("bvb_int_quant_fwd");
+}
+
+template <typename T, int RM>
+static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out,
+                                int64_t n, int64_t inner, int64_t count, int scale_f32, const QParams& p, int masked,
+                                cudaStream_t st) {
+    constexpr int V = DT<T>::VEC;
+    if (gscale_out) {
+        cudaError_t e = cudaMemsetAsync(gscale_out, 0, sizeof(float) * (size_t)count, st);
+        if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_int_quant_bwd: memset: %s", cudaGetErrorString(e));
+    }
+    int64_t nvec = 0;
+    int smode = (count == 1) ? 0 : 1;
+    bool vec_ok = aligned16(gy) && aligned16(x) && aligned16(gx);
+    if (smode == 1 && (inner % V) != 0) vec_ok = false;
+    if (vec_ok) nvec = n / V;
+    if (nvec > 0) {
+        unsigned grid = stream_grid(nvec, ST_THREADS * ST_UNROLL);
+        int_quant_bwd_kernel<T, RM><<<grid, ST_THREADS, 0, st>>>((const T*)gy, (const T*)x, (const T*)scale, (T*)gx,
+                                                                 gscale_out, nvec, smode ? inner / V : 1, count, smode,
+                                                                 scale_f32, masked, p);
+    }
+    int64_t done = nvec * V;
+    if (done < n) {
+        unsigned grid = stream_grid(n - done, 256);
+        int_quant_bwd_scalar_kernel<T, RM><<<grid, 256, 0, st>>>((const T*)gy, (const T*)x, (const T*)scale, (T*)gx,
+                                                                 gscale_out, done, n, inner, count, scale_f32, masked, p);
+    }
+    return check_launch("bvb_int_quant_bwd");
+}
+
+// geometry of the TMA rows kernel
+struct RowsGeom { int threads, stages, ctas_per_sm; uint32_t stage_stride; size_t smem; bool ok; };
+
+static RowsGeom rows_geometry(int64_t cols, int elem_size) {
+    RowsGeom g = {0, 0, 0, 0, 0, false};
+    const int64_t row_bytes = cols * elem_size;
+    if (row_bytes < 16 || (row_bytes & 15) != 0) return g;
+    const int64_t budget = 220 * 1024;                      // of the 227 KB per SM
+    g.stage_stride = (uint32_t)((row_bytes + 127) & ~(int64_t)127);
+    const int64_t nvec = row_bytes / 16;
+    int threads = 128;
+    while (threads < 512 && nvec > (int64_t)threads * 6) threads *= 2;
+    int max_total = (int)((budget) / (int64_t)g.stage_stride);   // row buffers that fit in one SM
+    if (max_total < 2) return g;
+    int ctas, stages;
+    if (max_total >= 4) {
+        stages = max_total >= 12 ? 4 : (max_total >= 6 ? 3 : 2);
+        ctas = max_total / stages;
+    } else {
+        stages = max_total;
+        ctas = 1;
+    }
+    int max_ctas = 2048 / threads;
+    if (max_ctas > 16) max_ctas = 16;
+    if (ctas > max_ctas) ctas = max_ctas;
+    const Tuning& t = tuning();
+    if (t.rows_threads > 0) threads = t.rows_threads;
+    if (t.rows_stages > 0) stages = t.rows_stages;
+    if (t.rows_ctas_per_sm > 0) ctas = t.rows_ctas_per_sm;
+    if (stages > ROWS_MAX_STAGES) stages = ROWS_MAX_STAGES;
+    // re-validate against the shared-memory budget
+    while (ctas > 1 && (int64_t)ctas * (ROWS_SMEM_HEADER + (int64_t)stages * g.stage_stride + 1024) > 227 * 1024) --ctas;
+    while (stages > 1 && (ROWS_SMEM_HEADER + (int64_t)stages * g.stage_stride) > 226 * 1024) --stages;
+    if (stages < 2) return g;
+    g.threads = threads;
+    g.stages = stages;
+    g.ctas_per_sm = ctas;
+    g.smem = ROWS_SMEM_HEADER + (size_t)stages * g.stage_stride;
+    g.ok = true;
+    return g;
+}
+
+template <typename T, int RM>
+static int launch_rows_fwd(const void* x, void* y, void* scale_out, void* absmax_out, int64_t rows, int64_t cols,
+                           float min_val, int has_min, float int_thr, const QParams& p, cudaStream_t st) {
+    RowsGeom g = rows_geometry(cols, (int)sizeof(T));
+    const bool tma_ok = g.ok && aligned16(x) && aligned16(y) && rows < (int64_t)1 << 30 && cols < (int64_t)1 << 30;
+    if (tma_ok) {
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(rows_fwd_tma_kernel<T, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024);
+            if (e != cudaSuccess) return fail(BVB_ECUDA, "rows_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        int64_t grid = (int64_t)g.ctas_per_sm * sm_count();
+        if (grid > rows) grid = rows;
+        rows_fwd_tma_kernel<T, RM><<<(unsigned)grid, g.threads, g.smem, st>>>(
+            (const T*)x, (T*)y, (T*)scale_out, (T*)absmax_out, (int)rows, (int)cols, g.stages, g.stage_stride,
+            min_val, has_min, int_thr, p);
+    } else {
+        int threads = cols >= 4096 ? 512 : (cols >= 512 ? 256 : 64);
+        int64_t grid = rows;
+        int64_t cap = (int64_t)sm_count() * (2048 / threads);
+        if (grid > cap) grid = cap;
+        rows_fwd_generic_kernel<T, RM><<<(unsigned)grid, threads, 0, st>>>(
+            (const T*)x, (T*)y, (T*)scale_out, (T*)absmax_out, rows, cols, min_val, has_min, int_thr, 1, p);
+    }
+    return check_launch("bvb_rows_absmax_int_quant_fwd");
+}
+
+template <typename T, int RM>
+static int launch_rows_bwd(const void* gy, const void* x, const void* scale, const void* gscale, void* gx,
+                           int64_t rows, int64_t cols, float int_thr, const QParams& p, int masked, cudaStream_t st) {
+    constexpr int V = DT<T>::VEC;
+    const bool vec_ok = aligned16(gy) && aligned16(x) && aligned16(gx) && (cols % V) == 0 && cols < (int64_t)1 << 31;
+    const int64_t nvec = cols / V;
+    int threads = 64;
+    if (vec_ok) { while (threads < 512 && nvec > (int64_t)threads * 4) threads *= 2; }
+    else        { while (threads < 512 && cols > (int64_t)threads * 8) threads *= 2; }
+    if (tuning().stream_threads > 0) threads = tuning().stream_threads;
+    int per_sm = 2048 / threads;
+    if (per_sm > 16) per_sm = 16;
+    if (tuning().stream_ctas_per_sm > 0) per_sm = tuning().stream_ctas_per_sm;
+    int64_t grid = rows;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    if (grid > cap) grid = cap;
+    if (vec_ok)
+        rows_bwd_kernel<T, RM, true><<<(unsigned)grid, threads, 0, st>>>((const T*)gy, (const T*)x, (const T*)scale,
+                                                                         (const T*)gscale, (T*)gx, rows, cols, int_thr, masked, p);
+    else
+        rows_bwd_kernel<T, RM, false><<<(unsigned)grid, threads, 0, st>>>((const T*)gy, (const T*)x, (const T*)scale,
+                                                                          (const T*)gscale, (T*)gx, rows, cols, int_thr, masked, p);
+    return check_launch("bvb_rows_absmax_int_quant_bwd");
+}
+
+template <typename T>
+static int launch_absmax_tensor(const void* x, int64_t n, void* ws, void* scale_out, void* absmax_out,
+                                float min_val, int has_min, float int_thr, int scale_f32, cudaStream_t st) {
+    constexpr int V = DT<T>::VEC;
+    cudaError_t e = cudaMemsetAsync(ws, 0, 16, st);
+    if (e != cudaSuccess) return fail(BVB_ECUDA, "absmax_tensor: memset: %s", cudaGetErrorString(e));
+    int vec_ok = aligned16(x) ? 1 : 0;
+    int64_t work = vec_ok ? (n / V + 1) : n;
+    unsigned grid = stream_grid(work, ST_THREADS * ST_UNROLL);
+    absmax_tensor_kernel<T><<<grid, ST_THREADS, 0, st>>>((const T*)x, n, vec_ok, (uint32_t*)ws, (T*)scale_out,
+                                                         (T*)absmax_out, min_val, has_min, int_thr, scale_f32);
+    return check_launch("absmax_tensor");
+}
+
+}  // namespace bvb
+
+using namespace bvb;
+
+// scale_dtype may differ from dtype only as "fp32 one-element scale with low-precision x"
+#define BVB_CHECK_SCALE_DTYPE(name)                                                         \
+    const int scale_f32 = (scale_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;             \
+    if (scale_dtype != dtype && !(scale_f32 && scale_count == 1))                           \
+        return fail(BVB_EUNSUPPORTED, name ": scale dtype must equal the tensor dtype, or be fp32 with one element");
+
+#define BVB_CHECK_COMMON(name, n)                                                           \
+    if ((n) < 0) return fail(BVB_EINVAL, name ": negative size");                           \
+    if (!(qmin <= qmax)) return fail(BVB_EINVAL, name ": qmin must be <= qmax");
+
+extern "C" int bvb_int_quant_fwd(const void* x, const void* scale, void* y, void* codes_out, int64_t n,
+                                 int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,
+                                 float qmax, int round_mode, int dtype, void* stream) {
+    BVB_CHECK_COMMON("bvb_int_quant_fwd", n)
+    BVB_CHECK_SCALE_DTYPE("bvb_int_quant_fwd")
+    if (n == 0) return BVB_OK;
+    if (!x || !scale || !y) return fail(BVB_EINVAL, "bvb_int_quant_fwd: null pointer");
+    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "bvb_int_quant_fwd: bad scale broadcast pattern");
+    QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_fwd<T, RM>(
+        x, scale, y, codes_out, n, scale_inner, scale_count, scale_f32, p, 0, (cudaStream_t)stream))));
+    return BVB_OK;
+}
+
+extern "C" int bvb_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out, int64_t n,
+                                 int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,
+                                 float qmax, int round_mode, int clamp_mode, int dtype, void* stream) {
+    BVB_CHECK_COMMON("bvb_int_quant_bwd", n)
+    BVB_CHECK_SCALE_DTYPE("bvb_int_quant_bwd")
+    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "bvb_int_quant_bwd: bad scale broadcast pattern");
+    if (n == 0) {
+        if (gscale_out) cudaMemsetAsync(gscale_out, 0, sizeof(float) * (size_t)scale_count, (cudaStream_t)stream);
+        return BVB_OK;
+    }
+    if (!gy || !x || !scale || !gx) return fail(BVB_EINVAL, "bvb_int_quant_bwd: null pointer");
+    QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    const int masked = clamp_mode == BVB_CLAMP_MASKED;
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_bwd<T, RM>(
+        gy, x, scale, gx, gscale_out, n, scale_inner, scale_count, scale_f32, p, masked, (cudaStream_t)stream))));
+    return BVB_OK;
+}
+
+extern "C" int bvb_rows_absmax_int_quant_fwd(const void* x, void* y, void* scale_out, void* absmax_out,
+                                             int64_t rows, int64_t cols, float scaling_min_val, float int_threshold,
+                                             float zero_point, float qmin, float qmax, int round_mode, int dtype,
+                                             void* stream) {
+    BVB_CHECK_COMMON("bvb_rows_absmax_int_quant_fwd", rows)
+    if (cols < 0) return fail(BVB_EINVAL, "bvb_rows_absmax_int_quant_fwd: negative cols");
+    if (rows == 0) return BVB_OK;
+    if (cols == 0) return fail(BVB_EINVAL, "bvb_rows_absmax_int_quant_fwd: abs-max over an empty row is undefined");
+    if (!x || !y || !scale_out) return fail(BVB_EINVAL, "bvb_rows_absmax_int_quant_fwd: null pointer");
+    QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    const int has_min = scaling_min_val > 0.f;
+    const float mv = round_to_dtype(scaling_min_val, dtype);
+    const float thr = int_threshold;      // 0-dim divisor: ATen keeps its fp32 value in opmath (not rounded to T)
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_rows_fwd<T, RM>(
+        x, y, scale_out, absmax_out, rows, cols, mv, has_min, thr, p, (cudaStream_t)stream))));
+    return BVB_OK;
+}
+
+extern "C" int bvb_rows_absmax_int_quant_bwd(const void* gy, const void* x, const void* scale, const void* gscale, void* gx,
+                                             int64_t rows, int64_t cols, float int_threshold, float zero_point,
+                                             float qmin, float qmax, int round_mode, int clamp_mode, int dtype,
+                                             void* stream) {
+    BVB_CHECK_COMMON("bvb_rows_absmax_int_quant_bwd", rows)
+    if (cols < 0) return fail(BVB_EINVAL, "bvb_rows_absmax_int_quant_bwd: negative cols");
+    if (rows == 0 || cols == 0) return BVB_OK;
+    if (!gy || !x || !scale || !gx) return fail(BVB_EINVAL, "bvb_rows_absmax_int_quant_bwd: null pointer");
+    QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    const int masked = clamp_mode == BVB_CLAMP_MASKED;
+    const float thr = int_threshold;
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_rows_bwd<T, RM>(
+        gy, x, scale, gscale, gx, rows, cols, thr, p, masked, (cudaStream_t)stream))));
+    return BVB_OK;
+}
+
+extern "C" int bvb_tensor_absmax_int_quant_fwd(const void* x, void* y, void* scale_out, void* absmax_out, int64_t n,
+                                               int scale_dtype, float scaling_min_val, float int_threshold,
+                                               float zero_point, float qmin, float qmax, int round_mode, int dtype,
+                                               void* workspace, void* stream) {
+    BVB_CHECK_COMMON("bvb_tensor_absmax_int_quant_fwd", n)
+    const int64_t scale_count = 1;
+    BVB_CHECK_SCALE_DTYPE("bvb_tensor_absmax_int_quant_fwd")
+    if (n == 0) return fail(BVB_EINVAL, "bvb_tensor_absmax_int_quant_fwd: abs-max over an empty tensor is undefined");
+    if (!x || !y || !scale_out || !workspace) return fail(BVB_EINVAL, "bvb_tensor_absmax_int_quant_fwd: null pointer");
+    QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    const int has_min = scaling_min_val > 0.f;
+    const float mv = round_to_dtype(scaling_min_val, dtype);
+    const float thr = int_threshold;
+    cudaStream_t st = (cudaStream_t)stream;
+    BVB_DISPATCH_DTYPE(dtype, {
+        int rc = launch_absmax_tensor<T>(x, n, workspace, scale_out, absmax_out, mv, has_min, thr, scale_f32, st);
+        if (rc != BVB_OK) return rc;
+    });
+    // second phase runs back to front: the tail of the tensor is what phase 1 left in L2
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_fwd<T, RM>(
+        x, scale_out, y, nullptr, n, 1, 1, scale_f32, p, 1, st))));
+    return BVB_OK;
+}
+
+extern "C" int bvb_tensor_absmax_int_quant_bwd(const void* gy, const void* x, const void* scale, const void* absmax,
+                                               const void* gscale, void* gx, int64_t n, int scale_dtype,
+                                               float int_threshold, float zero_point, float qmin, float qmax,
+                                               int round_mode, int clamp_mode, int dtype, void* workspace, void* stream) {
+    BVB_CHECK_COMMON("bvb_tensor_absmax_int_quant_bwd", n)
+    const int64_t scale_count = 1;
+    BVB_CHECK_SCALE_DTYPE("bvb_tensor_absmax_int_quant_bwd")
+    if (n == 0) return BVB_OK;
+    if (!gy || !x || !scale || !absmax || !gx || !workspace)
+        return fail(BVB_EINVAL, "bvb_tensor_absmax_int_quant_bwd: null pointer");
+    QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    const int masked = clamp_mode == BVB_CLAMP_MASKED;
+    const float thr = int_threshold;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, 16, st);
+    if (e != cudaSuccess) return fail(BVB_ECUDA, "tensor_bwd: memset: %s", cudaGetErrorString(e));
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, {
+        constexpr int V = DT<T>::VEC;
+        int vec_ok = (aligned16(gy) && aligned16(x) && aligned16(gx)) ? 1 : 0;
+        int64_t work = vec_ok ? (n / V + 1) : n;
+        unsigned grid = stream_grid(work, ST_THREADS * ST_UNROLL);
+        tensor_bwd_kernel<T, RM><<<grid, ST_THREADS, 0, st>>>((const T*)gy, (const T*)x, (const T*)scale, (const T*)absmax,
+                                                              (T*)gx, n, vec_ok, (uint32_t*)workspace, scale_f32, masked, p);
+        tensor_bwd_fixup_kernel<T><<<(unsigned)sm_count(), 256, 0, st>>>((const T*)x, (const T*)absmax, (const T*)gscale,
+                                                                          (T*)gx, n, (const uint32_t*)workspace, thr, scale_f32);
+    }));
+    return check_launch("bvb_tensor_absmax_int_quant_bwd");
+}
+
+extern "C" int bvb_absmax_rows(const void* x, void* out, int64_t rows, int64_t cols, int dtype, void* stream) {
+    if (rows < 0 || cols < 0) return fail(BVB_EINVAL, "bvb_absmax_rows: negative size");
+    if (rows == 0) return BVB_OK;
+    if (cols == 0) return fail(BVB_EINVAL, "bvb_absmax_rows: abs-max over an empty row is undefined");
+    if (!x || !out) return fail(BVB_EINVAL, "bvb_absmax_rows: null pointer");
+    QParams p = make_qparams(0.f, 0.f, 0.f, dtype);
+    BVB_DISPATCH_DTYPE(dtype, {
+        int threads = cols >= 4096 ? 512 : (cols >= 512 ? 256 : 64);
+        int64_t grid = rows;
+        int64_t cap = (int64_t)sm_count() * (2048 / threads);
+        if (grid > cap) grid = cap;
+        rows_fwd_generic_kernel<T, 0><<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
+            (const T*)x, nullptr, nullptr, (T*)out, rows, cols, 0.f, 0, 1.f, 0, p);
+    });
+    return check_launch("bvb_absmax_rows");
+}
+
+extern "C" int bvb_absmax_tensor(const void* x, void* out, int64_t n, int dtype, void* workspace, void* stream) {
+    if (n < 0) return fail(BVB_EINVAL, "bvb_absmax_tensor: negative size");
+    if (n == 0) return fail(BVB_EINVAL, "bvb_absmax_tensor: abs-max over an empty tensor is undefined");
+    if (!x || !out || !workspace) return fail(BVB_EINVAL, "bvb_absmax_tensor: null pointer");
+    BVB_DISPATCH_DTYPE(dtype, return launch_absmax_tensor<T>(x, n, workspace, nullptr, out, 0.f, 0, 1.f, 0, (cudaStream_t)stream));
+    return BVB_OK;
+}

@@ -1,0 +1,252 @@
+// brevitas_b200 :: scale statistics that are not fused into a quantizer kernel.
+//
+//   bvb_abs_kth_value_rows    AbsPercentile.forward   src/brevitas/core/stats/stats_op.py:41-66
+//                             = x.abs().kthvalue(k) flat or per row of a 2-D view.  Exact MSB-first radix
+//                             select on the bit pattern of |x| (IEEE ordering of non-negative floats equals
+//                             the unsigned ordering of their bits; NaN patterns sort above +inf, which is
+//                             where torch.kthvalue puts NaN).  One HBM read of x per 8-bit digit
+//                             (fp32: 4 passes, bf16/fp16: 2 passes) instead of a sort.
+//   bvb_running_stats_update  _RuntimeStats.forward   src/brevitas/core/stats/stats_wrapper.py:56-65
+//
+// Workspace layout for the select (uint32 words): hist[pass][row][256].
+#include "common.cuh"
+#include "host.cuh"
+
+namespace bvb {
+
+constexpr int KTH_THREADS = 256;
+constexpr int KTH_UNROLL = 4;
+constexpr int KTH_BINS = 256;
+
+template <typename T> struct KeyTraits;
+template <> struct KeyTraits<float> {
+    static constexpr int PASSES = 4;
+    __device__ __forceinline__ static uint32_t key(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+    __device__ __forceinline__ static float value(uint32_t k) { return __uint_as_float(k); }
+};
+template <> struct KeyTraits<__nv_bfloat16> {
+    static constexpr int PASSES = 2;
+    __device__ __forceinline__ static uint32_t key(float v) { return (__float_as_uint(v) >> 16) & 0x7fffu; }
+    __device__ __forceinline__ static float value(uint32_t k) { return __uint_as_float(k << 16); }
+};
+template <> struct KeyTraits<__half> {
+    static constexpr int PASSES = 2;
+    __device__ __forceinline__ static uint32_t key(float v) { return (uint32_t)(__half_as_ushort(__float2half_rn(v)) & 0x7fffu); }
+    __device__ __forceinline__ static float value(uint32_t k) {
+        __half_raw r; r.x = (unsigned short)k; return __half2float(__half(r));
+    }
+};
+
+// Resolve the digits fixed by passes [0, upto) for one row.  Executed by warp 0 of a block; returns
+// (prefix, remaining k) to every lane.  hist counts are exact, so the walk is deterministic.
+__device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, int64_t row, int upto, int64_t k,
+                                            uint32_t& prefix, int64_t& krem) {
+    const int lane = threadIdx.x & 31;
+    prefix = 0;
+    krem = k;
+    for (int q = 0; q < upto; ++q) {
+        const uint32_t* h = hist + ((int64_t)q * rows + row) * KTH_BINS;
+        // each lane owns 8 consecutive bins
+        uint32_t c[8];
+        int64_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = h[lane * 8 + j]; mine += c[j]; }
+        // exclusive prefix over lanes
+        int64_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int64_t excl = incl - mine;
+        // the lane whose range contains the krem-th element (1-indexed)
+        bool has = (krem > excl) && (krem <= incl);
+        uint32_t who = __ballot_sync(0xffffffffu, has);
+        int src = who ? (__ffs(who) - 1) : 31;
+        int bin = 0;
+        int64_t before = excl;
+        if (lane == src) {
+            int64_t run = excl;
+            bin = 7;
+            before = excl + mine - c[7];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (krem <= run + c[j]) { bin = j; before = run; break; }
+                run += c[j];
+            }
+            bin += lane * 8;
+        }
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        before = __shfl_sync(0xffffffffu, before, src);
+        prefix = (prefix << 8) | (uint32_t)bin;
+        krem -= before;
+    }
+}
+
+// one radix pass: histogram digit `pass` of the keys whose higher digits equal the resolved prefix
+template <typename T>
+__global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
+                                                                int vec_ok, int pass, int64_t k, uint32_t* hist) {
+    constexpr int V = DT<T>::VEC;
+    constexpr int P = KeyTraits<T>::PASSES;
+    __shared__ uint32_t sh[KTH_THREADS / 32][KTH_BINS];
+    __shared__ uint32_t s_prefix;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int shift = 8 * (P - 1 - pass);
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        for (int i = threadIdx.x; i < (KTH_THREADS / 32) * KTH_BINS; i += KTH_THREADS) (&sh[0][0])[i] = 0;
+        if (warp == 0) {
+            uint32_t prefix; int64_t krem;
+            kth_resolve(hist, rows, row, pass, k, prefix, krem);
+            if (lane == 0) s_prefix = prefix;
+        }
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const T* xr = x + row * cols;
+        uint32_t* myh = sh[warp];
+        // every lane of a warp runs the same trip count (bounds are rounded up to the block), so the
+        // warp-wide primitives below always see a full, converged warp
+        auto visit = [&](float v, bool valid) {
+            uint32_t key = KeyTraits<T>::key(v);
+            bool take = valid && ((pass == 0) || ((key >> (shift + 8)) == prefix));
+            uint32_t bin = take ? ((key >> shift) & 0xffu) : (0x100u + (uint32_t)lane);
+            // warp-aggregated shared atomics: one add per distinct bin per warp instruction
+            uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            if (take && lane == __ffs(peers) - 1) atomicAdd(&myh[bin], (uint32_t)__popc(peers));
+        };
+        const int64_t nvec = vec_ok ? cols / V : 0;
+        const uint4* xv = reinterpret_cast<const uint4*>(xr);
+        const int64_t gstride = (int64_t)gridDim.x * KTH_THREADS;
+        for (int64_t b0 = (int64_t)blockIdx.x * KTH_THREADS; b0 < nvec; b0 += gstride) {
+            const int64_t v0 = b0 + threadIdx.x;
+            const bool valid = v0 < nvec;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (valid) q = ldg_stream(xv + v0);
+            float e[V];
+            DT<T>::unpack(q, e);
+#pragma unroll
+            for (int i = 0; i < V; ++i) visit(e[i], valid);
+        }
+        for (int64_t b0 = nvec * V + (int64_t)blockIdx.x * KTH_THREADS; b0 < cols; b0 += gstride) {
+            const int64_t j = b0 + threadIdx.x;
+            const bool valid = j < cols;
+            visit(valid ? DT<T>::to_f(xr[j]) : 0.f, valid);
+        }
+        __syncthreads();
+        uint32_t* gh = hist + ((int64_t)pass * rows + row) * KTH_BINS;
+        for (int b = threadIdx.x; b < KTH_BINS; b += KTH_THREADS) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < KTH_THREADS / 32; ++w) t += sh[w][b];
+            if (t) atomicAdd(gh + b, t);
+        }
+        __syncthreads();
+    }
+}
+
+// all digits resolved: write the value; optionally locate the smallest index attaining it
+template <typename T>
+__global__ void __launch_bounds__(KTH_THREADS) kth_final_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
+                                                                 int64_t k, const uint32_t* hist, T* out,
+                                                                 long long* index_out) {
+    constexpr int P = KeyTraits<T>::PASSES;
+    __shared__ uint32_t s_key;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        if (warp == 0) {
+            uint32_t prefix; int64_t krem;
+            kth_resolve(hist, rows, row, P, k, prefix, krem);
+            if (lane == 0) s_key = prefix;
+        }
+        __syncthreads();
+        const uint32_t key = s_key;
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[row] = DT<T>::from_f(KeyTraits<T>::value(key));
+        if (index_out) {
+            const T* xr = x + row * cols;
+            long long best = 0x7fffffffffffffffLL;
+            for (int64_t j = (int64_t)blockIdx.x * KTH_THREADS + threadIdx.x; j < cols; j += (int64_t)gridDim.x * KTH_THREADS) {
+                if (KeyTraits<T>::key(DT<T>::to_f(xr[j])) == key) { best = j; break; }   // ascending per thread
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                long long t = __shfl_xor_sync(0xffffffffu, best, o);
+                best = t < best ? t : best;
+            }
+            if (lane == 0 && best != 0x7fffffffffffffffLL) atomicMin(index_out + row, best);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
+                      void* workspace, cudaStream_t st) {
+    constexpr int P = KeyTraits<T>::PASSES;
+    constexpr int V = DT<T>::VEC;
+    uint32_t* hist = (uint32_t*)workspace;
+    cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)P * (size_t)rows * KTH_BINS, st);
+    if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_abs_kth_value_rows: memset: %s", cudaGetErrorString(e));
+    if (index_out) {
+        e = cudaMemsetAsync(index_out, 0x7f, sizeof(int64_t) * (size_t)rows, st);
+        if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_abs_kth_value_rows: memset: %s", cudaGetErrorString(e));
+    }
+    const int vec_ok = (aligned16(x) && (cols % V) == 0) ? 1 : 0;
+    const int64_t work = vec_ok ? cols / V : cols;
+    int64_t gx = (work + (int64_t)KTH_THREADS * KTH_UNROLL - 1) / ((int64_t)KTH_THREADS * KTH_UNROLL);
+    int64_t gy = rows < 65535 ? rows : 65535;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (gx * gy > cap) gx = (cap + gy - 1) / gy;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    for (int pass = 0; pass < P; ++pass)
+        kth_hist_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist);
+    kth_final_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out);
+    return check_launch("bvb_abs_kth_value_rows");
+}
+
+template <typename T>
+__global__ void running_stats_kernel(float* running, const T* stat, int64_t count, float momentum,
+                                     float one_minus_momentum, int first) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float s = DT<T>::to_f(stat[i]);
+    float r = running[i];
+    if (first) {
+        r = fmul(r, s);                                     // running_stats *= out.detach()
+    } else {
+        r = fmul(r, one_minus_momentum);                    // running_stats *= (1 - momentum)  (python double -> fp32)
+        r = fadd(r, DT<T>::rnd(fmul(s, momentum)));         // running_stats += momentum * out.detach()  (T product)
+    }
+    running[i] = r;
+}
+
+}  // namespace bvb
+
+using namespace bvb;
+
+extern "C" int64_t bvb_kth_workspace_bytes(int64_t rows) {
+    if (rows < 1) rows = 1;
+    return (int64_t)sizeof(uint32_t) * 4 * rows * KTH_BINS;
+}
+
+extern "C" int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols,
+                                      int64_t k, int dtype, void* workspace, void* stream) {
+    if (rows < 0 || cols < 0) return fail(BVB_EINVAL, "bvb_abs_kth_value_rows: negative size");
+    if (rows == 0) return BVB_OK;
+    if (k < 1 || k > cols)
+        return fail(BVB_EINVAL, "bvb_abs_kth_value_rows: k = %lld out of range [1, %lld]", (long long)k, (long long)cols);
+    if (!x || !out || !workspace) return fail(BVB_EINVAL, "bvb_abs_kth_value_rows: null pointer");
+    BVB_DISPATCH_DTYPE(dtype, return launch_kth<T>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream));
+    return BVB_OK;
+}
+
+extern "C" int bvb_running_stats_update(float* running, const void* stat, int64_t count, float momentum,
+                                        float one_minus_momentum, int first, int dtype, void* stream) {
+    if (count < 0) return fail(BVB_EINVAL, "bvb_running_stats_update: negative size");
+    if (count == 0) return BVB_OK;
+    if (!running || !stat) return fail(BVB_EINVAL, "bvb_running_stats_update: null pointer");
+    const unsigned blocks = (unsigned)((count + 255) / 256);
+    BVB_DISPATCH_DTYPE(dtype, running_stats_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                                  running, (const T*)stat, count, momentum, one_minus_momentum, first));
+    return check_launch("bvb_running_stats_update");
+}

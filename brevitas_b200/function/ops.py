@@ -1,0 +1,73 @@
+"""Mirror of ``brevitas.function.ops`` (src/brevitas/function/ops.py) -- the non-STE helper functions.
+
+The integer-range helpers work on the tiny 0-dim ``bit_width`` tensors exactly like the reference (they stay
+on ATen); the element-wise functions over full tensors run on the sm_100a kernels.
+"""
+import torch
+from torch import Tensor
+
+__all__ = ['binary_sign', 'round_to_zero', 'dpu_round', 'tensor_clamp', 'tensor_clamp_', 'identity', 'max_int',
+           'min_int']
+
+
+def _k(name, x):
+    from .. import _kernels
+    return _kernels.unary(name, x)
+
+
+def binary_sign(x: Tensor) -> Tensor:
+    """2-valued sign ``(x >= 0) - (x < 0)`` (reference: function/ops.py:17-34).
+
+    Built from comparisons in the reference, so the result carries no gradient; same here (detached)."""
+    return _k("bvb_binary_sign_ste_impl", x.detach())
+
+
+def round_to_zero(x: Tensor) -> Tensor:
+    """``sign(x) * floor(abs(x))`` (reference: function/ops.py:38-53); forward values only (detached)."""
+    return _k("bvb_round_to_zero_ste_impl", x.detach())
+
+
+def dpu_round(x: Tensor) -> Tensor:
+    """DPU rounding (reference: function/ops.py:57-72); forward values only (detached)."""
+    return _k("bvb_dpu_round_ste_impl", x.detach())
+
+
+def tensor_clamp(x: Tensor, min_val: Tensor, max_val: Tensor) -> Tensor:
+    """Clamp with tensor bounds, differentiable w.r.t. x, min_val and max_val (reference: function/ops.py:76-100).
+
+    This is the *standalone* differentiable form; it keeps the reference's two ``torch.where`` calls so that the
+    autograd semantics (masked gradient, gradients to the bounds) are inherited verbatim.  Inside ``IntQuant`` the
+    same arithmetic is fused into the quant kernels (``brevitas_b200::int_quant`` with ``CLAMP_MASKED``).
+    """
+    out = torch.where(x > max_val, max_val.type_as(x), x)
+    out = torch.where(out < min_val, min_val.type_as(out), out)
+    return out
+
+
+def tensor_clamp_(x: Tensor, min_val: Tensor, max_val: Tensor) -> Tensor:
+    """In-place clamp, not differentiable (reference: function/ops.py:104-111). Returns ``x``."""
+    from .. import _kernels
+    _kernels.tensor_clamp(x.detach(), min_val, max_val, inplace=True)
+    return x
+
+
+def identity(x: Tensor) -> Tensor:
+    return x
+
+
+def max_int(signed: bool, narrow_range: bool, bit_width: Tensor) -> Tensor:
+    """Largest representable integer (reference: function/ops.py:133-160)."""
+    if not signed and not narrow_range:
+        return (2 ** bit_width) - 1
+    if not signed and narrow_range:
+        return (2 ** bit_width) - 2
+    return (2 ** (bit_width - 1)) - 1
+
+
+def min_int(signed: bool, narrow_range: bool, bit_width: Tensor) -> Tensor:
+    """Smallest representable integer (reference: function/ops.py:164-191)."""
+    if signed and narrow_range:
+        return - (2 ** (bit_width - 1)) + 1
+    if signed and not narrow_range:
+        return - (2 ** (bit_width - 1))
+    return 0 * bit_width

@@ -1,0 +1,421 @@
+"""torch.library registration of the B200 fake-quant kernels.
+
+Two dispatcher namespaces are defined:
+
+* ``autograd_ste_ops`` -- the reference's own native-plugin namespace with its 12 op names
+  (src/brevitas/csrc/autograd_ste_ops.cpp:258-271), so ``brevitas.function.ops_ste`` can dispatch to these
+  kernels through ``torch.ops.autograd_ste_ops.<name>`` without source changes.
+* ``brevitas_b200`` -- the fused quantizer ops used by the module layer (``brevitas_b200.core``).
+
+Every op has a CUDA implementation only (ctypes -> C-ABI -> sm_100a kernels), an autograd formula and a
+fake/meta implementation.  Calling any of them with CPU tensors raises: there is no CPU fallback.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.library import Library
+
+from . import _kernels as K
+from . import _lib
+
+# the reference's native extension must not be loaded in the same process (duplicate TORCH_LIBRARY DEF)
+_STE = Library("autograd_ste_ops", "DEF")
+_FQ = Library("brevitas_b200", "DEF")
+
+STE_NS = "autograd_ste_ops"
+FQ_NS = "brevitas_b200"
+
+
+def _no_cpu(name):
+    def _raise(*args, **kwargs):
+        raise RuntimeError(
+            f"{name}: CPU tensors are not supported -- brevitas_b200 is a CUDA (sm_100a) implementation with no "
+            "CPU fallback. Move the module and its inputs to a B200.")
+    return _raise
+
+
+# ============================================================================================================
+# 1. autograd_ste_ops: the 12 STE primitives
+# ============================================================================================================
+
+def _identity_backward(ctx, grad):
+    # csrc/autograd_ste_ops.cpp:22 returns grad_output[0] itself
+    return grad
+
+
+_UNARY_STE = {
+    "round_ste_impl": "bvb_round_ste_impl",                  # csrc:14-24
+    "ceil_ste_impl": "bvb_ceil_ste_impl",                    # csrc:100-110
+    "floor_ste_impl": "bvb_floor_ste_impl",                  # csrc:112-122
+    "binary_sign_ste_impl": "bvb_binary_sign_ste_impl",      # csrc:124-137
+    "ternary_sign_ste_impl": "bvb_ternary_sign_ste_impl",    # csrc:140-150
+    "round_to_zero_ste_impl": "bvb_round_to_zero_ste_impl",  # csrc:153-163
+    "dpu_round_ste_impl": "bvb_dpu_round_ste_impl",          # csrc:166-179
+}
+
+
+def _def_unary(op_name, c_name):
+    _STE.define(f"{op_name}(Tensor x) -> Tensor")
+    _STE.impl(op_name, lambda x, _c=c_name: K.unary(_c, x), "CUDA")
+    _STE.impl(op_name, _no_cpu(op_name), "CPU")
+    torch.library.register_fake(f"{STE_NS}::{op_name}", lambda x: torch.empty_like(x), lib=_STE)
+    torch.library.register_autograd(f"{STE_NS}::{op_name}", _identity_backward, lib=_STE)
+
+
+for _op, _c in _UNARY_STE.items():
+    _def_unary(_op, _c)
+
+# abs_binary_sign_grad_impl: forward abs, backward binary_sign(x) * g   (csrc:182-194)
+_STE.define("abs_binary_sign_grad_impl(Tensor x) -> Tensor")
+_STE.impl("abs_binary_sign_grad_impl", lambda x: K.unary("bvb_abs_binary_sign_grad_impl", x), "CUDA")
+_STE.impl("abs_binary_sign_grad_impl", _no_cpu("abs_binary_sign_grad_impl"), "CPU")
+torch.library.register_fake(f"{STE_NS}::abs_binary_sign_grad_impl", lambda x: torch.empty_like(x), lib=_STE)
+
+_FQ.define("abs_binary_sign_grad_backward(Tensor x, Tensor gy) -> Tensor")
+_FQ.impl("abs_binary_sign_grad_backward", lambda x, gy: K.abs_binary_sign_grad_bwd(x, gy), "CUDA")
+_FQ.impl("abs_binary_sign_grad_backward", _no_cpu("abs_binary_sign_grad_backward"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::abs_binary_sign_grad_backward", lambda x, gy: torch.empty_like(gy), lib=_FQ)
+
+
+def _absgrad_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+
+
+def _absgrad_backward(ctx, grad):
+    (x,) = ctx.saved_tensors
+    return torch.ops.brevitas_b200.abs_binary_sign_grad_backward(x, grad.to(x.dtype))
+
+
+torch.library.register_autograd(f"{STE_NS}::abs_binary_sign_grad_impl", _absgrad_backward,
+                                setup_context=_absgrad_setup, lib=_STE)
+
+# tensor_clamp_ste_impl: where-clamp with tensor bounds, gradient (g, None, None)   (csrc:27-44)
+_STE.define("tensor_clamp_ste_impl(Tensor x, Tensor min_val, Tensor max_val) -> Tensor")
+_STE.impl("tensor_clamp_ste_impl", lambda x, mn, mx: K.tensor_clamp(x, mn, mx, inplace=False), "CUDA")
+_STE.impl("tensor_clamp_ste_impl", _no_cpu("tensor_clamp_ste_impl"), "CPU")
+torch.library.register_fake(f"{STE_NS}::tensor_clamp_ste_impl", lambda x, mn, mx: torch.empty_like(x), lib=_STE)
+torch.library.register_autograd(f"{STE_NS}::tensor_clamp_ste_impl", lambda ctx, g: (g, None, None), lib=_STE)
+
+# tensor_clamp_ste_impl_: in place, returns its input.  Follows the reference's PYTHON backend
+# (ops/autograd_ste_ops.py:146-148); the C++ backend binds this name to the out-of-place function by mistake
+# (csrc:261).
+_STE.define("tensor_clamp_ste_impl_(Tensor(a!) x, Tensor min_val, Tensor max_val) -> Tensor(a!)")
+_STE.impl("tensor_clamp_ste_impl_", lambda x, mn, mx: K.tensor_clamp(x, mn, mx, inplace=True), "CUDA")
+_STE.impl("tensor_clamp_ste_impl_", _no_cpu("tensor_clamp_ste_impl_"), "CPU")
+
+
+class _InplaceTensorClampSte(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, min_val, max_val):
+        ctx.mark_dirty(x)
+        with torch._C._AutoDispatchBelowAutograd():
+            torch.ops.autograd_ste_ops.tensor_clamp_ste_impl_(x, min_val, max_val)
+        return x
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad, None, None
+
+
+_STE.impl("tensor_clamp_ste_impl_", lambda x, mn, mx: _InplaceTensorClampSte.apply(x, mn, mx), "Autograd")
+
+# scalar clamps (csrc:66-97)
+_STE.define("scalar_clamp_ste_impl(Tensor x, float min_val, float max_val) -> Tensor")
+_STE.impl("scalar_clamp_ste_impl", lambda x, lo, hi: K.scalar_clamp(x, lo, hi), "CUDA")
+_STE.impl("scalar_clamp_ste_impl", _no_cpu("scalar_clamp_ste_impl"), "CPU")
+torch.library.register_fake(f"{STE_NS}::scalar_clamp_ste_impl", lambda x, lo, hi: torch.empty_like(x), lib=_STE)
+torch.library.register_autograd(f"{STE_NS}::scalar_clamp_ste_impl", lambda ctx, g: (g, None, None), lib=_STE)
+
+_STE.define("scalar_clamp_min_ste_impl(Tensor x, float min_val) -> Tensor")
+_STE.impl("scalar_clamp_min_ste_impl", lambda x, lo: K.scalar_clamp_min(x, lo), "CUDA")
+_STE.impl("scalar_clamp_min_ste_impl", _no_cpu("scalar_clamp_min_ste_impl"), "CPU")
+torch.library.register_fake(f"{STE_NS}::scalar_clamp_min_ste_impl", lambda x, lo: torch.empty_like(x), lib=_STE)
+torch.library.register_autograd(f"{STE_NS}::scalar_clamp_min_ste_impl", lambda ctx, g: (g, None), lib=_STE)
+
+STE_OP_NAMES = tuple(_UNARY_STE) + ("abs_binary_sign_grad_impl", "tensor_clamp_ste_impl", "tensor_clamp_ste_impl_",
+                                    "scalar_clamp_ste_impl", "scalar_clamp_min_ste_impl")
+
+
+# ============================================================================================================
+# 2. brevitas_b200: fused quantizer ops
+# ============================================================================================================
+
+def _reduce_gscale(gs: Optional[Tensor], scale: Tensor) -> Optional[Tensor]:
+    if gs is None:
+        return None
+    return gs.to(scale.dtype).view(scale.shape)
+
+
+# ---- IntQuant with provided scale --------------------------------------------------------------------------
+_FQ.define("int_quant(Tensor x, Tensor scale, float zero_point, float qmin, float qmax, int round_mode, "
+           "int clamp_mode) -> Tensor")
+_FQ.define("int_quant_codes(Tensor x, Tensor scale, float zero_point, float qmin, float qmax, int round_mode) "
+           "-> (Tensor, Tensor)")
+_FQ.define("int_quant_backward(Tensor gy, Tensor x, Tensor scale, float zero_point, float qmin, float qmax, "
+           "int round_mode, int clamp_mode, bool want_gscale) -> (Tensor, Tensor)")
+
+
+def _int_quant_cuda(x, scale, zp, qmin, qmax, rm, cm):
+    return K.int_quant_fwd(x, scale, zp, qmin, qmax, rm)
+
+
+def _int_quant_codes_cuda(x, scale, zp, qmin, qmax, rm):
+    return K.int_quant_fwd(x, scale, zp, qmin, qmax, rm, want_codes=True)
+
+
+def _int_quant_backward_cuda(gy, x, scale, zp, qmin, qmax, rm, cm, want_gscale):
+    gx, gs = K.int_quant_bwd(gy, x, scale, zp, qmin, qmax, rm, cm, want_gscale)
+    if gs is None:
+        gs = torch.empty(0, dtype=torch.float32, device=x.device)
+    return gx, gs
+
+
+_FQ.impl("int_quant", _int_quant_cuda, "CUDA")
+_FQ.impl("int_quant", _no_cpu("int_quant"), "CPU")
+_FQ.impl("int_quant_codes", _int_quant_codes_cuda, "CUDA")
+_FQ.impl("int_quant_codes", _no_cpu("int_quant_codes"), "CPU")
+_FQ.impl("int_quant_backward", _int_quant_backward_cuda, "CUDA")
+_FQ.impl("int_quant_backward", _no_cpu("int_quant_backward"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::int_quant", lambda x, s, zp, a, b, rm, cm: torch.empty_like(x), lib=_FQ)
+torch.library.register_fake(f"{FQ_NS}::int_quant_codes",
+                            lambda x, s, zp, a, b, rm: (torch.empty_like(x), torch.empty_like(x)), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::int_quant_backward",
+    lambda gy, x, s, zp, a, b, rm, cm, w: (torch.empty_like(x), x.new_empty(s.numel() if w else 0, dtype=torch.float32)),
+    lib=_FQ)
+
+
+def _int_quant_setup(ctx, inputs, output):
+    x, scale, zp, qmin, qmax, rm, cm = inputs
+    ctx.save_for_backward(x, scale)
+    ctx.q = (zp, qmin, qmax, rm, cm)
+
+
+def _int_quant_bwd(ctx, gy):
+    x, scale = ctx.saved_tensors
+    zp, qmin, qmax, rm, cm = ctx.q
+    want_gs = ctx.needs_input_grad[1]
+    gx, gs = torch.ops.brevitas_b200.int_quant_backward(gy.to(x.dtype), x, scale, zp, qmin, qmax, rm, cm, want_gs)
+    return (gx if ctx.needs_input_grad[0] else None, _reduce_gscale(gs, scale) if want_gs else None,
+            None, None, None, None, None)
+
+
+torch.library.register_autograd(f"{FQ_NS}::int_quant", _int_quant_bwd, setup_context=_int_quant_setup, lib=_FQ)
+
+
+# ---- fused per-row abs-max + IntQuant ----------------------------------------------------------------------
+_FQ.define("rows_absmax_int_quant(Tensor x, int rows, int cols, float scaling_min_val, float int_threshold, "
+           "float zero_point, float qmin, float qmax, int round_mode, int clamp_mode) -> (Tensor, Tensor, Tensor)")
+_FQ.define("rows_absmax_int_quant_backward(Tensor gy, Tensor x, Tensor scale, Tensor? gscale, int rows, int cols, "
+           "float int_threshold, float zero_point, float qmin, float qmax, int round_mode, int clamp_mode) -> Tensor")
+
+
+def _rows_fwd_cuda(x, rows, cols, min_val, int_thr, zp, qmin, qmax, rm, cm):
+    return K.rows_absmax_int_quant_fwd(x, rows, cols, min_val, int_thr, zp, qmin, qmax, rm, want_absmax=True)
+
+
+def _rows_bwd_cuda(gy, x, scale, gscale, rows, cols, int_thr, zp, qmin, qmax, rm, cm):
+    return K.rows_absmax_int_quant_bwd(gy, x, scale, gscale, rows, cols, int_thr, zp, qmin, qmax, rm, cm)
+
+
+_FQ.impl("rows_absmax_int_quant", _rows_fwd_cuda, "CUDA")
+_FQ.impl("rows_absmax_int_quant", _no_cpu("rows_absmax_int_quant"), "CPU")
+_FQ.impl("rows_absmax_int_quant_backward", _rows_bwd_cuda, "CUDA")
+_FQ.impl("rows_absmax_int_quant_backward", _no_cpu("rows_absmax_int_quant_backward"), "CPU")
+torch.library.register_fake(
+    f"{FQ_NS}::rows_absmax_int_quant",
+    lambda x, rows, cols, mv, it, zp, a, b, rm, cm: (torch.empty_like(x), x.new_empty(rows), x.new_empty(rows)), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::rows_absmax_int_quant_backward",
+    lambda gy, x, s, gs, rows, cols, it, zp, a, b, rm, cm: torch.empty_like(x), lib=_FQ)
+
+
+def _rows_setup(ctx, inputs, output):
+    x, rows, cols, mv, it, zp, qmin, qmax, rm, cm = inputs
+    y, scale, absmax = output
+    ctx.save_for_backward(x, scale)
+    ctx.q = (rows, cols, it, zp, qmin, qmax, rm, cm)
+    ctx.mark_non_differentiable(absmax)
+    ctx.set_materialize_grads(False)
+
+
+def _rows_bwd(ctx, gy, gscale, gabsmax):
+    x, scale = ctx.saved_tensors
+    rows, cols, it, zp, qmin, qmax, rm, cm = ctx.q
+    if gy is None:
+        gy = torch.zeros_like(x)
+    if gscale is not None:
+        gscale = gscale.to(x.dtype).reshape(rows)
+    gx = torch.ops.brevitas_b200.rows_absmax_int_quant_backward(gy.to(x.dtype), x, scale, gscale, rows, cols, it, zp,
+                                                                qmin, qmax, rm, cm)
+    return (gx,) + (None,) * 9
+
+
+torch.library.register_autograd(f"{FQ_NS}::rows_absmax_int_quant", _rows_bwd, setup_context=_rows_setup, lib=_FQ)
+
+
+# ---- fused whole-tensor abs-max + IntQuant -----------------------------------------------------------------
+_FQ.define("tensor_absmax_int_quant(Tensor x, ScalarType scale_dtype, float scaling_min_val, float int_threshold, "
+           "float zero_point, float qmin, float qmax, int round_mode, int clamp_mode) -> (Tensor, Tensor, Tensor)")
+_FQ.define("tensor_absmax_int_quant_backward(Tensor gy, Tensor x, Tensor scale, Tensor absmax, Tensor? gscale, "
+           "float int_threshold, float zero_point, float qmin, float qmax, int round_mode, int clamp_mode) -> Tensor")
+
+
+def _tensor_fwd_cuda(x, scale_dtype, mv, it, zp, qmin, qmax, rm, cm):
+    return K.tensor_absmax_int_quant_fwd(x, scale_dtype, mv, it, zp, qmin, qmax, rm)
+
+
+def _tensor_bwd_cuda(gy, x, scale, absmax, gscale, it, zp, qmin, qmax, rm, cm):
+    return K.tensor_absmax_int_quant_bwd(gy, x, scale, absmax, gscale, it, zp, qmin, qmax, rm, cm)
+
+
+_FQ.impl("tensor_absmax_int_quant", _tensor_fwd_cuda, "CUDA")
+_FQ.impl("tensor_absmax_int_quant", _no_cpu("tensor_absmax_int_quant"), "CPU")
+_FQ.impl("tensor_absmax_int_quant_backward", _tensor_bwd_cuda, "CUDA")
+_FQ.impl("tensor_absmax_int_quant_backward", _no_cpu("tensor_absmax_int_quant_backward"), "CPU")
+torch.library.register_fake(
+    f"{FQ_NS}::tensor_absmax_int_quant",
+    lambda x, sd, mv, it, zp, a, b, rm, cm: (torch.empty_like(x), x.new_empty((), dtype=sd), x.new_empty(())), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::tensor_absmax_int_quant_backward",
+    lambda gy, x, s, am, gs, it, zp, a, b, rm, cm: torch.empty_like(x), lib=_FQ)
+
+
+def _tensor_setup(ctx, inputs, output):
+    x, sd, mv, it, zp, qmin, qmax, rm, cm = inputs
+    y, scale, absmax = output
+    ctx.save_for_backward(x, scale, absmax)
+    ctx.q = (it, zp, qmin, qmax, rm, cm)
+    ctx.mark_non_differentiable(absmax)
+    ctx.set_materialize_grads(False)
+
+
+def _tensor_bwd(ctx, gy, gscale, gabsmax):
+    x, scale, absmax = ctx.saved_tensors
+    it, zp, qmin, qmax, rm, cm = ctx.q
+    if gy is None:
+        gy = torch.zeros_like(x)
+    if gscale is not None:
+        gscale = gscale.to(scale.dtype).reshape(())
+    gx = torch.ops.brevitas_b200.tensor_absmax_int_quant_backward(gy.to(x.dtype), x, scale, absmax, gscale, it, zp,
+                                                                  qmin, qmax, rm, cm)
+    return (gx,) + (None,) * 8
+
+
+torch.library.register_autograd(f"{FQ_NS}::tensor_absmax_int_quant", _tensor_bwd, setup_context=_tensor_setup, lib=_FQ)
+
+
+# ---- BinaryQuant / ClampedBinaryQuant ----------------------------------------------------------------------
+_FQ.define("binary_quant(Tensor x, Tensor scale, bool clamped) -> Tensor")
+_FQ.define("binary_quant_backward(Tensor gy, Tensor x, Tensor scale, bool clamped, bool want_gscale) -> (Tensor, Tensor)")
+
+
+def _binary_bwd_cuda(gy, x, scale, clamped, want_gscale):
+    gx, gs = K.binary_quant_bwd(gy, x, scale, clamped, want_gscale)
+    if gs is None:
+        gs = torch.empty(0, dtype=torch.float32, device=x.device)
+    return gx, gs
+
+
+_FQ.impl("binary_quant", lambda x, s, c: K.binary_quant_fwd(x, s, c), "CUDA")
+_FQ.impl("binary_quant", _no_cpu("binary_quant"), "CPU")
+_FQ.impl("binary_quant_backward", _binary_bwd_cuda, "CUDA")
+_FQ.impl("binary_quant_backward", _no_cpu("binary_quant_backward"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::binary_quant", lambda x, s, c: torch.empty_like(x), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::binary_quant_backward",
+    lambda gy, x, s, c, w: (torch.empty_like(x), x.new_empty(s.numel() if w else 0, dtype=torch.float32)), lib=_FQ)
+
+
+def _binary_setup(ctx, inputs, output):
+    x, scale, clamped = inputs
+    ctx.save_for_backward(x, scale)
+    ctx.clamped = clamped
+
+
+def _binary_bwd(ctx, gy):
+    x, scale = ctx.saved_tensors
+    want_gs = ctx.needs_input_grad[1]
+    gx, gs = torch.ops.brevitas_b200.binary_quant_backward(gy.to(x.dtype), x, scale, ctx.clamped, want_gs)
+    return (gx if ctx.needs_input_grad[0] else None, _reduce_gscale(gs, scale) if want_gs else None, None)
+
+
+torch.library.register_autograd(f"{FQ_NS}::binary_quant", _binary_bwd, setup_context=_binary_setup, lib=_FQ)
+
+
+# ---- statistics (forward values; see brevitas_b200.core.stats for the module wrappers) ------------------------
+_FQ.define("absmax_rows(Tensor x, int rows, int cols) -> Tensor")
+_FQ.define("absmax_tensor(Tensor x) -> Tensor")
+_FQ.define("abs_kth_value_rows(Tensor x, int rows, int cols, int k) -> (Tensor, Tensor)")
+_FQ.define("running_stats_update_(Tensor(a!) running, Tensor stat, float momentum, bool first) -> ()")
+_FQ.impl("absmax_rows", lambda x, r, c: K.absmax_rows(x, r, c), "CUDA")
+_FQ.impl("absmax_rows", _no_cpu("absmax_rows"), "CPU")
+_FQ.impl("absmax_tensor", lambda x: K.absmax_tensor(x), "CUDA")
+_FQ.impl("absmax_tensor", _no_cpu("absmax_tensor"), "CPU")
+_FQ.impl("abs_kth_value_rows", lambda x, r, c, k: K.abs_kth_value_rows(x, r, c, k, want_index=True), "CUDA")
+_FQ.impl("abs_kth_value_rows", _no_cpu("abs_kth_value_rows"), "CPU")
+_FQ.impl("running_stats_update_", lambda r, s, m, f: (K.running_stats_update(r, s, m, f), None)[1], "CUDA")
+_FQ.impl("running_stats_update_", _no_cpu("running_stats_update_"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::absmax_rows", lambda x, r, c: x.new_empty(r), lib=_FQ)
+torch.library.register_fake(f"{FQ_NS}::absmax_tensor", lambda x: x.new_empty(()), lib=_FQ)
+torch.library.register_fake(f"{FQ_NS}::abs_kth_value_rows",
+                            lambda x, r, c, k: (x.new_empty(r), x.new_empty(r, dtype=torch.int64)), lib=_FQ)
+
+
+def _stat_setup_rows(ctx, inputs, output):
+    x, rows, cols = inputs
+    ctx.save_for_backward(x, output)
+    ctx.rc = (rows, cols)
+
+
+def _stat_bwd_rows(ctx, g):
+    # AbsMax(dim) backward: sign(x[argmax]) * g at the FIRST arg-max of each row
+    x, out = ctx.saved_tensors
+    rows, cols = ctx.rc
+    zero_scale = out  # any [rows] tensor: the scale value is irrelevant when gy == 0 and int_threshold == 1
+    gy = torch.zeros_like(x)
+    gx = torch.ops.brevitas_b200.rows_absmax_int_quant_backward(
+        gy, x, torch.ones_like(zero_scale), g.to(x.dtype).reshape(rows), rows, cols, 1.0, 0.0, 0.0, 0.0,
+        _lib.ROUND, _lib.CLAMP_STE)
+    return gx, None, None
+
+
+torch.library.register_autograd(f"{FQ_NS}::absmax_rows", _stat_bwd_rows, setup_context=_stat_setup_rows, lib=_FQ)
+
+
+def _stat_setup_tensor(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], output)
+
+
+def _stat_bwd_tensor(ctx, g):
+    # AbsMax(None) backward: g split evenly over all tied maxima, times sign(x)
+    x, out = ctx.saved_tensors
+    gy = torch.zeros_like(x)
+    gx = torch.ops.brevitas_b200.tensor_absmax_int_quant_backward(
+        gy, x, torch.ones_like(out), out, g.to(x.dtype).reshape(()), 1.0, 0.0, 0.0, 0.0, _lib.ROUND, _lib.CLAMP_STE)
+    return gx
+
+
+torch.library.register_autograd(f"{FQ_NS}::absmax_tensor", _stat_bwd_tensor, setup_context=_stat_setup_tensor, lib=_FQ)
+
+
+def _kth_setup(ctx, inputs, output):
+    x, rows, cols, k = inputs
+    val, idx = output
+    ctx.save_for_backward(x, idx)
+    ctx.rc = (rows, cols)
+    ctx.mark_non_differentiable(idx)
+
+
+def _kth_bwd(ctx, gval, gidx):
+    # x.abs().kthvalue(k): gradient goes to the selected index, times sign(x) (abs backward)
+    x, idx = ctx.saved_tensors
+    rows, cols = ctx.rc
+    gx = torch.zeros(rows, cols, dtype=x.dtype, device=x.device)
+    picked = x.reshape(rows, cols).gather(1, idx.view(rows, 1))
+    gx.scatter_(1, idx.view(rows, 1), (gval.to(x.dtype).view(rows, 1) * torch.sign(picked)))
+    return gx.view(x.shape), None, None, None
+
+
+torch.library.register_autograd(f"{FQ_NS}::abs_kth_value_rows", _kth_bwd, setup_context=_kth_setup, lib=_FQ)

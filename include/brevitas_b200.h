@@ -1,0 +1,153 @@
+/*
+ * brevitas_b200.h — C-ABI of the B200-native fake-quantization hot path.
+ *
+ * This is the drop-in boundary for the one native plugin of the reference (Giuseppe5/brevitas):
+ * `src/brevitas/csrc/autograd_ste_ops.cpp`, whose 12 entry points are registered at
+ * csrc/autograd_ste_ops.cpp:258-271 and consumed by `brevitas.function.ops_ste`
+ * (src/brevitas/function/ops_ste.py:38-43, 65-67) — plus the fused quantizer entry points that replace the
+ * ATen op chains issued by `brevitas.core.quant`, `brevitas.core.scaling` and `brevitas.core.stats`
+ * (SURVEY.md §8a).  Every function takes raw DEVICE pointers, element counts, a dtype tag and a
+ * `cudaStream_t` (passed as void*), returns an int status, never allocates, never synchronises and
+ * keeps no global mutable state, so it is re-entrant, honours the caller's stream and is capturable
+ * in CUDA graphs.  There is no CPU implementation behind this interface.
+ *
+ * All tensors are dense/contiguous.  "T" below is the element type selected by `dtype`.
+ * Scalars that the reference carries in 0-dim tensors are passed as floats holding the value the
+ * reference tensor holds.  The library applies ATen's (CPU, torch 2.11) rule for a 0-dim operand next to a
+ * low-precision tensor: add / sub / compare operands (zero_point, qmin, qmax, scaling_min_val) are rounded
+ * to T first; mul / div second operands (int_threshold, a one-element fp32 scale) keep their fp32 value in
+ * the fp32 "opmath" and only the result is rounded to T.
+ *
+ * `scale_dtype`: dtype tag of the scale tensor.  It must equal `dtype`, except that a ONE-element scale may
+ * be BVB_F32 while x is bf16/fp16 (fp32 quantizer modules fed low-precision activations).
+ */
+#ifndef BREVITAS_B200_H_
+#define BREVITAS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums ------------------------------------------------------------------------------------------- */
+enum { BVB_F32 = 0, BVB_BF16 = 1, BVB_F16 = 2 };                       /* dtype tags                */
+enum { BVB_OK = 0, BVB_EINVAL = 1, BVB_EUNSUPPORTED = 2, BVB_ECUDA = 3 };/* status codes              */
+/* float_to_int_impl flavours: RoundSte / FloorSte / CeilSte / RoundToZeroSte / DPURoundSte
+ * (src/brevitas/core/function_wrapper/ops_ste.py:14-92) */
+enum { BVB_ROUND = 0, BVB_FLOOR = 1, BVB_CEIL = 2, BVB_ROUND_TO_ZERO = 3, BVB_DPU_ROUND = 4 };
+/* tensor_clamp_impl flavours: TensorClampSte (pass-through gradient, ops/autograd_ste_ops.py:118-120)
+ * vs TensorClamp (torch.where autograd => masked gradient, function/ops.py:98-99) */
+enum { BVB_CLAMP_STE = 0, BVB_CLAMP_MASKED = 1 };
+
+/* ---- library ----------------------------------------------------------------------------------------- */
+int bvb_version(void);
+/* thread-local description of the last non-OK status returned on this thread */
+const char* bvb_last_error(void);
+/* number of SMs of the current device (cached per device), used for grid sizing */
+int bvb_sm_count(void);
+/* optional launch-geometry overrides for the fused per-row kernels (0 = heuristic); used by the
+ * tuning sweeps in bench.py, not by the product path */
+void bvb_set_tuning(int rows_threads, int rows_stages, int rows_ctas_per_sm, int stream_threads, int stream_ctas_per_sm);
+
+/* ---- 1. the 12 STE primitives: forward values of torch.ops.autograd_ste_ops.* -------------------------
+ * Backward of every op except abs_binary_sign_grad is the identity on the incoming gradient and
+ * needs no kernel (csrc/autograd_ste_ops.cpp:22, 42).  y may alias x (in-place).                       */
+int bvb_round_ste_impl(const void* x, void* y, int64_t n, int dtype, void* stream);          /* csrc:14-24   torch.round  */
+int bvb_ceil_ste_impl(const void* x, void* y, int64_t n, int dtype, void* stream);           /* csrc:100-110 torch.ceil   */
+int bvb_floor_ste_impl(const void* x, void* y, int64_t n, int dtype, void* stream);          /* csrc:112-122 torch.floor  */
+int bvb_binary_sign_ste_impl(const void* x, void* y, int64_t n, int dtype, void* stream);    /* csrc:124-137 (x>=0)-(x<0) */
+int bvb_ternary_sign_ste_impl(const void* x, void* y, int64_t n, int dtype, void* stream);   /* csrc:140-150 torch.sign   */
+int bvb_round_to_zero_ste_impl(const void* x, void* y, int64_t n, int dtype, void* stream);  /* csrc:153-163              */
+int bvb_dpu_round_ste_impl(const void* x, void* y, int64_t n, int dtype, void* stream);      /* csrc:166-179              */
+int bvb_abs_binary_sign_grad_impl(const void* x, void* y, int64_t n, int dtype, void* stream);/* csrc:182-194 torch.abs   */
+/* backward of abs_binary_sign_grad: gx = binary_sign(x) * gy (ops/autograd_ste_ops.py:374-377) */
+int bvb_abs_binary_sign_grad_bwd(const void* x, const void* gy, void* gx, int64_t n, int dtype, void* stream);
+/* tensor_clamp_ste_impl (csrc:27-44) / tensor_clamp_ste_impl_ (csrc:47-63; Python semantics, in place:
+ * pass y == x and inplace_minmax = 1 to get torch.min/torch.max NaN rules of function/ops.py:109-110).
+ * min/max are broadcast as element i -> m[(i / inner) % count]  (count = 1: scalar tensor;
+ * inner = 1, count = n: same shape; inner = cols, count = rows: per-row). */
+int bvb_tensor_clamp_ste_impl(const void* x, const void* min_val, const void* max_val, void* y, int64_t n,
+                              int64_t min_inner, int64_t min_count, int64_t max_inner, int64_t max_count,
+                              int inplace_minmax, int dtype, void* stream);
+int bvb_scalar_clamp_ste_impl(const void* x, void* y, int64_t n, double min_val, double max_val, int dtype, void* stream);   /* csrc:66-82 */
+int bvb_scalar_clamp_min_ste_impl(const void* x, void* y, int64_t n, double min_val, int dtype, void* stream);               /* csrc:85-97 */
+
+/* ---- 2. IntQuant with a provided scale (src/brevitas/core/quant/int_base.py:64-97) ----------------------
+ * y = (clamp(round(x / s + zp), qmin, qmax) - zp) * s, element i uses s[(i / scale_inner) % scale_count].
+ * codes_out (nullable, T) receives the integer codes of IntQuant.to_int.                                */
+int bvb_int_quant_fwd(const void* x, const void* scale, void* y, void* codes_out, int64_t n,
+                      int64_t scale_inner, int64_t scale_count, int scale_dtype,
+                      float zero_point, float qmin, float qmax, int round_mode, int dtype, void* stream);
+/* gx = ((gy * s) / s) * m  (m = 1 for BVB_CLAMP_STE, clamp mask on the rounded value for BVB_CLAMP_MASKED).
+ * If gscale_out (fp32, scale_count entries, zero-filled by the callee) is non-null it receives
+ * d(loss)/d(scale) = sum over each scale's region of gy*(q - zp) - m*(gy*s)*((x/s)/s)  (SURVEY.md A.4). */
+int bvb_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out, int64_t n,
+                      int64_t scale_inner, int64_t scale_count, int scale_dtype,
+                      float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
+                      int dtype, void* stream);
+
+/* ---- 3. RescalingIntQuant with abs-max statistics, fused (src/brevitas/core/quant/int.py:156-163 over
+ *         core/scaling/runtime.py:19-102, core/stats/stats_op.py:129-141) ----------------------------------
+ * Per row of a [rows, cols] view (OverOutputChannelView / OverBatchOverOutputChannelView + AbsMax(dim)):
+ *   absmax = max|x|;  thr = clamp_min(absmax, scaling_min_val) (skipped if scaling_min_val <= 0);
+ *   s = thr / int_threshold;  y = quant-dequant(x, s).   Single HBM pass: 1 read + 1 write per element.
+ * scale_out: [rows] T.  absmax_out: [rows] T, nullable (the un-clamped statistic, e.g. for running_stats). */
+int bvb_rows_absmax_int_quant_fwd(const void* x, void* y, void* scale_out, void* absmax_out,
+                                  int64_t rows, int64_t cols, float scaling_min_val, float int_threshold,
+                                  float zero_point, float qmin, float qmax, int round_mode, int dtype, void* stream);
+/* Backward with the gradient flowing through the statistic:
+ *   gx = ((gy*s)/s)*m, then gx[row, argmax] += sign(x[argmax]) * (Gs[row] + gscale[row]) / int_threshold,
+ *   Gs[row] = sum_j gy*(q - zp) - m*(gy*s)*((x/s)/s); argmax = first index of the row maximum.
+ * gscale (nullable, [rows] T) is the gradient arriving on the returned scale.                             */
+int bvb_rows_absmax_int_quant_bwd(const void* gy, const void* x, const void* scale, const void* gscale, void* gx,
+                                  int64_t rows, int64_t cols, float int_threshold,
+                                  float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
+                                  int dtype, void* stream);
+/* Whole-tensor statistic (OverTensorView + AbsMax(None)): two-phase grid reduction, then quant pass.
+ * workspace: >= bvb_workspace_bytes() bytes of device scratch.  absmax_out: 1 element of T; scale_out:
+ * 1 element of scale_dtype (fp32 when a 0-dim T threshold is divided by a 0-dim fp32 int_threshold).      */
+int bvb_tensor_absmax_int_quant_fwd(const void* x, void* y, void* scale_out, void* absmax_out, int64_t n,
+                                    int scale_dtype, float scaling_min_val, float int_threshold,
+                                    float zero_point, float qmin, float qmax, int round_mode, int dtype,
+                                    void* workspace, void* stream);
+/* Backward: torch.max() distributes the statistic's gradient evenly over all tied maxima. */
+int bvb_tensor_absmax_int_quant_bwd(const void* gy, const void* x, const void* scale, const void* absmax,
+                                    const void* gscale, void* gx, int64_t n, int scale_dtype, float int_threshold,
+                                    float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
+                                    int dtype, void* workspace, void* stream);
+int64_t bvb_workspace_bytes(void);
+
+/* ---- 4. BinaryQuant / ClampedBinaryQuant (src/brevitas/core/quant/binary.py:60-64, 120-125) -------------
+ * y = binary_sign(x) * s;  clamped != 0: y = binary_sign(where-clamp(x, -s, s)) * s (same values for s >= 0;
+ * the clamp shapes the gradient).                                                                        */
+int bvb_binary_quant_fwd(const void* x, const void* scale, void* y, int64_t n,
+                         int64_t scale_inner, int64_t scale_count, int scale_dtype, int clamped, int dtype,
+                         void* stream);
+/* gx = gy * s (plain) or gy * s * [!(x > s) & !(x < -s)] (clamped);
+ * gscale_out (nullable, fp32[scale_count]) = sum gy*sign_b(clamp(x)) (+ gy*s where x > s, - gy*s where x < -s) */
+int bvb_binary_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out, int64_t n,
+                         int64_t scale_inner, int64_t scale_count, int scale_dtype, int clamped, int dtype,
+                         void* stream);
+
+/* ---- 5. statistics (src/brevitas/core/stats/stats_op.py) ----------------------------------------------- */
+/* AbsMax(stats_reduce_dim=1) on a [rows, cols] view -> out[rows] (T); NaN-propagating (stats_op.py:137-141) */
+int bvb_absmax_rows(const void* x, void* out, int64_t rows, int64_t cols, int dtype, void* stream);
+/* AbsMax(None) -> out[1] (T) */
+int bvb_absmax_tensor(const void* x, void* out, int64_t n, int dtype, void* workspace, void* stream);
+/* AbsPercentile (stats_op.py:41-66): k-th smallest (1-indexed) of |x| over each row of a [rows, cols] view
+ * (rows = 1: flat).  out[rows] (T); index_out (nullable, int64[rows]) = an index attaining it.
+ * Exact radix select; workspace >= bvb_kth_workspace_bytes(rows).                                       */
+int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
+                           int dtype, void* workspace, void* stream);
+int64_t bvb_kth_workspace_bytes(int64_t rows);
+/* _RuntimeStats EMA (stats_wrapper.py:56-65): first != 0: running *= stat; else
+ * running = running * one_minus_momentum + (T)(momentum * stat).  The caller passes (float)(1.0 - m) computed
+ * in double like the Python expression.  running: fp32 [count]; stat: T [count]. */
+int bvb_running_stats_update(float* running, const void* stat, int64_t count, float momentum,
+                             float one_minus_momentum, int first, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREVITAS_B200_H_ */
