@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 fake-quant hot path (BASELINE.json: "fake-quant GB/s & % HBM peak").
+
+A "step" is one pass of the hot path over one weight: Int8 per-output-channel weight fake-quant FORWARD (abs-max
+per row -> scale -> quant-dequant) + STE BACKWARD (gradient incl. the path through the abs-max) on a 4096 x 11008
+fp32 linear weight (BASELINE.json configs[1], SURVEY.md §8d "C2").  Algorithmic bytes per step:
+fwd 1R+1W = 8 B/elem, bwd 2R+1W = 12 B/elem -> 20 B/elem x 45,088,768 = 901.8 MB.
+
+  value     GB/s with inputs resident in HBM (C-ABI calls, device timed with CUDA events)
+  e2e       the same metric through the public module API (RescalingIntQuant + autograd) with HOST pinned
+            buffers: H2D of weight and incoming gradient, D2H of the weight gradient and scales, every step
+  roofline  dominant kernel (backward) algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline   the oracle's ATen port of the reference chain (oracle/torch_port.py) on the host cores, on a
+            bounded row sample of the same workload
+
+`--impl reference` times only that CPU path (kind "port": /root/reference cannot travel to the GPU box).
+N > 1 (torchrun): the path shards trivially (independent weights) -> every rank runs its own replica of the
+workload, no data-path collective ("scaling": "weak"); value = units of all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ROWS, COLS = 4096, 11008
+FWD_B, BWD_B = 8, 12          # algorithmic bytes per element, fp32
+METRIC = "int8_per_channel_weight_fakequant_fwd_bwd_GBps"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def cpu_port_step(torch, P, w, g):
+    """one fwd+bwd of the reference op chain on the host cores (oracle/torch_port.py)"""
+    w.grad = None
+    y, scale, _, _ = P.rescaling_int_quant_absmax(w, "rows", 8, True, True, 1e-10, "round", True)
+    y.backward(g)
+    return w.grad
+
+
+def cpu_baseline(torch, sample_rows, reps):
+    from oracle import torch_port as P
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(0)
+    w = torch.randn(sample_rows, COLS, generator=gen).requires_grad_(True)
+    g = torch.randn(sample_rows, COLS, generator=gen)
+    cpu_port_step(torch, P, w, g)                     # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_port_step(torch, P, w, g)
+        ts.append(time.perf_counter() - t0)
+    t = sorted(ts)[len(ts) // 2]
+    gbps = sample_rows * COLS * (FWD_B + BWD_B) / t / 1e9
+    return {"value": round(gbps, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_rows} of {ROWS} rows x {COLS} fp32, fwd+bwd, median of {reps} "
+                      f"(oracle/torch_port.py: the reference's ATen op chain; {t * 1e3:.1f} ms)"}, t
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # each "step" = a bounded sample (512 rows) of the workload; K steps after W warm-ups
+    sample_rows = 512
+    from oracle import torch_port as P
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(0)
+    w = torch.randn(sample_rows, COLS, generator=gen).requires_grad_(True)
+    g = torch.randn(sample_rows, COLS, generator=gen)
+    for _ in range(args.warmup):
+        cpu_port_step(torch, P, w, g)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(torch, P, w, g)
+    dt = (time.perf_counter() - t0) / args.steps
+    gbps = sample_rows * COLS * (FWD_B + BWD_B) / dt / 1e9
+    sample = f"{sample_rows} of {ROWS} rows x {COLS} fp32 per step, fwd+bwd (oracle/torch_port.py, ATen on host cores)"
+    line = {"impl": "reference", "metric": METRIC, "value": round(gbps, 3), "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2: int8 per-output-channel weight fake-quant fwd + STE bwd, {ROWS}x{COLS} fp32"},
+            "cpu_baseline": {"value": round(gbps, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": round(gbps, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the bf16 / per-token / per-tensor extra kernels")
+    ap.add_argument("--cpu-rows", type=int, default=512)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import brevitas_b200  # noqa: F401  (fails loudly if the native library is missing)
+    from brevitas_b200 import _kernels as K
+    from brevitas_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n = ROWS * COLS
+    step_bytes = n * (FWD_B + BWD_B)
+
+    # ---- inputs: NSETS rotating (W, G) pairs so no step finds its inputs in the 126 MB L2 ---------------------
+    NSETS = 4
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    Ws = [torch.randn(ROWS, COLS, device=dev, generator=gen) for _ in range(NSETS)]
+    Gs = [torch.randn(ROWS, COLS, device=dev, generator=gen) for _ in range(NSETS)]
+    args_f = (1e-10, 127.0, 0.0, -127.0, 127.0, _lib.ROUND)
+
+    def step(i):
+        w, g = Ws[i % NSETS], Gs[i % NSETS]
+        y, scale, _ = K.rows_absmax_int_quant_fwd(w, ROWS, COLS, *args_f)
+        gx = K.rows_absmax_int_quant_bwd(g, w, scale, None, ROWS, COLS, 127.0, 0.0, -127.0, 127.0, _lib.ROUND,
+                                         _lib.CLAMP_STE)
+        return y, gx
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = K.launch_count
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        start.record()
+        for i in range(args.steps):
+            w, g = Ws[i % NSETS], Gs[i % NSETS]
+            ev[i][0].record()
+            y, scale, _ = K.rows_absmax_int_quant_fwd(w, ROWS, COLS, *args_f)
+            ev[i][1].record()
+            gx = K.rows_absmax_int_quant_bwd(g, w, scale, None, ROWS, COLS, 127.0, 0.0, -127.0, 127.0, _lib.ROUND,
+                                             _lib.CLAMP_STE)
+            ev[i][2].record()
+        end.record()
+        torch.cuda.synchronize()
+    launches = K.launch_count - launches0
+    total_ms = start.elapsed_time(end)
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    bwd_gbps = n * BWD_B / (bwd_ms * 1e-3) / 1e9
+    fwd_gbps = n * FWD_B / (fwd_ms * 1e-3) / 1e9
+
+    # ---- e2e: public module API, host pinned buffers, H2D + D2H inside the timed region -------------------------
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.bit_width import BitWidthConst
+    from brevitas_b200.core.quant import IntQuant, RescalingIntQuant
+    from brevitas_b200.core.restrict_val import FloatRestrictValue
+    from brevitas_b200.core.scaling import IntScaling, StatsFromParameterScaling
+    from brevitas_b200.core.stats import AbsMax
+    from brevitas_b200.core.zero_point import ZeroZeroPoint
+    w_param = torch.nn.Parameter(torch.empty(ROWS, COLS, device=dev))
+    tq = RescalingIntQuant(
+        IntQuant(narrow_range=True, signed=True, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClampSte()),
+        StatsFromParameterScaling(AbsMax(1), fw.OverOutputChannelView(None), 1, [w_param], FloatRestrictValue(),
+                                  (ROWS, 1), False, 1e-10),
+        IntScaling(True, True), ZeroZeroPoint(), BitWidthConst(8)).to(dev)
+    hw = torch.randn(ROWS, COLS).pin_memory()
+    hg = torch.randn(ROWS, COLS).pin_memory()
+    h_gw = torch.empty(ROWS, COLS).pin_memory()
+    h_scale = torch.empty(ROWS, 1).pin_memory()
+    g_dev = torch.empty(ROWS, COLS, device=dev)
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        with torch.no_grad():
+            w_param.copy_(hw, non_blocking=True)
+        g_dev.copy_(hg, non_blocking=True)
+        w_param.grad = None
+        y, scale, zp, bw = tq(w_param)
+        y.backward(g_dev)
+        h_gw.copy_(w_param.grad, non_blocking=True)
+        h_scale.copy_(scale.detach(), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2.record()
+    torch.cuda.synchronize()
+    e2e_ms = s2.elapsed_time(e2) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * step_bytes / (e2e_ms * 1e-3) / 1e9
+
+    # ---- extras: the other hot-path kernels at BASELINE sizes (reported, not the headline) ----------------------
+    extras = {}
+    if not args.no_extras and rank == 0:
+        def timeit(fn, reps=30, nsets=1):
+            for _ in range(3):
+                fn(0)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        def gb(nbytes, ms):
+            return round(nbytes / (ms * 1e-3) / 1e9, 1)
+
+        del Gs[2:]
+        Wb = [w.to(torch.bfloat16) for w in Ws]
+        Gb = [g.to(torch.bfloat16) for g in Gs]
+        sb = K.rows_absmax_int_quant_fwd(Wb[0], ROWS, COLS, *args_f)[1]
+        ms = timeit(lambda i: K.rows_absmax_int_quant_fwd(Wb[i % NSETS], ROWS, COLS, *args_f))
+        extras["c2_bf16_fwd"] = {"ms": round(ms, 4), "GBps": gb(n * 4, ms)}
+        ms = timeit(lambda i: K.rows_absmax_int_quant_bwd(Gb[i % 2], Wb[i % NSETS], sb, None, ROWS, COLS, 127.0, 0.0,
+                                                          -127.0, 127.0, 0, 0))
+        extras["c2_bf16_bwd"] = {"ms": round(ms, 4), "GBps": gb(n * 6, ms)}
+        # per-tensor weight quantizer (Int8WeightPerTensorFloat): two-phase reduction + quant pass, 2R+1W
+        ms = timeit(lambda i: K.tensor_absmax_int_quant_fwd(Ws[i % NSETS], torch.float32, 1e-10, 127.0, 0.0, -127.0,
+                                                            127.0, 0))
+        extras["c2_f32_per_tensor_fwd"] = {"ms": round(ms, 4), "GBps_algorithmic_12B": gb(n * 12, ms)}
+        # C3: per-token dynamic int8 activation quant, [8, 2048, 4096] bf16 (rows = 16384 tokens of 4096)
+        T, C = 8 * 2048, 4096
+        X = [torch.randn(T, C, device=dev, generator=gen).to(torch.bfloat16) for _ in range(4)]
+        GX = [torch.randn(T, C, device=dev, generator=gen).to(torch.bfloat16) for _ in range(2)]
+        c3 = (1e-10, 128.0, 0.0, -128.0, 127.0, 0)
+        sx = K.rows_absmax_int_quant_fwd(X[0], T, C, *c3)[1]
+        ms = timeit(lambda i: K.rows_absmax_int_quant_fwd(X[i % 4], T, C, *c3))
+        extras["c3_bf16_per_token_fwd"] = {"ms": round(ms, 4), "GBps": gb(T * C * 4, ms)}
+        ms = timeit(lambda i: K.rows_absmax_int_quant_bwd(GX[i % 2], X[i % 4], sx, None, T, C, 128.0, 0.0, -128.0,
+                                                          127.0, 0, 1))
+        extras["c3_bf16_per_token_bwd_masked"] = {"ms": round(ms, 4), "GBps": gb(T * C * 6, ms)}
+        # provided-scale activation quant (learned per-tensor scale), bf16, fwd and masked bwd with scale gradient
+        s0 = torch.tensor(0.02, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda i: K.int_quant_fwd(X[i % 4], s0, 0.0, 0.0, 255.0, 0))
+        extras["act_bf16_learned_scale_fwd"] = {"ms": round(ms, 4), "GBps": gb(T * C * 4, ms)}
+        ms = timeit(lambda i: K.int_quant_bwd(GX[i % 2], X[i % 4], s0, 0.0, 0.0, 255.0, 0, 1, True))
+        extras["act_bf16_learned_scale_bwd"] = {"ms": round(ms, 4), "GBps": gb(T * C * 6, ms)}
+        # eager PyTorch composition of the same chain on the same GPU (what a Brevitas user gets on a B200 today)
+        from oracle import torch_port as P
+        wt = Ws[0].clone().requires_grad_(True)
+
+        def eager(i):
+            wt.grad = None
+            yy, ss, _, _ = P.rescaling_int_quant_absmax(wt, "rows", 8, True, True, 1e-10, "round", True)
+            yy.backward(Gs[0])
+        ms = timeit(eager, reps=5)
+        extras["c2_f32_eager_aten_same_gpu_fwd_bwd"] = {"ms": round(ms, 3), "GBps_algorithmic": gb(step_bytes, ms)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    cpu, _ = cpu_baseline(torch, args.cpu_rows, 5)
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2 (BASELINE.json configs[1]): int8 per-output-channel weight fake-quant fwd + STE bwd, "
+                               f"{ROWS}x{COLS} fp32, one weight per rank",
+                   "algorithmic_bytes_per_step": step_bytes,
+                   "l2": f"inputs rotate over {NSETS} (W,G) sets of 2x{n * 4 // 2**20} MiB (> 126 MB L2)",
+                   "percent_of_hbm_peak": round(100 * value / world / peak, 1), "hbm_peak_gbs": peak,
+                   "hbm_peak_source": peak_src, "percent_of_nominal_8TBps": round(100 * value / world / 8000, 1)},
+        "roofline": {"bound": "hbm", "kernel": "rows_bwd_kernel<float,ROUND,vec> (STE backward + grad through abs-max)",
+                     "achieved": round(bwd_gbps, 1), "peak": peak, "unit": "GB/s", "frac": round(bwd_gbps / peak, 4),
+                     "traffic": None, "algorithmic_bytes_per_launch": n * BWD_B, "avg_launch_ms": round(bwd_ms, 5),
+                     "peak_source": peak_src,
+                     "other_kernels": {"rows_fwd_tma_kernel<float,ROUND>": {
+                         "achieved": round(fwd_gbps, 1), "frac": round(fwd_gbps / peak, 4),
+                         "algorithmic_bytes_per_launch": n * FWD_B, "avg_launch_ms": round(fwd_ms, 5)}}},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4,
+                "d2h_bytes_per_step": n * 4 + ROWS * 4, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
+                "api": "brevitas_b200.core.quant.RescalingIntQuant(w) + autograd backward, pinned host buffers"},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "extras": extras,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

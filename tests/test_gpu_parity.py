@@ -1,0 +1,345 @@
+"""GPU (-m gpu): the CUDA kernels, called through the C-ABI (ctypes -> libbrevitas_b200.so), against
+
+  (1) the golden vectors produced by the real reference (tests/golden), and
+  (2) the numpy oracle on fresh seeded inputs incl. ragged / unaligned / empty shapes, and
+  (3) at BASELINE.json's full sizes, through size-independent properties (idempotence, range, linearity of
+      the gradient, oracle on sampled rows).
+
+Bar (BASELINE.json north_star): integer codes, clamp masks and dequantized outputs bit-exact in fp32; here the
+per-op rounding emulation makes bf16/fp16 bit-exact as well (north star asks <= 1 ulp).  Only reductions that
+feed a scale gradient carry a tolerance (summation order), stated at each check.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import DTYPES, assert_bits_equal, case, load, ulp
+from oracle import fakequant_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TDT = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+RM = {"round": 0, "floor": 1, "ceil": 2, "round_to_zero": 3, "dpu_round": 4}
+CM = {"ste": 0, "masked": 1}
+INT_CASES = {
+    "s8n_round_ste_scalar": ("round", "ste"), "s8_round_masked_scalar": ("round", "masked"),
+    "u8_round_masked_scalar": ("round", "masked"), "u8_round_masked_scalar_zp": ("round", "masked"),
+    "s4n_floor_ste_rows": ("floor", "ste"), "s4_ceil_masked_rows": ("ceil", "masked"),
+    "u4n_rtz_masked_chan": ("round_to_zero", "masked"), "s8_dpu_masked_chan_zp": ("dpu_round", "masked"),
+    "s2n_round_masked_scalar": ("round", "masked"), "s8n_round_masked_token": ("round", "masked"),
+}
+
+
+@pytest.fixture(scope="module")
+def K():
+    import brevitas_b200  # noqa: F401  (loads the .so, registers the ops)
+    from brevitas_b200 import _kernels
+    return _kernels
+
+
+def dev(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(TDT[dtype]).cuda()
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+def close_sum(got, ref, n, mag, dtype):
+    tol = mag * (n * 2.0 ** -21 + 4 * ulp(dtype)) + 1e-6
+    both_nan = np.isnan(got) & np.isnan(ref)
+    assert np.all(both_nan | (np.abs(got - ref) <= tol)), (got, ref, tol)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", sorted(INT_CASES))
+def test_int_quant_golden(K, name, dtype):
+    c = case("int_quant", f"int_quant/{name}/{dtype}/")
+    signed, narrow, bits, zp = [float(v) for v in c["meta"]]
+    rm, cm = INT_CASES[name]
+    qmin, qmax = O.min_int(bool(signed), bool(narrow), bits), O.max_int(bool(signed), bool(narrow), bits)
+    x, s, g = dev(c["x"], dtype), dev(c["scale"], dtype), dev(c["g"], dtype)
+    y, codes = K.int_quant_fwd(x, s, zp, qmin, qmax, RM[rm], want_codes=True)
+    assert_bits_equal(host(y), c["y"], "y")
+    assert_bits_equal(host(codes), c["codes"], "codes")
+    gx, gs = K.int_quant_bwd(g, x, s, zp, qmin, qmax, RM[rm], CM[cm], True)
+    assert_bits_equal(host(gx), c["gx"], "gx")
+    if np.isfinite(c["gscale"]).all():
+        _, gs_el = O.int_quant_backward(c["g"], c["x"], c["scale"], zp, qmin, qmax, rm, cm, dtype)
+        n = c["x"].size // max(1, c["gscale"].size)
+        mag = np.abs(gs_el).sum() / max(1, c["gscale"].size) + 1.0
+        close_sum(host(gs).reshape(c["gscale"].shape), c["gscale"], n, mag, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tag", ["chan_lin", "chan_conv", "tensor_lin", "tensor_conv"])
+def test_weight_stats_golden(K, tag, dtype):
+    """Int8WeightPerChannelFloat / Int8WeightPerTensorFloat trees, fused kernel."""
+    c = case("weight_stats", f"weight_stats/{tag}/{dtype}/")
+    w, g = dev(c["w"], dtype), dev(c["g"], dtype)
+    per_channel = tag.startswith("chan")
+    a = np.abs(c["w"].reshape(c["w"].shape[0], -1)) if per_channel else np.abs(c["w"]).reshape(1, -1)
+    ismax = (a == a.max(axis=1, keepdims=True)).reshape(c["w"].shape)
+    if per_channel:
+        rows, cols = c["w"].shape[0], c["w"].size // c["w"].shape[0]
+        y, scale, am = K.rows_absmax_int_quant_fwd(w, rows, cols, 1e-10, 127.0, 0.0, -127.0, 127.0, 0, want_absmax=True)
+        assert_bits_equal(host(y), c["y"], "y")
+        assert_bits_equal(host(scale).reshape(c["scale"].shape), c["scale"], "scale")
+        assert_bits_equal(host(am), a.max(axis=1), "absmax")
+        for gs_in, key in ((None, "gw"), (dev(c["gs"].reshape(-1), dtype), "gw_with_gscale")):
+            gx = host(K.rows_absmax_int_quant_bwd(g, w, scale, gs_in, rows, cols, 127.0, 0.0, -127.0, 127.0, 0, 0))
+            assert_bits_equal(np.where(ismax, 0, gx), np.where(ismax, 0, c[key]), "gw off the arg-max")
+            close_sum(gx[ismax], c[key][ismax], cols, np.nanmax(np.abs(c[key][ismax])) + 1.0, dtype)
+    else:
+        sdt = torch.float32      # golden: fp32 quantizer buffers -> fp32 scale even for bf16/fp16 weights
+        y, scale, am = K.tensor_absmax_int_quant_fwd(w, sdt, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+        assert_bits_equal(host(y), c["y"], "y")
+        assert_bits_equal(host(scale), c["scale"], "scale")
+        for gs_in, key in ((None, "gw"), (torch.tensor(float(c["gs"]), device="cuda"), "gw_with_gscale")):
+            gx = host(K.tensor_absmax_int_quant_bwd(g, w, scale, am, gs_in, 127.0, 0.0, -127.0, 127.0, 0, 0))
+            assert_bits_equal(np.where(ismax, 0, gx), np.where(ismax, 0, c[key]), "gw off the arg-max")
+            close_sum(gx[ismax], c[key][ismax], c["w"].size, np.nanmax(np.abs(c[key][ismax])) + 1.0, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_runtime_token_golden(K, dtype):
+    """per-token dynamic activation quantizer (config 3 composition), training then eval"""
+    c = case("runtime_token", f"runtime_token/{dtype}/")
+    running = torch.ones(18, device="cuda")
+    for step in range(2):
+        x, g = dev(c[f"x{step}"], dtype), dev(c[f"g{step}"], dtype)
+        y, scale, am = K.rows_absmax_int_quant_fwd(x, 18, 64, 1e-10, 128.0, 0.0, -128.0, 127.0, 0, want_absmax=True)
+        assert_bits_equal(host(y), c[f"y{step}"], "y")
+        assert_bits_equal(host(scale).reshape(2, 9, 1), c[f"scale{step}"], "scale")
+        K.running_stats_update(running, am, 0.1, step == 0)
+        assert_bits_equal(host(running).reshape(2, 9, 1), c[f"running{step}"], "running_stats")
+        gx = host(K.rows_absmax_int_quant_bwd(g, x, scale, None, 18, 64, 128.0, 0.0, -128.0, 127.0, 0, 1)).reshape(18, 64)
+        ref = c[f"gx{step}"].reshape(18, 64)
+        a = np.abs(c[f"x{step}"].reshape(18, 64))
+        ismax = a == a.max(axis=1, keepdims=True)
+        assert_bits_equal(np.where(ismax, 0, gx), np.where(ismax, 0, ref), "gx off the arg-max")
+        close_sum(gx[ismax], ref[ismax], 64, np.abs(ref[ismax]).max() + 1.0, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("qname", ["binary", "clamped"])
+@pytest.mark.parametrize("sname", ["const", "param", "param_rows"])
+def test_binary_golden(K, qname, sname, dtype):
+    c = case("binary", f"binary/{qname}_{sname}/{dtype}/")
+    clamped = qname == "clamped"
+    x, s, g = dev(c["x"], dtype), dev(c["scale"], dtype), dev(c["g"], dtype)
+    assert_bits_equal(host(K.binary_quant_fwd(x, s, clamped)), c["y"], "y")
+    gx, gs = K.binary_quant_bwd(g, x, s, clamped, True)
+    assert_bits_equal(host(gx), c["gx"], "gx")
+    if "gvalue" in c:
+        n = c["x"].size // c["gvalue"].size
+        close_sum(host(gs).reshape(c["gvalue"].shape), c["gvalue"], n, np.abs(c["g"]).sum() / c["gvalue"].size + 1, dtype)
+
+
+def test_percentile_golden(K):
+    d = load("percentile")
+    for q in (99.999, 99.9, 90.0, 50.0, 1.0):
+        for dtype in DTYPES:
+            x = d[f"percentile/flat_q{q}/{dtype}/x"]
+            val, idx = K.abs_kth_value_rows(dev(x, dtype), 1, x.size, O.percentile_k(q, x.size), want_index=True)
+            assert_bits_equal(host(val).reshape(()), d[f"percentile/flat_q{q}/{dtype}/y"], f"q{q} {dtype}")
+            assert abs(x[int(idx.item())]) == float(host(val)[0])
+    for dtype in DTYPES:
+        x2 = d[f"percentile/rows_q99/{dtype}/x"]
+        val, _ = K.abs_kth_value_rows(dev(x2, dtype), 6, 250, O.percentile_k(99.0, 250))
+        assert_bits_equal(host(val), d[f"percentile/rows_q99/{dtype}/y"], "rows")
+    v = d["percentile/kat/x"]           # tests/brevitas/core/test_stats.py:12-18
+    got = [float(K.abs_kth_value_rows(dev(v, "f32"), 1, 10, O.percentile_k(10.0 * i, 10))[0]) for i in range(1, 11)]
+    assert got == [float(i) for i in range(1, 11)]
+
+
+STE_C = {"round_ste": "bvb_round_ste_impl", "ceil_ste": "bvb_ceil_ste_impl", "floor_ste": "bvb_floor_ste_impl",
+         "binary_sign_ste": "bvb_binary_sign_ste_impl", "ternary_sign_ste": "bvb_ternary_sign_ste_impl",
+         "round_to_zero_ste": "bvb_round_to_zero_ste_impl", "dpu_round_ste": "bvb_dpu_round_ste_impl",
+         "abs_binary_sign_grad": "bvb_abs_binary_sign_grad_impl"}
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ste_golden(K, dtype):
+    d = load("ste")
+    for name, cname in STE_C.items():
+        x = d[f"ste/{name}/{dtype}/x"]
+        assert_bits_equal(host(K.unary(cname, dev(x, dtype))), d[f"ste/{name}/{dtype}/y"], name)
+    x = d[f"ste/abs_binary_sign_grad/{dtype}/x"]
+    g = d[f"ste/abs_binary_sign_grad/{dtype}/g"]
+    assert_bits_equal(host(K.abs_binary_sign_grad_bwd(dev(x, dtype), dev(g, dtype))),
+                      d[f"ste/abs_binary_sign_grad/{dtype}/gx"], "abs grad bwd")
+    x = d[f"ste/tensor_clamp_ste/{dtype}/x"]
+    lo, hi = torch.tensor(-1.25, device="cuda").to(TDT[dtype]), torch.tensor(2.5, device="cuda").to(TDT[dtype])
+    assert_bits_equal(host(K.tensor_clamp(dev(x, dtype), lo, hi)), d[f"ste/tensor_clamp_ste/{dtype}/y"], "tclamp")
+    xm = dev(x, dtype)
+    r = K.tensor_clamp(xm, lo, hi, inplace=True)
+    assert r.data_ptr() == xm.data_ptr()
+    assert_bits_equal(host(xm), d[f"ste/tensor_clamp_ste_/{dtype}/y"], "tclamp_ (in place)")
+    assert_bits_equal(host(K.scalar_clamp(dev(x, dtype), -1.3, 2.7)), d[f"ste/scalar_clamp_ste/{dtype}/y"], "sclamp")
+    assert_bits_equal(host(K.scalar_clamp_min(dev(x, dtype), 0.3)), d[f"ste/scalar_clamp_min_ste/{dtype}/y"], "sclampmin")
+    r = case("ste", f"ste/tensor_clamp_rows/{dtype}/")
+    assert_bits_equal(host(K.tensor_clamp(dev(r["x"], dtype), dev(r["lo"], dtype), dev(r["hi"], dtype))), r["y"], "rows")
+
+
+def test_docstring_kats(K):
+    d = load("kat")
+    x = dev(d["kat/int_quant/x"], "f32")
+    y = K.int_quant_fwd(x, torch.tensor(0.01, device="cuda"), 0.0, -7.0, 7.0, 0)
+    assert_bits_equal(host(y), d["kat/int_quant/y"], "IntQuant docstring")
+    s = (torch.tensor(0.1) / torch.tensor(7.0)).cuda()     # a true division (CUDA ATen multiplies by 1/7 for a Python scalar)
+    assert_bits_equal(host(K.int_quant_fwd(x, s, 0.0, -7.0, 7.0, 0)), d["kat/rescaling/y"], "RescalingIntQuant docstring")
+    b = dev(d["kat/binary/x"], "f32")
+    sc = torch.tensor(0.1, device="cuda")
+    assert_bits_equal(host(K.binary_quant_fwd(b, sc, False)), d["kat/binary/y"])
+    assert_bits_equal(host(K.binary_quant_fwd(b, sc, True)), d["kat/clamped_binary/y"])
+    gx, _ = K.binary_quant_bwd(torch.ones(3, device="cuda"), b, sc, True, False)
+    assert_bits_equal(host(gx), d["kat/clamped_binary/gx"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle on fresh inputs: shapes that exercise every kernel variant
+# ---------------------------------------------------------------------------------------------------------------
+def rand_np(shape, seed, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,cols", [(1, 8), (3, 1), (5, 17), (7, 1000), (64, 4096), (33, 11008), (2, 60000),
+                                       (300, 264), (2, 131072)])
+def test_rows_fused_vs_oracle(K, rows, cols, dtype):
+    """TMA path (16-byte aligned rows), generic path (ragged rows) and oversized rows"""
+    x = O.rnd(rand_np((rows, cols), rows * 1000 + cols, 0.7), dtype)
+    g = O.rnd(rand_np((rows, cols), 7, 1.0), dtype)
+    if rows > 2 and cols > 4:
+        x[1, 2] = -x[1, 0] if abs(x[1, 0]) >= np.abs(x[1]).max() else -np.abs(x[1]).max()   # tie on the row max
+        x[2, :] = 0.0
+    yo, so, amo = O.rows_absmax_int_quant_forward(x, 1e-10, 127.0, 0.0, -127.0, 127.0, "round", dtype)
+    xd, gd = dev(x, dtype), dev(g, dtype)
+    y, s, am = K.rows_absmax_int_quant_fwd(xd, rows, cols, 1e-10, 127.0, 0.0, -127.0, 127.0, 0, want_absmax=True)
+    assert_bits_equal(host(am), amo, "absmax")
+    assert_bits_equal(host(s), so, "scale")
+    assert_bits_equal(host(y), yo, "y")
+    assert_bits_equal(host(K.absmax_rows(xd, rows, cols)), amo, "absmax_rows")
+    for cm in ("ste", "masked"):
+        gxo, _ = O.rows_absmax_int_quant_backward(g, x, so, None, 127.0, 0.0, -127.0, 127.0, "round", cm, dtype)
+        gx = host(K.rows_absmax_int_quant_bwd(gd, xd, s, None, rows, cols, 127.0, 0.0, -127.0, 127.0, 0, CM[cm]))
+        a = np.abs(x)
+        first = np.zeros_like(x, dtype=bool)
+        first[np.arange(rows), a.argmax(axis=1)] = True
+        assert_bits_equal(np.where(first, 0, gx), np.where(first, 0, gxo), f"gx off the arg-max ({cm})")
+        close_sum(gx[first], gxo[first], cols, np.nanmax(np.abs(gxo[first])) + 1.0, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 7, 1023, 4096, 100003, 1 << 20])
+def test_tensor_fused_vs_oracle(K, n, dtype):
+    x = O.rnd(rand_np((n,), n, 0.5), dtype)
+    g = O.rnd(rand_np((n,), n + 1, 1.0), dtype)
+    if n > 10:
+        m = np.abs(x).max()
+        x[3], x[n - 2] = m, -m                 # tied maxima: gradient is split evenly (torch.max() semantics)
+    yo, so, amo = O.tensor_absmax_int_quant_forward(x, 1e-10, 127.0, 0.0, -127.0, 127.0, "round", dtype)
+    xd, gd = dev(x, dtype), dev(g, dtype)
+    y, s, am = K.tensor_absmax_int_quant_fwd(xd, TDT[dtype], 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+    assert_bits_equal(host(am), amo, "absmax")
+    assert_bits_equal(host(s), so, "scale")
+    assert_bits_equal(host(y), yo, "y")
+    assert_bits_equal(host(K.absmax_tensor(xd)), amo, "absmax_tensor")
+    gxo, _ = O.tensor_absmax_int_quant_backward(g, x, so, None, 127.0, 0.0, -127.0, 127.0, "round", "masked", dtype)
+    gx = host(K.tensor_absmax_int_quant_bwd(gd, xd, s, am, None, 127.0, 0.0, -127.0, 127.0, 0, 1))
+    ties = np.abs(x) == np.abs(x).max()
+    assert_bits_equal(np.where(ties, 0, gx), np.where(ties, 0, gxo), "gx off the maxima")
+    close_sum(gx[ties], gxo[ties], n, np.nanmax(np.abs(gxo[ties])) + 1.0, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,sshape", [((1000,), ()), ((5, 3), (5, 1)), ((4, 6, 5, 5), (1, 6, 1, 1)),
+                                          ((4, 8, 16), (4, 8, 1)), ((3, 1001), (3, 1)), ((16, 64, 8, 8), (1, 64, 1, 1)),
+                                          ((2, 3, 4), (2, 3, 4))])
+@pytest.mark.parametrize("rm", ["round", "floor", "ceil", "round_to_zero", "dpu_round"])
+def test_int_quant_broadcast_vs_oracle(K, shape, sshape, rm, dtype):
+    x = O.rnd(rand_np(shape, 5, 30.0), dtype)
+    g = O.rnd(rand_np(shape, 6, 1.0), dtype)
+    s = O.rnd(np.abs(rand_np(sshape, 8, 0.3)) + 0.05, dtype)
+    zp = 2.0
+    yo = O.int_quant_forward(x, s, zp, 0.0, 255.0, rm, dtype)
+    assert_bits_equal(host(K.int_quant_fwd(dev(x, dtype), dev(s, dtype), zp, 0.0, 255.0, RM[rm])), yo, "y")
+    gxo, gs_el = O.int_quant_backward(g, x, s, zp, 0.0, 255.0, rm, "masked", dtype)
+    gx, gs = K.int_quant_bwd(dev(g, dtype), dev(x, dtype), dev(s, dtype), zp, 0.0, 255.0, RM[rm], 1, True)
+    assert_bits_equal(host(gx), gxo, "gx")
+    s_full = np.broadcast_to(s, shape)
+    # reduce the oracle's per-element terms over each scale's region
+    ref = np.zeros(max(1, s.size))
+    idx = np.broadcast_to(np.arange(max(1, s.size)).reshape(s.shape), shape)
+    np.add.at(ref, idx.reshape(-1), gs_el.reshape(-1))
+    mag = np.zeros_like(ref)
+    np.add.at(mag, idx.reshape(-1), np.abs(gs_el).reshape(-1))
+    n = x.size // max(1, s.size)
+    got = host(gs)
+    assert np.all(np.abs(got - ref) <= mag * (n * 2.0 ** -21 + 16 * ulp(dtype)) + 1e-5), (got, ref)
+
+
+def test_fp32_scalar_scale_with_lowp_input(K):
+    """fp32 quantizer modules fed bf16 activations: ATen's mul/div keep the fp32 0-dim scale in opmath"""
+    x = torch.randn(4099, generator=torch.Generator().manual_seed(3)).mul(20).to(torch.bfloat16)
+    s = torch.tensor(0.0371)
+    ref = (torch.clamp(torch.round(x / s + 0.0), -128, 127) - 0.0) * s
+    got = K.int_quant_fwd(x.cuda(), s.cuda(), 0.0, -128.0, 127.0, 0)
+    assert got.dtype == torch.bfloat16
+    assert_bits_equal(host(got), ref.float().numpy(), "bf16 x, fp32 0-dim scale")
+
+
+def test_empty_and_errors(K):
+    e = torch.empty(0, device="cuda")
+    assert K.int_quant_fwd(e, torch.tensor(1.0, device="cuda"), 0.0, -1.0, 1.0, 0).numel() == 0
+    assert K.unary("bvb_round_ste_impl", e).numel() == 0
+    with pytest.raises(RuntimeError):
+        K.unary("bvb_round_ste_impl", torch.randn(3))                 # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        K.unary("bvb_round_ste_impl", torch.randn(3, device="cuda").double())
+    with pytest.raises(RuntimeError):
+        K.abs_kth_value_rows(torch.randn(10, device="cuda"), 1, 10, 11)
+    x = torch.randn(1 << 16, device="cuda")
+    base = torch.randn((1 << 16) + 1, device="cuda")
+    un = base[1:]                                                        # 4-byte aligned only
+    un.copy_(x)
+    s = torch.tensor(0.05, device="cuda")
+    assert torch.equal(K.int_quant_fwd(un, s, 0.0, -127.0, 127.0, 0), K.int_quant_fwd(x, s, 0.0, -127.0, 127.0, 0))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: properties + oracle on sampled rows
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,rows,cols", [("f32", 4096, 11008), ("bf16", 4096, 11008), ("bf16", 16384, 4096)])
+def test_full_size_properties(K, dtype, rows, cols):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(rows, cols, device="cuda", generator=g).to(TDT[dtype])
+    signed_narrow = cols == 11008                   # C2: int8 narrow weights; C3: int8 full range activations
+    qmin, qmax, thr = (-127.0, 127.0, 127.0) if signed_narrow else (-128.0, 127.0, 128.0)
+    y, s, am = K.rows_absmax_int_quant_fwd(x, rows, cols, 1e-10, thr, 0.0, qmin, qmax, 0, want_absmax=True)
+    # (1) statistic: matches torch's own reduction bit for bit (max is order independent)
+    assert torch.equal(am, x.abs().amax(dim=1))
+    # (2) codes are integers inside the range, and quantization is idempotent at fixed scale
+    codes = K.int_quant_fwd(x, s.view(rows, 1), 0.0, qmin, qmax, 0, want_codes=True)[1].float()
+    assert torch.equal(codes, codes.round()) and codes.min() >= qmin and codes.max() <= qmax
+    y2 = K.int_quant_fwd(y, s.view(rows, 1), 0.0, qmin, qmax, 0)
+    if dtype == "f32":
+        assert (y2 - y).abs().max() <= s.max() * 1.0001    # re-quantizing moves at most one step (fp32 rounding)
+    # (3) oracle, bit-exact, on sampled rows
+    pick = [0, 1, rows // 2, rows - 1]
+    xs = host(x[pick])
+    yo, so, _ = O.rows_absmax_int_quant_forward(xs, 1e-10, thr, 0.0, qmin, qmax, "round", dtype)
+    assert_bits_equal(host(y[pick]), yo, "sampled rows y")
+    assert_bits_equal(host(s[pick]), so, "sampled rows scale")
+    # (4) backward: STE-clamp gradient is linear in the incoming gradient away from the arg-max entries
+    gr = torch.randn(rows, cols, device="cuda", generator=g).to(TDT[dtype])
+    gx = K.rows_absmax_int_quant_bwd(gr, x, s, None, rows, cols, thr, 0.0, qmin, qmax, 0, 0)
+    gxo, _ = O.rows_absmax_int_quant_backward(host(gr[pick]), xs, so, None, thr, 0.0, qmin, qmax, "round", "ste", dtype)
+    first = np.zeros_like(xs, dtype=bool)
+    first[np.arange(len(pick)), np.abs(xs).argmax(axis=1)] = True
+    assert_bits_equal(np.where(first, 0, host(gx[pick])), np.where(first, 0, gxo), "sampled rows gx")
+    close_sum(host(gx[pick])[first], gxo[first], cols, np.abs(gxo[first]).max() + 1.0, dtype)
