@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
     uint4* cv = reinterpret_cast<uint4*>(codes);
     const int64_t chunk = ST_THREADS * ST_UNROLL;
     const int64_t nchunks = (nvec + chunk - 1) / chunk;
-    float s0 = 0.f;
+    float s0 = 1.f;
     if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
+    const DivBy dv0(s0);
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const int64_t cc = reverse ? (nchunks - 1 - c) : c;
         const int64_t base = cc * chunk + threadIdx.x;
@@ -61,19 +62,11 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
         for (int u = 0; u < ST_UNROLL; ++u) {
             int64_t v = base + (int64_t)u * ST_THREADS;
             if (v < nvec) {
-                float s = s0;
-                if (smode != 0) s = DT<T>::to_f(scale[(v / inner_v) % count]);
+                DivBy dv = dv0;
+                if (smode != 0) dv = DivBy(DT<T>::to_f(scale[(v / inner_v) % count]));
                 float e[V], k[V];
                 DT<T>::unpack(q[u], e);
-#pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    float t1, t3, t5;
-                    to_int_chain<T, RM>(e[i], s, p, t1, t3, t5);
-                    k[i] = t5;
-                    float t6 = fsub(t5, p.zp);
-                    if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
-                    e[i] = fmul(t6, s);
-                }
+                quant_dequant_n<T, RM, V>(e, dv, p, codes ? k : nullptr);
                 stg_stream(yv + v, DT<T>::pack(e));
                 if (codes) stg_stream(cv + v, DT<T>::pack(k));
             }
@@ -89,7 +82,7 @@ __global__ void int_quant_fwd_scalar_kernel(const T* x, const T* scale, T* y, T*
     for (int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float s = count == 1 ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[(i / inner) % count]);
         float t1, t3, t5;
-        to_int_chain<T, RM>(DT<T>::to_f(x[i]), s, p, t1, t3, t5);
+        to_int_chain<T, RM>(DT<T>::to_f(x[i]), DivBy(s), p, t1, t3, t5);
         float t6 = fsub(t5, p.zp);
         if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
         y[i] = DT<T>::from_f(fmul(t6, s));
@@ -101,13 +94,13 @@ __global__ void int_quant_fwd_scalar_kernel(const T* x, const T* scale, T* y, T*
 // one element of the backward
 // ------------------------------------------------------------------------------------------------------
 template <typename T, int RM>
-__device__ __forceinline__ float bwd_elem(float g, float x, float s, float inv_s, const QParams& p, int masked,
+__device__ __forceinline__ float bwd_elem(float g, float x, const DivBy& dv, float inv_s, const QParams& p, int masked,
                                           bool want_gs, float& gs_acc) {
-    float gsv = DT<T>::rnd(fmul(g, s));                  // d y / d t6 : grad * scale
+    float gsv = DT<T>::rnd(fmul(g, dv.b));               // d y / d t6 : grad * scale
     float d = gsv;
     if (masked || want_gs) {
         float t1, t3, t5;
-        to_int_chain<T, RM>(x, s, p, t1, t3, t5);
+        to_int_chain<T, RM>(x, dv, p, t1, t3, t5);
         if (masked) {
             bool m = !(t3 > p.qmax) && !(t3 < p.qmin);   // torch.where backward of both clamp stages
             d = m ? gsv : 0.f;
@@ -116,10 +109,41 @@ __device__ __forceinline__ float bwd_elem(float g, float x, float s, float inv_s
             float t6 = fsub(t5, p.zp);
             // d(scale) = g * t6  -  d * ((x / s) / s); order-dependent sum => fp32 accumulation,
             // reciprocal for the second division is within the documented tolerance
-            gs_acc += g * t6 - d * (t1 * inv_s);
+            gs_acc = fmaf(g, t6, gs_acc);
+            gs_acc = fmaf(-d, t1 * inv_s, gs_acc);
         }
     }
-    return fdiv(d, s);                                   // d t1 / d x : grad / scale (rounded at store)
+    return dv(d);                                        // d t1 / d x : grad / scale (rounded at store)
+}
+
+// one 16-byte vector of the backward: eg[] holds the incoming gradient on entry, gx on exit
+template <typename T, int RM, int N>
+__device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], const DivBy& dv, float inv_s,
+                                      const QParams& p, int masked, bool want_gs, float& gs_acc) {
+    float d[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) d[i] = DT<T>::rnd(fmul(eg[i], dv.b));          // grad * scale
+    if (masked || want_gs) {
+        float t1[N];
+        dv.div_n<N>(ex, t1);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float t3, t5;
+            const float t1r = DT<T>::rnd(t1[i]);
+            to_int_from_t1<T, RM>(t1r, p, t3, t5);
+            const float dfull = d[i];
+            if (masked) {
+                const bool m = !(t3 > p.qmax) && !(t3 < p.qmin);
+                d[i] = m ? dfull : 0.f;
+            }
+            if (want_gs) {
+                const float t6 = fsub(t5, p.zp);
+                gs_acc = fmaf(eg[i], t6, gs_acc);
+                gs_acc = fmaf(-d[i], t1r * inv_s, gs_acc);
+            }
+        }
+    }
+    dv.div_n<N>(d, eg);                                                        // grad / scale (rounded at store)
 }
 
 // provided-scale backward; gscale_out (nullable) accumulated with float atomics
@@ -135,8 +159,10 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
     const bool want_gs = gscale_out != nullptr;
     const int64_t chunk = ST_THREADS * ST_UNROLL;
     const int64_t nchunks = (nvec + chunk - 1) / chunk;
-    float s0 = 0.f, inv0 = 0.f;
-    if (smode == 0) { s0 = load_scale0<T>(scale, scale_f32); inv0 = 1.f / s0; }
+    float s0 = 1.f;
+    if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
+    const DivBy dv0(s0);
+    const float inv0 = dv0.approx_recip();
     float acc = 0.f;          // smode 0: block-wide; smode 1: run of equal scale indices
     int64_t acc_idx = -1;
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -151,11 +177,12 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
         for (int u = 0; u < ST_UNROLL; ++u) {
             int64_t v = base + (int64_t)u * ST_THREADS;
             if (v < nvec) {
-                float s = s0, inv_s = inv0;
+                DivBy dv = dv0;
+                float inv_s = inv0;
                 if (smode != 0) {
                     int64_t idx = (v / inner_v) % count;
-                    s = DT<T>::to_f(scale[idx]);
-                    inv_s = 1.f / s;
+                    dv = DivBy(DT<T>::to_f(scale[idx]));
+                    inv_s = dv.approx_recip();
                     if (want_gs && idx != acc_idx) {
                         if (acc_idx >= 0) atomicAdd(gscale_out + acc_idx, acc);
                         acc = 0.f;
@@ -165,8 +192,7 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
                 float eg[V], ex[V];
                 DT<T>::unpack(qg[u], eg);
                 DT<T>::unpack(qx[u], ex);
-#pragma unroll
-                for (int i = 0; i < V; ++i) eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, want_gs, acc);
+                bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, want_gs, acc);
                 stg_stream(ov + v, DT<T>::pack(eg));
             }
         }
@@ -191,7 +217,8 @@ __global__ void int_quant_bwd_scalar_kernel(const T* gy, const T* x, const T* sc
         int64_t idx = count == 1 ? 0 : (i / inner) % count;
         float s = count == 1 ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[idx]);
         float acc = 0.f;
-        float r = bwd_elem<T, RM>(DT<T>::to_f(gy[i]), DT<T>::to_f(x[i]), s, 1.f / s, p, masked, want_gs, acc);
+        const DivBy dv(s);
+        float r = bwd_elem<T, RM>(DT<T>::to_f(gy[i]), DT<T>::to_f(x[i]), dv, dv.approx_recip(), p, masked, want_gs, acc);
         gx[i] = DT<T>::from_f(r);
         if (want_gs) atomicAdd(gscale_out + idx, acc);
     }
@@ -261,6 +288,7 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
 
         const float amax = DT<T>::bits_to_f(m);
         const float sc = finalize_scale<T>(amax, min_val, has_min, int_thr);
+        const DivBy dv(sc);
         if (tid == 0) {
             scale_out[row] = DT<T>::from_f(sc);
             if (absmax_out) absmax_out[row] = DT<T>::from_f(amax);
@@ -273,8 +301,7 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
             uint4 q = buf[v];
             float e[V];
             DT<T>::unpack(q, e);
-#pragma unroll
-            for (int i = 0; i < V; ++i) e[i] = quant_dequant<T, RM>(e[i], sc, p);
+            quant_dequant_n<T, RM, V>(e, dv, p);
             stg_stream(yrow + v, DT<T>::pack(e));
         }
         __syncthreads();      // everyone is done with buf[s] and red[]
@@ -308,8 +335,9 @@ __global__ void rows_fwd_generic_kernel(const T* __restrict__ x, T* __restrict__
         }
         if (quantize) {
             T* yr = y + row * cols;
+            const DivBy dv(sc);
             for (int64_t j = threadIdx.x; j < cols; j += blockDim.x)
-                yr[j] = DT<T>::from_f(quant_dequant<T, RM>(DT<T>::to_f(xr[j]), sc, p));
+                yr[j] = DT<T>::from_f(quant_dequant<T, RM>(DT<T>::to_f(xr[j]), dv, p));
         }
     }
 }
@@ -322,6 +350,9 @@ __device__ __forceinline__ uint32_t canon_abs_bits(float v) {
     return b > 0x7f800000u ? 0x7f800001u : b;        // all NaNs tie, like torch.max
 }
 
+// Arg-max bookkeeping costs ~1.5 instructions per element: each thread keeps the max |x| bit pattern (in T's
+// own bit domain) of the 16-byte vectors it visits and the index of the FIRST vector attaining it; the
+// element inside the winning vector is located once per row by thread 0.
 template <typename T, int RM, bool VECTOR>
 __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale,
                                 const T* __restrict__ gscale, T* __restrict__ gx, int64_t rows, int64_t cols,
@@ -331,54 +362,52 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
     __shared__ float red_f[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const float s = DT<T>::to_f(scale[row]);
-        const float inv_s = 1.f / s;
+        const DivBy dv(DT<T>::to_f(scale[row]));
+        const float inv_s = dv.approx_recip();
         const T* gr = gy + row * cols;
         const T* xr = x + row * cols;
         T* outr = gx + row * cols;
         float acc = 0.f;
-        uint32_t best = 0, best_idx = 0xffffffffu;
+        uint32_t best = 0, best_pos = 0xffffffffu;
         if (VECTOR) {
             const int nvec = (int)(cols / V);
             const uint4* gv = reinterpret_cast<const uint4*>(gr);
             const uint4* xv = reinterpret_cast<const uint4*>(xr);
             uint4* ov = reinterpret_cast<uint4*>(outr);
+            if (tid < nvec) best_pos = (uint32_t)tid;
             for (int v0 = tid; v0 < nvec; v0 += blockDim.x * 2) {
                 const int v1 = v0 + blockDim.x;
                 uint4 qg0 = ldg_stream(gv + v0), qx0 = ldg_stream(xv + v0);
                 uint4 qg1 = make_uint4(0, 0, 0, 0), qx1 = make_uint4(0, 0, 0, 0);
                 if (v1 < nvec) { qg1 = ldg_stream(gv + v1); qx1 = ldg_stream(xv + v1); }
                 float eg[V], ex[V];
-                DT<T>::unpack(qg0, eg);
-                DT<T>::unpack(qx0, ex);
-#pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    uint32_t b = canon_abs_bits(ex[i]);
-                    if (b > best) { best = b; best_idx = (uint32_t)(v0 * V + i); }
-                    eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, true, acc);
+                {
+                    const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx0));
+                    if (mv > best) { best = mv; best_pos = (uint32_t)v0; }
+                    DT<T>::unpack(qg0, eg);
+                    DT<T>::unpack(qx0, ex);
+                    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
+                    stg_stream(ov + v0, DT<T>::pack(eg));
                 }
-                stg_stream(ov + v0, DT<T>::pack(eg));
                 if (v1 < nvec) {
+                    const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx1));
+                    if (mv > best) { best = mv; best_pos = (uint32_t)v1; }
                     DT<T>::unpack(qg1, eg);
                     DT<T>::unpack(qx1, ex);
-#pragma unroll
-                    for (int i = 0; i < V; ++i) {
-                        uint32_t b = canon_abs_bits(ex[i]);
-                        if (b > best) { best = b; best_idx = (uint32_t)(v1 * V + i); }
-                        eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, true, acc);
-                    }
+                    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
                     stg_stream(ov + v1, DT<T>::pack(eg));
                 }
             }
         } else {
+            if (tid < cols) best_pos = (uint32_t)tid;
             for (int64_t j = tid; j < cols; j += blockDim.x) {
-                float xe = DT<T>::to_f(xr[j]);
-                uint32_t b = canon_abs_bits(xe);
-                if (b > best) { best = b; best_idx = (uint32_t)j; }
-                outr[j] = DT<T>::from_f(bwd_elem<T, RM>(DT<T>::to_f(gr[j]), xe, s, inv_s, p, masked, true, acc));
+                const float xe = DT<T>::to_f(xr[j]);
+                const uint32_t b = DT<T>::abs_bits_s(xe);
+                if (b > best) { best = b; best_pos = (uint32_t)j; }
+                outr[j] = DT<T>::from_f(bwd_elem<T, RM>(DT<T>::to_f(gr[j]), xe, dv, inv_s, p, masked, true, acc));
             }
         }
-        // row reductions: max bits, sum, then the smallest index attaining the max
+        // row reductions: max bits, sum, then the smallest position attaining the max
         uint32_t wm = warp_max_u32(best);
         float ws = warp_sum_f(acc);
         if (lane == 0) { red_u[warp] = wm; red_f[warp] = ws; }
@@ -386,7 +415,7 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
         const uint32_t rmax = warp_max_u32(lane < nw ? red_u[lane] : 0u);
         const float rsum = warp_sum_f(lane < nw ? red_f[lane] : 0.f);
         __syncthreads();
-        uint32_t cand = (best == rmax) ? best_idx : 0xffffffffu;
+        uint32_t cand = (best == rmax) ? best_pos : 0xffffffffu;
         cand = warp_min_u32(cand);
         if (lane == 0) red_u[warp] = cand;
         __syncthreads();      // also orders this block's gx stores before the fix-up read below
@@ -394,14 +423,20 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
             uint32_t amin = 0xffffffffu;
             for (int w = 0; w < nw; ++w) amin = min(amin, red_u[w]);
             if (amin != 0xffffffffu) {     // cols > 0
+                int64_t idx = amin;
+                if (VECTOR) {              // first element of the winning vector that attains the row max
+                    idx = (int64_t)amin * V;
+                    for (int i = 0; i < V; ++i)
+                        if (DT<T>::abs_bits_s(DT<T>::to_f(xr[idx + i])) == rmax) { idx += i; break; }
+                }
                 float gsc = rsum + (gscale ? DT<T>::to_f(gscale[row]) : 0.f);
                 // scale = thr / int_thr  =>  d thr = d scale / int_thr; clamp_min_ste and view are identity;
                 // max(dim) routes it to the arg-max, abs multiplies by sgn(x)
                 float dthr = DT<T>::rnd(fdiv(DT<T>::rnd(gsc), int_thr));
-                float xe = DT<T>::to_f(xr[amin]);
+                float xe = DT<T>::to_f(xr[idx]);
                 float contrib = fmul(dthr, sign3(xe));
-                float cur = DT<T>::to_f(outr[amin]);
-                outr[amin] = DT<T>::from_f(fadd(cur, contrib));
+                float cur = DT<T>::to_f(outr[idx]);
+                outr[idx] = DT<T>::from_f(fadd(cur, contrib));
             }
         }
         __syncthreads();
@@ -469,8 +504,8 @@ __global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
         T* __restrict__ gx, int64_t n, int vec_ok, uint32_t* ws, int scale_f32, int masked, QParams p) {
     constexpr int V = DT<T>::VEC;
     __shared__ float red[32];
-    const float s = load_scale0<T>(scale, scale_f32);
-    const float inv_s = 1.f / s;
+    const DivBy dv(load_scale0<T>(scale, scale_f32));
+    const float inv_s = dv.approx_recip();
     const uint32_t mbits = canon_abs_bits(DT<T>::to_f(absmax[0]));
     long long* list = reinterpret_cast<long long*>(ws + WS_LIST);
     float acc = 0.f;
@@ -501,8 +536,8 @@ __global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
                         uint32_t slot = atomicAdd(ws + WS_TIES, 1u);
                         if (slot < TIE_CAP) list[slot] = v * V + i;
                     }
-                    eg[i] = bwd_elem<T, RM>(eg[i], ex[i], s, inv_s, p, masked, true, acc);
                 }
+                bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
                 stg_stream(ov + v, DT<T>::pack(eg));
             }
         }
@@ -514,7 +549,7 @@ __global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
             uint32_t slot = atomicAdd(ws + WS_TIES, 1u);
             if (slot < TIE_CAP) list[slot] = i;
         }
-        gx[i] = DT<T>::from_f(bwd_elem<T, RM>(DT<T>::to_f(gy[i]), xe, s, inv_s, p, masked, true, acc));
+        gx[i] = DT<T>::from_f(bwd_elem<T, RM>(DT<T>::to_f(gy[i]), xe, dv, inv_s, p, masked, true, acc));
     }
     float t = block_sum_f(acc, red);
     if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(ws + WS_GS), t);

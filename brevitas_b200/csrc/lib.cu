@@ -1,4 +1,5 @@
-// brevitas_b200 :: library-level C-ABI (version, errors, device info, tuning knobs)
+// brevitas_b200 :: library-level C-ABI (version, errors, device info, tuning knobs, numerics self-test)
+#include "common.cuh"
 #include "host.cuh"
 
 namespace bvb {
@@ -41,9 +42,35 @@ Tuning& tuning() {
     return t;
 }
 
+// DivBy (common.cuh) against the compiler's IEEE division, over `count` consecutive numerator bit patterns
+__global__ void selftest_div_kernel(float divisor, uint32_t first_bits, unsigned long long count,
+                                    unsigned long long* mismatches) {
+    const DivBy dv(divisor);
+    unsigned long long bad = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float a = __uint_as_float(first_bits + (uint32_t)i);
+        const uint32_t got = __float_as_uint(dv(a));
+        const uint32_t ref = __float_as_uint(__fdiv_rn(a, divisor));
+        bad += (got != ref) ? 1ull : 0ull;
+    }
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace bvb
 
 extern "C" {
+
+int bvb_selftest_div(float divisor, uint32_t first_bits, uint64_t count, uint64_t* mismatches, void* stream) {
+    if (!mismatches) return bvb::fail(BVB_EINVAL, "bvb_selftest_div: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), st);
+    if (e != cudaSuccess) return bvb::fail(BVB_ECUDA, "bvb_selftest_div: memset: %s", cudaGetErrorString(e));
+    bvb::selftest_div_kernel<<<bvb::sm_count() * 8, 256, 0, st>>>(divisor, first_bits, (unsigned long long)count,
+                                                                  (unsigned long long*)mismatches);
+    return bvb::check_launch("bvb_selftest_div");
+}
 
 int bvb_version(void) { return 100; }
 

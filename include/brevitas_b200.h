@@ -50,6 +50,12 @@ int bvb_sm_count(void);
  * tuning sweeps in bench.py, not by the product path */
 void bvb_set_tuning(int rows_threads, int rows_stages, int rows_ctas_per_sm, int stream_threads, int stream_ctas_per_sm);
 
+/* numerics self-test: the kernels divide by a row-/tensor-constant scale with nvcc's own div.rn.f32 instruction
+ * sequence, its loop-invariant reciprocal refinement hoisted (csrc/common.cuh DivBy).  This entry point compares
+ * that against the compiler's IEEE division for `count` consecutive numerator bit patterns starting at
+ * `first_bits` and writes the number of bitwise mismatches to *mismatches (device pointer, uint64).           */
+int bvb_selftest_div(float divisor, uint32_t first_bits, uint64_t count, uint64_t* mismatches, void* stream);
+
 /* ---- 1. the 12 STE primitives: forward values of torch.ops.autograd_ste_ops.* -------------------------
  * Backward of every op except abs_binary_sign_grad is the identity on the incoming gradient and
  * needs no kernel (csrc/autograd_ste_ops.cpp:22, 42).  y may alias x (in-place).                       */

@@ -293,6 +293,24 @@ def test_fp32_scalar_scale_with_lowp_input(K):
     assert_bits_equal(host(got), ref.float().numpy(), "bf16 x, fp32 0-dim scale")
 
 
+def test_division_bit_identity():
+    """The kernels divide by the (row-/tensor-constant) scale with nvcc's div.rn.f32 sequence, reciprocal refinement
+    hoisted (csrc/common.cuh DivBy).  It must equal IEEE division bit for bit: ALL 2^32 numerators for a set of
+    divisors (ordinary scales, powers of two, all-ones mantissa, tiny/huge/denormal/inf/nan/negative divisors)."""
+    import ctypes
+    from brevitas_b200 import _lib
+    lib = _lib.load()
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    rng = np.random.default_rng(0)
+    divisors = [1.0, 0.5, 127.0, 1e-10 / 127, 0.0078740157, 3.0, 1.9999999, 1.0000001, 0.037, 255.0, 6.0 / 15,
+                2.0 ** -40, 2.0 ** 40 * 0.999, 2.0 ** -41, 2.0 ** 41, 1e-38, 1e-45, 3e38, float("inf"), float("nan"),
+                0.0, -0.0, -0.25, -1e-3]
+    divisors += [float(np.float32(v)) for v in np.exp(rng.uniform(-12, 6, 12))]
+    for d in divisors:
+        _lib.call("bvb_selftest_div", ctypes.c_float(d), 0, 1 << 32, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert int(out.item()) == 0, f"divisor {d!r}: {int(out.item())} of 2^32 quotients differ from IEEE division"
+
+
 def test_empty_and_errors(K):
     e = torch.empty(0, device="cuda")
     assert K.int_quant_fwd(e, torch.tensor(1.0, device="cuda"), 0.0, -1.0, 1.0, 0).numel() == 0
