@@ -444,6 +444,131 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// per-row backward, TMA-pipelined: a producer warp streams tiles of the gradient row and the input row
+// into a shared-memory ring with bulk copies (mbarrier full/empty pairs), consumer warps compute from
+// shared memory and store gx with 128-bit streaming stores.  Loads are decoupled from the (heavy)
+// arithmetic, so the HBM queue stays full regardless of register pressure / occupancy.
+// dynamic smem: [0,64) full barriers | [64,128) empty barriers | [128,512) reduction scratch |
+//               [512, ...) stages x (gradient tile | input tile)
+// ------------------------------------------------------------------------------------------------------
+constexpr int BWD_MAX_STAGES = 8;
+constexpr int BWD_SMEM_HEADER = 512;
+
+template <typename T, int RM>
+__global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale,
+                                    const T* __restrict__ gscale, T* __restrict__ gx, int rows, int cols,
+                                    int tile_vecs, int stages, float int_thr, int masked, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = reinterpret_cast<uint64_t*>(smem + 64);
+    uint32_t* red_u = reinterpret_cast<uint32_t*>(smem + 128);
+    float* red_f = reinterpret_cast<float*>(smem + 256);
+    unsigned char* ring = smem + BWD_SMEM_HEADER;
+
+    const int tid = threadIdx.x;
+    const int ncw = (blockDim.x >> 5) - 1;                // consumer warps (warp 0 is the producer)
+    const int nct = ncw * 32;
+    const uint32_t tile_bytes = (uint32_t)tile_vecs * 16u;
+    const uint32_t row_bytes = (uint32_t)cols * (uint32_t)sizeof(T);
+    const int row_vecs = (int)(row_bytes >> 4);
+    const int tiles_per_row = (row_vecs + tile_vecs - 1) / tile_vecs;
+    const int first = blockIdx.x, step = gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)ncw); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid < 32) {
+        // ---------------- producer: one elected lane issues the bulk copies ----------------
+        if (tid != 0) return;
+        int it = 0;
+        for (int row = first; row < rows; row += step) {
+            const unsigned char* grow = reinterpret_cast<const unsigned char*>(gy + (size_t)row * cols);
+            const unsigned char* xrow = reinterpret_cast<const unsigned char*>(x + (size_t)row * cols);
+            for (int t = 0; t < tiles_per_row; ++t, ++it) {
+                const int s = it % stages;
+                const int use = it / stages;
+                if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+                const uint32_t off = (uint32_t)t * tile_bytes;
+                const uint32_t bytes = min(tile_bytes, row_bytes - off);
+                unsigned char* gbuf = ring + (size_t)s * 2u * tile_bytes;
+                mbar_arrive_expect_tx(&full[s], 2u * bytes);
+                bulk_g2s(gbuf, grow + off, bytes, &full[s]);
+                bulk_g2s(gbuf + tile_bytes, xrow + off, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int ctid = tid - 32, lane = tid & 31, cw = (tid >> 5) - 1;
+    int it = 0;
+    float s_next = (first < rows) ? DT<T>::to_f(scale[first]) : 1.f;
+    for (int row = first; row < rows; row += step) {
+        const DivBy dv(s_next);
+        if (row + step < rows) s_next = DT<T>::to_f(scale[row + step]);     // prefetch: hides the load latency
+        const float inv_s = dv.approx_recip();
+        const T* xr = x + (size_t)row * cols;
+        T* outr = gx + (size_t)row * cols;
+        uint4* ov = reinterpret_cast<uint4*>(outr);
+        float acc = 0.f;
+        uint32_t best = 0, best_pos = (ctid < row_vecs) ? (uint32_t)ctid : 0xffffffffu;
+        for (int t = 0; t < tiles_per_row; ++t, ++it) {
+            const int s = it % stages;
+            mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+            const int v_base = t * tile_vecs;
+            const int nv = min(tile_vecs, row_vecs - v_base);
+            const uint4* gbuf = reinterpret_cast<const uint4*>(ring + (size_t)s * 2u * tile_bytes);
+            const uint4* xbuf = gbuf + tile_vecs;
+            for (int v = ctid; v < nv; v += nct) {
+                const uint4 qg = gbuf[v];
+                const uint4 qx = xbuf[v];
+                const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx));
+                if (mv > best) { best = mv; best_pos = (uint32_t)(v_base + v); }
+                float eg[V], ex[V];
+                DT<T>::unpack(qg, eg);
+                DT<T>::unpack(qx, ex);
+                bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
+                stg_stream(ov + v_base + v, DT<T>::pack(eg));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);            // this warp no longer reads stage s
+        }
+        // ---- row epilogue among the consumer warps: max bits, sum, smallest position attaining the max
+        uint32_t wm = warp_max_u32(best);
+        float ws = warp_sum_f(acc);
+        if (lane == 0) { red_u[cw] = wm; red_f[cw] = ws; }
+        named_bar_sync(1, nct);
+        const uint32_t rmax = warp_max_u32(lane < ncw ? red_u[lane] : 0u);
+        const float rsum = warp_sum_f(lane < ncw ? red_f[lane] : 0.f);
+        uint32_t cand = (best == rmax) ? best_pos : 0xffffffffu;
+        cand = warp_min_u32(cand);
+        if (lane == 0) red_u[32 + cw] = cand;
+        named_bar_sync(1, nct);          // also orders this CTA's gx stores before the fix-up read below
+        if (ctid == 0) {
+            uint32_t amin = 0xffffffffu;
+            for (int w = 0; w < ncw; ++w) amin = min(amin, red_u[32 + w]);
+            if (amin != 0xffffffffu) {
+                int64_t idx = (int64_t)amin * V;
+                for (int i = 0; i < V; ++i)
+                    if (DT<T>::abs_bits_s(DT<T>::to_f(xr[idx + i])) == rmax) { idx += i; break; }
+                float gsc = rsum + (gscale ? DT<T>::to_f(gscale[row]) : 0.f);
+                float dthr = DT<T>::rnd(fdiv(DT<T>::rnd(gsc), int_thr));
+                float xe = DT<T>::to_f(xr[idx]);
+                float contrib = fmul(dthr, sign3(xe));
+                float cur = DT<T>::to_f(outr[idx]);
+                outr[idx] = DT<T>::from_f(fadd(cur, contrib));
+            }
+        }
+        // red_u[0..ncw) / red_f are rewritten only after the next row's tiles, i.e. after every consumer
+        // passed the second barrier above; red_u[32..] only after the next row's first barrier.
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // whole-tensor abs-max: phase 1 block maxima -> atomicMax, last block finalises the scale
 // workspace words: [0] max bits  [1] ticket  [2] Gs (float)  [3] tie count  [4..] tie indices (int64)
 // ------------------------------------------------------------------------------------------------------
@@ -673,8 +798,11 @@ static RowsGeom rows_geometry(int64_t cols, int elem_size) {
     if (max_total < 2) return g;
     int ctas, stages;
     if (max_total >= 4) {
-        stages = max_total >= 12 ? 4 : (max_total >= 6 ? 3 : 2);
+        // measured (tools/kbench.py sweeps, B200): two stages per CTA and as many CTAs as fit (up to 6) beat
+        // deeper rings with fewer CTAs for every shape tried (C2 fp32/bf16, C3 bf16/fp32)
+        stages = 2;
         ctas = max_total / stages;
+        if (ctas > 6) ctas = 6;
     } else {
         stages = max_total;
         ctas = 1;
@@ -730,19 +858,70 @@ static int launch_rows_fwd(const void* x, void* y, void* scale_out, void* absmax
     return check_launch("bvb_rows_absmax_int_quant_fwd");
 }
 
+// geometry of the TMA backward: consumer warps, tile size, ring depth, CTAs per SM
+struct BwdGeom { int threads, tile_vecs, stages, ctas_per_sm; size_t smem; bool ok; };
+
+static BwdGeom bwd_geometry(int64_t cols, int elem_size) {
+    BwdGeom g = {0, 0, 0, 0, 0, false};
+    const int64_t row_bytes = cols * elem_size;
+    if (row_bytes < 16 || (row_bytes & 15) != 0 || row_bytes >= ((int64_t)1 << 31)) return g;
+    const int64_t row_vecs = row_bytes / 16;
+    // defaults from tools/kbench.py sweeps on a B200 (C2 4096x11008 fp32/bf16, C3 16384x4096 bf16)
+    int ncw = row_vecs >= 512 ? 8 : (row_vecs >= 128 ? 4 : (row_vecs >= 64 ? 2 : 1));
+    int per_thread = 4;                                     // vectors per consumer thread per tile
+    const Tuning& t = tuning();
+    if (t.stream_threads > 0) ncw = t.stream_threads / 32;
+    if (t.rows_threads > 0) per_thread = t.rows_threads;     // (tuning sweeps reuse this knob)
+    int64_t tile_vecs = (int64_t)ncw * 32 * per_thread;
+    if (tile_vecs > row_vecs) tile_vecs = row_vecs;
+    const int64_t stage_bytes = 2 * tile_vecs * 16;
+    int ctas = t.stream_ctas_per_sm > 0 ? t.stream_ctas_per_sm : (ncw >= 8 ? 2 : (ncw >= 4 ? 4 : 6));
+    int64_t per_cta = (200 * 1024) / ctas - BWD_SMEM_HEADER;
+    int stages = (int)(per_cta / stage_bytes);
+    if (stages > 3 && ncw >= 8) stages = 3;
+    if (t.rows_stages > 0) stages = t.rows_stages;
+    if (stages > BWD_MAX_STAGES) stages = BWD_MAX_STAGES;
+    if (stages < 2) return g;
+    int max_ctas = 2048 / ((ncw + 1) * 32);
+    if (ctas > max_ctas) ctas = max_ctas;
+    g.threads = (ncw + 1) * 32;
+    g.tile_vecs = (int)tile_vecs;
+    g.stages = stages;
+    g.ctas_per_sm = ctas;
+    g.smem = BWD_SMEM_HEADER + (size_t)stages * (size_t)stage_bytes;
+    g.ok = g.smem <= 227 * 1024;
+    return g;
+}
+
 template <typename T, int RM>
 static int launch_rows_bwd(const void* gy, const void* x, const void* scale, const void* gscale, void* gx,
                            int64_t rows, int64_t cols, float int_thr, const QParams& p, int masked, cudaStream_t st) {
     constexpr int V = DT<T>::VEC;
     const bool vec_ok = aligned16(gy) && aligned16(x) && aligned16(gx) && (cols % V) == 0 && cols < (int64_t)1 << 31;
+    BwdGeom g = bwd_geometry(cols, (int)sizeof(T));
+    if (vec_ok && g.ok && rows < ((int64_t)1 << 31)) {
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(rows_bwd_tma_kernel<T, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024);
+            if (e != cudaSuccess) return fail(BVB_ECUDA, "rows_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        int64_t grid = (int64_t)g.ctas_per_sm * sm_count();
+        if (grid > rows) grid = rows;
+        rows_bwd_tma_kernel<T, RM><<<(unsigned)grid, g.threads, g.smem, st>>>(
+            (const T*)gy, (const T*)x, (const T*)scale, (const T*)gscale, (T*)gx, (int)rows, (int)cols, g.tile_vecs,
+            g.stages, int_thr, masked, p);
+        return check_launch("bvb_rows_absmax_int_quant_bwd");
+    }
     const int64_t nvec = cols / V;
     int threads = 64;
     if (vec_ok) { while (threads < 512 && nvec > (int64_t)threads * 4) threads *= 2; }
     else        { while (threads < 512 && cols > (int64_t)threads * 8) threads *= 2; }
-    if (tuning().stream_threads > 0) threads = tuning().stream_threads;
     int per_sm = 2048 / threads;
     if (per_sm > 16) per_sm = 16;
-    if (tuning().stream_ctas_per_sm > 0) per_sm = tuning().stream_ctas_per_sm;
     int64_t grid = rows;
     int64_t cap = (int64_t)sm_count() * per_sm;
     if (grid > cap) grid = cap;

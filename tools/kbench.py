@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmark / tuning sweep for the per-row fused kernels (run on the GPU box).
+
+    python tools/kbench.py --kernel bwd --dtype f32 --rows 4096 --cols 11008 --sweep
+Prints one line per geometry: kernel time (CUDA events, inputs rotated over > L2 worth of buffers) and GB/s.
+bvb_set_tuning(rows_threads, rows_stages, rows_ctas_per_sm, stream_threads, stream_ctas_per_sm):
+  fwd: threads, stages, CTAs/SM            bwd: stream_threads = 32*consumer warps, rows_threads = vectors per
+  thread per tile, rows_stages = ring depth, stream_ctas_per_sm = CTAs/SM
+"""
+import argparse
+import itertools
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import brevitas_b200  # noqa: E402,F401
+from brevitas_b200 import _lib  # noqa: E402
+
+DT = {"f32": (torch.float32, _lib.F32, 4), "bf16": (torch.bfloat16, _lib.BF16, 2), "f16": (torch.float16, _lib.F16, 2)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kernel", default="bwd", choices=["fwd", "bwd"])
+    ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--rows", type=int, default=4096)
+    ap.add_argument("--cols", type=int, default=11008)
+    ap.add_argument("--masked", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=40)
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--tuning", type=str, default="")
+    a = ap.parse_args()
+    tdt, tag, esz = DT[a.dtype]
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    n = a.rows * a.cols
+    nsets = max(2, int(400e6 // (n * esz)) + 1)
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = [torch.randn(a.rows, a.cols, device=dev, generator=g).to(tdt) for _ in range(nsets)]
+    G = [torch.randn(a.rows, a.cols, device=dev, generator=g).to(tdt) for _ in range(nsets)]
+    Y = torch.empty_like(X[0])
+    S = torch.empty(a.rows, device=dev, dtype=tdt)
+    st = torch.cuda.current_stream().cuda_stream
+    qmin, qmax, thr = -127.0, 127.0, 127.0
+    lib.bvb_rows_absmax_int_quant_fwd(X[0].data_ptr(), Y.data_ptr(), S.data_ptr(), None, a.rows, a.cols, 1e-10, thr,
+                                      0.0, qmin, qmax, 0, tag, st)
+
+    def run(i):
+        k = i % nsets
+        if a.kernel == "fwd":
+            return lib.bvb_rows_absmax_int_quant_fwd(X[k].data_ptr(), Y.data_ptr(), S.data_ptr(), None, a.rows, a.cols,
+                                                     1e-10, thr, 0.0, qmin, qmax, 0, tag, st)
+        return lib.bvb_rows_absmax_int_quant_bwd(G[k].data_ptr(), X[k].data_ptr(), S.data_ptr(), None, Y.data_ptr(),
+                                                 a.rows, a.cols, thr, 0.0, qmin, qmax, 0, a.masked, tag, st)
+
+    def timeit():
+        for i in range(5):
+            if run(i):
+                return None
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.reps):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / a.reps
+
+    bytes_ = n * esz * (2 if a.kernel == "fwd" else 3)
+    if a.tuning:
+        combos = [tuple(int(v) for v in a.tuning.split(","))]
+    elif not a.sweep:
+        combos = [(0, 0, 0, 0, 0)]
+    elif a.kernel == "fwd":
+        combos = [(t, s, c, 0, 0) for t, s, c in itertools.product([128, 256, 512, 1024], [2, 3, 4], [1, 2, 3, 4, 6])]
+    else:
+        combos = [(pt, s, 0, 32 * (w + 1), c) for w, pt, s, c in
+                  itertools.product([4, 8, 12, 16], [1, 2, 4], [2, 3, 4, 6], [1, 2, 3, 4])]
+    best = None
+    for c in combos:
+        lib.bvb_set_tuning(*c)
+        ms = timeit()
+        if ms is None:
+            print(c, "launch failed:", _lib.last_error())
+            torch.cuda.synchronize()
+            continue
+        gbps = bytes_ / (ms * 1e-3) / 1e9
+        print(f"{a.kernel} {a.dtype} {a.rows}x{a.cols} tuning={c}: {ms * 1e3:.1f} us  {gbps:.0f} GB/s")
+        if best is None or ms < best[0]:
+            best = (ms, c)
+    if best:
+        print("BEST", best[1], f"{best[0] * 1e3:.1f} us", f"{bytes_ / (best[0] * 1e-3) / 1e9:.0f} GB/s")
+    lib.bvb_set_tuning(0, 0, 0, 0, 0)
+
+
+if __name__ == "__main__":
+    main()
