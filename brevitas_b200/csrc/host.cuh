@@ -52,4 +52,15 @@ inline int dtype_size(int dtype) { return dtype == BVB_F32 ? 4 : 2; }
         default: return ::bvb::fail(BVB_EINVAL, "unknown round mode %d", (int)(rm)); \
     }
 
+// forward kernels: specialise round-half-even with a zero zero-point (the default quantizers)
+#define BVB_DISPATCH_MODE_FWD(rm, zp_is_zero, ...)                                  \
+    if ((rm) == BVB_ROUND && (zp_is_zero)) { constexpr int RM = 0 | 8; __VA_ARGS__; } \
+    else BVB_DISPATCH_ROUND(rm, __VA_ARGS__)
+
+// backward kernels: additionally fix the clamp-gradient mode at compile time
+#define BVB_DISPATCH_MODE_BWD(rm, zp_is_zero, masked, ...)                          \
+    if ((rm) == BVB_ROUND && (zp_is_zero) && !(masked)) { constexpr int RM = 0 | 8 | 16; __VA_ARGS__; }      \
+    else if ((rm) == BVB_ROUND && (zp_is_zero) && (masked)) { constexpr int RM = 0 | 8 | 16 | 32; __VA_ARGS__; } \
+    else BVB_DISPATCH_ROUND(rm, __VA_ARGS__)
+
 }  // namespace bvb

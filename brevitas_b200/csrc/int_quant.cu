@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
     const int64_t nchunks = (nvec + chunk - 1) / chunk;
     float s0 = 1.f;
     if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
-    const DivBy dv0(s0);
+    const DivBy dv0(s0, DT<T>::MUL_DIV_EXACT && !scale_f32);
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const int64_t cc = reverse ? (nchunks - 1 - c) : c;
         const int64_t base = cc * chunk + threadIdx.x;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
             int64_t v = base + (int64_t)u * ST_THREADS;
             if (v < nvec) {
                 DivBy dv = dv0;
-                if (smode != 0) dv = DivBy(DT<T>::to_f(scale[(v / inner_v) % count]));
+                if (smode != 0) dv = DivBy(DT<T>::to_f(scale[(v / inner_v) % count]), DT<T>::MUL_DIV_EXACT);
                 float e[V], k[V];
                 DT<T>::unpack(q[u], e);
                 quant_dequant_n<T, RM, V>(e, dv, p, codes ? k : nullptr);
@@ -119,17 +119,20 @@ __device__ __forceinline__ float bwd_elem(float g, float x, const DivBy& dv, flo
 // one 16-byte vector of the backward: eg[] holds the incoming gradient on entry, gx on exit
 template <typename T, int RM, int N>
 __device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], const DivBy& dv, float inv_s,
-                                      const QParams& p, int masked, bool want_gs, float& gs_acc) {
+                                      const QParams& p, int masked_rt, bool want_gs, float& gs_acc) {
+    const bool masked = (RM & RM_MASK_KNOWN) ? ((RM & RM_MASKED) != 0) : (masked_rt != 0);
     float d[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) d[i] = DT<T>::rnd(fmul(eg[i], dv.b));          // grad * scale
+    for (int i = 0; i < N; ++i) d[i] = fmul(eg[i], dv.b);                      // grad * scale
+    DT<T>::template rnd_n<N>(d);
     if (masked || want_gs) {
         float t1[N];
         dv.div_n<N>(ex, t1);
+        DT<T>::template rnd_n<N>(t1);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             float t3, t5;
-            const float t1r = DT<T>::rnd(t1[i]);
+            const float t1r = t1[i];
             to_int_from_t1<T, RM>(t1r, p, t3, t5);
             const float dfull = d[i];
             if (masked) {
@@ -137,7 +140,7 @@ __device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], cons
                 d[i] = m ? dfull : 0.f;
             }
             if (want_gs) {
-                const float t6 = fsub(t5, p.zp);
+                const float t6 = (RM & RM_ZP0) ? t5 : fsub(t5, p.zp);
                 gs_acc = fmaf(eg[i], t6, gs_acc);
                 gs_acc = fmaf(-d[i], t1r * inv_s, gs_acc);
             }
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
     const int64_t nchunks = (nvec + chunk - 1) / chunk;
     float s0 = 1.f;
     if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
-    const DivBy dv0(s0);
+    const DivBy dv0(s0, DT<T>::MUL_DIV_EXACT && !scale_f32);
     const float inv0 = dv0.approx_recip();
     float acc = 0.f;          // smode 0: block-wide; smode 1: run of equal scale indices
     int64_t acc_idx = -1;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
                 float inv_s = inv0;
                 if (smode != 0) {
                     int64_t idx = (v / inner_v) % count;
-                    dv = DivBy(DT<T>::to_f(scale[idx]));
+                    dv = DivBy(DT<T>::to_f(scale[idx]), DT<T>::MUL_DIV_EXACT);
                     inv_s = dv.approx_recip();
                     if (want_gs && idx != acc_idx) {
                         if (acc_idx >= 0) atomicAdd(gscale_out + acc_idx, acc);
@@ -288,7 +291,7 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
 
         const float amax = DT<T>::bits_to_f(m);
         const float sc = finalize_scale<T>(amax, min_val, has_min, int_thr);
-        const DivBy dv(sc);
+        const DivBy dv(sc, DT<T>::MUL_DIV_EXACT);
         if (tid == 0) {
             scale_out[row] = DT<T>::from_f(sc);
             if (absmax_out) absmax_out[row] = DT<T>::from_f(amax);
@@ -335,7 +338,7 @@ __global__ void rows_fwd_generic_kernel(const T* __restrict__ x, T* __restrict__
         }
         if (quantize) {
             T* yr = y + row * cols;
-            const DivBy dv(sc);
+            const DivBy dv(sc, DT<T>::MUL_DIV_EXACT);
             for (int64_t j = threadIdx.x; j < cols; j += blockDim.x)
                 yr[j] = DT<T>::from_f(quant_dequant<T, RM>(DT<T>::to_f(xr[j]), dv, p));
         }
@@ -362,7 +365,7 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
     __shared__ float red_f[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const DivBy dv(DT<T>::to_f(scale[row]));
+        const DivBy dv(DT<T>::to_f(scale[row]), DT<T>::MUL_DIV_EXACT);
         const float inv_s = dv.approx_recip();
         const T* gr = gy + row * cols;
         const T* xr = x + row * cols;
@@ -449,10 +452,10 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
 // shared memory and store gx with 128-bit streaming stores.  Loads are decoupled from the (heavy)
 // arithmetic, so the HBM queue stays full regardless of register pressure / occupancy.
 // dynamic smem: [0,64) full barriers | [64,128) empty barriers | [128,512) reduction scratch |
-//               [512, ...) stages x (gradient tile | input tile)
+//               [1024, ...) stages x (gradient tile | input tile)
 // ------------------------------------------------------------------------------------------------------
 constexpr int BWD_MAX_STAGES = 8;
-constexpr int BWD_SMEM_HEADER = 512;
+constexpr int BWD_SMEM_HEADER = 1024;
 
 template <typename T, int RM>
 __global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale,
@@ -462,8 +465,8 @@ __global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restric
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = reinterpret_cast<uint64_t*>(smem + 64);
-    uint32_t* red_u = reinterpret_cast<uint32_t*>(smem + 128);
-    float* red_f = reinterpret_cast<float*>(smem + 256);
+    uint32_t* red_u = reinterpret_cast<uint32_t*>(smem + 128);      // 2 x 64 words
+    float* red_f = reinterpret_cast<float*>(smem + 640);            // 2 x 32 floats
     unsigned char* ring = smem + BWD_SMEM_HEADER;
 
     const int tid = threadIdx.x;
@@ -506,15 +509,42 @@ __global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restric
     // ---------------- consumers ----------------
     const int ctid = tid - 32, lane = tid & 31, cw = (tid >> 5) - 1;
     int it = 0;
+    int par = 0;                                               // reduction scratch is double-buffered by row parity
+    // The one-element fix-up of a row (gradient through the abs-max) is software-pipelined ACROSS rows: the thread
+    // that owns the arg-max vector re-loads that vector of x and of its own output at the end of row r and applies
+    // the fix-up at the end of row r+1, so the loads' latency never stalls a consumer warp (and with it the ring).
+    bool pend = false;
+    uint4 pend_x = make_uint4(0, 0, 0, 0), pend_o = make_uint4(0, 0, 0, 0);
+    uint32_t pend_rmax = 0;
+    float pend_dthr = 0.f;
+    T* pend_ptr = nullptr;
+    auto apply_pending = [&]() {
+        float fx[V], fo[V];
+        DT<T>::unpack(pend_x, fx);
+        DT<T>::unpack(pend_o, fo);
+        int sel = 0;
+        bool found = false;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const bool hit = !found && (DT<T>::abs_bits_s(fx[i]) == pend_rmax);
+            if (hit) sel = i;
+            found = found || hit;
+        }
+        float xe = fx[0], cur = fo[0];
+#pragma unroll
+        for (int i = 1; i < V; ++i) { if (sel == i) { xe = fx[i]; cur = fo[i]; } }
+        pend_ptr[sel] = DT<T>::from_f(fadd(cur, fmul(pend_dthr, sign3(xe))));
+    };
     float s_next = (first < rows) ? DT<T>::to_f(scale[first]) : 1.f;
-    for (int row = first; row < rows; row += step) {
-        const DivBy dv(s_next);
+    for (int row = first; row < rows; row += step, par ^= 1) {
+        const DivBy dv(s_next, DT<T>::MUL_DIV_EXACT);
         if (row + step < rows) s_next = DT<T>::to_f(scale[row + step]);     // prefetch: hides the load latency
         const float inv_s = dv.approx_recip();
-        const T* xr = x + (size_t)row * cols;
         T* outr = gx + (size_t)row * cols;
         uint4* ov = reinterpret_cast<uint4*>(outr);
+        const uint4* xv = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
         float acc = 0.f;
+        // arg-max bookkeeping: bit pattern of the largest |x| this thread has seen and the first vector attaining it
         uint32_t best = 0, best_pos = (ctid < row_vecs) ? (uint32_t)ctid : 0xffffffffu;
         for (int t = 0; t < tiles_per_row; ++t, ++it) {
             const int s = it % stages;
@@ -527,45 +557,44 @@ __global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restric
                 const uint4 qg = gbuf[v];
                 const uint4 qx = xbuf[v];
                 const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx));
-                if (mv > best) { best = mv; best_pos = (uint32_t)(v_base + v); }
                 float eg[V], ex[V];
                 DT<T>::unpack(qg, eg);
                 DT<T>::unpack(qx, ex);
                 bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
                 stg_stream(ov + v_base + v, DT<T>::pack(eg));
+                if (mv > best) { best = mv; best_pos = (uint32_t)(v_base + v); }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);            // this warp no longer reads stage s
         }
-        // ---- row epilogue among the consumer warps: max bits, sum, smallest position attaining the max
-        uint32_t wm = warp_max_u32(best);
-        float ws = warp_sum_f(acc);
-        if (lane == 0) { red_u[cw] = wm; red_f[cw] = ws; }
+        // ---- row epilogue (ONE named barrier): per-warp (max bits, first position, sum) -> shared -> every warp
+        const uint32_t wmax = warp_max_u32(best);
+        const uint32_t wpos = warp_min_u32(best == wmax ? best_pos : 0xffffffffu);
+        const float wsum = warp_sum_f(acc);
+        uint32_t* ru = red_u + par * 64;
+        float* rf = red_f + par * 32;
+        if (lane == 0) { ru[cw] = wmax; ru[32 + cw] = wpos; rf[cw] = wsum; }
         named_bar_sync(1, nct);
-        const uint32_t rmax = warp_max_u32(lane < ncw ? red_u[lane] : 0u);
-        const float rsum = warp_sum_f(lane < ncw ? red_f[lane] : 0.f);
-        uint32_t cand = (best == rmax) ? best_pos : 0xffffffffu;
-        cand = warp_min_u32(cand);
-        if (lane == 0) red_u[32 + cw] = cand;
-        named_bar_sync(1, nct);          // also orders this CTA's gx stores before the fix-up read below
-        if (ctid == 0) {
-            uint32_t amin = 0xffffffffu;
-            for (int w = 0; w < ncw; ++w) amin = min(amin, red_u[32 + w]);
-            if (amin != 0xffffffffu) {
-                int64_t idx = (int64_t)amin * V;
-                for (int i = 0; i < V; ++i)
-                    if (DT<T>::abs_bits_s(DT<T>::to_f(xr[idx + i])) == rmax) { idx += i; break; }
-                float gsc = rsum + (gscale ? DT<T>::to_f(gscale[row]) : 0.f);
-                float dthr = DT<T>::rnd(fdiv(DT<T>::rnd(gsc), int_thr));
-                float xe = DT<T>::to_f(xr[idx]);
-                float contrib = fmul(dthr, sign3(xe));
-                float cur = DT<T>::to_f(outr[idx]);
-                outr[idx] = DT<T>::from_f(fadd(cur, contrib));
-            }
+        const uint32_t m_l = lane < ncw ? ru[lane] : 0u;
+        const uint32_t p_l = lane < ncw ? ru[32 + lane] : 0xffffffffu;
+        const uint32_t rmax = warp_max_u32(m_l);
+        const uint32_t amin = warp_min_u32(m_l == rmax ? p_l : 0xffffffffu);
+        const float rsum = warp_sum_f(lane < ncw ? rf[lane] : 0.f);
+        if (pend) { apply_pending(); pend = false; }           // previous row's fix-up: its loads landed long ago
+        if (best == rmax && best_pos == amin && amin != 0xffffffffu) {
+            // exactly one thread: it owns the first vector attaining the row maximum
+            const float gsc = rsum + (gscale ? DT<T>::to_f(gscale[row]) : 0.f);
+            // scale = thr / int_thr  =>  d thr = d scale / int_thr; clamp_min_ste and the view are identity;
+            // max(dim) routes it to the FIRST arg-max element, abs multiplies by sgn(x)
+            pend_dthr = DT<T>::rnd(fdiv(DT<T>::rnd(gsc), int_thr));
+            pend_rmax = rmax;
+            pend_x = ldg_stream(xv + amin);
+            pend_o = ldg_coherent(ov + amin);                 // this thread's own earlier store: same-thread RAW order
+            pend_ptr = outr + (size_t)amin * V;
+            pend = true;
         }
-        // red_u[0..ncw) / red_f are rewritten only after the next row's tiles, i.e. after every consumer
-        // passed the second barrier above; red_u[32..] only after the next row's first barrier.
     }
+    if (pend) apply_pending();
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -629,7 +658,7 @@ __global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
         T* __restrict__ gx, int64_t n, int vec_ok, uint32_t* ws, int scale_f32, int masked, QParams p) {
     constexpr int V = DT<T>::VEC;
     __shared__ float red[32];
-    const DivBy dv(load_scale0<T>(scale, scale_f32));
+    const DivBy dv(load_scale0<T>(scale, scale_f32), DT<T>::MUL_DIV_EXACT && !scale_f32);
     const float inv_s = dv.approx_recip();
     const uint32_t mbits = canon_abs_bits(DT<T>::to_f(absmax[0]));
     long long* list = reinterpret_cast<long long*>(ws + WS_LIST);
@@ -866,8 +895,9 @@ static BwdGeom bwd_geometry(int64_t cols, int elem_size) {
     const int64_t row_bytes = cols * elem_size;
     if (row_bytes < 16 || (row_bytes & 15) != 0 || row_bytes >= ((int64_t)1 << 31)) return g;
     const int64_t row_vecs = row_bytes / 16;
-    // defaults from tools/kbench.py sweeps on a B200 (C2 4096x11008 fp32/bf16, C3 16384x4096 bf16)
-    int ncw = row_vecs >= 512 ? 8 : (row_vecs >= 128 ? 4 : (row_vecs >= 64 ? 2 : 1));
+    // defaults from tools/kbench.py sweeps on a B200 (C2 4096x11008 fp32/bf16, C3 16384x4096 bf16): 8 KB tiles,
+    // 4 consumer warps, a 2-deep ring per CTA and 4 CTAs per SM won or tied every sweep; bigger tiles lose.
+    int ncw = row_vecs >= 512 ? 4 : (row_vecs >= 128 ? 2 : 1);
     int per_thread = 4;                                     // vectors per consumer thread per tile
     const Tuning& t = tuning();
     if (t.stream_threads > 0) ncw = t.stream_threads / 32;
@@ -875,13 +905,11 @@ static BwdGeom bwd_geometry(int64_t cols, int elem_size) {
     int64_t tile_vecs = (int64_t)ncw * 32 * per_thread;
     if (tile_vecs > row_vecs) tile_vecs = row_vecs;
     const int64_t stage_bytes = 2 * tile_vecs * 16;
-    int ctas = t.stream_ctas_per_sm > 0 ? t.stream_ctas_per_sm : (ncw >= 8 ? 2 : (ncw >= 4 ? 4 : 6));
-    int64_t per_cta = (200 * 1024) / ctas - BWD_SMEM_HEADER;
-    int stages = (int)(per_cta / stage_bytes);
-    if (stages > 3 && ncw >= 8) stages = 3;
+    int ctas = t.stream_ctas_per_sm > 0 ? t.stream_ctas_per_sm : (ncw >= 4 ? 4 : (ncw >= 2 ? 6 : 8));
+    int stages = (int)((32 * 1024) / stage_bytes);           // ~32 KB in flight per CTA
+    if (stages < 2) stages = 2;
     if (t.rows_stages > 0) stages = t.rows_stages;
     if (stages > BWD_MAX_STAGES) stages = BWD_MAX_STAGES;
-    if (stages < 2) return g;
     int max_ctas = 2048 / ((ncw + 1) * 32);
     if (ctas > max_ctas) ctas = max_ctas;
     g.threads = (ncw + 1) * 32;
@@ -971,7 +999,7 @@ extern "C" int bvb_int_quant_fwd(const void* x, const void* scale, void* y, void
     if (!x || !scale || !y) return fail(BVB_EINVAL, "bvb_int_quant_fwd: null pointer");
     if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "bvb_int_quant_fwd: bad scale broadcast pattern");
     QParams p = make_qparams(zero_point, qmin, qmax, dtype);
-    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_fwd<T, RM>(
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_FWD(round_mode, zero_point == 0.f, return (launch_int_quant_fwd<T, RM>(
         x, scale, y, codes_out, n, scale_inner, scale_count, scale_f32, p, 0, (cudaStream_t)stream))));
     return BVB_OK;
 }
@@ -989,7 +1017,7 @@ extern "C" int bvb_int_quant_bwd(const void* gy, const void* x, const void* scal
     if (!gy || !x || !scale || !gx) return fail(BVB_EINVAL, "bvb_int_quant_bwd: null pointer");
     QParams p = make_qparams(zero_point, qmin, qmax, dtype);
     const int masked = clamp_mode == BVB_CLAMP_MASKED;
-    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_bwd<T, RM>(
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_BWD(round_mode, zero_point == 0.f, masked, return (launch_int_quant_bwd<T, RM>(
         gy, x, scale, gx, gscale_out, n, scale_inner, scale_count, scale_f32, p, masked, (cudaStream_t)stream))));
     return BVB_OK;
 }
@@ -1007,7 +1035,7 @@ extern "C" int bvb_rows_absmax_int_quant_fwd(const void* x, void* y, void* scale
     const int has_min = scaling_min_val > 0.f;
     const float mv = round_to_dtype(scaling_min_val, dtype);
     const float thr = int_threshold;      // 0-dim divisor: ATen keeps its fp32 value in opmath (not rounded to T)
-    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_rows_fwd<T, RM>(
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_FWD(round_mode, zero_point == 0.f, return (launch_rows_fwd<T, RM>(
         x, y, scale_out, absmax_out, rows, cols, mv, has_min, thr, p, (cudaStream_t)stream))));
     return BVB_OK;
 }
@@ -1023,7 +1051,7 @@ extern "C" int bvb_rows_absmax_int_quant_bwd(const void* gy, const void* x, cons
     QParams p = make_qparams(zero_point, qmin, qmax, dtype);
     const int masked = clamp_mode == BVB_CLAMP_MASKED;
     const float thr = int_threshold;
-    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_rows_bwd<T, RM>(
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_BWD(round_mode, zero_point == 0.f, masked, return (launch_rows_bwd<T, RM>(
         gy, x, scale, gscale, gx, rows, cols, thr, p, masked, (cudaStream_t)stream))));
     return BVB_OK;
 }
@@ -1047,7 +1075,7 @@ extern "C" int bvb_tensor_absmax_int_quant_fwd(const void* x, void* y, void* sca
         if (rc != BVB_OK) return rc;
     });
     // second phase runs back to front: the tail of the tensor is what phase 1 left in L2
-    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_fwd<T, RM>(
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_FWD(round_mode, zero_point == 0.f, return (launch_int_quant_fwd<T, RM>(
         x, scale_out, y, nullptr, n, 1, 1, scale_f32, p, 1, st))));
     return BVB_OK;
 }
@@ -1068,7 +1096,7 @@ extern "C" int bvb_tensor_absmax_int_quant_bwd(const void* gy, const void* x, co
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(workspace, 0, 16, st);
     if (e != cudaSuccess) return fail(BVB_ECUDA, "tensor_bwd: memset: %s", cudaGetErrorString(e));
-    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, {
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_BWD(round_mode, zero_point == 0.f, masked, {
         constexpr int V = DT<T>::VEC;
         int vec_ok = (aligned16(gy) && aligned16(x) && aligned16(gx)) ? 1 : 0;
         int64_t work = vec_ok ? (n / V + 1) : n;

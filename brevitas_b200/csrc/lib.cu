@@ -58,9 +58,51 @@ __global__ void selftest_div_kernel(float divisor, uint32_t first_bits, unsigned
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
+// the bf16 (fp16) "product with the correctly rounded reciprocal" shortcut against IEEE division rounded to T,
+// for ALL pairs (numerator, divisor) of T values: blockIdx.y enumerates divisors, threads enumerate numerators
+template <typename T>
+__global__ void selftest_lowp_div_kernel(unsigned long long* mismatches, unsigned long long* eligible) {
+    unsigned long long bad = 0, elig = 0;
+    for (uint32_t bb = blockIdx.x; bb < 65536u; bb += gridDim.x) {
+        const unsigned short bs = (unsigned short)bb;
+        const float b = DT<T>::to_f(*reinterpret_cast<const T*>(&bs));
+        const DivBy dv(b, true);
+        if (!dv.mul_only) continue;              // divisor outside the window: the kernels use the full sequence
+        for (uint32_t aa = threadIdx.x; aa < 65536u; aa += blockDim.x) {
+            const unsigned short as = (unsigned short)aa;
+            const float a = DT<T>::to_f(*reinterpret_cast<const T*>(&as));
+            const float got = DT<T>::rnd(dv(a));
+            const float ref = DT<T>::rnd(__fdiv_rn(a, b));
+            const bool same = (__float_as_uint(got) == __float_as_uint(ref)) || (got != got && ref != ref);
+            bad += same ? 0ull : 1ull;
+            elig += 1ull;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        elig += __shfl_xor_sync(0xffffffffu, elig, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(mismatches, bad);
+        atomicAdd(eligible, elig);
+    }
+}
+
 }  // namespace bvb
 
 extern "C" {
+
+int bvb_selftest_lowp_div(int dtype, uint64_t* out2, void* stream) {
+    if (!out2) return bvb::fail(BVB_EINVAL, "bvb_selftest_lowp_div: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(uint64_t), st);
+    if (e != cudaSuccess) return bvb::fail(BVB_ECUDA, "bvb_selftest_lowp_div: memset: %s", cudaGetErrorString(e));
+    unsigned long long* o = (unsigned long long*)out2;
+    if (dtype == BVB_BF16) bvb::selftest_lowp_div_kernel<__nv_bfloat16><<<bvb::sm_count() * 8, 256, 0, st>>>(o, o + 1);
+    else if (dtype == BVB_F16) bvb::selftest_lowp_div_kernel<__half><<<bvb::sm_count() * 8, 256, 0, st>>>(o, o + 1);
+    else return bvb::fail(BVB_EINVAL, "bvb_selftest_lowp_div: dtype must be BVB_BF16 or BVB_F16");
+    return bvb::check_launch("bvb_selftest_lowp_div");
+}
 
 int bvb_selftest_div(float divisor, uint32_t first_bits, uint64_t count, uint64_t* mismatches, void* stream) {
     if (!mismatches) return bvb::fail(BVB_EINVAL, "bvb_selftest_div: null pointer");

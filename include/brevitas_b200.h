@@ -55,6 +55,11 @@ void bvb_set_tuning(int rows_threads, int rows_stages, int rows_ctas_per_sm, int
  * that against the compiler's IEEE division for `count` consecutive numerator bit patterns starting at
  * `first_bits` and writes the number of bitwise mismatches to *mismatches (device pointer, uint64).           */
 int bvb_selftest_div(float divisor, uint32_t first_bits, uint64_t count, uint64_t* mismatches, void* stream);
+/* bf16 kernels divide a bf16 numerator by a bf16 scale as RN_bf16(a * RN_f32(1/b)); this enumerates ALL 2^16 x 2^16
+ * (a, b) pairs of `dtype` (BVB_BF16 / BVB_F16) whose divisor lies in the shortcut's window and compares with
+ * RN_T(a / b).  out2 (device, uint64[2]) = { mismatches, pairs checked }.  bf16: 0 mismatches (why the shortcut is
+ * used); fp16: > 0 (why it is not).                                                                              */
+int bvb_selftest_lowp_div(int dtype, uint64_t* out2, void* stream);
 
 /* ---- 1. the 12 STE primitives: forward values of torch.ops.autograd_ste_ops.* -------------------------
  * Backward of every op except abs_binary_sign_grad is the identity on the incoming gradient and

@@ -311,6 +311,21 @@ def test_division_bit_identity():
         assert int(out.item()) == 0, f"divisor {d!r}: {int(out.item())} of 2^32 quotients differ from IEEE division"
 
 
+def test_lowp_division_shortcut_exhaustive():
+    """bf16 kernels compute RN_bf16(a / b) as RN_bf16(a * RN_f32(1/b)); checked for ALL pairs of bf16 values whose
+    divisor is inside the shortcut's window.  The same enumeration for fp16 finds mismatches, which is why the fp16
+    kernels keep the full division sequence (DT<__half>::MUL_DIV_EXACT = false)."""
+    from brevitas_b200 import _lib
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _lib.call("bvb_selftest_lowp_div", _lib.BF16, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    bad, checked = [int(v) for v in out.tolist()]
+    assert checked > 2 ** 30 and bad == 0, f"bf16: {bad} of {checked} quotients differ"
+    _lib.call("bvb_selftest_lowp_div", _lib.F16, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    bad16, checked16 = [int(v) for v in out.tolist()]
+    print(f"fp16 shortcut would be wrong for {bad16} of {checked16} pairs (not used)")
+    assert checked16 > 2 ** 28
+
+
 def test_empty_and_errors(K):
     e = torch.empty(0, device="cuda")
     assert K.int_quant_fwd(e, torch.tensor(1.0, device="cuda"), 0.0, -1.0, 1.0, 0).numel() == 0
