@@ -228,6 +228,83 @@ __global__ void int_quant_bwd_scalar_kernel(const T* gy, const T* x, const T* sc
 }
 
 // ------------------------------------------------------------------------------------------------------
+// provided scale with a channel / row broadcast: element i uses scale[(i / inner) % count], i.e. the tensor is a
+// sequence of contiguous "planes" of `inner` elements sharing one scale ([O,1,..] rows, [1,C,1,1] NCHW channels,
+// [B,T,1] tokens).  A group of G threads (a warp for small planes, the CTA for large ones) owns a plane: the
+// divisor set-up is hoisted per plane and d(scale) is reduced inside the group, then ONE atomic per plane.
+// ------------------------------------------------------------------------------------------------------
+constexpr int PL_THREADS = 256;
+
+template <typename T, int RM, bool BWD>
+__global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
+        const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ out,
+        T* __restrict__ codes, float* gscale_out, int64_t nplanes, int64_t inner, int64_t count, int group,
+        int vec_ok, int masked, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31;
+    const int gid = (group == 32) ? (threadIdx.x >> 5) : 0;               // group index inside the CTA
+    const int gtid = (group == 32) ? lane : threadIdx.x;                    // thread index inside the group
+    const int groups_per_cta = PL_THREADS / group;
+    const bool want_gs = BWD && gscale_out != nullptr;
+    for (int64_t pl = (int64_t)blockIdx.x * groups_per_cta + gid; pl < nplanes;
+         pl += (int64_t)gridDim.x * groups_per_cta) {
+        const int64_t sidx = pl % count;
+        const DivBy dv(DT<T>::to_f(scale[sidx]), DT<T>::MUL_DIV_EXACT);
+        const float inv_s = dv.approx_recip();
+        const int64_t base = pl * inner;
+        float acc = 0.f;
+        if (vec_ok) {
+            const int64_t nv = inner / V;
+            const uint4* xv = reinterpret_cast<const uint4*>(x + base);
+            const uint4* gv = reinterpret_cast<const uint4*>(BWD ? gy + base : x + base);
+            uint4* ov = reinterpret_cast<uint4*>(out + base);
+            uint4* cv = codes ? reinterpret_cast<uint4*>(codes + base) : nullptr;
+            for (int64_t v = gtid; v < nv; v += group) {
+                const uint4 qx = ldg_stream(xv + v);
+                float ex[V];
+                DT<T>::unpack(qx, ex);
+                if (BWD) {
+                    const uint4 qg = ldg_stream(gv + v);
+                    float eg[V];
+                    DT<T>::unpack(qg, eg);
+                    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, want_gs, acc);
+                    stg_stream(ov + v, DT<T>::pack(eg));
+                } else {
+                    float k[V];
+                    quant_dequant_n<T, RM, V>(ex, dv, p, cv ? k : nullptr);
+                    stg_stream(ov + v, DT<T>::pack(ex));
+                    if (cv) stg_stream(cv + v, DT<T>::pack(k));
+                }
+            }
+        } else {
+            for (int64_t j = gtid; j < inner; j += group) {
+                float ex[1] = {DT<T>::to_f(x[base + j])};
+                if (BWD) {
+                    float eg[1] = {DT<T>::to_f(gy[base + j])};
+                    bwd_n<T, RM, 1>(eg, ex, dv, inv_s, p, masked, want_gs, acc);
+                    out[base + j] = DT<T>::from_f(eg[0]);
+                } else {
+                    float k[1];
+                    quant_dequant_n<T, RM, 1>(ex, dv, p, codes ? k : nullptr);
+                    out[base + j] = DT<T>::from_f(ex[0]);
+                    if (codes) codes[base + j] = DT<T>::from_f(k[0]);
+                }
+            }
+        }
+        if (want_gs) {
+            if (group == 32) {
+                const float t = warp_sum_f(acc);
+                if (lane == 0) atomicAdd(gscale_out + sidx, t);
+            } else {
+                const float t = block_sum_f(acc, red);
+                if (threadIdx.x == 0) atomicAdd(gscale_out + sidx, t);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // fused per-row abs-max + quant-dequant, TMA-staged (the C2 / C3 headline kernel)
 // dynamic smem: [0,64) mbarriers | [64,192) reduction scratch | [256, ...) `stages` row buffers
 // ------------------------------------------------------------------------------------------------------
@@ -766,6 +843,17 @@ static int launch_int_quant_fwd(const void* x, const void* scale, void* y, void*
     int64_t nvec = 0;
     int smode = (count == 1) ? 0 : 1;
     bool vec_ok = aligned16(x) && aligned16(y) && (!codes || aligned16(codes));
+    if (smode == 1 && inner > 1) {          // planes of `inner` elements sharing one scale
+        const int64_t nplanes = n / inner;
+        const int group = inner * (int64_t)sizeof(T) <= 4096 ? 32 : PL_THREADS;
+        const int pv = (vec_ok && (inner % V) == 0) ? 1 : 0;
+        int64_t grid = (nplanes + (PL_THREADS / group) - 1) / (PL_THREADS / group);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (grid > cap) grid = cap;
+        int_quant_planes_kernel<T, RM, false><<<(unsigned)grid, PL_THREADS, 0, st>>>(
+            nullptr, (const T*)x, (const T*)scale, (T*)y, (T*)codes, nullptr, nplanes, inner, count, group, pv, 0, p);
+        return check_launch("bvb_int_quant_fwd");
+    }
     if (smode == 1 && (inner % V) != 0) vec_ok = false;
     if (vec_ok) nvec = n / V;
     if (nvec > 0) {
@@ -794,6 +882,18 @@ static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale
     int64_t nvec = 0;
     int smode = (count == 1) ? 0 : 1;
     bool vec_ok = aligned16(gy) && aligned16(x) && aligned16(gx);
+    if (smode == 1 && inner > 1) {
+        const int64_t nplanes = n / inner;
+        const int group = inner * (int64_t)sizeof(T) <= 4096 ? 32 : PL_THREADS;
+        const int pv = (vec_ok && (inner % V) == 0) ? 1 : 0;
+        int64_t grid = (nplanes + (PL_THREADS / group) - 1) / (PL_THREADS / group);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (grid > cap) grid = cap;
+        int_quant_planes_kernel<T, RM, true><<<(unsigned)grid, PL_THREADS, 0, st>>>(
+            (const T*)gy, (const T*)x, (const T*)scale, (T*)gx, nullptr, gscale_out, nplanes, inner, count, group, pv,
+            masked, p);
+        return check_launch("bvb_int_quant_bwd");
+    }
     if (smode == 1 && (inner % V) != 0) vec_ok = false;
     if (vec_ok) nvec = n / V;
     if (nvec > 0) {

@@ -1,0 +1,272 @@
+"""The BASELINE.json model workloads, built from ``brevitas_b200.nn`` layers with the reference's quantizers.
+
+* ``tfc``          bnn_pynq TFC (src/brevitas_examples/bnn_pynq/models/FC.py:19-69, common.py:16-42, cfg/tfc_2w2a.ini)
+* ``resnet18``     torchvision-topology ResNet-18 with every Conv2d -> QuantConv2d (default Int8WeightPerTensorFloat,
+                   nn/quant_conv.py:129), every ReLU -> QuantReLU (default Uint8ActPerTensorFloat,
+                   nn/quant_activation.py:18), Linear -> QuantLinear (the reference has no ResNet-18)
+* ``mobilenet_v1`` src/brevitas_examples/imagenet_classification/models/mobilenetv1.py:76-184 with
+                   CommonIntWeightPerChannelQuant / CommonUintActQuant (models/common.py:10-47); the truncating
+                   average pool and the integer bias of the classifier need the input scale and
+                   run un-quantized here -- stated wherever a number from this model is reported.
+"""
+from functools import reduce
+from operator import mul
+
+import torch
+from torch import nn
+
+from brevitas_b200.nn import QuantConv2d, QuantIdentity, QuantLinear, QuantReLU
+from brevitas_b200.quant import (ActQuantizer, Int8WeightPerTensorFloat, Uint8ActPerTensorFloatMaxInit,
+                                 WeightQuantizer)
+
+
+# ---- bnn_pynq -------------------------------------------------------------------------------------------------
+class _CommonQuant:
+    """bnn_pynq/models/common.py:16-33: CONST scaling, FP restriction, narrow signed; 1 bit -> binary"""
+    scaling_impl_type = "CONST"
+    restrict_scaling_type = "FP"
+    float_to_int_impl_type = "ROUND"
+    scaling_per_output_channel = False
+    narrow_range = True
+    signed = True
+
+    @classmethod
+    def _quant_type(cls):
+        if cls.bit_width is None:
+            return "FP"
+        return "BINARY" if cls.bit_width == 1 else "INT"
+
+
+class CommonWeightQuant(_CommonQuant, WeightQuantizer):
+    scaling_const = 1.0
+
+
+class CommonActQuant(_CommonQuant, ActQuantizer):
+    min_val = -1.0
+    max_val = 1.0
+
+
+class TensorNorm(nn.Module):
+    """bnn_pynq/models/tensor_norm.py: batch-norm over the whole tensor (scalar statistics)"""
+
+    def __init__(self, eps=1e-4, momentum=0.1):
+        super().__init__()
+        self.eps, self.momentum = eps, momentum
+        self.weight = nn.Parameter(torch.ones(1))
+        self.bias = nn.Parameter(torch.zeros(1))
+        self.register_buffer('running_mean', torch.zeros(1))
+        self.register_buffer('running_var', torch.ones(1))
+
+    def forward(self, x):
+        if self.training:
+            mean = x.mean()
+            unbias_var = x.var(unbiased=True)
+            biased_var = x.var(unbiased=False)
+            self.running_mean = (1 - self.momentum) * self.running_mean + self.momentum * mean.detach()
+            self.running_var = (1 - self.momentum) * self.running_var + self.momentum * unbias_var.detach()
+            inv_std = 1 / (biased_var + self.eps).pow(0.5)
+            return (x - mean) * inv_std * self.weight + self.bias
+        return ((x - self.running_mean) / (self.running_var + self.eps).pow(0.5)) * self.weight + self.bias
+
+
+class FC(nn.Module):
+    """bnn_pynq FC (FC.py:19-69)"""
+    DROPOUT = 0.2
+
+    def __init__(self, num_classes=10, weight_bit_width=2, act_bit_width=2, in_bit_width=2, out_features=(64, 64, 64),
+                 in_features=(28, 28)):
+        super().__init__()
+        self.features = nn.ModuleList()
+        self.features.append(QuantIdentity(act_quant=CommonActQuant, bit_width=in_bit_width))
+        self.features.append(nn.Dropout(p=self.DROPOUT))
+        fin = reduce(mul, in_features)
+        for fout in out_features:
+            self.features.append(QuantLinear(fin, fout, bias=False, weight_bit_width=weight_bit_width,
+                                             weight_quant=CommonWeightQuant))
+            fin = fout
+            self.features.append(nn.BatchNorm1d(num_features=fin))
+            self.features.append(QuantIdentity(act_quant=CommonActQuant, bit_width=act_bit_width))
+            self.features.append(nn.Dropout(p=self.DROPOUT))
+        self.features.append(QuantLinear(fin, num_classes, bias=False, weight_bit_width=weight_bit_width,
+                                         weight_quant=CommonWeightQuant))
+        self.features.append(TensorNorm())
+        for m in self.modules():
+            if isinstance(m, QuantLinear):
+                torch.nn.init.uniform_(m.weight.data, -1, 1)
+
+    def clip_weights(self, min_val, max_val):
+        for mod in self.features:
+            if isinstance(mod, QuantLinear):
+                mod.weight.data.clamp_(min_val, max_val)
+
+    def forward(self, x):
+        x = x.view(x.shape[0], -1)
+        x = 2.0 * x - 1.0
+        for mod in self.features:
+            x = mod(x)
+        return x
+
+
+class SqrHingeLoss(nn.Module):
+    """bnn_pynq/models/losses.py:9-31: mean(max(0, 1 - y*t)^2) with targets in {-1, +1}"""
+
+    def forward(self, predictions, targets):
+        out = (1. - predictions * targets).clamp_min(0.)
+        return (out * out).mean()
+
+
+def tfc(weight_bit_width=2, act_bit_width=2, in_bit_width=2):
+    return FC(10, weight_bit_width, act_bit_width, in_bit_width)
+
+
+# ---- ResNet-18 ------------------------------------------------------------------------------------------------
+def _act(**kw):
+    return QuantReLU(**kw)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, act_kw=None):
+        super().__init__()
+        act_kw = act_kw or {}
+        self.conv1 = QuantConv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu1 = _act(**act_kw)
+        self.conv2 = QuantConv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.relu2 = _act(**act_kw)
+        self.downsample = downsample
+
+    def forward(self, x):
+        identity = x
+        out = self.relu1(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        if self.downsample is not None:
+            identity = self.downsample(x)
+        return self.relu2(out + identity)
+
+
+class ResNet18(nn.Module):
+    def __init__(self, num_classes=1000, act_kw=None):
+        super().__init__()
+        act_kw = act_kw or {}
+        self.conv1 = QuantConv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = _act(**act_kw)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.inplanes = 64
+        self.layer1 = self._make_layer(64, 2, 1, act_kw)
+        self.layer2 = self._make_layer(128, 2, 2, act_kw)
+        self.layer3 = self._make_layer(256, 2, 2, act_kw)
+        self.layer4 = self._make_layer(512, 2, 2, act_kw)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = QuantLinear(512, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+
+    def _make_layer(self, planes, blocks, stride, act_kw):
+        downsample = None
+        if stride != 1 or self.inplanes != planes:
+            downsample = nn.Sequential(QuantConv2d(self.inplanes, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+        layers = [BasicBlock(self.inplanes, planes, stride, downsample, act_kw)]
+        self.inplanes = planes
+        for _ in range(1, blocks):
+            layers.append(BasicBlock(planes, planes, act_kw=act_kw))
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+def resnet18(num_classes=1000, collect_stats_steps=300):
+    return ResNet18(num_classes, act_kw={"collect_stats_steps": collect_stats_steps})
+
+
+# ---- MobileNetV1 (imagenet_classification) --------------------------------------------------------------------
+class CommonIntWeightPerTensorQuant(Int8WeightPerTensorFloat):
+    """imagenet_classification/models/common.py:10-17"""
+    scaling_min_val = 2e-16
+    bit_width = None
+
+
+class CommonIntWeightPerChannelQuant(CommonIntWeightPerTensorQuant):
+    """models/common.py:19-24"""
+    scaling_per_output_channel = True
+
+
+class CommonUintActQuant(Uint8ActPerTensorFloatMaxInit):
+    """models/common.py:39-47: learned LOG_FP scale initialised at 6.0"""
+    scaling_min_val = 2e-16
+    bit_width = None
+    max_val = 6.0
+    restrict_scaling_type = "LOG_FP"
+
+
+FIRST_LAYER_BIT_WIDTH = 8
+
+
+class ConvBlock(nn.Module):
+    """mobilenetv1.py:76-115"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, weight_bit_width, act_bit_width, stride=1, padding=0,
+                 groups=1, bn_eps=1e-5, activation_scaling_per_channel=False):
+        super().__init__()
+        self.conv = QuantConv2d(in_channels, out_channels, kernel_size, stride, padding, groups=groups, bias=False,
+                                weight_quant=CommonIntWeightPerChannelQuant, weight_bit_width=weight_bit_width)
+        self.bn = nn.BatchNorm2d(out_channels, eps=bn_eps)
+        self.activation = QuantReLU(act_quant=CommonUintActQuant, bit_width=act_bit_width,
+                                    per_channel_broadcastable_shape=(1, out_channels, 1, 1),
+                                    scaling_per_output_channel=activation_scaling_per_channel)
+
+    def forward(self, x):
+        return self.activation(self.bn(self.conv(x)))
+
+
+class DwsConvBlock(nn.Module):
+    """mobilenetv1.py:45-73"""
+
+    def __init__(self, in_channels, out_channels, stride, bit_width, pw_activation_scaling_per_channel=False):
+        super().__init__()
+        self.dw_conv = ConvBlock(in_channels, in_channels, 3, bit_width, bit_width, stride, 1, groups=in_channels)
+        self.pw_conv = ConvBlock(in_channels, out_channels, 1, bit_width, bit_width,
+                                 activation_scaling_per_channel=pw_activation_scaling_per_channel)
+
+    def forward(self, x):
+        return self.pw_conv(self.dw_conv(x))
+
+
+class MobileNetV1(nn.Module):
+    """mobilenetv1.py:118-166 (4-bit by default, first layer 8-bit)"""
+
+    def __init__(self, bit_width=4, num_classes=1000, width_scale=1.0):
+        super().__init__()
+        channels = [[32], [64], [128, 128], [256, 256], [512] * 6, [1024, 1024]]
+        if width_scale != 1.0:
+            channels = [[int(c * width_scale) for c in ci] for ci in channels]
+        self.features = nn.Sequential()
+        cin = channels[0][0]
+        self.features.add_module('init_block', ConvBlock(3, cin, 3, FIRST_LAYER_BIT_WIDTH, bit_width, stride=2,
+                                                         activation_scaling_per_channel=True))
+        for i, stage_channels in enumerate(channels[1:]):
+            stage = nn.Sequential()
+            per_channel = i < len(channels[1:]) - 1
+            for j, cout in enumerate(stage_channels):
+                stride = 2 if (j == 0 and i != 0) else 1
+                stage.add_module(f'unit{j + 1}', DwsConvBlock(cin, cout, stride, bit_width, per_channel))
+                cin = cout
+            self.features.add_module(f'stage{i + 1}', stage)
+        self.final_pool = nn.AvgPool2d(7, 1)            # QuantAvgPool2d (trunc) in the reference: next-tier, see module doc
+        self.output = QuantLinear(cin, num_classes, bias=True, weight_quant=CommonIntWeightPerTensorQuant,
+                                  weight_bit_width=bit_width)
+
+    def forward(self, x):
+        x = self.final_pool(self.features(x))
+        return self.output(x.view(x.size(0), -1))
+
+
+def mobilenet_v1(bit_width=4, num_classes=1000):
+    return MobileNetV1(bit_width, num_classes)
