@@ -131,6 +131,31 @@ def cpu_baseline(torch, sample_rows, reps):
                       f"(oracle/torch_port.py: the reference's ATen op chain; {t * 1e3:.1f} ms)"}, t
 
 
+def cpu_tfc_baseline(torch):
+    """BASELINE.json configs[0]: bnn_pynq TFC 2W2A fwd+bwd, batch 256, on the host cores (oracle/ref_models.py)"""
+    from oracle import ref_models as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    sizes = [(64, 784), (64, 64), (64, 64), (10, 64)]
+    ws = [(torch.rand(s, generator=g) * 2 - 1).requires_grad_(True) for s in sizes]
+    bn = [(torch.ones(64, requires_grad=True), torch.zeros(64, requires_grad=True), torch.zeros(64), torch.ones(64))
+          for _ in range(3)]
+    tn = (torch.ones(1, requires_grad=True), torch.zeros(1, requires_grad=True))
+    x = torch.rand(256, 1, 28, 28, generator=g)
+    y = torch.full((256, 10), -1.0)
+    y.scatter_(1, torch.randint(0, 10, (256, 1), generator=g), 1.0)
+    ts = []
+    for i in range(25):
+        for w in ws:
+            w.grad = None
+        t0 = time.perf_counter()
+        R.sqr_hinge(R.tfc_forward(x, ws, bn, tn), y).backward()
+        ts.append(time.perf_counter() - t0)
+    t = sorted(ts[5:])[10]
+    return {"samples_per_s": round(256 / t, 1), "ms_per_step": round(t * 1e3, 3), "cores": torch.get_num_threads(),
+            "kind": "port", "what": "TFC 2W2A fwd+bwd (no optimizer step), batch 256, oracle/ref_models.py"}
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -171,6 +196,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the bf16 / per-token / per-tensor extra kernels")
     ap.add_argument("--cpu-rows", type=int, default=512)
+    ap.add_argument("--no-qat", action="store_true", help="skip the QAT-step workloads")
+    ap.add_argument("--qat-all", action="store_true", help="also run MobileNetV1 at N=1")
+    ap.add_argument("--qat-batch", type=int, default=256, help="per-GPU batch of the ResNet-18 QAT step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -230,6 +258,7 @@ def main():
     launches = 0
     with ClockSampler(local) as clocks:
         torch.cuda.synchronize()
+        # timed region: EXACTLY K steps, per-kernel events recorded in-stream (they are what the roofline uses)
         start.record()
         for i in range(args.steps):
             k = i % NSETS
@@ -238,7 +267,7 @@ def main():
             ev[i][1].record()
             rc |= c_bwd(*bwd_args[k])
             ev[i][2].record()
-            launches += 2            # rows_fwd_tma_kernel + rows_bwd_kernel, one kernel per C-ABI call
+            launches += 2            # rows_fwd_tma_kernel + rows_bwd_tma_kernel, one kernel per C-ABI call
             if rc:
                 raise RuntimeError(_lib.last_error())
         end.record()
@@ -366,11 +395,27 @@ def main():
         ms = timeit(eager, reps=5)
         extras["c2_f32_eager_aten_same_gpu_fwd_bwd"] = {"ms": round(ms, 3), "GBps_algorithmic": gb(step_bytes, ms)}
 
+    # ---- QAT step (north star: data-parallel QAT across 1/2/4/8 GPUs, NCCL gradient all-reduce) ---------------------
+    qat = {}
+    if not args.no_qat:
+        del Ws, Gs
+        torch.cuda.empty_cache()
+        from qat.train import run as qat_run
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
+        qat["resnet18_int8"] = qat_run("resnet18", args.qat_batch, 10, 3)          # BASELINE.json configs[3]
+        qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
+        qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
+        if world > 1 or args.qat_all:
+            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3)            # configs[4] (avg-pool trunc / int
+                                                                                     # bias un-quantized)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
     cpu, _ = cpu_baseline(torch, args.cpu_rows, 5)
+    if not args.no_qat:
+        qat["tfc_2w2a_cpu_port"] = cpu_tfc_baseline(torch)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
@@ -381,7 +426,7 @@ def main():
                    "l2": f"inputs rotate over {NSETS} (W,G) sets of 2x{n * 4 // 2**20} MiB (> 126 MB L2)",
                    "percent_of_hbm_peak": round(100 * value / world / peak, 1), "hbm_peak_gbs": peak,
                    "hbm_peak_source": peak_src, "percent_of_nominal_8TBps": round(100 * value / world / 8000, 1)},
-        "roofline": {"bound": "hbm", "kernel": "rows_bwd_kernel<float,ROUND,vec> (STE backward + grad through abs-max)",
+        "roofline": {"bound": "hbm", "kernel": "rows_bwd_tma_kernel<float,ROUND|ZP0|STE> (STE backward + grad through abs-max)",
                      "achieved": round(bwd_gbps, 1), "peak": peak, "unit": "GB/s", "frac": round(bwd_gbps / peak, 4),
                      "traffic": None, "algorithmic_bytes_per_launch": n * BWD_B, "avg_launch_ms": round(bwd_ms, 5),
                      "peak_source": peak_src,
@@ -394,6 +439,7 @@ def main():
                 "api": "brevitas_b200.core.quant.RescalingIntQuant(w) + autograd backward, pinned host buffers"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
+        "qat_step": qat,
         "extras": extras,
     }
     print(json.dumps(line))

@@ -49,10 +49,56 @@ def build(name: str, device, collect_stats_steps: int = 300, channels_last: bool
     return model, loss_fn, spec
 
 
-def make_optimizer(model, spec):
+def make_optimizer(model, spec, capturable=False):
     if spec["opt"] == "adam":
-        return torch.optim.Adam(model.parameters(), lr=spec["lr"])
+        return torch.optim.Adam(model.parameters(), lr=spec["lr"], capturable=capturable)
     return torch.optim.SGD(model.parameters(), lr=spec["lr"], momentum=0.9, weight_decay=1e-4)
+
+
+class GraphedStep:
+    """The whole training step (forward, loss, backward, gradient all-reduce, optimizer, weight clip) captured in
+    ONE CUDA graph: small models such as TFC are launch-bound (~150 kernels of a few microseconds per step), and the
+    C-ABI is capture-safe by construction (no allocation outside torch's caching allocator, no sync, current stream).
+    Data-parallel ranks exchange gradients with a captured NCCL all-reduce over one flat bucket."""
+
+    def __init__(self, raw_model, loss_fn, opt, x, y, world=1, dist=None):
+        self.raw, self.loss_fn, self.opt, self.world, self.dist = raw_model, loss_fn, opt, world, dist
+        self.x, self.y = x.clone(), y.clone()
+        self.params = [p for p in raw_model.parameters() if p.requires_grad]
+        from brevitas_b200 import _kernels as K
+        for _ in range(3):                       # warm-up on the (non-default) current stream, see run()
+            self._eager_step()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        before = K.launch_count
+        with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream()):
+            self.loss = self._eager_step()
+        self.captured_launches = K.launch_count - before
+
+    def _eager_step(self):
+        self.opt.zero_grad(set_to_none=False)
+        loss = self.loss_fn(self.raw(self.x), self.y)
+        loss.backward()
+        if self.world > 1:
+            grads = [p.grad for p in self.params if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            self.dist.all_reduce(flat)
+            flat /= self.world
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self.opt.step()
+        if hasattr(self.raw, "clip_weights"):
+            self.raw.clip_weights(-1, 1)
+        return loss
+
+    def __call__(self, x=None, y=None):
+        if x is not None:
+            self.x.copy_(x)
+            self.y.copy_(y)
+        self.graph.replay()
+        return self.loss
 
 
 def make_batch(spec, batch, device, seed):
@@ -79,7 +125,7 @@ def train_step(model, raw_model, x, y, loss_fn, opt):
     return loss
 
 
-def run(name, batch, steps, warmup, collect_stats_steps=2, log=None):
+def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False):
     """returns a dict with samples/s (all ranks), ms/step, kernel-launch count per step of OUR kernels"""
     import brevitas_b200  # noqa: F401
     from brevitas_b200 import _kernels as K
@@ -93,18 +139,30 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None):
         import torch.distributed as dist
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=device)
+    if graph:
+        # autograd's grad-accumulator nodes remember the stream they were first used on; a graph can only be captured
+        # if that is not the legacy default stream, so the whole life of the model runs on a side stream
+        torch.cuda.set_stream(torch.cuda.Stream(device))
     torch.manual_seed(1234)                               # identical initial weights on every rank
     raw, loss_fn, spec = build(name, device, collect_stats_steps)
     model = raw
-    if world > 1:
+    if world > 1 and not graph:
         model = nn.parallel.DistributedDataParallel(raw, device_ids=[local], gradient_as_bucket_view=True,
                                                     broadcast_buffers=True)
-    opt = make_optimizer(raw, spec)
+    opt = make_optimizer(raw, spec, capturable=graph)
     model.train()
     batches = [make_batch(spec, batch, device, 100 + rank * 7 + i) for i in range(2)]
     # warm-up runs past the statistics-collection phase of the activation quantizers (steady state)
     for i in range(max(warmup, collect_stats_steps + 2)):
         loss = train_step(model, raw, *batches[i % 2], loss_fn, opt)
+    torch.cuda.synchronize()
+    if graph:
+        gstep = GraphedStep(raw, loss_fn, opt, *batches[0], world=world, dist=dist)
+        step_fn = lambda i: gstep(*batches[i % 2])
+    else:
+        step_fn = lambda i: train_step(model, raw, *batches[i % 2], loss_fn, opt)
+    for i in range(3):
+        step_fn(i)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -113,12 +171,12 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None):
     torch.cuda.profiler.start()             # ncu --profile-from-start off: only the timed steps
     e0.record()
     for i in range(steps):
-        loss = train_step(model, raw, *batches[i % 2], loss_fn, opt)
+        loss = step_fn(i)
     e1.record()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1) / steps
-    launches = (K.launch_count - l0) / steps
+    launches = gstep.captured_launches if graph else (K.launch_count - l0) / steps
     loss_val = float(loss.detach())
     if dist is not None:
         t = torch.tensor([ms], device=device)
@@ -127,7 +185,9 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None):
     return {"model": name, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
             "samples_per_s": round(world * batch / (ms * 1e-3), 1), "fakequant_launches_per_step": launches,
             "final_loss": round(loss_val, 4), "dtype": "f32", "data": "synthetic",
-            "phase": f"steady state (after {collect_stats_steps} collect steps)"}
+            "phase": f"steady state (after {collect_stats_steps} collect steps)",
+            "step": "one CUDA graph (fwd+loss+bwd+allreduce+optimizer)" if graph else "eager launches"
+                    + (" + DDP bucketed NCCL all-reduce" if world > 1 else "")}
 
 
 def main():
@@ -137,10 +197,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--collect-stats-steps", type=int, default=2)
+    ap.add_argument("--graph", action="store_true", help="capture the whole step in a CUDA graph")
     a = ap.parse_args()
     os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
     os.environ.setdefault("NCCL_IB_DISABLE", "1")
-    res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps)
+    res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps, graph=a.graph)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(res))
     import torch.distributed as dist

@@ -23,7 +23,7 @@ DT = {"f32": (torch.float32, _lib.F32, 4), "bf16": (torch.bfloat16, _lib.BF16, 2
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--kernel", default="bwd", choices=["fwd", "bwd"])
+    ap.add_argument("--kernel", default="bwd", choices=["fwd", "bwd", "both"])
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--rows", type=int, default=4096)
     ap.add_argument("--cols", type=int, default=11008)
@@ -42,6 +42,7 @@ def main():
     X = [torch.randn(a.rows, a.cols, device=dev, generator=g).to(tdt) for _ in range(nsets)]
     G = [torch.randn(a.rows, a.cols, device=dev, generator=g).to(tdt) for _ in range(nsets)]
     Y = torch.empty_like(X[0])
+    GXO = torch.empty_like(X[0])
     S = torch.empty(a.rows, device=dev, dtype=tdt)
     st = torch.cuda.current_stream().cuda_stream
     qmin, qmax, thr = -127.0, 127.0, 127.0
@@ -50,6 +51,12 @@ def main():
 
     def run(i):
         k = i % nsets
+        if a.kernel == "both":           # the bench.py step: forward then backward of the same weight
+            rc = lib.bvb_rows_absmax_int_quant_fwd(X[k].data_ptr(), Y.data_ptr(), S.data_ptr(), None, a.rows, a.cols,
+                                                   1e-10, thr, 0.0, qmin, qmax, 0, tag, st)
+            return rc | lib.bvb_rows_absmax_int_quant_bwd(G[k].data_ptr(), X[k].data_ptr(), S.data_ptr(), None,
+                                                          GXO.data_ptr(), a.rows, a.cols, thr, 0.0, qmin, qmax, 0,
+                                                          a.masked, tag, st)
         if a.kernel == "fwd":
             return lib.bvb_rows_absmax_int_quant_fwd(X[k].data_ptr(), Y.data_ptr(), S.data_ptr(), None, a.rows, a.cols,
                                                      1e-10, thr, 0.0, qmin, qmax, 0, tag, st)
@@ -71,7 +78,7 @@ def main():
         torch.cuda.profiler.stop()
         return e0.elapsed_time(e1) / a.reps
 
-    bytes_ = n * esz * (2 if a.kernel == "fwd" else 3)
+    bytes_ = n * esz * {"fwd": 2, "bwd": 3, "both": 5}[a.kernel]
     if a.tuning:
         combos = [tuple(int(v) for v in a.tuning.split(","))]
     elif not a.sweep:
