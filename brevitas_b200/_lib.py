@@ -30,6 +30,7 @@ SIGNATURES = {
     "bvb_set_tuning": (None, [_I, _I, _I, _I, _I]),
     "bvb_selftest_div": (c_int, [c_float, ctypes.c_uint32, ctypes.c_uint64, _P, _P]),
     "bvb_selftest_lowp_div": (c_int, [_I, _P, _P]),
+    "bvb_debug_packed_constants": (c_int, [_F, _F, _F, _I, _P]),
     "bvb_round_ste_impl": (c_int, _UNARY),
     "bvb_ceil_ste_impl": (c_int, _UNARY),
     "bvb_floor_ste_impl": (c_int, _UNARY),

@@ -40,7 +40,6 @@ template <typename T, int RM>
 __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
         const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ y, T* __restrict__ codes,
         int64_t nvec, int64_t inner_v, int64_t count, int smode, int scale_f32, int reverse, QParams p) {
-    constexpr int V = DT<T>::VEC;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     uint4* yv = reinterpret_cast<uint4*>(y);
     uint4* cv = reinterpret_cast<uint4*>(codes);
@@ -64,11 +63,10 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
             if (v < nvec) {
                 DivBy dv = dv0;
                 if (smode != 0) dv = DivBy(DT<T>::to_f(scale[(v / inner_v) % count]), DT<T>::MUL_DIV_EXACT);
-                float e[V], k[V];
-                DT<T>::unpack(q[u], e);
-                quant_dequant_n<T, RM, V>(e, dv, p, codes ? k : nullptr);
-                stg_stream(yv + v, DT<T>::pack(e));
-                if (codes) stg_stream(cv + v, DT<T>::pack(k));
+                uint4 kq;
+                const uint4 yq = qdq_vec<T, RM>(q[u], dv, p, !scale_f32, codes ? &kq : nullptr);
+                stg_stream(yv + v, yq);
+                if (codes) stg_stream(cv + v, kq);
             }
         }
     }
@@ -149,12 +147,67 @@ __device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], cons
     dv.div_n<N>(d, eg);                                                        // grad / scale (rounded at store)
 }
 
+// One 16-byte vector of the backward; returns gx.  bf16 / fp16 with the default modes use packed-pair arithmetic
+// (see qdq_vec in common.cuh): grad*scale is one HMUL2 (the fp32 product of two T values is exact, hence a single
+// rounding), the clamp mask is two packed compares of t2 = rnd_T(x/s)+0 against thresholds the host derived from
+// round()'s monotonicity (round(v) > qmax <=> v > thr_hi), and the integer code for d(scale) is
+// round(clamp(t2)) by magic-number adds.  Element-wise results are bit-identical to the literal sequence; the
+// d(scale) partial sum only changes its summation order (tolerance-bound by contract).
+template <typename T, int RM>
+__device__ __forceinline__ uint4 bwd_vec(const uint4& qg, const uint4& qx, const DivBy& dv, float inv_s,
+                                         const QParams& p, int masked_rt, bool want_gs, float& gs_acc, bool scale_in_T) {
+    constexpr int V = DT<T>::VEC;
+    if constexpr (PackedPath<T, RM>::value) {
+        if (p.pk_ok && scale_in_T && dv.fast) {
+            const bool masked = (RM & RM_MASK_KNOWN) ? ((RM & RM_MASKED) != 0) : (masked_rt != 0);
+            const uint32_t s2 = DT<T>::pack2(dv.b, dv.b);
+            uint32_t d[V / 2] = {DT<T>::p_mul(qg.x, s2), DT<T>::p_mul(qg.y, s2), DT<T>::p_mul(qg.z, s2),
+                                 DT<T>::p_mul(qg.w, s2)};                              // rnd_T(grad * scale)
+            float dm[V];
+            if (masked || want_gs) {
+                float ex[V], t1[V];
+                DT<T>::unpack(qx, ex);
+                dv.div_n<V>(ex, t1);
+                float s_gt = 0.f, s_dt = 0.f;
+#pragma unroll
+                for (int j = 0; j < V / 2; ++j) {
+                    const uint32_t t1p = DT<T>::pack2(t1[2 * j], t1[2 * j + 1]);
+                    const uint32_t t2 = DT<T>::p_add(t1p, 0u);
+                    if (masked) d[j] &= ~(DT<T>::p_gt_mask(t2, p.pk_thr_hi) | DT<T>::p_lt_mask(t2, p.pk_thr_lo));
+                    DT<T>::p_unpack(d[j], dm[2 * j], dm[2 * j + 1]);
+                    if (want_gs) {
+                        const uint32_t c = DT<T>::p_max_nan(DT<T>::p_min_nan(t2, p.pk_hi), p.pk_lo);
+                        float k0, k1, g0, g1, a0, a1;
+                        DT<T>::p_rint_f(c, k0, k1);                                    // t6 (zero-point is 0)
+                        DT<T>::p_unpack(j == 0 ? qg.x : (j == 1 ? qg.y : (j == 2 ? qg.z : qg.w)), g0, g1);
+                        DT<T>::p_unpack(t1p, a0, a1);
+                        s_gt = fmaf(g0, k0, s_gt); s_gt = fmaf(g1, k1, s_gt);
+                        s_dt = fmaf(dm[2 * j], a0, s_dt); s_dt = fmaf(dm[2 * j + 1], a1, s_dt);
+                    }
+                }
+                // d(scale) += sum g*t6 - sum d*((x/s)/s)
+                if (want_gs) gs_acc += fmaf(-inv_s, s_dt, s_gt);
+            } else {
+#pragma unroll
+                for (int j = 0; j < V / 2; ++j) DT<T>::p_unpack(d[j], dm[2 * j], dm[2 * j + 1]);
+            }
+            float gx[V];
+            dv.div_n<V>(dm, gx);                                                       // grad / scale
+            return DT<T>::pack(gx);
+        }
+    }
+    float eg[V], ex[V];
+    DT<T>::unpack(qg, eg);
+    DT<T>::unpack(qx, ex);
+    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked_rt, want_gs, gs_acc);
+    return DT<T>::pack(eg);
+}
+
 // provided-scale backward; gscale_out (nullable) accumulated with float atomics
 template <typename T, int RM>
 __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
         const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ gx,
         float* gscale_out, int64_t nvec, int64_t inner_v, int64_t count, int smode, int scale_f32, int masked, QParams p) {
-    constexpr int V = DT<T>::VEC;
     __shared__ float red[32];
     const uint4* gv = reinterpret_cast<const uint4*>(gy);
     const uint4* xv = reinterpret_cast<const uint4*>(x);
@@ -192,11 +245,7 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
                         acc_idx = idx;
                     }
                 }
-                float eg[V], ex[V];
-                DT<T>::unpack(qg[u], eg);
-                DT<T>::unpack(qx[u], ex);
-                bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, want_gs, acc);
-                stg_stream(ov + v, DT<T>::pack(eg));
+                stg_stream(ov + v, bwd_vec<T, RM>(qg[u], qx[u], dv, inv_s, p, masked, want_gs, acc, !scale_f32));
             }
         }
     }
@@ -234,6 +283,7 @@ __global__ void int_quant_bwd_scalar_kernel(const T* gy, const T* x, const T* sc
 // divisor set-up is hoisted per plane and d(scale) is reduced inside the group, then ONE atomic per plane.
 // ------------------------------------------------------------------------------------------------------
 constexpr int PL_THREADS = 256;
+constexpr int PL_UNROLL = 4;
 
 template <typename T, int RM, bool BWD>
 __global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
@@ -260,21 +310,31 @@ __global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
             const uint4* gv = reinterpret_cast<const uint4*>(BWD ? gy + base : x + base);
             uint4* ov = reinterpret_cast<uint4*>(out + base);
             uint4* cv = codes ? reinterpret_cast<uint4*>(codes + base) : nullptr;
-            for (int64_t v = gtid; v < nv; v += group) {
-                const uint4 qx = ldg_stream(xv + v);
-                float ex[V];
-                DT<T>::unpack(qx, ex);
-                if (BWD) {
-                    const uint4 qg = ldg_stream(gv + v);
-                    float eg[V];
-                    DT<T>::unpack(qg, eg);
-                    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, want_gs, acc);
-                    stg_stream(ov + v, DT<T>::pack(eg));
-                } else {
-                    float k[V];
-                    quant_dequant_n<T, RM, V>(ex, dv, p, cv ? k : nullptr);
-                    stg_stream(ov + v, DT<T>::pack(ex));
-                    if (cv) stg_stream(cv + v, DT<T>::pack(k));
+            // PL_UNROLL independent 16-byte loads in flight per thread before any arithmetic (ncu r01b: one load at
+            // a time left this kernel latency-bound at 42 % issue utilisation and 4.6 TB/s)
+            for (int64_t v0 = gtid; v0 < nv; v0 += (int64_t)group * PL_UNROLL) {
+                uint4 qx[PL_UNROLL], qg[PL_UNROLL];
+#pragma unroll
+                for (int u = 0; u < PL_UNROLL; ++u) {
+                    const int64_t v = v0 + (int64_t)u * group;
+                    if (v < nv) {
+                        qx[u] = ldg_stream(xv + v);
+                        if (BWD) qg[u] = ldg_stream(gv + v);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PL_UNROLL; ++u) {
+                    const int64_t v = v0 + (int64_t)u * group;
+                    if (v < nv) {
+                        if (BWD) {
+                            stg_stream(ov + v, bwd_vec<T, RM>(qg[u], qx[u], dv, inv_s, p, masked, want_gs, acc, true));
+                        } else {
+                            uint4 kq;
+                            const uint4 yq = qdq_vec<T, RM>(qx[u], dv, p, true, cv ? &kq : nullptr);
+                            stg_stream(ov + v, yq);
+                            if (cv) stg_stream(cv + v, kq);
+                        }
+                    }
                 }
             }
         } else {
@@ -325,7 +385,6 @@ template <typename T, int RM>
 __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ scale_out,
                                     T* __restrict__ absmax_out, int rows, int cols, int stages, uint32_t stage_stride,
                                     float min_val, int has_min, float int_thr, QParams p) {
-    constexpr int V = DT<T>::VEC;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint32_t* red = reinterpret_cast<uint32_t*>(smem + 64);
@@ -378,11 +437,7 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
         uint4* yrow = reinterpret_cast<uint4*>(y + (size_t)row * cols);
 #pragma unroll 2
         for (int v = tid; v < nvec; v += blockDim.x) {
-            uint4 q = buf[v];
-            float e[V];
-            DT<T>::unpack(q, e);
-            quant_dequant_n<T, RM, V>(e, dv, p);
-            stg_stream(yrow + v, DT<T>::pack(e));
+            stg_stream(yrow + v, qdq_vec<T, RM>(buf[v], dv, p, true));
         }
         __syncthreads();      // everyone is done with buf[s] and red[]
         if (tid == 0 && it + stages < my_rows) {
@@ -460,22 +515,15 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
                 uint4 qg0 = ldg_stream(gv + v0), qx0 = ldg_stream(xv + v0);
                 uint4 qg1 = make_uint4(0, 0, 0, 0), qx1 = make_uint4(0, 0, 0, 0);
                 if (v1 < nvec) { qg1 = ldg_stream(gv + v1); qx1 = ldg_stream(xv + v1); }
-                float eg[V], ex[V];
                 {
                     const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx0));
                     if (mv > best) { best = mv; best_pos = (uint32_t)v0; }
-                    DT<T>::unpack(qg0, eg);
-                    DT<T>::unpack(qx0, ex);
-                    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
-                    stg_stream(ov + v0, DT<T>::pack(eg));
+                    stg_stream(ov + v0, bwd_vec<T, RM>(qg0, qx0, dv, inv_s, p, masked, true, acc, true));
                 }
                 if (v1 < nvec) {
                     const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx1));
                     if (mv > best) { best = mv; best_pos = (uint32_t)v1; }
-                    DT<T>::unpack(qg1, eg);
-                    DT<T>::unpack(qx1, ex);
-                    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
-                    stg_stream(ov + v1, DT<T>::pack(eg));
+                    stg_stream(ov + v1, bwd_vec<T, RM>(qg1, qx1, dv, inv_s, p, masked, true, acc, true));
                 }
             }
         } else {
@@ -634,11 +682,7 @@ __global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restric
                 const uint4 qg = gbuf[v];
                 const uint4 qx = xbuf[v];
                 const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx));
-                float eg[V], ex[V];
-                DT<T>::unpack(qg, eg);
-                DT<T>::unpack(qx, ex);
-                bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
-                stg_stream(ov + v_base + v, DT<T>::pack(eg));
+                stg_stream(ov + v_base + v, bwd_vec<T, RM>(qg, qx, dv, inv_s, p, masked, true, acc, true));
                 if (mv > best) { best = mv; best_pos = (uint32_t)(v_base + v); }
             }
             __syncwarp();
@@ -672,6 +716,106 @@ __global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restric
         }
     }
     if (pend) apply_pending();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// provided-scale backward, TMA-pipelined (learned / constant / running-statistic scales: ParameterScaling,
+// ParameterFromRuntimeStatsScaling, ConstScaling).  Same producer / consumer ring as rows_bwd_tma_kernel, minus the
+// statistic: the tensor is a sequence of `nrows` chunks of `row_vecs` 16-byte vectors (the last one may be shorter);
+// chunk r uses scale[r % count].  count == 1 (one scale for the tensor): d(scale) is accumulated over the whole CTA
+// and added once; count > 1 (a scale per output channel / NCHW channel / token): one atomic per warp and chunk.
+// ncu r01b: the register-staged streaming kernel it replaces ran at 24 % occupancy, loads not overlapped with the
+// arithmetic (4.5 TB/s bf16, 5.3 TB/s fp32).
+// dynamic smem: [0,64) full barriers | [64,128) empty barriers | [128,256) reduction scratch | [1024, ...) ring
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int RM>
+__global__ void scaled_bwd_tma_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale,
+                                      T* __restrict__ gx, float* gscale_out, long long n_vecs, int row_vecs,
+                                      long long nrows, long long count, int tile_vecs, int stages, int scale_f32,
+                                      int masked, QParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = reinterpret_cast<uint64_t*>(smem + 64);
+    float* red_f = reinterpret_cast<float*>(smem + 128);
+    unsigned char* ring = smem + BWD_SMEM_HEADER;
+
+    const int tid = threadIdx.x;
+    const int ncw = (blockDim.x >> 5) - 1;                // consumer warps (warp 0 is the producer)
+    const int nct = ncw * 32;
+    const uint32_t tile_bytes = (uint32_t)tile_vecs * 16u;
+    const long long first = blockIdx.x, step = gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)ncw); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid < 32) {
+        if (tid != 0) return;
+        const unsigned char* gb = reinterpret_cast<const unsigned char*>(gy);
+        const unsigned char* xb = reinterpret_cast<const unsigned char*>(x);
+        int it = 0;
+        for (long long row = first; row < nrows; row += step) {
+            const long long v0 = row * row_vecs;
+            const int rv = (int)min((long long)row_vecs, n_vecs - v0);
+            for (int t = 0; t * tile_vecs < rv; ++t, ++it) {
+                const int s = it % stages;
+                const int use = it / stages;
+                if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+                const uint32_t bytes = (uint32_t)min(tile_vecs, rv - t * tile_vecs) * 16u;
+                const size_t off = ((size_t)v0 + (size_t)t * tile_vecs) * 16u;
+                unsigned char* gbuf = ring + (size_t)s * 2u * tile_bytes;
+                mbar_arrive_expect_tx(&full[s], 2u * bytes);
+                bulk_g2s(gbuf, gb + off, bytes, &full[s]);
+                bulk_g2s(gbuf + tile_bytes, xb + off, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    const int ctid = tid - 32, lane = tid & 31, cw = (tid >> 5) - 1;
+    const bool want_gs = gscale_out != nullptr;
+    const bool one_scale = count == 1;
+    uint4* ov = reinterpret_cast<uint4*>(gx);
+    int it = 0;
+    float acc = 0.f;
+    float s_next = 1.f;
+    if (first < nrows) s_next = one_scale ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[first % count]);
+    for (long long row = first; row < nrows; row += step) {
+        const DivBy dv(s_next, DT<T>::MUL_DIV_EXACT && !scale_f32);
+        if (!one_scale && row + step < nrows) s_next = DT<T>::to_f(scale[(row + step) % count]);   // prefetch
+        const float inv_s = dv.approx_recip();
+        const long long v0 = row * row_vecs;
+        const int rv = (int)min((long long)row_vecs, n_vecs - v0);
+        for (int t = 0; t * tile_vecs < rv; ++t, ++it) {
+            const int s = it % stages;
+            mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+            const int v_base = t * tile_vecs;
+            const int nv = min(tile_vecs, rv - v_base);
+            const uint4* gbuf = reinterpret_cast<const uint4*>(ring + (size_t)s * 2u * tile_bytes);
+            const uint4* xbuf = gbuf + tile_vecs;
+            for (int v = ctid; v < nv; v += nct)
+                stg_stream(ov + v0 + v_base + v,
+                           bwd_vec<T, RM>(gbuf[v], xbuf[v], dv, inv_s, p, masked, want_gs, acc, !scale_f32));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (want_gs && !one_scale) {
+            const float wsum = warp_sum_f(acc);
+            if (lane == 0) atomicAdd(gscale_out + (row % count), wsum);
+            acc = 0.f;
+        }
+    }
+    if (want_gs && one_scale) {
+        const float wsum = warp_sum_f(acc);
+        if (lane == 0) red_f[cw] = wsum;
+        named_bar_sync(1, nct);
+        if (cw == 0) {
+            const float tsum = warp_sum_f(lane < ncw ? red_f[lane] : 0.f);
+            if (lane == 0) atomicAdd(gscale_out, tsum);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -768,8 +912,7 @@ __global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
                         if (slot < TIE_CAP) list[slot] = v * V + i;
                     }
                 }
-                bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked, true, acc);
-                stg_stream(ov + v, DT<T>::pack(eg));
+                stg_stream(ov + v, bwd_vec<T, RM>(qg[u], qx[u], dv, inv_s, p, masked, true, acc, !scale_f32));
             }
         }
     }
@@ -817,12 +960,55 @@ __global__ void tensor_bwd_fixup_kernel(const T* __restrict__ x, const T* __rest
 // ------------------------------------------------------------------------------------------------------
 // host-side launch logic
 // ------------------------------------------------------------------------------------------------------
+// ---- host-side helpers for the packed low-precision path: walk T's value grid through 16-bit patterns ----
+static inline uint16_t t_bits(float v, int dtype) {
+    if (dtype == BVB_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+static inline float t_value(uint16_t b, int dtype) {
+    if (dtype == BVB_BF16) { __nv_bfloat16 h; *reinterpret_cast<uint16_t*>(&h) = b; return __bfloat162float(h); }
+    __half h;
+    *reinterpret_cast<uint16_t*>(&h) = b;
+    return __half2float(h);
+}
+static inline uint16_t t_step(uint16_t b, int dir) {        // next representable value above (dir > 0) / below
+    if ((b & 0x7fffu) == 0) return dir > 0 ? (uint16_t)0x0001u : (uint16_t)0x8001u;
+    const bool neg = (b & 0x8000u) != 0;
+    return (uint16_t)((neg == (dir < 0)) ? b + 1 : b - 1);
+}
+
 static inline QParams make_qparams(float zero_point, float qmin, float qmax, int dtype) {
     QParams p;
     p.qmin = round_to_dtype(qmin, dtype);
     p.qmax = round_to_dtype(qmax, dtype);
     p.zp = round_to_dtype(zero_point, dtype);
     p.zp_nonzero = (zero_point != 0.f) ? 1 : 0;
+    p.pk_ok = p.pk_lo_zero = p.pk_lo = p.pk_hi = p.pk_lo_pre = p.pk_thr_lo = p.pk_thr_hi = 0;
+    if (dtype == BVB_F32 || zero_point != 0.f) return p;
+    // magic-number rounding range: fp16 adds 1536 in fp16 ([-512, 511] keeps the sum in the ulp-1 binade), bf16 adds
+    // 1.5*2^23 in fp32; the bounds must be the integers the caller asked for (a 16-bit range is not representable)
+    const float lim = dtype == BVB_F16 ? 511.f : 2097152.f;
+    const float lo = p.qmin, hi = p.qmax, lo_pre = (lo == 0.f) ? -1.f : lo;
+    if (!(lo == qmin && hi == qmax && lo == rintf(lo) && hi == rintf(hi) && lo_pre >= -lim - 1.f && hi <= lim && lo <= hi))
+        return p;
+    // thr_hi: the largest T value v with round(v) <= hi;  thr_lo: the smallest with round(v) >= lo  (round-half-even,
+    // monotone), found by walking T's grid from a nearby starting point
+    uint16_t bh = t_bits(hi + 1.f, dtype), bl = t_bits(lo - 1.f, dtype);
+    int guard = 0;
+    while (rintf(t_value(bh, dtype)) > hi && ++guard < 4096) bh = t_step(bh, -1);
+    while (rintf(t_value(t_step(bh, +1), dtype)) <= hi && ++guard < 4096) bh = t_step(bh, +1);
+    while (rintf(t_value(bl, dtype)) < lo && ++guard < 4096) bl = t_step(bl, +1);
+    while (rintf(t_value(t_step(bl, -1), dtype)) >= lo && ++guard < 4096) bl = t_step(bl, -1);
+    if (guard >= 4096) return p;
+    auto dup = [&](float v) { const uint32_t b = t_bits(v, dtype); return b | (b << 16); };
+    p.pk_lo = dup(lo);
+    p.pk_hi = dup(hi);
+    p.pk_lo_pre = dup(lo_pre);
+    p.pk_lo_zero = (lo == 0.f) ? 1u : 0u;
+    p.pk_thr_hi = (uint32_t)bh | ((uint32_t)bh << 16);
+    p.pk_thr_lo = (uint32_t)bl | ((uint32_t)bl << 16);
+    p.pk_ok = 1;
     return p;
 }
 
@@ -870,6 +1056,36 @@ static int launch_int_quant_fwd(const void* x, const void* scale, void* y, void*
     return check_launch("bvb_int_quant_fwd");
 }
 
+struct BwdGeom { int threads, tile_vecs, stages, ctas_per_sm; size_t smem; bool ok; };
+static BwdGeom bwd_geometry(int64_t cols, int elem_size);
+
+// TMA-pipelined provided-scale backward over n_vecs 16-byte vectors cut into chunks of row_vecs
+template <typename T, int RM>
+static int launch_scaled_bwd_tma(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out,
+                                 int64_t n_vecs, int64_t row_vecs, int64_t count, int scale_f32, const QParams& p,
+                                 int masked, cudaStream_t st, bool* launched) {
+    *launched = false;
+    BwdGeom g = bwd_geometry(row_vecs * 16 / (int64_t)sizeof(T), (int)sizeof(T));
+    if (!g.ok || row_vecs >= ((int64_t)1 << 27)) return BVB_OK;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(scaled_bwd_tma_kernel<T, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
+        if (e != cudaSuccess) return fail(BVB_ECUDA, "scaled_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int64_t nrows = (n_vecs + row_vecs - 1) / row_vecs;
+    int64_t grid = (int64_t)g.ctas_per_sm * sm_count();
+    if (grid > nrows) grid = nrows;
+    scaled_bwd_tma_kernel<T, RM><<<(unsigned)grid, g.threads, g.smem, st>>>(
+        (const T*)gy, (const T*)x, (const T*)scale, (T*)gx, gscale_out, (long long)n_vecs, (int)row_vecs,
+        (long long)nrows, (long long)count, g.tile_vecs, g.stages, scale_f32, masked, p);
+    *launched = true;
+    return check_launch("bvb_int_quant_bwd");
+}
+
 template <typename T, int RM>
 static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out,
                                 int64_t n, int64_t inner, int64_t count, int scale_f32, const QParams& p, int masked,
@@ -886,6 +1102,12 @@ static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale
         const int64_t nplanes = n / inner;
         const int group = inner * (int64_t)sizeof(T) <= 4096 ? 32 : PL_THREADS;
         const int pv = (vec_ok && (inner % V) == 0) ? 1 : 0;
+        if (pv && inner * (int64_t)sizeof(T) >= 4096 && n * (int64_t)sizeof(T) >= (1 << 20)) {
+            bool launched = false;            // large planes: the TMA producer / consumer ring
+            int rc = launch_scaled_bwd_tma<T, RM>(gy, x, scale, gx, gscale_out, n / V, inner / V, count, 0, p, masked, st,
+                                                  &launched);
+            if (rc != BVB_OK || launched) return rc;
+        }
         int64_t grid = (nplanes + (PL_THREADS / group) - 1) / (PL_THREADS / group);
         const int64_t cap = (int64_t)sm_count() * 8;
         if (grid > cap) grid = cap;
@@ -896,7 +1118,13 @@ static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale
     }
     if (smode == 1 && (inner % V) != 0) vec_ok = false;
     if (vec_ok) nvec = n / V;
-    if (nvec > 0) {
+    bool tma_done = false;
+    if (smode == 0 && nvec >= (1 << 16)) {    // one scale, >= 1 MiB: chunks of 64 KiB through the TMA ring
+        int rc = launch_scaled_bwd_tma<T, RM>(gy, x, scale, gx, gscale_out, nvec, 4096, 1, scale_f32, p, masked, st,
+                                              &tma_done);
+        if (rc != BVB_OK) return rc;
+    }
+    if (nvec > 0 && !tma_done) {
         unsigned grid = stream_grid(nvec, ST_THREADS * ST_UNROLL);
         int_quant_bwd_kernel<T, RM><<<grid, ST_THREADS, 0, st>>>((const T*)gy, (const T*)x, (const T*)scale, (T*)gx,
                                                                  gscale_out, nvec, smode ? inner / V : 1, count, smode,
@@ -988,7 +1216,6 @@ static int launch_rows_fwd(const void* x, void* y, void* scale_out, void* absmax
 }
 
 // geometry of the TMA backward: consumer warps, tile size, ring depth, CTAs per SM
-struct BwdGeom { int threads, tile_vecs, stages, ctas_per_sm; size_t smem; bool ok; };
 
 static BwdGeom bwd_geometry(int64_t cols, int elem_size) {
     BwdGeom g = {0, 0, 0, 0, 0, false};
@@ -1089,6 +1316,15 @@ using namespace bvb;
 #define BVB_CHECK_COMMON(name, n)                                                           \
     if ((n) < 0) return fail(BVB_EINVAL, name ": negative size");                           \
     if (!(qmin <= qmax)) return fail(BVB_EINVAL, name ": qmin must be <= qmax");
+
+extern "C" int bvb_debug_packed_constants(float zero_point, float qmin, float qmax, int dtype, uint32_t* out7) {
+    if (!out7) return fail(BVB_EINVAL, "bvb_debug_packed_constants: null pointer");
+    if (dtype != BVB_F32 && dtype != BVB_BF16 && dtype != BVB_F16) return fail(BVB_EINVAL, "unknown dtype tag %d", dtype);
+    const QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    const uint32_t v[7] = {p.pk_ok, p.pk_lo_zero, p.pk_lo, p.pk_hi, p.pk_lo_pre, p.pk_thr_lo, p.pk_thr_hi};
+    for (int i = 0; i < 7; ++i) out7[i] = v[i];
+    return BVB_OK;
+}
 
 extern "C" int bvb_int_quant_fwd(const void* x, const void* scale, void* y, void* codes_out, int64_t n,
                                  int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,

@@ -61,6 +61,13 @@ int bvb_selftest_div(float divisor, uint32_t first_bits, uint64_t count, uint64_
  * used); fp16: > 0 (why it is not).                                                                              */
 int bvb_selftest_lowp_div(int dtype, uint64_t* out2, void* stream);
 
+/* host-only introspection (no GPU needed): the constants the bf16 / fp16 kernels' packed fast path derives from an
+ * integer range (csrc/common.cuh qdq_vec).  out7 (HOST pointer, uint32[7]) = { ok, lo_is_zero, lo, hi, lo_pre,
+ * thr_lo, thr_hi } as 16-bit patterns of `dtype` duplicated in both halves: round(v) < qmin <=> v < thr_lo and
+ * round(v) > qmax <=> v > thr_hi for every value v of the dtype.  ok = 0 means the kernels use the literal op
+ * sequence for this range.                                                                                       */
+int bvb_debug_packed_constants(float zero_point, float qmin, float qmax, int dtype, uint32_t* out7);
+
 /* ---- 1. the 12 STE primitives: forward values of torch.ops.autograd_ste_ops.* -------------------------
  * Backward of every op except abs_binary_sign_grad is the identity on the incoming gradient and
  * needs no kernel (csrc/autograd_ste_ops.cpp:22, 42).  y may alias x (in-place).                       */

@@ -283,6 +283,34 @@ def test_int_quant_broadcast_vs_oracle(K, shape, sshape, rm, dtype):
     assert np.all(np.abs(got - ref) <= mag * (n * 2.0 ** -21 + 16 * ulp(dtype)) + 1e-5), (got, ref)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,sshape", [(((1 << 20) + 4096 * 3 + 5,), ()), ((600, 2048), (600, 1)),
+                                          ((3, 40, 64, 64), (1, 40, 1, 1)), ((2, 300, 4096), (2, 300, 1))])
+@pytest.mark.parametrize("cm", ["ste", "masked"])
+def test_provided_scale_large_vs_oracle(K, shape, sshape, cm, dtype):
+    """>= 1 MiB tensors take the TMA-pipelined provided-scale backward (scaled_bwd_tma_kernel): one scale with a
+    ragged tail, a scale per row, per NCHW channel (scale index wraps over the batch) and per token."""
+    x = O.rnd(rand_np(shape, 21, 30.0), dtype)
+    g = O.rnd(rand_np(shape, 22, 1.0), dtype)
+    s = O.rnd(np.abs(rand_np(sshape, 23, 0.3)) + 0.05, dtype)
+    yo = O.int_quant_forward(x, s, 0.0, -128.0, 127.0, "round", dtype)
+    assert_bits_equal(host(K.int_quant_fwd(dev(x, dtype), dev(s, dtype), 0.0, -128.0, 127.0, 0)), yo, "y")
+    gxo, gs_el = O.int_quant_backward(g, x, s, 0.0, -128.0, 127.0, "round", cm, dtype)
+    gx, gs = K.int_quant_bwd(dev(g, dtype), dev(x, dtype), dev(s, dtype), 0.0, -128.0, 127.0, 0, CM[cm], True)
+    assert_bits_equal(host(gx), gxo, "gx")
+    gx2, none = K.int_quant_bwd(dev(g, dtype), dev(x, dtype), dev(s, dtype), 0.0, -128.0, 127.0, 0, CM[cm], False)
+    assert none is None
+    assert_bits_equal(host(gx2), gxo, "gx without d(scale)")
+    ref = np.zeros(max(1, s.size))
+    mag = np.zeros_like(ref)
+    idx = np.broadcast_to(np.arange(max(1, s.size)).reshape(s.shape), shape).reshape(-1)
+    np.add.at(ref, idx, gs_el.reshape(-1))
+    np.add.at(mag, idx, np.abs(gs_el).reshape(-1))
+    n = x.size // max(1, s.size)
+    got = host(gs).reshape(-1)
+    assert np.all(np.abs(got - ref) <= mag * (n * 2.0 ** -21 + 16 * ulp(dtype)) + 1e-5), (got[:4], ref[:4])
+
+
 def test_fp32_scalar_scale_with_lowp_input(K):
     """fp32 quantizer modules fed bf16 activations: ATen's mul/div keep the fp32 0-dim scale in opmath"""
     x = torch.randn(4099, generator=torch.Generator().manual_seed(3)).mul(20).to(torch.bfloat16)
@@ -324,6 +352,53 @@ def test_lowp_division_shortcut_exhaustive():
     bad16, checked16 = [int(v) for v in out.tolist()]
     print(f"fp16 shortcut would be wrong for {bad16} of {checked16} pairs (not used)")
     assert checked16 > 2 ** 28
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("qmin,qmax", [(-127.0, 127.0), (-128.0, 127.0), (0.0, 255.0), (-8.0, 7.0), (0.0, 15.0),
+                                       (-1.0, 1.0), (0.0, 65535.0)])
+def test_lowp_exhaustive(K, dtype, qmin, qmax):
+    """bf16 / fp16 kernels use packed-pair arithmetic on the default modes (csrc/common.cuh qdq_vec, int_quant.cu
+    bwd_vec; (0, 65535) is not representable and takes the literal path).  ALL 2^16 input bit patterns (incl. +-0,
+    denormals, +-inf, NaNs) x a set of scales: outputs, integer codes and element-wise gradients (STE and masked)
+    bit-exact against the oracle, through the scalar-scale, per-row-scale and fused per-row abs-max kernels."""
+    tdt = TDT[dtype]
+    allx = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(tdt)
+    x = allx.float().numpy()
+    g = O.rnd(rand_np((65536,), 11, 1.0), dtype)
+    scales = [1.0, 0.5, 0.0371, 3.0, 2.0 ** -7, 0.11, 1.7e-3, 40.0]
+    for sv in scales:
+        s = O.rnd(np.float32(sv), dtype)
+        yo = O.int_quant_forward(x, s, 0.0, qmin, qmax, "round", dtype)
+        co = O.int_quant_chain(x, s, 0.0, qmin, qmax, "round", dtype)
+        sd = dev(np.asarray(s), dtype)
+        y, codes = K.int_quant_fwd(allx.cuda(), sd, 0.0, qmin, qmax, 0, want_codes=True)
+        assert_bits_equal(host(y), yo, f"y scale={sv}")
+        assert_bits_equal(host(codes), co[-1] if isinstance(co, tuple) else co, f"codes scale={sv}")
+        for cm in ("ste", "masked"):
+            gxo, gs_el = O.int_quant_backward(g, x, s, 0.0, qmin, qmax, "round", cm, dtype)
+            gx, gs = K.int_quant_bwd(dev(g, dtype), allx.cuda(), sd, 0.0, qmin, qmax, 0, CM[cm], True)
+            assert_bits_equal(host(gx), gxo, f"gx {cm} scale={sv}")
+            fin = np.isfinite(gs_el) & (np.abs(x) < 1e4) & (np.abs(x) > 1e-4)   # keep the fp32 sum far from overflow
+            x_f = torch.from_numpy(np.where(fin, x, 1.0)).to(tdt).cuda()       # finite inputs only for the sum
+            _, gs = K.int_quant_bwd(dev(g, dtype), x_f, sd, 0.0, qmin, qmax, 0, CM[cm], True)
+            _, gs_ref = O.int_quant_backward(g, host(x_f), s, 0.0, qmin, qmax, "round", cm, dtype)
+            mag = float(np.abs(gs_ref).sum()) + 1.0
+            assert abs(float(gs) - float(gs_ref.astype(np.float64).sum())) <= mag * (65536 * 2.0 ** -21 + 16 * ulp(dtype))
+    # per-row scales (planes kernel) and the fused abs-max kernel: 8 rows of 8192 covering all patterns
+    xr = allx.view(8, 8192)
+    srow = O.rnd(np.array([1.0, 0.25, 0.0371, 3.0, 0.5, 0.11, 2.0, 0.9], dtype=np.float32).reshape(8, 1), dtype)
+    yo = O.int_quant_forward(xr.float().numpy(), srow, 0.0, qmin, qmax, "round", dtype)
+    assert_bits_equal(host(K.int_quant_fwd(xr.cuda(), dev(srow, dtype), 0.0, qmin, qmax, 0)), yo, "rows provided")
+    gxo, _ = O.int_quant_backward(g.reshape(8, 8192), xr.float().numpy(), srow, 0.0, qmin, qmax, "round", "masked", dtype)
+    gx, _ = K.int_quant_bwd(dev(g.reshape(8, 8192), dtype), xr.cuda(), dev(srow, dtype), 0.0, qmin, qmax, 0, 1, True)
+    assert_bits_equal(host(gx), gxo, "rows provided gx")
+    finite = torch.where(torch.isfinite(xr.float()), xr, torch.ones((), dtype=tdt)).contiguous()
+    thr = max(abs(qmin), abs(qmax))
+    yo, so, _ = O.rows_absmax_int_quant_forward(finite.float().numpy(), 1e-10, thr, 0.0, qmin, qmax, "round", dtype)
+    y, sc, _ = K.rows_absmax_int_quant_fwd(finite.cuda(), 8, 8192, 1e-10, thr, 0.0, qmin, qmax, 0)
+    assert_bits_equal(host(sc), so, "fused scale")
+    assert_bits_equal(host(y), yo, "fused y")
 
 
 def test_empty_and_errors(K):

@@ -160,3 +160,71 @@ def test_percentile_k():
     from brevitas_b200._kernels import percentile_k
     assert [percentile_k(10.0 * v, 10) for v in range(1, 11)] == list(range(1, 11))   # test_stats.py:12-18
     assert percentile_k(99.999, 1000) == 1000 and percentile_k(90.0, 10) == 9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# packed bf16x2 / f16x2 fast path (csrc/common.cuh qdq_vec, int_quant.cu bwd_vec): the algebra it relies on, checked
+# for ALL 2^16 values of the dtype with the constants the library's host code derives (no GPU needed)
+# ---------------------------------------------------------------------------------------------------------------
+PACKED_RANGES = [(-127, 127), (-128, 127), (0, 255), (0, 254), (-8, 7), (-7, 7), (0, 15), (-1, 1), (0, 1), (-2, 1),
+                 (0, 3), (-512, 511), (-32, 31)]
+
+
+def _packed_constants(lo, hi, dtype):
+    from brevitas_b200 import _lib
+    out = (ctypes.c_uint32 * 7)()
+    _lib.call("bvb_debug_packed_constants", 0.0, float(lo), float(hi), {"bf16": _lib.BF16, "f16": _lib.F16}[dtype], out)
+    return list(out)
+
+
+def _from_bits16(bits, tdt):
+    import numpy as np
+    return torch.from_numpy(np.asarray(bits, dtype=np.uint16).view(np.int16)).view(tdt)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("lo,hi", PACKED_RANGES)
+def test_packed_path_algebra_exhaustive(dtype, lo, hi):
+    """clamp(round(v)) == signfix(magic_round(clamp'(v))) and the threshold masks == the masks on round(v), bit for
+    bit, for every value v of the dtype (v plays t1 = rnd_T(x / s))."""
+    import numpy as np
+    tdt = {"bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    ok, lo_zero, plo, phi, plo_pre, pthr_lo, pthr_hi = _packed_constants(lo, hi, dtype)
+    representable = all(float(torch.tensor(float(b)).to(tdt)) == b for b in (lo, hi))
+    if not representable or (dtype == "f16" and (lo < -512 or hi > 511)):
+        assert ok == 0                                                 # the kernels keep the literal op sequence
+        return
+    assert ok == 1 and lo_zero == int(lo == 0)
+    half = lambda w: _from_bits16([w & 0xffff], tdt)[0]
+    assert float(half(plo)) == lo and float(half(phi)) == hi and float(half(plo_pre)) == (-1 if lo == 0 else lo)
+    v = _from_bits16(np.arange(65536, dtype=np.uint32).astype(np.uint16), tdt)
+    t2 = v + torch.zeros((), dtype=tdt)                               # the reference's "+ zero_point" (0): -0 -> +0
+    t3 = torch.round(t2)
+    qlo, qhi = torch.tensor(float(lo), dtype=tdt), torch.tensor(float(hi), dtype=tdt)
+    t5 = torch.where(t3 > qhi, qhi, t3)
+    t5 = torch.where(t5 < qlo, qlo, t5)                                # brevitas.function.ops.tensor_clamp
+    keep = ~(t3 > qhi) & ~(t3 < qlo)
+    # --- packed formulation ---
+    c = torch.maximum(torch.minimum(t2, half(phi)), half(plo_pre))     # HMNMX2.NAN (torch.minimum propagates NaN)
+    if dtype == "bf16":
+        r = ((c.float() + 12582912.0) - 12582912.0).to(tdt)            # fp32 magic adds, exact pack
+    else:
+        m = torch.tensor(1536.0, dtype=tdt)
+        r = (c + m) - m                                                # two fp16 adds (each rounded to fp16)
+    rb = r.view(torch.int16).numpy().view(np.uint16) | (c.view(torch.int16).numpy().view(np.uint16) & 0x8000)
+    r = _from_bits16(rb, tdt)
+    if lo_zero:
+        r = torch.where(r < 0, torch.zeros((), dtype=tdt), r)
+    nan = torch.isnan(t5) & torch.isnan(r)
+    same = (t5.view(torch.int16) == r.view(torch.int16)) | nan
+    assert bool(same.all()), f"{int((~same).sum())} codes differ, e.g. v={v[~same][:4]}"
+    keep2 = ~(t2 > half(pthr_hi)) & ~(t2 < half(pthr_lo))
+    assert bool((keep == keep2).all()), f"masks differ at v={v[keep != keep2][:4]}"
+
+
+def test_packed_constants_reject_unrepresentable_ranges():
+    assert _packed_constants(0, 65535, "bf16")[0] == 0      # 65535 rounds to 65536 in bf16: literal path
+    assert _packed_constants(-32768, 32767, "f16")[0] == 0
+    assert _packed_constants(0, 1023, "f16")[0] == 0        # outside the fp16 magic-rounding range
+    assert _packed_constants(0, 1023, "bf16")[0] == 0       # 1023 needs 10 significant bits
+    assert _packed_constants(0, 1024, "bf16")[0] == 1

@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Launch every hot-path kernel at its BASELINE size a few times (for `ncu --profile-from-start off` captures and for
+quick CUDA-event timings).  python tools/prof_all.py [--reps N] [--only name,name]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import brevitas_b200  # noqa: E402,F401
+from brevitas_b200 import _kernels as K  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--ncu", action="store_true", help="plain launches between profiler start/stop (for ncu)")
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(0)
+    R, C = 4096, 11008
+    T, D = 8 * 2048, 4096
+    NS = 3
+    W = [torch.randn(R, C, device=dev, generator=gen) for _ in range(NS)]
+    G = [torch.randn(R, C, device=dev, generator=gen) for _ in range(2)]
+    Wb = [w.to(torch.bfloat16) for w in W]
+    Gb = [g.to(torch.bfloat16) for g in G]
+    X = [torch.randn(T, D, device=dev, generator=gen).to(torch.bfloat16) for _ in range(NS)]
+    GX = [torch.randn(T, D, device=dev, generator=gen).to(torch.bfloat16) for _ in range(2)]
+    c2 = (1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+    c3 = (1e-10, 128.0, 0.0, -128.0, 127.0, 0)
+    s32 = K.rows_absmax_int_quant_fwd(W[0], R, C, *c2)[1]
+    sb = K.rows_absmax_int_quant_fwd(Wb[0], R, C, *c2)[1]
+    sx = K.rows_absmax_int_quant_fwd(X[0], T, D, *c3)[1]
+    s0 = torch.tensor(0.02, device=dev, dtype=torch.bfloat16)
+    s0f = torch.tensor(0.02, device=dev)
+    sch = (torch.rand(R, device=dev) * 0.02 + 0.01)
+    cases = {
+        "c2_f32_fwd": (lambda i: K.rows_absmax_int_quant_fwd(W[i % NS], R, C, *c2), R * C * 8),
+        "c2_f32_bwd": (lambda i: K.rows_absmax_int_quant_bwd(G[i % 2], W[i % NS], s32, None, R, C, 127.0, 0.0, -127.0, 127.0, 0, 0), R * C * 12),
+        "c2_bf16_fwd": (lambda i: K.rows_absmax_int_quant_fwd(Wb[i % NS], R, C, *c2), R * C * 4),
+        "c2_bf16_bwd": (lambda i: K.rows_absmax_int_quant_bwd(Gb[i % 2], Wb[i % NS], sb, None, R, C, 127.0, 0.0, -127.0, 127.0, 0, 0), R * C * 6),
+        "c3_bf16_fwd": (lambda i: K.rows_absmax_int_quant_fwd(X[i % NS], T, D, *c3), T * D * 4),
+        "c3_bf16_bwd_masked": (lambda i: K.rows_absmax_int_quant_bwd(GX[i % 2], X[i % NS], sx, None, T, D, 128.0, 0.0, -128.0, 127.0, 0, 1), T * D * 6),
+        "c2_f32_tensor_fwd": (lambda i: K.tensor_absmax_int_quant_fwd(W[i % NS], torch.float32, 1e-10, 127.0, 0.0, -127.0, 127.0, 0), R * C * 12),
+        "act_bf16_scalar_fwd": (lambda i: K.int_quant_fwd(X[i % NS], s0, 0.0, 0.0, 255.0, 0), T * D * 4),
+        "act_bf16_scalar_bwd_gs": (lambda i: K.int_quant_bwd(GX[i % 2], X[i % NS], s0, 0.0, 0.0, 255.0, 0, 1, True), T * D * 6),
+        "act_f32_scalar_fwd": (lambda i: K.int_quant_fwd(W[i % NS], s0f, 0.0, 0.0, 255.0, 0), R * C * 8),
+        "act_f32_scalar_bwd_gs": (lambda i: K.int_quant_bwd(G[i % 2], W[i % NS], s0f, 0.0, 0.0, 255.0, 0, 1, True), R * C * 12),
+        "w_f32_rows_provided_fwd": (lambda i: K.int_quant_fwd(W[i % NS], sch.view(R, 1), 0.0, -127.0, 127.0, 0), R * C * 8),
+    }
+    only = [s for s in a.only.split(",") if s]
+    period = 6                                    # lcm of the input rotations above
+    for name, (fn, nbytes) in cases.items():
+        if only and name not in only:
+            continue
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        if a.ncu:                                 # plain launches for the profiler
+            torch.cuda.profiler.start()
+            for i in range(a.reps):
+                fn(i)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            continue
+        # The Python wrappers allocate outputs and marshal arguments (tens of us of host time, more than these kernels
+        # take), so the timing replays a CUDA graph of `period` launches: device time only, inputs rotating over > L2.
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            keep = [fn(i) for i in range(period)]
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.reps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (a.reps * period)
+        print(f"{name:28s} {ms * 1e3:8.1f} us  {nbytes / ms / 1e6:7.0f} GB/s", flush=True)
+        del graph, keep
+
+
+if __name__ == "__main__":
+    main()
