@@ -34,6 +34,20 @@ FWD_B, BWD_B = 8, 12          # algorithmic bytes per element, fp32 (SURVEY.md Â
 METRIC = "int8_per_channel_weight_fakequant_fwd_bwd_GBps"
 
 
+def ncu_traffic(kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_extract.py); None if absent"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            for name, rec in json.load(f).items():
+                if name.startswith(kernel_prefix):
+                    return int(rec["traffic_bytes"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -253,20 +267,28 @@ def main():
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    # per-kernel events (what the roofline uses) are recorded INSIDE the timed region, but only on every EV_EVERY-th
+    # step: an event record between two kernels keeps the next launch from being staged behind the running one and
+    # costs 2-3 us of idle HBM each (3 per step = 5 % of a 160 us step), a measurement artefact, not workload
+    EV_EVERY = 4
+    ev = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, args.steps, EV_EVERY)}
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     with ClockSampler(local) as clocks:
         torch.cuda.synchronize()
-        # timed region: EXACTLY K steps, per-kernel events recorded in-stream (they are what the roofline uses)
+        # timed region: EXACTLY K steps
         start.record()
         for i in range(args.steps):
             k = i % NSETS
-            ev[i][0].record()
-            rc = c_fwd(*fwd_args[k])
-            ev[i][1].record()
-            rc |= c_bwd(*bwd_args[k])
-            ev[i][2].record()
+            e = ev.get(i)
+            if e is None:
+                rc = c_fwd(*fwd_args[k]) | c_bwd(*bwd_args[k])
+            else:
+                e[0].record()
+                rc = c_fwd(*fwd_args[k])
+                e[1].record()
+                rc |= c_bwd(*bwd_args[k])
+                e[2].record()
             launches += 2            # rows_fwd_tma_kernel + rows_bwd_tma_kernel, one kernel per C-ABI call
             if rc:
                 raise RuntimeError(_lib.last_error())
@@ -280,8 +302,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev.values()) / len(ev)
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev.values()) / len(ev)
     value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
     peak, peak_src = peaks()
     bwd_gbps = n * BWD_B / (bwd_ms * 1e-3) / 1e9
@@ -308,7 +330,7 @@ def main():
     g_dev = torch.empty(ROWS, COLS, device=dev)
     e2e_steps = max(3, min(args.steps, 20))
 
-    def e2e_step():
+    def e2e_module_step():
         with torch.no_grad():
             w_param.copy_(hw, non_blocking=True)
         g_dev.copy_(hg, non_blocking=True)
@@ -318,38 +340,69 @@ def main():
         h_gw.copy_(w_param.grad, non_blocking=True)
         h_scale.copy_(scale.detach(), non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e2.record()
-    torch.cuda.synchronize()
-    e2e_ms = s2.elapsed_time(e2) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    # the host-buffer entry point (C-ABI bvb_host_rows_fakequant_fwd_bwd): row chunks pipelined over three streams so
+    # H2D, kernels and D2H overlap; same bytes moved, same results (tests/test_gpu_parity.py::test_host_pipeline_*)
+    from brevitas_b200.host_pipeline import weight_fake_quant_fwd_bwd_host
+
+    def e2e_host_step():
+        weight_fake_quant_fwd_bwd_host(hw, hg, bit_width=8, signed=True, narrow_range=True, out_grad=h_gw,
+                                       out_scale=h_scale, synchronize=False)
+
+    def time_e2e(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(e2e_steps):
+            fn()
+        e2.record()
+        torch.cuda.synchronize()
+        ms = s2.elapsed_time(e2) / e2e_steps
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    e2e_module_ms = time_e2e(e2e_module_step)
+    e2e_ms = time_e2e(e2e_host_step)
     e2e_val = world * step_bytes / (e2e_ms * 1e-3) / 1e9
+    e2e_module_val = world * step_bytes / (e2e_module_ms * 1e-3) / 1e9
+    del w_param, g_dev, tq
+    torch.cuda.empty_cache()
 
     # ---- extras: the other hot-path kernels at BASELINE sizes (reported, not the headline) ----------------------
     extras = {}
     if not args.no_extras and rank == 0:
-        def timeit(fn, reps=30, nsets=1):
-            for _ in range(3):
-                fn(0)
+        def timeit(fn, reps=30, period=4, graph=True):
+            """device time per launch: a CUDA graph of `period` launches (inputs rotating over > L2) replayed `reps`
+            times -- the Python wrappers' allocation / marshalling costs more host time than these kernels take"""
+            for i in range(3):
+                fn(i)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if not graph:
+                a.record()
+                for i in range(reps):
+                    fn(i)
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / reps
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                keep = [fn(i) for i in range(period)]
+            cg.replay()
+            torch.cuda.synchronize()
             a.record()
-            for i in range(reps):
-                fn(i)
+            for _ in range(reps):
+                cg.replay()
             b.record()
             torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
+            del keep
+            return a.elapsed_time(b) / (reps * period)
 
         def gb(nbytes, ms):
             return round(nbytes / (ms * 1e-3) / 1e9, 1)
@@ -392,7 +445,7 @@ def main():
             wt.grad = None
             yy, ss, _, _ = P.rescaling_int_quant_absmax(wt, "rows", 8, True, True, 1e-10, "round", True)
             yy.backward(Gs[0])
-        ms = timeit(eager, reps=5)
+        ms = timeit(eager, reps=5, graph=False)
         extras["c2_f32_eager_aten_same_gpu_fwd_bwd"] = {"ms": round(ms, 3), "GBps_algorithmic": gb(step_bytes, ms)}
 
     # ---- QAT step (north star: data-parallel QAT across 1/2/4/8 GPUs, NCCL gradient all-reduce) ---------------------
@@ -428,7 +481,12 @@ def main():
                    "hbm_peak_source": peak_src, "percent_of_nominal_8TBps": round(100 * value / world / 8000, 1)},
         "roofline": {"bound": "hbm", "kernel": "rows_bwd_tma_kernel<float,ROUND|ZP0|STE> (STE backward + grad through abs-max)",
                      "achieved": round(bwd_gbps, 1), "peak": peak, "unit": "GB/s", "frac": round(bwd_gbps / peak, 4),
-                     "traffic": None, "algorithmic_bytes_per_launch": n * BWD_B, "avg_launch_ms": round(bwd_ms, 5),
+                     "traffic": ncu_traffic("rows_bwd_tma_kernel<float"),
+                     "traffic_note": "ncu --set full, one isolated launch (profiles/): below the algorithmic bytes because "
+                                     "part of the output is still dirty in L2 when the launch ends",
+                     "algorithmic_bytes_per_launch": n * BWD_B, "avg_launch_ms": round(bwd_ms, 5),
+                     "launches_timed": f"{len(ev)} of {args.steps} (CUDA events around every {EV_EVERY}th step's kernels, "
+                                       "inside the timed region)",
                      "peak_source": peak_src,
                      "other_kernels": {"rows_fwd_tma_kernel<float,ROUND>": {
                          "achieved": round(fwd_gbps, 1), "frac": round(fwd_gbps / peak, 4),
@@ -436,7 +494,10 @@ def main():
         "cpu_baseline": cpu,
         "e2e": {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4,
                 "d2h_bytes_per_step": n * 4 + ROWS * 4, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-                "api": "brevitas_b200.core.quant.RescalingIntQuant(w) + autograd backward, pinned host buffers"},
+                "api": "brevitas_b200.host_pipeline.weight_fake_quant_fwd_bwd_host (C-ABI bvb_host_rows_fakequant_fwd_bwd): "
+                       "pinned host W and G in, dW and scales out, 16 row chunks pipelined over 3 streams",
+                "module_api": {"value": round(e2e_module_val, 2), "ms_per_step": round(e2e_module_ms, 3),
+                               "api": "RescalingIntQuant(w) + autograd backward with whole-tensor H2D / D2H copies"}},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "qat_step": qat,

@@ -31,6 +31,8 @@ SIGNATURES = {
     "bvb_selftest_div": (c_int, [c_float, ctypes.c_uint32, ctypes.c_uint64, _P, _P]),
     "bvb_selftest_lowp_div": (c_int, [_I, _P, _P]),
     "bvb_debug_packed_constants": (c_int, [_F, _F, _F, _I, _P]),
+    "bvb_host_rows_fakequant_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _F, _F, _F, _F, _F, _I, _I, _I, _P, _L, _P]),
+    "bvb_host_pipeline_workspace_bytes": (_L, [_L, _L, _L, _I, _I]),
     "bvb_round_ste_impl": (c_int, _UNARY),
     "bvb_ceil_ste_impl": (c_int, _UNARY),
     "bvb_floor_ste_impl": (c_int, _UNARY),

@@ -122,6 +122,19 @@ int bvb_rows_absmax_int_quant_bwd(const void* gy, const void* x, const void* sca
                                   int64_t rows, int64_t cols, float int_threshold,
                                   float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
                                   int dtype, void* stream);
+/* Host-buffer variant of the two calls above, for tensors that live in HOST memory (pinned for full speed): rows are
+ * independent, so the weight is cut into chunks of `chunk_rows` rows and pipelined over three internal streams --
+ * H2D of chunk c+1, fwd+bwd kernels of chunk c, D2H of chunk c-1 -- through a ring of device staging slots in
+ * `workspace` (>= bvb_host_pipeline_workspace_bytes(...) bytes of device memory).  h_x, h_gy: inputs; h_gx
+ * (d loss / d x incl. the path through the abs-max), h_scale ([rows] T): outputs; h_y (the quant-dequantized
+ * weight) nullable.  The work is ordered after everything already enqueued on `stream`, and `stream` waits for the
+ * last copy: synchronise `stream` before reading the outputs.  Creates / destroys its streams and events per call,
+ * therefore NOT capturable in a CUDA graph.  Same arithmetic, same kernels, same results as the device calls.    */
+int bvb_host_rows_fakequant_fwd_bwd(const void* h_x, const void* h_gy, void* h_y, void* h_gx, void* h_scale,
+                                    int64_t rows, int64_t cols, int64_t chunk_rows, float scaling_min_val,
+                                    float int_threshold, float zero_point, float qmin, float qmax, int round_mode,
+                                    int clamp_mode, int dtype, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t bvb_host_pipeline_workspace_bytes(int64_t rows, int64_t cols, int64_t chunk_rows, int want_y, int dtype);
 /* Whole-tensor statistic (OverTensorView + AbsMax(None)): two-phase grid reduction, then quant pass.
  * workspace: >= bvb_workspace_bytes() bytes of device scratch.  absmax_out: 1 element of T; scale_out:
  * 1 element of scale_dtype (fp32 when a 0-dim T threshold is divided by a 0-dim fp32 int_threshold).      */

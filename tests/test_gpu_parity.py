@@ -311,6 +311,34 @@ def test_provided_scale_large_vs_oracle(K, shape, sshape, cm, dtype):
     assert np.all(np.abs(got - ref) <= mag * (n * 2.0 ** -21 + 16 * ulp(dtype)) + 1e-5), (got[:4], ref[:4])
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,cols,chunk", [(37, 1000, 8), (64, 4096, None), (5, 264, 100), (300, 11008, 64)])
+def test_host_pipeline_matches_device_path(K, rows, cols, chunk, dtype):
+    """bvb_host_rows_fakequant_fwd_bwd (host buffers, chunked three-stream pipeline, ragged last chunk) returns the
+    bits of the device-resident fwd + bwd calls, and of the oracle."""
+    from brevitas_b200.host_pipeline import weight_fake_quant_fwd_bwd_host
+    x = O.rnd(rand_np((rows, cols), rows + cols, 0.7), dtype)
+    g = O.rnd(rand_np((rows, cols), 9, 1.0), dtype)
+    hx = torch.from_numpy(x).to(TDT[dtype]).pin_memory()
+    hg = torch.from_numpy(g).to(TDT[dtype]).pin_memory()
+    for want_q in (False, True):
+        gw, sc, wq = weight_fake_quant_fwd_bwd_host(hx, hg, bit_width=8, signed=True, narrow_range=True,
+                                                    chunk_rows=chunk, want_quantized=want_q)
+        y, s, _ = K.rows_absmax_int_quant_fwd(hx.cuda(), rows, cols, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+        gx = K.rows_absmax_int_quant_bwd(hg.cuda(), hx.cuda(), s, None, rows, cols, 127.0, 0.0, -127.0, 127.0, 0, 0)
+        assert gw.shape == (rows, cols) and sc.shape == (rows, 1) and not gw.is_cuda
+        assert_bits_equal(gw.float().numpy(), host(gx), "grad (host pipeline vs device calls)")
+        assert_bits_equal(sc.float().numpy().reshape(-1), host(s), "scale")
+        yo, so, _ = O.rows_absmax_int_quant_forward(x, 1e-10, 127.0, 0.0, -127.0, 127.0, "round", dtype)
+        assert_bits_equal(sc.float().numpy().reshape(-1), so, "scale vs oracle")
+        if want_q:
+            assert_bits_equal(wq.float().numpy(), yo, "quantized weight vs oracle")
+        else:
+            assert wq is None
+    with pytest.raises(RuntimeError):
+        weight_fake_quant_fwd_bwd_host(hx.cuda(), hg.cuda())
+
+
 def test_fp32_scalar_scale_with_lowp_input(K):
     """fp32 quantizer modules fed bf16 activations: ATen's mul/div keep the fp32 0-dim scale in opmath"""
     x = torch.randn(4099, generator=torch.Generator().manual_seed(3)).mul(20).to(torch.bfloat16)
