@@ -198,7 +198,7 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": round(gbps, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    args.emit(line)
     return 0
 
 
@@ -215,6 +215,16 @@ def main():
     ap.add_argument("--qat-batch", type=int, default=256, help="per-GPU batch of the ResNet-18 QAT step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: libraries (NCCL's version banner, cuDNN warnings) write to fd 1 directly,
+    # so fd 1 is pointed at stderr for the duration of the run and the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    args.emit = emit
     if args.impl == "reference":
         return run_reference(args)
 
@@ -503,7 +513,7 @@ def main():
         "qat_step": qat,
         "extras": extras,
     }
-    print(json.dumps(line))
+    args.emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

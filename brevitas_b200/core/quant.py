@@ -21,7 +21,7 @@ from torch import Tensor, nn
 from .. import _lib
 from .. import ops as _ops  # noqa: F401
 from ..function.ops import max_int, min_int
-from ..function.ops_ste import binary_sign_ste
+from ..function.ops_ste import binary_sign_ste, round_ste, ternary_sign_ste
 from .bit_width import BitWidthConst
 from .function_wrapper import CLAMP_MODE_OF, ROUND_MODE_OF, RoundSte, TensorClamp
 from .scaling import IntScaling, PowerOfTwoIntScaling
@@ -262,5 +262,158 @@ class ClampedBinaryQuant(nn.Module):
         else:
             y = self.tensor_clamp_impl(x, - scale, scale)
             y = binary_sign_ste(y) * scale
+        y = self.delay_wrapper(x, y)
+        return y, scale, self.zero_point(), self.bit_width()
+
+
+# ---- quantizers either side of the conv / linear of a quantized layer ---------------------
+class PrescaledRestrictIntQuantWithInputBitWidth(nn.Module):
+    """Scale given by the caller, zero-point 0, bit-width derived from an input bit-width (int.py:17-68); the bias
+    quantizer ``Int*Bias`` with an accumulator-dependent bit-width."""
+
+    def __init__(self, int_quant: nn.Module, bit_width_impl: nn.Module):
+        super().__init__()
+        self.int_quant = int_quant
+        self.msb_clamp_bit_width_impl = bit_width_impl
+        self.zero_point = StatelessBuffer(torch.tensor(0.0))
+
+    def forward(self, x: Tensor, scale: Tensor, input_bit_width: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        bit_width = self.msb_clamp_bit_width_impl(input_bit_width)
+        zero_point = self.zero_point()
+        y = self.int_quant(scale, zero_point, bit_width, x)
+        return y, scale, zero_point, bit_width
+
+
+class PrescaledRestrictIntQuant(nn.Module):
+    """Scale given by the caller, zero-point 0, own bit-width (int.py:71-91): ``IntBias``-style quantizers.  With a
+    constant bit-width the integer range is a host constant and ``x`` goes through ONE fused kernel."""
+
+    def __init__(self, int_quant: nn.Module, bit_width_impl: nn.Module):
+        super().__init__()
+        self.int_quant = int_quant
+        self.msb_clamp_bit_width_impl = bit_width_impl
+        self.zero_point = StatelessBuffer(torch.tensor(0.0))
+
+    def forward(self, x: Tensor, scale: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        msb_clamp_bit_width = self.msb_clamp_bit_width_impl()
+        zero_point = self.zero_point()
+        iq = self.int_quant
+        if x.is_cuda and type(iq) is IntQuant and type(self.msb_clamp_bit_width_impl) is BitWidthConst:
+            bw = self.msb_clamp_bit_width_impl.bit_width_value
+            qmin, qmax = int_range(iq.signed, iq.narrow_range, bw, msb_clamp_bit_width.dtype)
+            y = iq.forward_fused(scale, 0.0, qmin, qmax, x)
+            if y is not None:
+                return y, scale, zero_point, msb_clamp_bit_width
+        y = iq(scale, zero_point, msb_clamp_bit_width, x)
+        return y, scale, zero_point, msb_clamp_bit_width
+
+
+class TruncIntQuant(nn.Module):
+    """Drop LSBs of an already quantized value: ``round(x/s + zp) / 2^(in_bits - out_bits)`` -> float_to_int (floor
+    by default) -> dequantize (int.py:199-229; ``QuantAvgPool2d``).  The tensors involved are pooled activations
+    (small), the bit-widths are device tensors: literal sequence on the STE kernels."""
+
+    def __init__(self, float_to_int_impl: nn.Module, bit_width_impl: nn.Module, quant_delay_steps: int = 0):
+        super().__init__()
+        self.msb_clamp_bit_width_impl = bit_width_impl
+        self.float_to_int_impl = float_to_int_impl
+        self.delay_wrapper = DelayWrapper(quant_delay_steps)
+
+    def forward(self, x: Tensor, scale: Tensor, zero_point: Tensor, input_bit_width: Tensor):
+        y = x / scale
+        y = y + zero_point
+        y = round_ste(y)  # clean up floating point error
+        output_bit_width = self.msb_clamp_bit_width_impl()
+        trunc_bit_width = input_bit_width - output_bit_width
+        trunc_scale = 2.0 ** trunc_bit_width
+        y = y / trunc_scale
+        y = self.float_to_int_impl(y)
+        y = y - zero_point
+        y = y * scale
+        y = self.delay_wrapper(x, y)
+        return y, scale, zero_point, output_bit_width
+
+
+# ---- decoupled / ternary (SURVEY.md §8f rank 3) ------------------------------------------------------------------
+class DecoupledIntQuant(nn.Module):
+    """Integer quantization whose rounding uses (pre_scale, pre_zero_point) and whose dequantization uses
+    (scale, zero_point) (int_base.py:100-182)."""
+
+    def __init__(self, narrow_range: bool, signed: bool, float_to_int_impl: Optional[nn.Module] = None,
+                 tensor_clamp_impl: Optional[nn.Module] = None, quant_delay_steps: int = 0):
+        super().__init__()
+        self.float_to_int_impl = float_to_int_impl if float_to_int_impl is not None else RoundSte()
+        self.tensor_clamp_impl = tensor_clamp_impl if tensor_clamp_impl is not None else TensorClamp()
+        self.signed = signed
+        self.narrow_range = narrow_range
+        self.delay_wrapper = DelayWrapper(quant_delay_steps)
+
+    def to_int(self, pre_scale: Tensor, pre_zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
+        y = x / pre_scale
+        y = y + pre_zero_point
+        min_int_val = self.min_int(bit_width)
+        max_int_val = self.max_int(bit_width)
+        y = self.float_to_int_impl(y)
+        y = self.tensor_clamp_impl(y, min_val=min_int_val, max_val=max_int_val)
+        return y
+
+    def min_int(self, bit_width):
+        return min_int(self.signed, self.narrow_range, bit_width)
+
+    def max_int(self, bit_width):
+        return max_int(self.signed, self.narrow_range, bit_width)
+
+    def forward(self, pre_scale: Tensor, pre_zero_point: Tensor, scale: Tensor, zero_point: Tensor, bit_width: Tensor,
+                x: Tensor) -> Tensor:
+        y_int = self.to_int(pre_scale, pre_zero_point, bit_width, x)
+        y = y_int - zero_point
+        y = y * scale
+        return self.delay_wrapper(x, y)
+
+
+class DecoupledRescalingIntQuant(nn.Module):
+    """int.py:166-196: returns ``(y, scale, zero_point, bit_width, pre_scale, pre_zero_point)``."""
+
+    def __init__(self, decoupled_int_quant: nn.Module, pre_scaling_impl: nn.Module, scaling_impl: nn.Module,
+                 int_scaling_impl: nn.Module, pre_zero_point_impl: nn.Module, zero_point_impl: nn.Module,
+                 bit_width_impl: nn.Module):
+        super().__init__()
+        self.decoupled_int_quant = decoupled_int_quant
+        self.pre_scaling_impl = pre_scaling_impl
+        self.scaling_impl = scaling_impl
+        self.int_scaling_impl = int_scaling_impl
+        self.pre_zero_point_impl = pre_zero_point_impl
+        self.zero_point_impl = zero_point_impl
+        self.msb_clamp_bit_width_impl = bit_width_impl
+
+    def forward(self, x: Tensor):
+        bit_width = self.msb_clamp_bit_width_impl()
+        int_threshold = self.int_scaling_impl(bit_width)
+        pre_threshold = self.pre_scaling_impl(x)
+        pre_scale = pre_threshold / int_threshold
+        pre_zero_point = self.pre_zero_point_impl(x, pre_scale, bit_width)
+        threshold = self.scaling_impl(x)
+        scale = threshold / int_threshold
+        zero_point = self.zero_point_impl(x, scale, bit_width)
+        y = self.decoupled_int_quant(pre_scale, pre_zero_point, scale, zero_point, bit_width, x)
+        return y, scale, zero_point, bit_width, pre_scale, pre_zero_point
+
+
+class TernaryQuant(nn.Module):
+    """``y = (|x| > threshold * scale) * ternary_sign_ste(x) * scale``; zero-point 0, bit-width 2 (ternary.py:17-72)."""
+
+    def __init__(self, scaling_impl: nn.Module, threshold: float, quant_delay_steps: int = None):
+        super().__init__()
+        self.scaling_impl = scaling_impl
+        self.threshold = threshold
+        self.bit_width = BitWidthConst(2)
+        self.zero_point = StatelessBuffer(torch.tensor(0.0))
+        self.delay_wrapper = DelayWrapper(quant_delay_steps)
+
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        scale = self.scaling_impl(x)
+        mask = x.abs().gt(self.threshold * scale)
+        y = mask.float() * ternary_sign_ste(x)
+        y = y * scale
         y = self.delay_wrapper(x, y)
         return y, scale, self.zero_point(), self.bit_width()

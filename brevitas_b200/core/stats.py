@@ -77,6 +77,192 @@ class AbsPercentile(nn.Module):
         return val
 
 
+# ---- remaining statistics of stats_op.py.  Those built on the per-row abs-max reuse the
+# sm_100a reduction; min / mean / variance / signed k-th value are the same ATen reductions the reference issues
+# (they run once per tensor on statistics-sized outputs and are outside the measured hot path) -----------------
+DEFAULT_STD_DEV_EPSILON = 1e-8
+
+
+def _zero_like_scalar(t: Tensor) -> Tensor:
+    return torch.zeros((), dtype=t.dtype, device=t.device)
+
+
+class NegativeMinOrZero(nn.Module):
+    """``min(x)`` (whole tensor or along a dim) if it is <= 0 else 0 (stats_op.py:22-39)."""
+
+    def __init__(self, stats_reduce_dim: Optional[int] = None) -> None:
+        super().__init__()
+        self.stats_reduce_dim = stats_reduce_dim
+
+    def forward(self, x: Tensor) -> Tensor:
+        if self.stats_reduce_dim is None:
+            min_val = torch.min(x)
+        else:
+            min_val = torch.min(x, dim=self.stats_reduce_dim)[0]
+        zero = _zero_like_scalar(min_val)
+        return torch.where(min_val <= zero, min_val, zero)
+
+
+class NegativePercentileOrZero(nn.Module):
+    """k-th smallest (signed) value with ``k = ceil(.01 * q * n)``, or 0 if positive (stats_op.py:69-97)."""
+
+    def __init__(self, low_percentile_q, stats_reduce_dim: Optional[int] = None) -> None:
+        super().__init__()
+        self.stats_reduce_dim = stats_reduce_dim
+        self.q = low_percentile_q
+
+    def forward(self, x: Tensor) -> Tensor:
+        if self.stats_reduce_dim is None:
+            k = int(math.ceil(.01 * self.q * x.numel()))
+            result = x.view(-1).kthvalue(k).values
+        else:
+            assert len(x.size()) == 2, "Only 2-dim input is supported."
+            k = int(math.ceil(.01 * self.q * x.shape[self.stats_reduce_dim]))
+            result = x.kthvalue(k, dim=self.stats_reduce_dim).values
+        zero = _zero_like_scalar(result)
+        return torch.where(result <= zero, result, zero)
+
+
+class PercentileInterval(nn.Module):
+    """``|high percentile - low percentile|`` (stats_op.py:100-126)."""
+
+    def __init__(self, low_percentile_q, high_percentile_q, stats_reduce_dim: Optional[int] = None) -> None:
+        super().__init__()
+        self.stats_reduce_dim = stats_reduce_dim
+        self.low_q = low_percentile_q
+        self.high_q = high_percentile_q
+
+    def forward(self, x: Tensor) -> Tensor:
+        if self.stats_reduce_dim is None:
+            n = x.numel()
+            low_k = int(math.ceil(.01 * self.low_q * n))
+            high_k = int(math.floor(.01 * self.high_q * n + 0.5))
+            low_result = x.view(-1).kthvalue(low_k).values
+            high_result = x.view(-1).kthvalue(high_k).values
+        else:
+            assert len(x.size()) == 2, "Only 2-dim input is supported."
+            n = x.shape[self.stats_reduce_dim]
+            low_k = int(math.ceil(.01 * self.low_q * n))
+            high_k = int(math.floor(.01 * self.high_q * n + 0.5))
+            low_result = x.kthvalue(low_k, dim=self.stats_reduce_dim).values
+            high_result = x.kthvalue(high_k, dim=self.stats_reduce_dim).values
+        return torch.abs(high_result - low_result)
+
+
+class AbsMinMax(nn.Module):
+    """``|max(x) - min(x)|`` (stats_op.py:144-158)."""
+
+    def __init__(self, stats_reduce_dim: Optional[int] = None) -> None:
+        super().__init__()
+        self.stats_reduce_dim = stats_reduce_dim
+
+    def forward(self, x: Tensor):
+        if self.stats_reduce_dim is None:
+            return torch.abs(torch.max(x) - torch.min(x))
+        max_val = torch.max(x, dim=self.stats_reduce_dim)[0]
+        min_val = torch.min(x, dim=self.stats_reduce_dim)[0]
+        return torch.abs(max_val - min_val)
+
+
+class AbsMaxAve(nn.Module):
+    """Mean of the per-row abs-max (stats_op.py:161-170); the abs-max is the sm_100a row reduction."""
+
+    def __init__(self, stats_reduce_dim: int) -> None:
+        super().__init__()
+        self.absmax = AbsMax(stats_reduce_dim)
+
+    def forward(self, x: Tensor):
+        return torch.mean(self.absmax(x))
+
+
+class AbsMaxL2(nn.Module):
+    """L2 norm of the per-row abs-max over sqrt(#rows) (stats_op.py:173-185)."""
+
+    def __init__(self, stats_reduce_dim: int) -> None:
+        super().__init__()
+        self.absmax = AbsMax(stats_reduce_dim)
+
+    def forward(self, x: Tensor):
+        per_channel_max = self.absmax(x)
+        out = torch.norm(per_channel_max, p=2)
+        return out / math.sqrt(per_channel_max.view(-1).shape[0])
+
+
+class AbsAve(nn.Module):
+    """``mean(abs(x))`` (stats_op.py:188-200)."""
+
+    def __init__(self, stats_reduce_dim: Optional[int] = None) -> None:
+        super().__init__()
+        self.stats_reduce_dim = stats_reduce_dim
+
+    def forward(self, x: Tensor):
+        if self.stats_reduce_dim is None:
+            return torch.mean(torch.abs(x))
+        return torch.mean(torch.abs(x), dim=self.stats_reduce_dim)
+
+
+class _MeanSigmaStdImpl(nn.Module):
+    """``mean(|x|) + sigma * sqrt(var(|x|) + eps)`` (stats_op.py:221-246)."""
+
+    def __init__(self, stats_reduce_dim: Optional[int] = None, std_dev_epsilon: float = DEFAULT_STD_DEV_EPSILON) -> None:
+        super().__init__()
+        self.stats_reduce_dim = stats_reduce_dim
+        self.epsilon = std_dev_epsilon
+
+    def forward(self, x: Tensor, sigma: Tensor):
+        abs_val = torch.abs(x)
+        if self.stats_reduce_dim is None:
+            mean_val = torch.mean(abs_val)
+            std_val = torch.sqrt(torch.var(abs_val) + self.epsilon)
+        else:
+            mean_val = torch.mean(torch.abs(x), dim=self.stats_reduce_dim)
+            std_val = torch.sqrt(torch.var(abs_val, dim=self.stats_reduce_dim) + self.epsilon)
+            mean_val = mean_val.view(-1)
+            std_val = std_val.view(-1)
+        return mean_val + sigma * std_val
+
+
+class MeanSigmaStd(nn.Module):
+    """stats_op.py:203-218 (constant sigma)."""
+
+    def __init__(self, sigma: float, stats_reduce_dim: Optional[int] = None,
+                 std_dev_epsilon: float = DEFAULT_STD_DEV_EPSILON) -> None:
+        super().__init__()
+        from .utils import StatelessBuffer
+        self.impl = _MeanSigmaStdImpl(stats_reduce_dim, std_dev_epsilon)
+        self.sigma = StatelessBuffer(torch.tensor(sigma))
+
+    def forward(self, x: Tensor):
+        return self.impl(x, self.sigma())
+
+
+class MeanLearnedSigmaStd(nn.Module):
+    """stats_op.py:249-285 (learned sigma; the reference's forward reads ``self.sigma`` while the parameter is
+    registered as ``value`` -- here the parameter is ``sigma``, the name its state-dict hooks use)."""
+
+    def __init__(self, sigma: float, stats_output_shape: Tuple[int, ...], stats_reduce_dim: Optional[int] = None,
+                 std_dev_epsilon: float = DEFAULT_STD_DEV_EPSILON) -> None:
+        super().__init__()
+        self.impl = _MeanSigmaStdImpl(stats_reduce_dim, std_dev_epsilon)
+        if stats_output_shape == SCALAR_SHAPE:
+            self.sigma = nn.Parameter(torch.tensor(sigma))
+        else:
+            self.sigma = nn.Parameter(torch.full(stats_output_shape, sigma))
+
+    def forward(self, x: Tensor):
+        return self.impl(x, self.sigma.view(self.sigma.shape))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        value_key, retro_key = prefix + 'sigma', prefix + 'learned_sigma'
+        if retro_key in state_dict:
+            state_dict[value_key] = state_dict.pop(retro_key)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+        if IGNORE_MISSING_KEYS and value_key in missing_keys:
+            missing_keys.remove(value_key)
+
+
 def absmax_plan(stats_impl: nn.Module, view_impl: nn.Module, x: Tensor) -> Optional[AbsMaxPlan]:
     """Return the fused geometry when (view, AbsMax) reduces contiguous trailing elements of ``x``."""
     if type(stats_impl) is not AbsMax or not x.is_contiguous() or x.numel() == 0:

@@ -47,29 +47,35 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
     const int64_t nchunks = (nvec + chunk - 1) / chunk;
     float s0 = 1.f;
     if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
-    const DivBy dv0(s0, DT<T>::MUL_DIV_EXACT && !scale_f32);
-    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const int64_t cc = reverse ? (nchunks - 1 - c) : c;
-        const int64_t base = cc * chunk + threadIdx.x;
-        uint4 q[ST_UNROLL];
+    const ScaleCtx<T> cx0(s0, !scale_f32, p, smode == 0 && PackedPath<T, RM>::value);
+    with_mode<T, RM, true>(cx0.mode, [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            const int64_t cc = reverse ? (nchunks - 1 - c) : c;
+            const int64_t base = cc * chunk + threadIdx.x;
+            uint4 q[ST_UNROLL];
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) {
-            int64_t v = base + (int64_t)u * ST_THREADS;
-            if (v < nvec) q[u] = ldg_stream(xv + v);
-        }
+            for (int u = 0; u < ST_UNROLL; ++u) {
+                int64_t v = base + (int64_t)u * ST_THREADS;
+                if (v < nvec) q[u] = ldg_stream(xv + v);
+            }
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) {
-            int64_t v = base + (int64_t)u * ST_THREADS;
-            if (v < nvec) {
-                DivBy dv = dv0;
-                if (smode != 0) dv = DivBy(DT<T>::to_f(scale[(v / inner_v) % count]), DT<T>::MUL_DIV_EXACT);
-                uint4 kq;
-                const uint4 yq = qdq_vec<T, RM>(q[u], dv, p, !scale_f32, codes ? &kq : nullptr);
-                stg_stream(yv + v, yq);
-                if (codes) stg_stream(cv + v, kq);
+            for (int u = 0; u < ST_UNROLL; ++u) {
+                int64_t v = base + (int64_t)u * ST_THREADS;
+                if (v < nvec) {
+                    uint4 kq, yq;
+                    if (smode != 0) {      // scale index constant within a vector (literal formulation)
+                        const ScaleCtx<T> cxv(DT<T>::to_f(scale[(v / inner_v) % count]), true, p, false);
+                        yq = qdq_vec<T, RM, VM_LITERAL>(q[u], cxv, p, codes ? &kq : nullptr);
+                    } else {
+                        yq = qdq_vec<T, RM, MODE>(q[u], cx0, p, codes ? &kq : nullptr);
+                    }
+                    stg_stream(yv + v, yq);
+                    if (codes) stg_stream(cv + v, kq);
+                }
             }
         }
-    }
+    });
 }
 
 // element-wise fallback for [start, n): any broadcast pattern, any alignment
@@ -153,54 +159,54 @@ __device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], cons
 // round()'s monotonicity (round(v) > qmax <=> v > thr_hi), and the integer code for d(scale) is
 // round(clamp(t2)) by magic-number adds.  Element-wise results are bit-identical to the literal sequence; the
 // d(scale) partial sum only changes its summation order (tolerance-bound by contract).
-template <typename T, int RM>
-__device__ __forceinline__ uint4 bwd_vec(const uint4& qg, const uint4& qx, const DivBy& dv, float inv_s,
-                                         const QParams& p, int masked_rt, bool want_gs, float& gs_acc, bool scale_in_T) {
+template <typename T, int RM, int MODE>
+__device__ __forceinline__ uint4 bwd_vec(const uint4& qg, const uint4& qx, const ScaleCtx<T>& cx, const QParams& p,
+                                         int masked_rt, bool want_gs, float& gs_acc) {
     constexpr int V = DT<T>::VEC;
-    if constexpr (PackedPath<T, RM>::value) {
-        if (p.pk_ok && scale_in_T && dv.fast) {
-            const bool masked = (RM & RM_MASK_KNOWN) ? ((RM & RM_MASKED) != 0) : (masked_rt != 0);
-            const uint32_t s2 = DT<T>::pack2(dv.b, dv.b);
-            uint32_t d[V / 2] = {DT<T>::p_mul(qg.x, s2), DT<T>::p_mul(qg.y, s2), DT<T>::p_mul(qg.z, s2),
-                                 DT<T>::p_mul(qg.w, s2)};                              // rnd_T(grad * scale)
-            float dm[V];
-            if (masked || want_gs) {
-                float ex[V], t1[V];
-                DT<T>::unpack(qx, ex);
-                dv.div_n<V>(ex, t1);
-                float s_gt = 0.f, s_dt = 0.f;
+    if constexpr (MODE != VM_LITERAL && PackedPath<T, RM>::value) {
+        const bool masked = (RM & RM_MASK_KNOWN) ? ((RM & RM_MASKED) != 0) : (masked_rt != 0);
+        const uint32_t qgw[4] = {qg.x, qg.y, qg.z, qg.w};
+        uint32_t d[V / 2];
 #pragma unroll
-                for (int j = 0; j < V / 2; ++j) {
-                    const uint32_t t1p = DT<T>::pack2(t1[2 * j], t1[2 * j + 1]);
-                    const uint32_t t2 = DT<T>::p_add(t1p, 0u);
-                    if (masked) d[j] &= ~(DT<T>::p_gt_mask(t2, p.pk_thr_hi) | DT<T>::p_lt_mask(t2, p.pk_thr_lo));
-                    DT<T>::p_unpack(d[j], dm[2 * j], dm[2 * j + 1]);
-                    if (want_gs) {
-                        const uint32_t c = DT<T>::p_max_nan(DT<T>::p_min_nan(t2, p.pk_hi), p.pk_lo);
-                        float k0, k1, g0, g1, a0, a1;
-                        DT<T>::p_rint_f(c, k0, k1);                                    // t6 (zero-point is 0)
-                        DT<T>::p_unpack(j == 0 ? qg.x : (j == 1 ? qg.y : (j == 2 ? qg.z : qg.w)), g0, g1);
-                        DT<T>::p_unpack(t1p, a0, a1);
-                        s_gt = fmaf(g0, k0, s_gt); s_gt = fmaf(g1, k1, s_gt);
-                        s_dt = fmaf(dm[2 * j], a0, s_dt); s_dt = fmaf(dm[2 * j + 1], a1, s_dt);
-                    }
+        for (int j = 0; j < V / 2; ++j) d[j] = DT<T>::p_mul(qgw[j], cx.s2);           // rnd_T(grad * scale)
+        float dm[V];
+        if (masked || want_gs) {
+            float ex[V], t1[V];
+            DT<T>::unpack(qx, ex);
+            cx.dv.template div_n<V>(ex, t1);
+            float s_gt = 0.f, s_dt = 0.f;
+#pragma unroll
+            for (int j = 0; j < V / 2; ++j) {
+                const uint32_t t1p = DT<T>::pack2(t1[2 * j], t1[2 * j + 1]);
+                const uint32_t t2 = DT<T>::p_add(t1p, 0u);
+                if (masked) d[j] &= ~(DT<T>::p_gt_mask(t2, p.pk_thr_hi) | DT<T>::p_lt_mask(t2, p.pk_thr_lo));
+                DT<T>::p_unpack(d[j], dm[2 * j], dm[2 * j + 1]);
+                if (want_gs) {
+                    const uint32_t c = DT<T>::p_max_nan(DT<T>::p_min_nan(t2, p.pk_hi), p.pk_lo);
+                    float k0, k1, g0, g1, a0, a1;
+                    DT<T>::p_rint_f(c, k0, k1);                                        // t6 (zero-point is 0)
+                    DT<T>::p_unpack(qgw[j], g0, g1);
+                    DT<T>::p_unpack(t1p, a0, a1);
+                    s_gt = fmaf(g0, k0, s_gt); s_gt = fmaf(g1, k1, s_gt);
+                    s_dt = fmaf(dm[2 * j], a0, s_dt); s_dt = fmaf(dm[2 * j + 1], a1, s_dt);
                 }
-                // d(scale) += sum g*t6 - sum d*((x/s)/s)
-                if (want_gs) gs_acc += fmaf(-inv_s, s_dt, s_gt);
-            } else {
-#pragma unroll
-                for (int j = 0; j < V / 2; ++j) DT<T>::p_unpack(d[j], dm[2 * j], dm[2 * j + 1]);
             }
-            float gx[V];
-            dv.div_n<V>(dm, gx);                                                       // grad / scale
-            return DT<T>::pack(gx);
+            // d(scale) += sum g*t6 - sum d*((x/s)/s)
+            if (want_gs) gs_acc += fmaf(-cx.inv_s, s_dt, s_gt);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V / 2; ++j) DT<T>::p_unpack(d[j], dm[2 * j], dm[2 * j + 1]);
         }
+        float gx[V];
+        cx.dv.template div_n<V>(dm, gx);                                               // grad / scale
+        return DT<T>::pack(gx);
+    } else {
+        float eg[V], ex[V];
+        DT<T>::unpack(qg, eg);
+        DT<T>::unpack(qx, ex);
+        bwd_n<T, RM, V>(eg, ex, cx.dv, cx.inv_s, p, masked_rt, want_gs, gs_acc);
+        return DT<T>::pack(eg);
     }
-    float eg[V], ex[V];
-    DT<T>::unpack(qg, eg);
-    DT<T>::unpack(qx, ex);
-    bwd_n<T, RM, V>(eg, ex, dv, inv_s, p, masked_rt, want_gs, gs_acc);
-    return DT<T>::pack(eg);
 }
 
 // provided-scale backward; gscale_out (nullable) accumulated with float atomics
@@ -217,38 +223,39 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
     const int64_t nchunks = (nvec + chunk - 1) / chunk;
     float s0 = 1.f;
     if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
-    const DivBy dv0(s0, DT<T>::MUL_DIV_EXACT && !scale_f32);
-    const float inv0 = dv0.approx_recip();
+    const ScaleCtx<T> cx0(s0, !scale_f32, p, smode == 0 && PackedPath<T, RM>::value);
     float acc = 0.f;          // smode 0: block-wide; smode 1: run of equal scale indices
     int64_t acc_idx = -1;
-    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const int64_t base = c * chunk + threadIdx.x;
-        uint4 qg[ST_UNROLL], qx[ST_UNROLL];
+    with_mode<T, RM, false>(cx0.mode, [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            const int64_t base = c * chunk + threadIdx.x;
+            uint4 qg[ST_UNROLL], qx[ST_UNROLL];
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) {
-            int64_t v = base + (int64_t)u * ST_THREADS;
-            if (v < nvec) { qg[u] = ldg_stream(gv + v); qx[u] = ldg_stream(xv + v); }
-        }
+            for (int u = 0; u < ST_UNROLL; ++u) {
+                int64_t v = base + (int64_t)u * ST_THREADS;
+                if (v < nvec) { qg[u] = ldg_stream(gv + v); qx[u] = ldg_stream(xv + v); }
+            }
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) {
-            int64_t v = base + (int64_t)u * ST_THREADS;
-            if (v < nvec) {
-                DivBy dv = dv0;
-                float inv_s = inv0;
-                if (smode != 0) {
-                    int64_t idx = (v / inner_v) % count;
-                    dv = DivBy(DT<T>::to_f(scale[idx]), DT<T>::MUL_DIV_EXACT);
-                    inv_s = dv.approx_recip();
-                    if (want_gs && idx != acc_idx) {
-                        if (acc_idx >= 0) atomicAdd(gscale_out + acc_idx, acc);
-                        acc = 0.f;
-                        acc_idx = idx;
+            for (int u = 0; u < ST_UNROLL; ++u) {
+                int64_t v = base + (int64_t)u * ST_THREADS;
+                if (v < nvec) {
+                    if (smode != 0) {
+                        const int64_t idx = (v / inner_v) % count;
+                        const ScaleCtx<T> cxv(DT<T>::to_f(scale[idx]), true, p, false);
+                        if (want_gs && idx != acc_idx) {
+                            if (acc_idx >= 0) atomicAdd(gscale_out + acc_idx, acc);
+                            acc = 0.f;
+                            acc_idx = idx;
+                        }
+                        stg_stream(ov + v, bwd_vec<T, RM, VM_LITERAL>(qg[u], qx[u], cxv, p, masked, want_gs, acc));
+                    } else {
+                        stg_stream(ov + v, bwd_vec<T, RM, MODE>(qg[u], qx[u], cx0, p, masked, want_gs, acc));
                     }
                 }
-                stg_stream(ov + v, bwd_vec<T, RM>(qg[u], qx[u], dv, inv_s, p, masked, want_gs, acc, !scale_f32));
             }
         }
-    }
+    });
     if (want_gs) {
         if (smode == 0) {
             float t = block_sum_f(acc, red);
@@ -300,8 +307,7 @@ __global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
     for (int64_t pl = (int64_t)blockIdx.x * groups_per_cta + gid; pl < nplanes;
          pl += (int64_t)gridDim.x * groups_per_cta) {
         const int64_t sidx = pl % count;
-        const DivBy dv(DT<T>::to_f(scale[sidx]), DT<T>::MUL_DIV_EXACT);
-        const float inv_s = dv.approx_recip();
+        const ScaleCtx<T> cx(DT<T>::to_f(scale[sidx]), true, p, PackedPath<T, RM>::value);
         const int64_t base = pl * inner;
         float acc = 0.f;
         if (vec_ok) {
@@ -312,41 +318,44 @@ __global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
             uint4* cv = codes ? reinterpret_cast<uint4*>(codes + base) : nullptr;
             // PL_UNROLL independent 16-byte loads in flight per thread before any arithmetic (ncu r01b: one load at
             // a time left this kernel latency-bound at 42 % issue utilisation and 4.6 TB/s)
-            for (int64_t v0 = gtid; v0 < nv; v0 += (int64_t)group * PL_UNROLL) {
-                uint4 qx[PL_UNROLL], qg[PL_UNROLL];
+            with_mode<T, RM, !BWD>(cx.mode, [&](auto mode_tag) {
+                constexpr int MODE = decltype(mode_tag)::value;
+                for (int64_t v0 = gtid; v0 < nv; v0 += (int64_t)group * PL_UNROLL) {
+                    uint4 qx[PL_UNROLL], qg[PL_UNROLL];
 #pragma unroll
-                for (int u = 0; u < PL_UNROLL; ++u) {
-                    const int64_t v = v0 + (int64_t)u * group;
-                    if (v < nv) {
-                        qx[u] = ldg_stream(xv + v);
-                        if (BWD) qg[u] = ldg_stream(gv + v);
+                    for (int u = 0; u < PL_UNROLL; ++u) {
+                        const int64_t v = v0 + (int64_t)u * group;
+                        if (v < nv) {
+                            qx[u] = ldg_stream(xv + v);
+                            if (BWD) qg[u] = ldg_stream(gv + v);
+                        }
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < PL_UNROLL; ++u) {
-                    const int64_t v = v0 + (int64_t)u * group;
-                    if (v < nv) {
-                        if (BWD) {
-                            stg_stream(ov + v, bwd_vec<T, RM>(qg[u], qx[u], dv, inv_s, p, masked, want_gs, acc, true));
-                        } else {
-                            uint4 kq;
-                            const uint4 yq = qdq_vec<T, RM>(qx[u], dv, p, true, cv ? &kq : nullptr);
-                            stg_stream(ov + v, yq);
-                            if (cv) stg_stream(cv + v, kq);
+                    for (int u = 0; u < PL_UNROLL; ++u) {
+                        const int64_t v = v0 + (int64_t)u * group;
+                        if (v < nv) {
+                            if (BWD) {
+                                stg_stream(ov + v, bwd_vec<T, RM, MODE>(qg[u], qx[u], cx, p, masked, want_gs, acc));
+                            } else {
+                                uint4 kq;
+                                const uint4 yq = qdq_vec<T, RM, MODE>(qx[u], cx, p, cv ? &kq : nullptr);
+                                stg_stream(ov + v, yq);
+                                if (cv) stg_stream(cv + v, kq);
+                            }
                         }
                     }
                 }
-            }
+            });
         } else {
             for (int64_t j = gtid; j < inner; j += group) {
                 float ex[1] = {DT<T>::to_f(x[base + j])};
                 if (BWD) {
                     float eg[1] = {DT<T>::to_f(gy[base + j])};
-                    bwd_n<T, RM, 1>(eg, ex, dv, inv_s, p, masked, want_gs, acc);
+                    bwd_n<T, RM, 1>(eg, ex, cx.dv, cx.inv_s, p, masked, want_gs, acc);
                     out[base + j] = DT<T>::from_f(eg[0]);
                 } else {
                     float k[1];
-                    quant_dequant_n<T, RM, 1>(ex, dv, p, codes ? k : nullptr);
+                    quant_dequant_n<T, RM, 1>(ex, cx.dv, p, codes ? k : nullptr);
                     out[base + j] = DT<T>::from_f(ex[0]);
                     if (codes) codes[base + j] = DT<T>::from_f(k[0]);
                 }
@@ -416,18 +425,18 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
         mbar_wait(&bars[s], parity);
         const uint4* buf = reinterpret_cast<const uint4*>(bufs + (size_t)s * stage_stride);
 
-        // pass 1 (shared memory): max |x| as raw bits
-        uint32_t m = 0;
+        // pass 1 (shared memory): max |x| on raw bit patterns, 128-bit loads
+        AbsMaxAcc<T> am;
 #pragma unroll 4
-        for (int v = tid; v < nvec; v += blockDim.x) m = DT<T>::absmax_acc(m, buf[v]);
-        m = warp_max_u32(DT<T>::absmax_fold(m));
+        for (int v = tid; v < nvec; v += blockDim.x) am.add(lds128(buf + v));
+        uint32_t m = warp_max_u32(am.result());
         if (lane == 0) red[warp] = m;
         __syncthreads();
         m = warp_max_u32(lane < nw ? red[lane] : 0u);
 
         const float amax = DT<T>::bits_to_f(m);
         const float sc = finalize_scale<T>(amax, min_val, has_min, int_thr);
-        const DivBy dv(sc, DT<T>::MUL_DIV_EXACT);
+        const ScaleCtx<T> cx(sc, true, p, PackedPath<T, RM>::value);
         if (tid == 0) {
             scale_out[row] = DT<T>::from_f(sc);
             if (absmax_out) absmax_out[row] = DT<T>::from_f(amax);
@@ -435,10 +444,12 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
 
         // pass 2 (shared memory -> HBM): quant-dequant, 128-bit stores
         uint4* yrow = reinterpret_cast<uint4*>(y + (size_t)row * cols);
+        with_mode<T, RM, true>(cx.mode, [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll 2
-        for (int v = tid; v < nvec; v += blockDim.x) {
-            stg_stream(yrow + v, qdq_vec<T, RM>(buf[v], dv, p, true));
-        }
+            for (int v = tid; v < nvec; v += blockDim.x)
+                stg_stream(yrow + v, qdq_vec<T, RM, MODE>(lds128(buf + v), cx, p));
+        });
         __syncthreads();      // everyone is done with buf[s] and red[]
         if (tid == 0 && it + stages < my_rows) {
             mbar_arrive_expect_tx(&bars[s], row_bytes);
@@ -497,8 +508,9 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
     __shared__ float red_f[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const DivBy dv(DT<T>::to_f(scale[row]), DT<T>::MUL_DIV_EXACT);
-        const float inv_s = dv.approx_recip();
+        const ScaleCtx<T> cx(DT<T>::to_f(scale[row]), true, p, false);       // generic path: literal formulation
+        const DivBy& dv = cx.dv;
+        const float inv_s = cx.inv_s;
         const T* gr = gy + row * cols;
         const T* xr = x + row * cols;
         T* outr = gx + row * cols;
@@ -518,12 +530,12 @@ __global__ void rows_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ 
                 {
                     const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx0));
                     if (mv > best) { best = mv; best_pos = (uint32_t)v0; }
-                    stg_stream(ov + v0, bwd_vec<T, RM>(qg0, qx0, dv, inv_s, p, masked, true, acc, true));
+                    stg_stream(ov + v0, bwd_vec<T, RM, VM_LITERAL>(qg0, qx0, cx, p, masked, true, acc));
                 }
                 if (v1 < nvec) {
                     const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx1));
                     if (mv > best) { best = mv; best_pos = (uint32_t)v1; }
-                    stg_stream(ov + v1, bwd_vec<T, RM>(qg1, qx1, dv, inv_s, p, masked, true, acc, true));
+                    stg_stream(ov + v1, bwd_vec<T, RM, VM_LITERAL>(qg1, qx1, cx, p, masked, true, acc));
                 }
             }
         } else {
@@ -662,32 +674,34 @@ __global__ void rows_bwd_tma_kernel(const T* __restrict__ gy, const T* __restric
     };
     float s_next = (first < rows) ? DT<T>::to_f(scale[first]) : 1.f;
     for (int row = first; row < rows; row += step, par ^= 1) {
-        const DivBy dv(s_next, DT<T>::MUL_DIV_EXACT);
+        const ScaleCtx<T> cx(s_next, true, p, PackedPath<T, RM>::value);
         if (row + step < rows) s_next = DT<T>::to_f(scale[row + step]);     // prefetch: hides the load latency
-        const float inv_s = dv.approx_recip();
         T* outr = gx + (size_t)row * cols;
         uint4* ov = reinterpret_cast<uint4*>(outr);
         const uint4* xv = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
         float acc = 0.f;
         // arg-max bookkeeping: bit pattern of the largest |x| this thread has seen and the first vector attaining it
         uint32_t best = 0, best_pos = (ctid < row_vecs) ? (uint32_t)ctid : 0xffffffffu;
-        for (int t = 0; t < tiles_per_row; ++t, ++it) {
-            const int s = it % stages;
-            mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
-            const int v_base = t * tile_vecs;
-            const int nv = min(tile_vecs, row_vecs - v_base);
-            const uint4* gbuf = reinterpret_cast<const uint4*>(ring + (size_t)s * 2u * tile_bytes);
-            const uint4* xbuf = gbuf + tile_vecs;
-            for (int v = ctid; v < nv; v += nct) {
-                const uint4 qg = gbuf[v];
-                const uint4 qx = xbuf[v];
-                const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx));
-                stg_stream(ov + v_base + v, bwd_vec<T, RM>(qg, qx, dv, inv_s, p, masked, true, acc, true));
-                if (mv > best) { best = mv; best_pos = (uint32_t)(v_base + v); }
+        with_mode<T, RM, false>(cx.mode, [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            for (int t = 0; t < tiles_per_row; ++t, ++it) {
+                const int s = it % stages;
+                mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+                const int v_base = t * tile_vecs;
+                const int nv = min(tile_vecs, row_vecs - v_base);
+                const uint4* gbuf = reinterpret_cast<const uint4*>(ring + (size_t)s * 2u * tile_bytes);
+                const uint4* xbuf = gbuf + tile_vecs;
+                for (int v = ctid; v < nv; v += nct) {
+                    const uint4 qg = lds128(gbuf + v);
+                    const uint4 qx = lds128(xbuf + v);
+                    const uint32_t mv = DT<T>::absmax_fold(DT<T>::absmax_acc(0u, qx));
+                    stg_stream(ov + v_base + v, bwd_vec<T, RM, MODE>(qg, qx, cx, p, masked, true, acc));
+                    if (mv > best) { best = mv; best_pos = (uint32_t)(v_base + v); }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);            // this warp no longer reads stage s
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);            // this warp no longer reads stage s
-        }
+        });
         // ---- row epilogue (ONE named barrier): per-warp (max bits, first position, sum) -> shared -> every warp
         const uint32_t wmax = warp_max_u32(best);
         const uint32_t wpos = warp_min_u32(best == wmax ? best_pos : 0xffffffffu);
@@ -783,24 +797,26 @@ __global__ void scaled_bwd_tma_kernel(const T* __restrict__ gy, const T* __restr
     float s_next = 1.f;
     if (first < nrows) s_next = one_scale ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[first % count]);
     for (long long row = first; row < nrows; row += step) {
-        const DivBy dv(s_next, DT<T>::MUL_DIV_EXACT && !scale_f32);
+        const ScaleCtx<T> cx(s_next, !scale_f32, p, PackedPath<T, RM>::value);
         if (!one_scale && row + step < nrows) s_next = DT<T>::to_f(scale[(row + step) % count]);   // prefetch
-        const float inv_s = dv.approx_recip();
         const long long v0 = row * row_vecs;
         const int rv = (int)min((long long)row_vecs, n_vecs - v0);
-        for (int t = 0; t * tile_vecs < rv; ++t, ++it) {
-            const int s = it % stages;
-            mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
-            const int v_base = t * tile_vecs;
-            const int nv = min(tile_vecs, rv - v_base);
-            const uint4* gbuf = reinterpret_cast<const uint4*>(ring + (size_t)s * 2u * tile_bytes);
-            const uint4* xbuf = gbuf + tile_vecs;
-            for (int v = ctid; v < nv; v += nct)
-                stg_stream(ov + v0 + v_base + v,
-                           bwd_vec<T, RM>(gbuf[v], xbuf[v], dv, inv_s, p, masked, want_gs, acc, !scale_f32));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
+        with_mode<T, RM, false>(cx.mode, [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            for (int t = 0; t * tile_vecs < rv; ++t, ++it) {
+                const int s = it % stages;
+                mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+                const int v_base = t * tile_vecs;
+                const int nv = min(tile_vecs, rv - v_base);
+                const uint4* gbuf = reinterpret_cast<const uint4*>(ring + (size_t)s * 2u * tile_bytes);
+                const uint4* xbuf = gbuf + tile_vecs;
+                for (int v = ctid; v < nv; v += nct)
+                    stg_stream(ov + v0 + v_base + v,
+                               bwd_vec<T, RM, MODE>(lds128(gbuf + v), lds128(xbuf + v), cx, p, masked, want_gs, acc));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+        });
         if (want_gs && !one_scale) {
             const float wsum = warp_sum_f(acc);
             if (lane == 0) atomicAdd(gscale_out + (row % count), wsum);
@@ -879,8 +895,9 @@ __global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
         T* __restrict__ gx, int64_t n, int vec_ok, uint32_t* ws, int scale_f32, int masked, QParams p) {
     constexpr int V = DT<T>::VEC;
     __shared__ float red[32];
-    const DivBy dv(load_scale0<T>(scale, scale_f32), DT<T>::MUL_DIV_EXACT && !scale_f32);
-    const float inv_s = dv.approx_recip();
+    const ScaleCtx<T> cx(load_scale0<T>(scale, scale_f32), !scale_f32, p, PackedPath<T, RM>::value);
+    const DivBy& dv = cx.dv;
+    const float inv_s = cx.inv_s;
     const uint32_t mbits = canon_abs_bits(DT<T>::to_f(absmax[0]));
     long long* list = reinterpret_cast<long long*>(ws + WS_LIST);
     float acc = 0.f;
@@ -912,7 +929,8 @@ __global__ void __launch_bounds__(ST_THREADS) tensor_bwd_kernel(
                         if (slot < TIE_CAP) list[slot] = v * V + i;
                     }
                 }
-                stg_stream(ov + v, bwd_vec<T, RM>(qg[u], qx[u], dv, inv_s, p, masked, true, acc, !scale_f32));
+                if (cx.mode == VM_LITERAL) stg_stream(ov + v, bwd_vec<T, RM, VM_LITERAL>(qg[u], qx[u], cx, p, masked, true, acc));
+                else stg_stream(ov + v, bwd_vec<T, RM, VM_PACKED>(qg[u], qx[u], cx, p, masked, true, acc));
             }
         }
     }
@@ -1146,35 +1164,40 @@ static RowsGeom rows_geometry(int64_t cols, int elem_size) {
     RowsGeom g = {0, 0, 0, 0, 0, false};
     const int64_t row_bytes = cols * elem_size;
     if (row_bytes < 16 || (row_bytes & 15) != 0) return g;
-    const int64_t budget = 220 * 1024;                      // of the 227 KB per SM
     g.stage_stride = (uint32_t)((row_bytes + 127) & ~(int64_t)127);
-    const int64_t nvec = row_bytes / 16;
-    int threads = 128;
-    while (threads < 512 && nvec > (int64_t)threads * 6) threads *= 2;
-    int max_total = (int)((budget) / (int64_t)g.stage_stride);   // row buffers that fit in one SM
-    if (max_total < 2) return g;
-    int ctas, stages;
-    if (max_total >= 4) {
-        // measured (tools/kbench.py sweeps, B200): two stages per CTA and as many CTAs as fit (up to 6) beat
-        // deeper rings with fewer CTAs for every shape tried (C2 fp32/bf16, C3 bf16/fp32)
-        stages = 2;
-        ctas = max_total / stages;
-        if (ctas > 6) ctas = 6;
+    const int64_t stride = g.stage_stride;
+    if (2 * stride + ROWS_SMEM_HEADER > 226 * 1024) return g;       // a row pair must fit in one SM's shared memory
+    // Geometry from tools/kbench.py sweeps on a B200 (profiles/r01f_sweeps.md; 45 M elements, row lengths 2 Ki .. 14 Ki
+    // elements).  Both dtypes want FEW threads per SM -- the arithmetic is cheap next to the HBM time, and more
+    // concurrently storing warps made every shape slower -- and a bounded amount of prefetch:
+    //   fp32          ~512 threads and ~64-130 KB of row buffers per SM: 4 CTAs x 128 threads for 8 KB rows,
+    //                 2 x 256 for 16 KB, 1 x 512 with 3 stages for 32 KB, 1 x 512 with 2 stages beyond
+    //   bf16 / fp16   (heavier per byte) 128-thread CTAs, 2 stages, as many CTAs as fit up to 6
+    int threads, stages = 2, ctas;
+    if (elem_size == 4) {
+        ctas = (int)((32 * 1024 + stride / 2) / stride);
+        if (ctas < 1) ctas = 1;
+        if (ctas > 8) ctas = 8;
+        threads = 512 / ctas;
+        if (threads < 64) threads = 64;
+        if (ctas == 1 && 3 * stride <= 100 * 1024) stages = 3;
     } else {
-        stages = max_total;
-        ctas = 1;
+        threads = 128;
+        ctas = (int)((200 * 1024) / (2 * stride));
+        if (ctas > 6) ctas = 6;
+        if (ctas < 1) { ctas = 1; threads = 256; }
     }
-    int max_ctas = 2048 / threads;
-    if (max_ctas > 16) max_ctas = 16;
-    if (ctas > max_ctas) ctas = max_ctas;
     const Tuning& t = tuning();
     if (t.rows_threads > 0) threads = t.rows_threads;
     if (t.rows_stages > 0) stages = t.rows_stages;
     if (t.rows_ctas_per_sm > 0) ctas = t.rows_ctas_per_sm;
     if (stages > ROWS_MAX_STAGES) stages = ROWS_MAX_STAGES;
+    int max_ctas = 2048 / threads;
+    if (max_ctas > 16) max_ctas = 16;
+    if (ctas > max_ctas) ctas = max_ctas;
     // re-validate against the shared-memory budget
-    while (ctas > 1 && (int64_t)ctas * (ROWS_SMEM_HEADER + (int64_t)stages * g.stage_stride + 1024) > 227 * 1024) --ctas;
-    while (stages > 1 && (ROWS_SMEM_HEADER + (int64_t)stages * g.stage_stride) > 226 * 1024) --stages;
+    while (ctas > 1 && (int64_t)ctas * (ROWS_SMEM_HEADER + (int64_t)stages * stride + 1024) > 227 * 1024) --ctas;
+    while (stages > 1 && (ROWS_SMEM_HEADER + (int64_t)stages * stride) > 226 * 1024) --stages;
     if (stages < 2) return g;
     g.threads = threads;
     g.stages = stages;
