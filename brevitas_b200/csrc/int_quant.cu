@@ -1075,7 +1075,19 @@ static int launch_int_quant_fwd(const void* x, const void* scale, void* y, void*
 }
 
 struct BwdGeom { int threads, tile_vecs, stages, ctas_per_sm; size_t smem; bool ok; };
-static BwdGeom bwd_geometry(int64_t cols, int elem_size);
+
+// persistent grids must fit in ONE resident wave: a grid of 4 CTAs/SM of which only 3 are resident runs a second,
+// quarter-full wave (sweeps: 100.9 us against 90.5 us for the same kernel)
+template <typename K>
+static int resident_ctas(K kernel, int threads, size_t smem, int wanted) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return wanted;
+    }
+    return wanted < occ ? wanted : occ;
+}
+static BwdGeom bwd_geometry(int64_t cols, int elem_size, bool provided_scale = false);
 
 // TMA-pipelined provided-scale backward over n_vecs 16-byte vectors cut into chunks of row_vecs
 template <typename T, int RM>
@@ -1083,7 +1095,7 @@ static int launch_scaled_bwd_tma(const void* gy, const void* x, const void* scal
                                  int64_t n_vecs, int64_t row_vecs, int64_t count, int scale_f32, const QParams& p,
                                  int masked, cudaStream_t st, bool* launched) {
     *launched = false;
-    BwdGeom g = bwd_geometry(row_vecs * 16 / (int64_t)sizeof(T), (int)sizeof(T));
+    BwdGeom g = bwd_geometry(row_vecs * 16 / (int64_t)sizeof(T), (int)sizeof(T), true);
     if (!g.ok || row_vecs >= ((int64_t)1 << 27)) return BVB_OK;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -1095,7 +1107,7 @@ static int launch_scaled_bwd_tma(const void* gy, const void* x, const void* scal
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int64_t nrows = (n_vecs + row_vecs - 1) / row_vecs;
-    int64_t grid = (int64_t)g.ctas_per_sm * sm_count();
+    int64_t grid = (int64_t)resident_ctas(scaled_bwd_tma_kernel<T, RM>, g.threads, g.smem, g.ctas_per_sm) * sm_count();
     if (grid > nrows) grid = nrows;
     scaled_bwd_tma_kernel<T, RM><<<(unsigned)grid, g.threads, g.smem, st>>>(
         (const T*)gy, (const T*)x, (const T*)scale, (T*)gx, gscale_out, (long long)n_vecs, (int)row_vecs,
@@ -1222,7 +1234,7 @@ static int launch_rows_fwd(const void* x, void* y, void* scale_out, void* absmax
             if (e != cudaSuccess) return fail(BVB_ECUDA, "rows_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
-        int64_t grid = (int64_t)g.ctas_per_sm * sm_count();
+        int64_t grid = (int64_t)resident_ctas(rows_fwd_tma_kernel<T, RM>, g.threads, g.smem, g.ctas_per_sm) * sm_count();
         if (grid > rows) grid = rows;
         rows_fwd_tma_kernel<T, RM><<<(unsigned)grid, g.threads, g.smem, st>>>(
             (const T*)x, (T*)y, (T*)scale_out, (T*)absmax_out, (int)rows, (int)cols, g.stages, g.stage_stride,
@@ -1240,14 +1252,30 @@ static int launch_rows_fwd(const void* x, void* y, void* scale_out, void* absmax
 
 // geometry of the TMA backward: consumer warps, tile size, ring depth, CTAs per SM
 
-static BwdGeom bwd_geometry(int64_t cols, int elem_size) {
+static BwdGeom bwd_geometry(int64_t cols, int elem_size, bool provided_scale) {
     BwdGeom g = {0, 0, 0, 0, 0, false};
     const int64_t row_bytes = cols * elem_size;
     if (row_bytes < 16 || (row_bytes & 15) != 0 || row_bytes >= ((int64_t)1 << 31)) return g;
     const int64_t row_vecs = row_bytes / 16;
     // defaults from tools/kbench.py sweeps on a B200 (C2 4096x11008 fp32/bf16, C3 16384x4096 bf16): 8 KB tiles,
     // 4 consumer warps, a 2-deep ring per CTA and 4 CTAs per SM won or tied every sweep; bigger tiles lose.
-    int ncw = row_vecs >= 512 ? 4 : (row_vecs >= 128 ? 2 : 1);
+    // re-swept after the packed-arithmetic rewrite (profiles/r01f_sweeps.md): like the forward, ~500-770 threads per SM
+    // win -- fp32: 3 consumer warps x 4 CTAs (85.5 vs 90.4 us on C2); 16-bit long rows: 4 x 4; 16-bit rows below
+    // 16 KB (C3): 2 consumer warps x 8 CTAs with 4 KB tiles (67.9 vs 74.4 us)
+    // The provided-scale kernel (masked clamp + d(scale), the literal fp32 chain is its heaviest case) wants 8 consumer
+    // warps and exactly one resident wave: 3 CTAs/SM fp32 (90.5 vs 102 us), 2 CTAs/SM 16-bit (70.2 vs 72.3 us).
+    int ncw, ctas_default;
+    if (provided_scale) {
+        ncw = row_vecs >= 1024 ? 8 : (row_vecs >= 256 ? 4 : 2);
+        ctas_default = elem_size == 4 ? 3 : 2;
+        if (ncw < 8) ctas_default = 4;
+    } else if (elem_size == 4) {
+        ncw = row_vecs >= 384 ? 3 : (row_vecs >= 128 ? 2 : 1);
+        ctas_default = ncw >= 3 ? 4 : (ncw >= 2 ? 6 : 8);
+    } else {
+        ncw = row_vecs >= 1024 ? 4 : (row_vecs >= 128 ? 2 : 1);
+        ctas_default = ncw >= 4 ? 4 : 8;
+    }
     int per_thread = 4;                                     // vectors per consumer thread per tile
     const Tuning& t = tuning();
     if (t.stream_threads > 0) ncw = t.stream_threads / 32;
@@ -1255,9 +1283,8 @@ static BwdGeom bwd_geometry(int64_t cols, int elem_size) {
     int64_t tile_vecs = (int64_t)ncw * 32 * per_thread;
     if (tile_vecs > row_vecs) tile_vecs = row_vecs;
     const int64_t stage_bytes = 2 * tile_vecs * 16;
-    int ctas = t.stream_ctas_per_sm > 0 ? t.stream_ctas_per_sm : (ncw >= 4 ? 4 : (ncw >= 2 ? 6 : 8));
-    int stages = (int)((32 * 1024) / stage_bytes);           // ~32 KB in flight per CTA
-    if (stages < 2) stages = 2;
+    int ctas = t.stream_ctas_per_sm > 0 ? t.stream_ctas_per_sm : ctas_default;
+    int stages = 2;                                          // deeper rings lost every sweep
     if (t.rows_stages > 0) stages = t.rows_stages;
     if (stages > BWD_MAX_STAGES) stages = BWD_MAX_STAGES;
     int max_ctas = 2048 / ((ncw + 1) * 32);
@@ -1287,7 +1314,7 @@ static int launch_rows_bwd(const void* gy, const void* x, const void* scale, con
             if (e != cudaSuccess) return fail(BVB_ECUDA, "rows_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
-        int64_t grid = (int64_t)g.ctas_per_sm * sm_count();
+        int64_t grid = (int64_t)resident_ctas(rows_bwd_tma_kernel<T, RM>, g.threads, g.smem, g.ctas_per_sm) * sm_count();
         if (grid > rows) grid = rows;
         rows_bwd_tma_kernel<T, RM><<<(unsigned)grid, g.threads, g.smem, st>>>(
             (const T*)gy, (const T*)x, (const T*)scale, (const T*)gscale, (T*)gx, (int)rows, (int)cols, g.tile_vecs,

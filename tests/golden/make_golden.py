@@ -315,12 +315,167 @@ def gen_docstring_kats(out):
     out["kat/clamped_binary/y"], out["kat/clamped_binary/gx"] = npf(cy), npf(ci.grad)
 
 
+def _stats_ops():
+    from brevitas.core import stats as S
+    return {
+        "neg_min_or_zero": lambda dim: S.NegativeMinOrZero(dim),
+        "neg_percentile_or_zero": lambda dim: S.NegativePercentileOrZero(10.0, dim),
+        "percentile_interval": lambda dim: S.PercentileInterval(5.0, 95.0, dim),
+        "abs_min_max": lambda dim: S.AbsMinMax(dim),
+        "abs_max_ave": lambda dim: S.AbsMaxAve(1) if dim == 1 else None,
+        "abs_max_l2": lambda dim: S.AbsMaxL2(1) if dim == 1 else None,
+        "abs_ave": lambda dim: S.AbsAve(dim),
+        "mean_sigma_std": lambda dim: S.MeanSigmaStd(3.0, dim),
+    }
+
+
+def gen_widen(out):
+    """remaining statistics, bias / trunc / decoupled / ternary quantizers, asymmetric
+    (zero-point) weight quantizers, learned bit-width."""
+    from brevitas.core import function_wrapper as fw
+    from brevitas.core.bit_width import BitWidthConst, BitWidthParameter, MsbClampBitWidth, RemoveBitwidthParameter
+    from brevitas.core.quant import (DecoupledIntQuant, IntQuant, PrescaledRestrictIntQuant,
+                                     PrescaledRestrictIntQuantWithInputBitWidth, RescalingIntQuant, TernaryQuant,
+                                     TruncIntQuant)
+    from brevitas.core.restrict_val import FloatRestrictValue
+    from brevitas.core.scaling import IntScaling, ParameterScaling, StatsFromParameterScaling
+    from brevitas.core.stats import AbsMinMax, NegativeMinOrZero
+    from brevitas.core.zero_point import ParameterFromRuntimeZeroPoint, ParameterZeroPoint, StatsFromParameterZeroPoint
+    # ---- A. statistics (values and autograd gradients) ----
+    for dname, dt in DT.items():
+        x2 = make_input((6, 40), 41, 2.0, with_edges=False).to(dt)
+        x2[1, 3] = x2[1].max()            # a tie on one row maximum
+        for name, make in _stats_ops().items():
+            for dim in (None, 1):
+                op = make(dim)
+                if op is None:
+                    continue
+                xi = x2.clone().requires_grad_(True)
+                y = op(xi if dim is not None else xi.reshape(-1))
+                gsc = torch.linspace(0.5, 1.5, max(1, y.numel())).to(dt).view(y.shape)
+                (y * gsc).sum().backward()
+                k = f"widen/stats/{name}/{'rows' if dim == 1 else 'flat'}/{dname}/"
+                out[k + "x"], out[k + "y"], out[k + "g"], out[k + "gx"] = npf(x2), npf(y), npf(gsc), npf(xi.grad)
+    # ---- B. bias quantizers: externally supplied scale ----
+    for dname, dt in DT.items():
+        xb = make_input((48,), 51, 0.5, with_edges=False).to(dt)
+        gb = make_input((48,), 52, 1.0, with_edges=False).to(dt)
+        for sname, sc in (("scalar", torch.tensor(0.0173)), ("chan", torch.rand(48, generator=torch.Generator().manual_seed(5)) * 0.02 + 0.005)):
+            iq = IntQuant(narrow_range=True, signed=True, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClamp())
+            for qname, q, extra in (("prescaled", PrescaledRestrictIntQuant(iq, BitWidthConst(8)), ()),
+                                    ("prescaled_in_bw", PrescaledRestrictIntQuantWithInputBitWidth(
+                                        iq, MsbClampBitWidth(RemoveBitwidthParameter(3), 2, 16)), (torch.tensor(9.0),))):
+                xi = xb.clone().requires_grad_(True)
+                si = sc.to(dt).clone().requires_grad_(True)
+                y, s_out, zp, bw = q(xi, si, *extra)
+                (y * gb).sum().backward()
+                k = f"widen/{qname}/{sname}/{dname}/"
+                out[k + "x"], out[k + "scale"], out[k + "g"] = npf(xb), npf(sc.to(dt)), npf(gb)
+                out[k + "y"], out[k + "bit_width"] = npf(y), npf(bw)
+                out[k + "gx"], out[k + "gscale"] = npf(xi.grad), npf(si.grad)
+    # docstring KAT (int.py:33-47)
+    iq = IntQuant(narrow_range=True, signed=True)
+    kat = PrescaledRestrictIntQuantWithInputBitWidth(iq, fw.Identity())
+    yk, _, _, bwk = kat(torch.Tensor([0.042, -0.053, 0.31, -0.44]), torch.tensor(0.01), torch.tensor(4.))
+    out["widen/kat/prescaled/y"], out["widen/kat/prescaled/bw"] = npf(yk), npf(bwk)
+    # ---- C. TruncIntQuant (QuantAvgPool2d): 12-bit accumulator values truncated to 8 bits ----
+    for dname, dt in DT.items():
+        sc = torch.tensor(0.03125).to(dt)                        # power of two: x = codes * scale is exact in T
+        codes = torch.randint(-90, 91, (5, 33), generator=torch.Generator().manual_seed(61)).to(dt)
+        xt = (codes * sc).clone().requires_grad_(True)
+        tq = TruncIntQuant(fw.FloorSte(), BitWidthConst(4))
+        y, s_out, zp, bw = tq(xt, sc, torch.tensor(0.0).to(dt), torch.tensor(8.0))
+        gt = make_input((5, 33), 62, 1.0, False).to(dt)
+        (y * gt).sum().backward()
+        k = f"widen/trunc/{dname}/"
+        out[k + "x"], out[k + "scale"], out[k + "g"] = npf(xt), npf(sc), npf(gt)
+        out[k + "y"], out[k + "bit_width"], out[k + "gx"] = npf(y), npf(bw), npf(xt.grad)
+    # ---- D. DecoupledIntQuant ----
+    dq = DecoupledIntQuant(narrow_range=True, signed=True)
+    yk = dq(torch.tensor(0.02), torch.tensor(0.), torch.tensor(0.01), torch.tensor(0.), torch.tensor(4.),
+            torch.Tensor([0.042, -0.053, 0.31, -0.44]))           # docstring KAT (int_base.py:118-125)
+    out["widen/kat/decoupled/y"] = npf(yk)
+    for dname, dt in DT.items():
+        xd = make_input((7, 29), 71, 3.0, with_edges=False).to(dt)
+        gd = make_input((7, 29), 72, 1.0, False).to(dt)
+        xi = xd.clone().requires_grad_(True)
+        ps = torch.tensor(0.05).to(dt).requires_grad_(True)
+        sc = torch.tensor(0.047).to(dt).requires_grad_(True)
+        dq = DecoupledIntQuant(narrow_range=False, signed=True, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClamp())
+        y = dq(ps, torch.tensor(0.).to(dt), sc, torch.tensor(0.).to(dt), torch.tensor(6.), xi)
+        (y * gd).sum().backward()
+        k = f"widen/decoupled/{dname}/"
+        out[k + "x"], out[k + "g"], out[k + "y"], out[k + "gx"] = npf(xd), npf(gd), npf(y), npf(xi.grad)
+        out[k + "g_pre_scale"], out[k + "g_scale"] = npf(ps.grad), npf(sc.grad)
+    # ---- E. TernaryQuant ----
+    tk = TernaryQuant(ParameterScaling(1.0), 0.5)
+    out["widen/kat/ternary/y"] = npf(tk(torch.Tensor([0.04, -0.6, 3.3]))[0])       # docstring KAT (ternary.py:34-38)
+    for dname, dt in DT.items():
+        xq = make_input((9, 31), 81, 1.0, with_edges=True).to(dt)
+        gq = make_input((9, 31), 82, 1.0, False).to(dt)
+        tq = TernaryQuant(ParameterScaling(0.7), 0.5).to(dt)
+        xi = xq.clone().requires_grad_(True)
+        y, s_out, zp, bw = tq(xi)
+        (torch.nan_to_num(y) * gq).sum().backward()
+        k = f"widen/ternary/{dname}/"
+        out[k + "x"], out[k + "g"], out[k + "y"], out[k + "gx"] = npf(xq), npf(gq), npf(y), npf(xi.grad)
+        out[k + "gvalue"] = npf(tq.scaling_impl.value.grad)
+    # ---- F. asymmetric weight quantizers: ShiftedUint8WeightPer{Tensor,Channel}Float wiring
+    #         (quant/shifted_scaled_int.py:45-75 = ShiftedMinUintQuant + MinMaxStatsScaling) ----
+    for dname, dt in DT.items():
+        for per_channel in (False, True):
+            w = torch.nn.Parameter((make_input((12, 50), 91, 0.3, with_edges=False) + 0.05).to(dt))
+            if per_channel:
+                view, concat, shape, dim = fw.OverOutputChannelView(None), 1, (12, 1), 1
+            else:
+                view, concat, shape, dim = fw.OverTensorView(), 0, (), None
+            iq = IntQuant(narrow_range=False, signed=False, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClampSte())
+            tq = RescalingIntQuant(
+                iq, StatsFromParameterScaling(AbsMinMax(dim), view, concat, [w], FloatRestrictValue(), shape, False, 1e-10),
+                IntScaling(False, False),
+                StatsFromParameterZeroPoint(iq, True, view, concat, NegativeMinOrZero(dim), shape, [w]),
+                BitWidthConst(8))
+            y, scale, zp, bw = tq(w)
+            gw = make_input((12, 50), 92, 1.0, False).to(dt)
+            (y * gw).sum().backward()
+            k = f"widen/shifted_weight/{'chan' if per_channel else 'tensor'}/{dname}/"
+            out[k + "w"], out[k + "g"], out[k + "y"] = npf(w), npf(gw), npf(y)
+            out[k + "scale"], out[k + "zero_point"], out[k + "gw"] = npf(scale), npf(zp), npf(w.grad)
+    # ---- G. learned bit-width ----
+    bwp = BitWidthParameter(6, min_bit_width=2)
+    v = bwp()
+    (v * 2.5).backward()
+    out["widen/bit_width_parameter/value"], out["widen/bit_width_parameter/g_offset"] = npf(v), npf(bwp.bit_width_offset.grad)
+    rbp = RemoveBitwidthParameter(3)
+    out["widen/remove_bit_width/value"] = npf(rbp())
+    out["widen/msb_clamp/value"] = npf(MsbClampBitWidth(RemoveBitwidthParameter(3), 2, 16)(torch.tensor(24.0)))
+    # ---- H. zero-point from runtime statistics, then learned (3 collection steps + steady state + eval) ----
+    iq = IntQuant(narrow_range=False, signed=False, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClamp())
+    zpm = ParameterFromRuntimeZeroPoint(3, iq, True, NegativeMinOrZero(None), (), fw.OverTensorView(), 0.1)
+    zpm.train()
+    sc8, bw8 = torch.tensor(0.04), torch.tensor(8.0)
+    for step in range(5):
+        xa = make_input((4, 25), 100 + step, 1.0, False) - 0.3
+        out[f"widen/runtime_zero_point/x{step}"] = npf(xa)
+        out[f"widen/runtime_zero_point/zp{step}"] = npf(zpm(xa, sc8, bw8))
+        out[f"widen/runtime_zero_point/buffer{step}"] = npf(zpm.buffer)
+        out[f"widen/runtime_zero_point/value{step}"] = npf(zpm.value)
+    zpm.eval()
+    out["widen/runtime_zero_point/zp_eval"] = npf(zpm(xa, sc8, bw8))
+    pz = ParameterZeroPoint(-0.37, iq, True, None)
+    out["widen/parameter_zero_point/zp"] = npf(pz(xa, sc8, bw8))
+
+
 def main():
     import_reference()
     torch.manual_seed(123456)
     groups = {"ste": gen_ste, "int_quant": gen_int_quant, "weight_stats": gen_weight_stats,
               "runtime_token": gen_runtime_token, "binary": gen_binary, "percentile": gen_percentile,
-              "param_from_stats": gen_param_from_stats, "int_tables": gen_int_tables, "kat": gen_docstring_kats}
+              "param_from_stats": gen_param_from_stats, "int_tables": gen_int_tables, "kat": gen_docstring_kats,
+              "widen": gen_widen}
+    only = sys.argv[1:]
+    if only:
+        groups = {k: v for k, v in groups.items() if k in only}
     for gname, fn in groups.items():
         out = {}
         fn(out)

@@ -1,0 +1,238 @@
+"""GPU (-m gpu): the quantizers / statistics either side of the hot path against golden
+vectors produced by the real reference (tests/golden/widen.npz, make_golden.py::gen_widen).
+
+Element-wise results (outputs, integer codes, zero-points, element-wise gradients) are bit-exact.  Values that are
+floating-point REDUCTIONS in the reference as well (mean, variance, norms, the gradient arriving on a scale or on a
+tied maximum) depend on the summation order of the device and carry the tolerance written at the check."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import DTYPES, assert_bits_equal, case, load, ulp
+
+pytestmark = pytest.mark.gpu
+TDT = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+
+
+def dev(a, dtype):
+    a = np.asarray(a)
+    return torch.from_numpy(np.array(a, copy=True)).reshape(a.shape).to(TDT[dtype]).cuda()      # keeps 0-dim
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+def close(got, ref, dtype, k=8.0, what=""):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    tol = k * ulp(dtype) * (np.abs(ref) + np.abs(ref).max() * 0.05 + 1e-6)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert np.all(np.abs(got - ref) <= tol), (what, got.reshape(-1)[:6], ref.reshape(-1)[:6])
+
+
+EXACT_STATS = {"neg_min_or_zero", "neg_percentile_or_zero", "percentile_interval", "abs_min_max"}   # selections only
+
+
+def _make_stat(name, dim):
+    from brevitas_b200.core import stats as S
+    return {"neg_min_or_zero": lambda: S.NegativeMinOrZero(dim),
+            "neg_percentile_or_zero": lambda: S.NegativePercentileOrZero(10.0, dim),
+            "percentile_interval": lambda: S.PercentileInterval(5.0, 95.0, dim),
+            "abs_min_max": lambda: S.AbsMinMax(dim), "abs_max_ave": lambda: S.AbsMaxAve(1),
+            "abs_max_l2": lambda: S.AbsMaxL2(1), "abs_ave": lambda: S.AbsAve(dim),
+            "mean_sigma_std": lambda: S.MeanSigmaStd(3.0, dim)}[name]()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", ["neg_min_or_zero", "neg_percentile_or_zero", "percentile_interval", "abs_min_max",
+                                  "abs_max_ave", "abs_max_l2", "abs_ave", "mean_sigma_std"])
+def test_statistics(name, dtype):
+    for layout, dim in (("flat", None), ("rows", 1)):
+        c = case("widen", f"widen/stats/{name}/{layout}/{dtype}/")
+        if not c:
+            assert dim is None and name in ("abs_max_ave", "abs_max_l2")
+            continue
+        op = _make_stat(name, dim).cuda()
+        x = dev(c["x"], dtype).requires_grad_(True)
+        y = op(x if dim is not None else x.reshape(-1))
+        (y * dev(c["g"], dtype).view(y.shape)).sum().backward()
+        if name in EXACT_STATS:
+            assert_bits_equal(host(y), c["y"], f"{name} {layout}")
+            # the selected VALUE is unique but, among equal elements (bf16 / fp16 inputs repeat values), which INDEX
+            # min / max / kthvalue reports differs between ATen's CPU and CUDA kernels: compare the gradient summed
+            # over elements of equal value, per row
+            got, ref, xs = host(x.grad), c["gx"], c["x"]
+            if dim is None:
+                got, ref, xs = got.reshape(1, -1), ref.reshape(1, -1), xs.reshape(1, -1)
+            for r in range(xs.shape[0]):
+                for val in np.unique(xs[r][(got[r] != 0) | (ref[r] != 0)]):
+                    sel = xs[r] == val
+                    assert got[r][sel].sum() == ref[r][sel].sum(), (name, layout, r, val)
+            assert np.count_nonzero(got) == np.count_nonzero(ref)
+        else:
+            close(host(y), c["y"], dtype, what=f"{name} {layout}")
+            close(host(x.grad), c["gx"], dtype, k=16.0, what=f"{name} {layout} grad")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sname", ["scalar", "chan"])
+@pytest.mark.parametrize("qname", ["prescaled", "prescaled_in_bw"])
+def test_bias_quantizers(qname, sname, dtype):
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.bit_width import BitWidthConst, MsbClampBitWidth, RemoveBitwidthParameter
+    from brevitas_b200.core.quant import IntQuant, PrescaledRestrictIntQuant, PrescaledRestrictIntQuantWithInputBitWidth
+    c = case("widen", f"widen/{qname}/{sname}/{dtype}/")
+    iq = IntQuant(narrow_range=True, signed=True, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClamp())
+    if qname == "prescaled":
+        q, extra = PrescaledRestrictIntQuant(iq, BitWidthConst(8)).cuda(), ()
+    else:
+        q = PrescaledRestrictIntQuantWithInputBitWidth(iq, MsbClampBitWidth(RemoveBitwidthParameter(3), 2, 16)).cuda()
+        extra = (torch.tensor(9.0, device="cuda"),)
+    x = dev(c["x"], dtype).requires_grad_(True)
+    s = dev(c["scale"], dtype).requires_grad_(True)
+    y, s_out, zp, bw = q(x, s, *extra)
+    (y * dev(c["g"], dtype)).sum().backward()
+    assert_bits_equal(host(y), c["y"], "y")
+    assert_bits_equal(host(bw), c["bit_width"], "bit width")
+    assert float(zp) == 0.0 and s_out is s
+    assert_bits_equal(host(x.grad), c["gx"], "gx")
+    if sname == "chan":                      # one element per scale: no reduction involved
+        assert_bits_equal(host(s.grad), c["gscale"], "gscale")
+    else:
+        close(host(s.grad), c["gscale"], dtype, k=16.0, what="gscale (sum over 48 elements)")
+
+
+def test_docstring_kats():
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.quant import DecoupledIntQuant, IntQuant, PrescaledRestrictIntQuantWithInputBitWidth, TernaryQuant
+    from brevitas_b200.core.scaling import ParameterScaling
+    d = load("widen")
+    t = lambda v: torch.tensor(v, device="cuda")
+    q = PrescaledRestrictIntQuantWithInputBitWidth(IntQuant(narrow_range=True, signed=True), fw.Identity()).cuda()
+    y, _, _, bw = q(t([0.042, -0.053, 0.31, -0.44]), t(0.01), t(4.))
+    assert_bits_equal(host(y), d["widen/kat/prescaled/y"], "int.py:33-47")
+    assert float(bw) == float(d["widen/kat/prescaled/bw"])
+    dq = DecoupledIntQuant(narrow_range=True, signed=True).cuda()
+    y = dq(t(0.02), t(0.), t(0.01), t(0.), t(4.), t([0.042, -0.053, 0.31, -0.44]))
+    assert_bits_equal(host(y), d["widen/kat/decoupled/y"], "int_base.py:118-125")
+    tq = TernaryQuant(ParameterScaling(1.0), 0.5).cuda()
+    assert_bits_equal(host(tq(t([0.04, -0.6, 3.3]))[0]), d["widen/kat/ternary/y"], "ternary.py:34-38")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_trunc_int_quant(dtype):
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.bit_width import BitWidthConst
+    from brevitas_b200.core.quant import TruncIntQuant
+    c = case("widen", f"widen/trunc/{dtype}/")
+    tq = TruncIntQuant(fw.FloorSte(), BitWidthConst(4)).cuda()
+    x = dev(c["x"], dtype).requires_grad_(True)
+    y, s, zp, bw = tq(x, dev(c["scale"], dtype), torch.tensor(0.0, device="cuda").to(TDT[dtype]), torch.tensor(8.0, device="cuda"))
+    (y * dev(c["g"], dtype)).sum().backward()
+    assert_bits_equal(host(y), c["y"], "y")
+    assert_bits_equal(host(bw), c["bit_width"], "bit width")
+    assert_bits_equal(host(x.grad), c["gx"], "gx")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_decoupled_int_quant(dtype):
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.quant import DecoupledIntQuant
+    c = case("widen", f"widen/decoupled/{dtype}/")
+    T = TDT[dtype]
+    dq = DecoupledIntQuant(narrow_range=False, signed=True, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClamp()).cuda()
+    x = dev(c["x"], dtype).requires_grad_(True)
+    ps = torch.tensor(0.05).to(T).cuda().requires_grad_(True)
+    sc = torch.tensor(0.047).to(T).cuda().requires_grad_(True)
+    z = torch.tensor(0.).to(T).cuda()
+    y = dq(ps, z, sc, z, torch.tensor(6., device="cuda"), x)
+    (y * dev(c["g"], dtype)).sum().backward()
+    assert_bits_equal(host(y), c["y"], "y")
+    assert_bits_equal(host(x.grad), c["gx"], "gx")
+    close(host(ps.grad), c["g_pre_scale"], dtype, k=32.0, what="d pre_scale (sum)")
+    close(host(sc.grad), c["g_scale"], dtype, k=32.0, what="d scale (sum)")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ternary_quant(dtype):
+    from brevitas_b200.core.quant import TernaryQuant
+    from brevitas_b200.core.scaling import ParameterScaling
+    c = case("widen", f"widen/ternary/{dtype}/")
+    tq = TernaryQuant(ParameterScaling(0.7), 0.5).to(TDT[dtype]).cuda()
+    x = dev(c["x"], dtype).requires_grad_(True)
+    y, s, zp, bw = tq(x)
+    (torch.nan_to_num(y) * dev(c["g"], dtype)).sum().backward()
+    assert_bits_equal(host(y), c["y"], "y")
+    assert_bits_equal(host(x.grad), c["gx"], "gx")
+    assert float(bw) == 2.0 and float(zp) == 0.0
+    close(host(tq.scaling_impl.value.grad), c["gvalue"], dtype, k=32.0, what="d scale (sum)")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("layout", ["tensor", "chan"])
+def test_shifted_uint8_weight_quantizers(layout, dtype):
+    """ShiftedUint8WeightPer{Tensor,Channel}Float (quant/shifted_scaled_int.py:45-75): scale from |max - min|,
+    integer zero-point from -min through the quantizer's own to_int."""
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.bit_width import BitWidthConst
+    from brevitas_b200.core.quant import IntQuant, RescalingIntQuant
+    from brevitas_b200.core.restrict_val import FloatRestrictValue
+    from brevitas_b200.core.scaling import IntScaling, StatsFromParameterScaling
+    from brevitas_b200.core.stats import AbsMinMax, NegativeMinOrZero
+    from brevitas_b200.core.zero_point import StatsFromParameterZeroPoint
+    c = case("widen", f"widen/shifted_weight/{layout}/{dtype}/")
+    w = torch.nn.Parameter(dev(c["w"], dtype))
+    if layout == "chan":
+        view, concat, shape, dim = fw.OverOutputChannelView(None), 1, (12, 1), 1
+    else:
+        view, concat, shape, dim = fw.OverTensorView(), 0, (), None
+    iq = IntQuant(narrow_range=False, signed=False, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClampSte())
+    tq = RescalingIntQuant(
+        iq, StatsFromParameterScaling(AbsMinMax(dim), view, concat, [w], FloatRestrictValue(), shape, False, 1e-10),
+        IntScaling(False, False), StatsFromParameterZeroPoint(iq, True, view, concat, NegativeMinOrZero(dim), shape, [w]),
+        BitWidthConst(8)).cuda()
+    y, scale, zp, bw = tq(w)
+    (y * dev(c["g"], dtype)).sum().backward()
+    assert_bits_equal(host(scale), c["scale"], "scale")
+    assert_bits_equal(host(zp), c["zero_point"], "zero point")
+    assert_bits_equal(host(y), c["y"], "y")
+    # the gradient is element-wise except on each region's min / max entries, which also receive the reduced
+    # d(scale) and d(zero_point) terms (order-dependent sums)
+    wn = c["w"]
+    if layout == "chan":
+        ext = (wn == wn.max(axis=1, keepdims=True)) | (wn == wn.min(axis=1, keepdims=True))
+    else:
+        ext = (wn == wn.max()) | (wn == wn.min())
+    got = host(w.grad)
+    assert_bits_equal(np.where(ext, 0, got), np.where(ext, 0, c["gw"]), "gw off the extrema")
+    close(got[ext], c["gw"][ext], dtype, k=64.0, what="gw on the extrema")
+
+
+def test_learned_bit_width_and_zero_points():
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.bit_width import BitWidthParameter, MsbClampBitWidth, RemoveBitwidthParameter
+    from brevitas_b200.core.quant import IntQuant
+    from brevitas_b200.core.stats import NegativeMinOrZero
+    from brevitas_b200.core.zero_point import ParameterFromRuntimeZeroPoint, ParameterZeroPoint
+    d = load("widen")
+    bwp = BitWidthParameter(6, min_bit_width=2).cuda()
+    v = bwp()
+    (v * 2.5).backward()
+    assert_bits_equal(host(v), d["widen/bit_width_parameter/value"], "learned bit width")
+    assert_bits_equal(host(bwp.bit_width_offset.grad), d["widen/bit_width_parameter/g_offset"], "d offset")
+    assert_bits_equal(host(RemoveBitwidthParameter(3).cuda()()), d["widen/remove_bit_width/value"], "bits to remove")
+    assert_bits_equal(host(MsbClampBitWidth(RemoveBitwidthParameter(3), 2, 16).cuda()(torch.tensor(24.0, device="cuda"))),
+                      d["widen/msb_clamp/value"], "msb clamp")
+    iq = IntQuant(narrow_range=False, signed=False, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClamp())
+    zpm = ParameterFromRuntimeZeroPoint(3, iq, True, NegativeMinOrZero(None), (), fw.OverTensorView(), 0.1).cuda()
+    zpm.train()
+    sc8, bw8 = torch.tensor(0.04, device="cuda"), torch.tensor(8.0, device="cuda")
+    for step in range(5):
+        xa = dev(d[f"widen/runtime_zero_point/x{step}"], "f32")
+        assert_bits_equal(host(zpm(xa, sc8, bw8)), d[f"widen/runtime_zero_point/zp{step}"], f"zero point, step {step}")
+        assert_bits_equal(host(zpm.buffer), d[f"widen/runtime_zero_point/buffer{step}"], f"buffer, step {step}")
+        assert_bits_equal(host(zpm.value), d[f"widen/runtime_zero_point/value{step}"], f"value, step {step}")
+    zpm.eval()
+    assert_bits_equal(host(zpm(xa, sc8, bw8)), d["widen/runtime_zero_point/zp_eval"], "eval")
+    pz = ParameterZeroPoint(-0.37, iq, True, None).cuda()
+    assert_bits_equal(host(pz(xa, sc8, bw8)), d["widen/parameter_zero_point/zp"], "learned zero point")

@@ -23,7 +23,7 @@ DT = {"f32": (torch.float32, _lib.F32, 4), "bf16": (torch.bfloat16, _lib.BF16, 2
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--kernel", default="bwd", choices=["fwd", "bwd", "both"])
+    ap.add_argument("--kernel", default="bwd", choices=["fwd", "bwd", "both", "scaled_bwd"])
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--rows", type=int, default=4096)
     ap.add_argument("--cols", type=int, default=11008)
@@ -44,6 +44,7 @@ def main():
     Y = torch.empty_like(X[0])
     GXO = torch.empty_like(X[0])
     S = torch.empty(a.rows, device=dev, dtype=tdt)
+    GS = torch.zeros(1, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     qmin, qmax, thr = -127.0, 127.0, 127.0
     lib.bvb_rows_absmax_int_quant_fwd(X[0].data_ptr(), Y.data_ptr(), S.data_ptr(), None, a.rows, a.cols, 1e-10, thr,
@@ -57,6 +58,9 @@ def main():
             return rc | lib.bvb_rows_absmax_int_quant_bwd(G[k].data_ptr(), X[k].data_ptr(), S.data_ptr(), None,
                                                           GXO.data_ptr(), a.rows, a.cols, thr, 0.0, qmin, qmax, 0,
                                                           a.masked, tag, st)
+        if a.kernel == "scaled_bwd":     # provided scalar scale, d(scale) wanted (learned activation scale)
+            return lib.bvb_int_quant_bwd(G[k].data_ptr(), X[k].data_ptr(), S.data_ptr(), Y.data_ptr(), GS.data_ptr(), n, 1, 1,
+                                         tag, 0.0, 0.0, 255.0, 0, a.masked, tag, st)
         if a.kernel == "fwd":
             return lib.bvb_rows_absmax_int_quant_fwd(X[k].data_ptr(), Y.data_ptr(), S.data_ptr(), None, a.rows, a.cols,
                                                      1e-10, thr, 0.0, qmin, qmax, 0, tag, st)
@@ -78,7 +82,9 @@ def main():
         torch.cuda.profiler.stop()
         return e0.elapsed_time(e1) / a.reps
 
-    bytes_ = n * esz * {"fwd": 2, "bwd": 3, "both": 5}[a.kernel]
+    bytes_ = n * esz * {"fwd": 2, "bwd": 3, "both": 5, "scaled_bwd": 3}[a.kernel]
+    if a.kernel == "scaled_bwd":
+        S.fill_(0.02)
     if a.tuning:
         combos = [tuple(int(v) for v in a.tuning.split(","))]
     elif not a.sweep:
@@ -86,8 +92,8 @@ def main():
     elif a.kernel == "fwd":
         combos = [(t, s, c, 0, 0) for t, s, c in itertools.product([128, 256, 512, 1024], [2, 3, 4], [1, 2, 3, 4, 6])]
     else:
-        combos = [(pt, s, 0, 32 * (w + 1), c) for w, pt, s, c in
-                  itertools.product([4, 8, 12, 16], [1, 2, 4], [2, 3, 4, 6], [1, 2, 3, 4])]
+        combos = [(pt, s, 0, 32 * w, c) for w, pt, s, c in           # w = consumer warps
+                  itertools.product([2, 3, 4, 6, 8], [2, 4, 8], [2, 3], [2, 3, 4, 6, 8])]
     best = None
     for c in combos:
         lib.bvb_set_tuning(*c)
