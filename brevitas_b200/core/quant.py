@@ -61,6 +61,28 @@ class DelayWrapper(nn.Module):
         return self.delay_impl(x, y)
 
 
+# ---- mixed-dtype scalar operands in the literal sequences -----------------------------------------------------------
+# A 0-dim fp32 scale next to a bf16 / fp16 tensor (fp32 quantizer buffers, low-precision weights or activations): the
+# reference result (ATen on CPU, which the golden vectors record) keeps the scale in fp32 "opmath" for mul / div and
+# rounds once to the tensor dtype; ATen on CUDA instead casts a 0-dim CUDA tensor to the common dtype first, i.e.
+# rounds the scale to 16 bits.  The fused kernels implement the former (``scale_dtype`` argument of the C-ABI); the
+# literal sequences below do the same explicitly so that both paths agree with the reference bit for bit.
+def _is_fp32_scalar_with_lowp(x: Tensor, s: Tensor) -> bool:
+    return s.numel() == 1 and s.dtype == torch.float32 and x.dtype in (torch.bfloat16, torch.float16)
+
+
+def scalar_div(x: Tensor, s: Tensor) -> Tensor:
+    if _is_fp32_scalar_with_lowp(x, s):
+        return (x.float() / s).to(x.dtype)
+    return x / s
+
+
+def scalar_mul(x: Tensor, s: Tensor) -> Tensor:
+    if _is_fp32_scalar_with_lowp(x, s):
+        return (x.float() * s).to(x.dtype)
+    return x * s
+
+
 # ---- host copies of the 0-dim range tensors ------------------------------------------------------------------
 @lru_cache(maxsize=None)
 def int_range(signed: bool, narrow_range: bool, bit_width: int, dtype: torch.dtype) -> Tuple[float, float]:
@@ -111,7 +133,7 @@ class IntQuant(nn.Module):
 
     def to_int(self, scale: Tensor, zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
         """Integer codes as floats (int_base.py:64-76), literal op sequence on the STE kernels."""
-        y = x / scale
+        y = scalar_div(x, scale)
         y = y + zero_point
         min_int_val = self.min_int(bit_width)
         max_int_val = self.max_int(bit_width)
@@ -140,7 +162,7 @@ class IntQuant(nn.Module):
                 return y
         y_int = self.to_int(scale, zero_point, bit_width, x)
         y = y_int - zero_point
-        y = y * scale
+        y = scalar_mul(y, scale)
         return self.delay_wrapper(x, y)
 
 
@@ -320,7 +342,7 @@ class TruncIntQuant(nn.Module):
         self.delay_wrapper = DelayWrapper(quant_delay_steps)
 
     def forward(self, x: Tensor, scale: Tensor, zero_point: Tensor, input_bit_width: Tensor):
-        y = x / scale
+        y = scalar_div(x, scale)
         y = y + zero_point
         y = round_ste(y)  # clean up floating point error
         output_bit_width = self.msb_clamp_bit_width_impl()
@@ -329,7 +351,7 @@ class TruncIntQuant(nn.Module):
         y = y / trunc_scale
         y = self.float_to_int_impl(y)
         y = y - zero_point
-        y = y * scale
+        y = scalar_mul(y, scale)
         y = self.delay_wrapper(x, y)
         return y, scale, zero_point, output_bit_width
 
@@ -349,7 +371,7 @@ class DecoupledIntQuant(nn.Module):
         self.delay_wrapper = DelayWrapper(quant_delay_steps)
 
     def to_int(self, pre_scale: Tensor, pre_zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
-        y = x / pre_scale
+        y = scalar_div(x, pre_scale)
         y = y + pre_zero_point
         min_int_val = self.min_int(bit_width)
         max_int_val = self.max_int(bit_width)
@@ -367,7 +389,7 @@ class DecoupledIntQuant(nn.Module):
                 x: Tensor) -> Tensor:
         y_int = self.to_int(pre_scale, pre_zero_point, bit_width, x)
         y = y_int - zero_point
-        y = y * scale
+        y = scalar_mul(y, scale)
         return self.delay_wrapper(x, y)
 
 
