@@ -83,23 +83,21 @@ class AbsPercentile(nn.Module):
 DEFAULT_STD_DEV_EPSILON = 1e-8
 
 
-def _zero_like_scalar(t: Tensor) -> Tensor:
-    return torch.zeros((), dtype=t.dtype, device=t.device)
-
-
 class NegativeMinOrZero(nn.Module):
     """``min(x)`` (whole tensor or along a dim) if it is <= 0 else 0 (stats_op.py:22-39)."""
 
     def __init__(self, stats_reduce_dim: Optional[int] = None) -> None:
         super().__init__()
+        from .utils import StatelessBuffer
         self.stats_reduce_dim = stats_reduce_dim
+        self.zero = StatelessBuffer(torch.tensor(0.0))
 
     def forward(self, x: Tensor) -> Tensor:
         if self.stats_reduce_dim is None:
             min_val = torch.min(x)
         else:
             min_val = torch.min(x, dim=self.stats_reduce_dim)[0]
-        zero = _zero_like_scalar(min_val)
+        zero = self.zero().to(min_val.dtype)
         return torch.where(min_val <= zero, min_val, zero)
 
 
@@ -108,8 +106,10 @@ class NegativePercentileOrZero(nn.Module):
 
     def __init__(self, low_percentile_q, stats_reduce_dim: Optional[int] = None) -> None:
         super().__init__()
+        from .utils import StatelessBuffer
         self.stats_reduce_dim = stats_reduce_dim
         self.q = low_percentile_q
+        self.zero = StatelessBuffer(torch.tensor(0.0))
 
     def forward(self, x: Tensor) -> Tensor:
         if self.stats_reduce_dim is None:
@@ -119,7 +119,7 @@ class NegativePercentileOrZero(nn.Module):
             assert len(x.size()) == 2, "Only 2-dim input is supported."
             k = int(math.ceil(.01 * self.q * x.shape[self.stats_reduce_dim]))
             result = x.kthvalue(k, dim=self.stats_reduce_dim).values
-        zero = _zero_like_scalar(result)
+        zero = self.zero().to(result.dtype)
         return torch.where(result <= zero, result, zero)
 
 
@@ -237,26 +237,27 @@ class MeanSigmaStd(nn.Module):
 
 
 class MeanLearnedSigmaStd(nn.Module):
-    """stats_op.py:249-285 (learned sigma; the reference's forward reads ``self.sigma`` while the parameter is
-    registered as ``value`` -- here the parameter is ``sigma``, the name its state-dict hooks use)."""
+    """stats_op.py:249-285 (learned sigma).  The parameter is registered as ``value`` like in the reference (whose
+    forward reads a non-existent ``self.sigma``, stats_op.py:269); older key names are mapped on load."""
 
     def __init__(self, sigma: float, stats_output_shape: Tuple[int, ...], stats_reduce_dim: Optional[int] = None,
                  std_dev_epsilon: float = DEFAULT_STD_DEV_EPSILON) -> None:
         super().__init__()
         self.impl = _MeanSigmaStdImpl(stats_reduce_dim, std_dev_epsilon)
         if stats_output_shape == SCALAR_SHAPE:
-            self.sigma = nn.Parameter(torch.tensor(sigma))
+            self.value = nn.Parameter(torch.tensor(sigma))
         else:
-            self.sigma = nn.Parameter(torch.full(stats_output_shape, sigma))
+            self.value = nn.Parameter(torch.full(stats_output_shape, sigma))
 
     def forward(self, x: Tensor):
-        return self.impl(x, self.sigma.view(self.sigma.shape))
+        return self.impl(x, self.value.view(self.value.shape))
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
-        value_key, retro_key = prefix + 'sigma', prefix + 'learned_sigma'
-        if retro_key in state_dict:
-            state_dict[value_key] = state_dict.pop(retro_key)
+        value_key = prefix + 'value'
+        for retro_key in (prefix + 'sigma', prefix + 'learned_sigma'):
+            if retro_key in state_dict:
+                state_dict[value_key] = state_dict.pop(retro_key)
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
         if IGNORE_MISSING_KEYS and value_key in missing_keys:

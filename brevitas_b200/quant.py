@@ -17,12 +17,13 @@ from torch import nn
 
 from .core import function_wrapper as fw
 from .core.bit_width import BitWidthConst
-from .core.quant import BinaryQuant, ClampedBinaryQuant, IntQuant, RescalingIntQuant
+from .core.quant import (BinaryQuant, ClampedBinaryQuant, IntQuant, PrescaledRestrictIntQuant,
+                         PrescaledRestrictIntQuantWithInputBitWidth, RescalingIntQuant, TernaryQuant, TruncIntQuant)
 from .core.restrict_val import FloatRestrictValue, LogFloatRestrictValue, PowerOfTwoRestrictValue
 from .core.scaling import (ConstScaling, IntScaling, ParameterFromRuntimeStatsScaling, ParameterScaling,
                            PowerOfTwoIntScaling, RuntimeStatsScaling, StatsFromParameterScaling)
-from .core.stats import AbsMax, AbsPercentile
-from .core.zero_point import ZeroZeroPoint
+from .core.stats import AbsMax, AbsMinMax, AbsPercentile, NegativeMinOrZero
+from .core.zero_point import StatsFromParameterZeroPoint, ZeroZeroPoint
 
 SCALING_STATS_REDUCE_DIM = 1
 
@@ -245,3 +246,94 @@ class Int8ActPerTokenDynamic(ActQuantizer):
         scaling = RuntimeStatsScaling(AbsMax(2), fw.OverBatchOverOutputChannelView(), FloatRestrictValue(),
                                       (batch, tokens, 1), False, cls.scaling_stats_momentum, cls.scaling_min_val)
         return cls._rescaling_int_quant(scaling, fw.TensorClamp())
+
+
+# ---- bias / accumulator quantizers (quant/scaled_int.py:64-127, :185-204; quant/solver/bias.py, trunc.py) --------
+class BiasQuantizer(Quantizer):
+    """``IntBias`` family: signed, scale = input scale x weight scale supplied by the layer, zero-point 0."""
+    narrow_range = False
+    signed = True
+    requires_input_scale = True
+    requires_input_bit_width = True            # IntBias: bit-width of the accumulator the bias is added to
+    bit_width: Optional[int] = None
+
+    @classmethod
+    def tensor_quant(cls) -> nn.Module:
+        iq = IntQuant(narrow_range=cls.narrow_range, signed=cls.signed,
+                      float_to_int_impl=_FLOAT_TO_INT[cls.float_to_int_impl_type](), tensor_clamp_impl=fw.TensorClamp())
+        if cls.requires_input_bit_width:
+            return PrescaledRestrictIntQuantWithInputBitWidth(iq, fw.Identity())
+        return PrescaledRestrictIntQuant(iq, BitWidthConst(int(cls.bit_width)))
+
+
+class IntBias(BiasQuantizer):
+    """quant/scaled_int.py:64-76"""
+
+
+class Int8Bias(IntBias):
+    bit_width = 8
+    requires_input_bit_width = False
+
+
+class Int16Bias(IntBias):
+    bit_width = 16
+    requires_input_bit_width = False
+
+
+class Int24Bias(IntBias):
+    bit_width = 24
+    requires_input_bit_width = False
+
+
+class Int32Bias(IntBias):
+    bit_width = 32
+    requires_input_bit_width = False
+
+
+class TruncQuantizer(Quantizer):
+    """``IntTrunc`` (quant/base.py): keeps the input scale and zero-point, drops LSBs with FLOOR."""
+    float_to_int_impl_type = "FLOOR"
+
+    @classmethod
+    def tensor_quant(cls) -> nn.Module:
+        return TruncIntQuant(_FLOAT_TO_INT[cls.float_to_int_impl_type](), BitWidthConst(int(cls.bit_width)),
+                             cls.quant_delay_steps)
+
+
+class TruncTo8bit(TruncQuantizer):
+    """quant/scaled_int.py:196-204"""
+    bit_width = 8
+
+
+# ---- asymmetric weight quantizers (quant/shifted_scaled_int.py:45-75 = ShiftedMinUintQuant + MinMaxStatsScaling) ----
+class ShiftedUint8WeightPerTensorFloat(WeightQuantizer):
+    narrow_range = False
+    signed = False
+    scaling_impl_type = "STATS"
+    scaling_stats_op = "MIN_MAX"
+    scaling_min_val = 1e-10
+    bit_width = 8
+    quantize_zero_point = True
+
+    @classmethod
+    def tensor_quant(cls, weight: nn.Parameter, output_channel_dim: int = 0) -> nn.Module:
+        if output_channel_dim != 0:
+            raise NotImplementedError("output channels must be dim 0 (Linear / Conv weights)")
+        if cls.scaling_per_output_channel:
+            shape = (weight.shape[0],) + (1,) * (weight.dim() - 1)
+            mk_view, reduce_dim, concat = (lambda: fw.OverOutputChannelView(None)), SCALING_STATS_REDUCE_DIM, 1
+        else:
+            shape, mk_view, reduce_dim, concat = (), fw.OverTensorView, None, 0
+        iq = IntQuant(narrow_range=cls.narrow_range, signed=cls.signed,
+                      float_to_int_impl=_FLOAT_TO_INT[cls.float_to_int_impl_type](),
+                      tensor_clamp_impl=fw.TensorClampSte(), quant_delay_steps=cls.quant_delay_steps)
+        scaling = StatsFromParameterScaling(AbsMinMax(reduce_dim), mk_view(), concat, [weight], cls._restrict(), shape,
+                                            False, cls.scaling_min_val)
+        zero_point = StatsFromParameterZeroPoint(iq, cls.quantize_zero_point, mk_view(), concat,
+                                                 NegativeMinOrZero(reduce_dim), shape, [weight])
+        return RescalingIntQuant(int_quant=iq, scaling_impl=scaling, int_scaling_impl=cls._int_scaling(),
+                                 zero_point_impl=zero_point, bit_width_impl=BitWidthConst(int(cls.bit_width)))
+
+
+class ShiftedUint8WeightPerChannelFloat(ShiftedUint8WeightPerTensorFloat):
+    scaling_per_output_channel = True

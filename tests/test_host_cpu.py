@@ -228,3 +228,43 @@ def test_packed_constants_reject_unrepresentable_ranges():
     assert _packed_constants(0, 1023, "f16")[0] == 0        # outside the fp16 magic-rounding range
     assert _packed_constants(0, 1023, "bf16")[0] == 0       # 1023 needs 10 significant bits
     assert _packed_constants(0, 1024, "bf16")[0] == 1
+
+
+def test_widened_modules_mirror_reference_trees():
+    """state-dict keys and sub-module names of the quantizers / zero-points / bit-widths added for SURVEY.md §8f,
+    recorded from the reference's own classes (brevitas.core, BREVITAS_JIT=0): checkpoints stay interchangeable."""
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.bit_width import BitWidthConst, BitWidthParameter, MsbClampBitWidth, RemoveBitwidthParameter
+    from brevitas_b200.core.quant import (IntQuant, PrescaledRestrictIntQuantWithInputBitWidth, RescalingIntQuant,
+                                          TernaryQuant, TruncIntQuant)
+    from brevitas_b200.core.restrict_val import FloatRestrictValue
+    from brevitas_b200.core.scaling import IntScaling, ParameterScaling, StatsFromParameterScaling
+    from brevitas_b200.core.stats import AbsMinMax, MeanLearnedSigmaStd, NegativeMinOrZero
+    from brevitas_b200.core.zero_point import ParameterFromRuntimeZeroPoint, ParameterZeroPoint, StatsFromParameterZeroPoint
+    w = torch.nn.Parameter(torch.randn(4, 6))
+    iq = IntQuant(narrow_range=False, signed=False)
+    view = lambda: fw.OverOutputChannelView(None)
+    shifted = RescalingIntQuant(
+        iq, StatsFromParameterScaling(AbsMinMax(1), view(), 1, [w], FloatRestrictValue(), (4, 1), False, 1e-10),
+        IntScaling(False, False), StatsFromParameterZeroPoint(iq, True, view(), 1, NegativeMinOrZero(1), (4, 1), [w]),
+        BitWidthConst(8))
+    assert list(shifted.state_dict().keys()) == []
+    names = {n for n, _ in shifted.named_modules()}
+    for expected in ("zero_point_impl.parameter_list_stats.first_tracked_param.view_shape_impl",
+                     "zero_point_impl.parameter_list_stats.stats.stats_impl.zero", "zero_point_impl.scale_shift_zero_point",
+                     "scaling_impl.parameter_list_stats.stats.stats_impl", "msb_clamp_bit_width_impl.bit_width"):
+        assert expected in names, expected
+    rz = ParameterFromRuntimeZeroPoint(3, iq, True, NegativeMinOrZero(None), (), fw.OverTensorView(), 0.1)
+    assert list(rz.state_dict().keys()) == []                       # nothing to save before the first step
+    rz.counter = 2
+    assert list(rz.state_dict().keys()) == ["value"]                # the running buffer, saved under `value`
+    assert sorted(ParameterZeroPoint(0.5, iq, True, None).state_dict()) == ["value"]
+    pre = PrescaledRestrictIntQuantWithInputBitWidth(iq, MsbClampBitWidth(RemoveBitwidthParameter(3), 2, 16))
+    assert sorted(pre.state_dict()) == ["msb_clamp_bit_width_impl.bit_width_to_remove_impl.bit_width_coeff"]
+    assert sorted(BitWidthParameter(6).state_dict()) == ["bit_width_offset"]
+    assert sorted(TernaryQuant(ParameterScaling(0.7), 0.5).state_dict()) == ["scaling_impl.value"]
+    assert sorted(TruncIntQuant(fw.FloorSte(), BitWidthConst(4)).state_dict()) == []
+    assert sorted(MeanLearnedSigmaStd(3.0, ()).state_dict()) == ["value"]
+    # CPU tensors are rejected by every kernel-backed op (no CPU fallback)
+    with pytest.raises(RuntimeError):
+        shifted(w)
