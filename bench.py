@@ -470,8 +470,7 @@ def main():
         qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
         qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
         if world > 1 or args.qat_all:
-            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3)            # configs[4] (avg-pool trunc / int
-                                                                                     # bias un-quantized)
+            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3)            # BASELINE.json configs[4]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -9,9 +9,10 @@ nn/mixin/base.py:64-68).  Same sub-module names as the reference so checkpoints 
 (proxy/parameter_quant.py:83-89, proxy/runtime_quant.py:73-84).  The matmul / convolution itself is the stock
 cuDNN / cuBLAS call exactly as in the reference (`F.linear`, `F.conv2d`): it is not part of the fake-quant path.
 
-Not covered here (SURVEY.md §8f "next"): bias / accumulator quantizers that need the input scale, QuantTensor
-arithmetic, export handlers.  ``return_quant_tensor`` returns a light ``QuantTensor`` tuple without the reference's
-operator overloading.
+Bias quantizers that take the accumulator scale / bit-width (``IntBias`` ...; nn/quant_layer.py:302-365) and the
+truncating average pool (``QuantAvgPool2d``, nn/quant_avg_pool.py:21-73) are covered; QuantTensor arithmetic and export
+handlers are not (SURVEY.md §8 out of scope).  ``QuantTensor`` is a light tuple with ``set`` / ``view`` / ``reshape`` /
+``flatten`` but without the reference's operator overloading.
 """
 from typing import NamedTuple, Optional, Type, Union
 
@@ -19,8 +20,10 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
-from .quant import (ActQuantizer, Int8ActPerTensorFloat, Int8WeightPerTensorFloat, Uint8ActPerTensorFloat,
-                    WeightQuantizer)
+from .function.ops import max_int
+from .function.ops_ste import ceil_ste
+from .quant import (ActQuantizer, BiasQuantizer, Int8ActPerTensorFloat, Int8WeightPerTensorFloat, TruncQuantizer,
+                    TruncTo8bit, Uint8ActPerTensorFloat, WeightQuantizer)
 
 
 class QuantTensor(NamedTuple):
@@ -32,6 +35,30 @@ class QuantTensor(NamedTuple):
     signed: Optional[bool] = None
     training: Optional[bool] = None
 
+    @property
+    def is_not_none(self):
+        return (self.value is not None and self.scale is not None and self.zero_point is not None
+                and self.bit_width is not None and self.signed is not None)
+
+    def set(self, **kwargs):
+        return self._replace(**kwargs)
+
+    def view(self, *args, **kwargs):
+        return self.set(value=self.value.view(*args, **kwargs))
+
+    def reshape(self, *args, **kwargs):
+        return self.set(value=self.value.reshape(*args, **kwargs))
+
+    def flatten(self, *args, **kwargs):
+        return self.set(value=self.value.flatten(*args, **kwargs))
+
+    def size(self, *args, **kwargs):
+        return self.value.size(*args, **kwargs)
+
+    @property
+    def shape(self):
+        return self.value.shape
+
 
 def _filter(prefix: str, kwargs: dict) -> dict:
     """``weight_bit_width=4`` -> ``{'bit_width': 4}`` (src/brevitas/nn/mixin/base.py:64-68)"""
@@ -42,6 +69,10 @@ def _unpack(x: Union[Tensor, QuantTensor]) -> Tensor:
     return x.value if isinstance(x, QuantTensor) else x
 
 
+def _as_quant_tensor(x: Union[Tensor, QuantTensor], training: bool) -> QuantTensor:
+    return x if isinstance(x, QuantTensor) else QuantTensor(x, training=training)
+
+
 class WeightQuantProxy(nn.Module):
     """proxy/parameter_quant.py:65-89: owns ``tensor_quant`` for one layer's weight"""
 
@@ -49,16 +80,71 @@ class WeightQuantProxy(nn.Module):
         super().__init__()
         self.tensor_quant = quantizer.tensor_quant(weight) if quantizer is not None else None
         self.signed = quantizer.signed if quantizer is not None else None
+        self.is_narrow_range = bool(quantizer.narrow_range) if quantizer is not None else False
 
     @property
     def is_quant_enabled(self):
         return self.tensor_quant is not None
+
+    def max_uint_value(self, bit_width):
+        """proxy/parameter_quant.py:61-62"""
+        return max_int(False, self.is_narrow_range, bit_width)
 
     def forward(self, w: Tensor) -> QuantTensor:
         if self.tensor_quant is None:
             return QuantTensor(w)
         out, scale, zero_point, bit_width = self.tensor_quant(w)
         return QuantTensor(out, scale, zero_point, bit_width, self.signed, self.training)
+
+
+class BiasQuantProxy(nn.Module):
+    """proxy/parameter_quant.py:110-176: the bias quantizer may need the accumulator's scale and bit-width"""
+
+    def __init__(self, quantizer: Optional[Type[BiasQuantizer]]):
+        super().__init__()
+        self.tensor_quant = quantizer.tensor_quant() if quantizer is not None else None
+        self.signed = quantizer.signed if quantizer is not None else None
+        self.requires_input_scale = bool(quantizer.requires_input_scale) if quantizer is not None else False
+        self.requires_input_bit_width = bool(quantizer.requires_input_bit_width) if quantizer is not None else False
+
+    @property
+    def is_quant_enabled(self):
+        return self.tensor_quant is not None
+
+    def forward(self, x: Tensor, input_scale: Optional[Tensor] = None, input_bit_width: Optional[Tensor] = None):
+        if self.tensor_quant is None:
+            return QuantTensor(x, training=self.training)
+        if self.requires_input_scale and input_scale is None:
+            raise RuntimeError("Input scale required")
+        if self.requires_input_bit_width and input_bit_width is None:
+            raise RuntimeError("Input bit-width required")
+        if self.requires_input_scale and self.requires_input_bit_width:
+            out = self.tensor_quant(x, input_scale.view(-1), input_bit_width)
+        elif self.requires_input_scale:
+            out = self.tensor_quant(x, input_scale.view(-1))
+        elif not self.requires_input_bit_width:
+            out = self.tensor_quant(x)
+        else:
+            raise RuntimeError("Internally defined bit-width required")
+        return QuantTensor(out[0], out[1], out[2], out[3], self.signed, self.training)
+
+
+class TruncQuantProxy(nn.Module):
+    """proxy/runtime_quant.py:178-198"""
+
+    def __init__(self, quantizer: Optional[Type[TruncQuantizer]]):
+        super().__init__()
+        self.tensor_quant = quantizer.tensor_quant() if quantizer is not None else None
+
+    @property
+    def is_quant_enabled(self):
+        return self.tensor_quant is not None
+
+    def forward(self, x: QuantTensor) -> QuantTensor:
+        if self.tensor_quant is None:
+            return x
+        v, s, zp, bw = self.tensor_quant(x.value, x.scale, x.zero_point, x.bit_width)
+        return QuantTensor(v, s, zp, bw, x.signed, self.training)
 
 
 class FusedActivationQuantProxy(nn.Module):
@@ -136,14 +222,16 @@ class QuantHardTanh(_QuantActLayer):
 
 
 class _QuantWBIOL:
-    """the weight / input / output quantizer plumbing shared by Linear and Conv (nn/quant_layer.py:250-365)"""
+    """the weight / bias / input / output quantizer plumbing shared by Linear and Conv (nn/quant_layer.py:250-365)"""
 
-    def _init_quant(self, weight_quant, input_quant, output_quant, return_quant_tensor, kwargs):
+    def _init_quant(self, weight_quant, bias_quant, input_quant, output_quant, return_quant_tensor, kwargs):
         self.return_quant_tensor = return_quant_tensor
         wq = weight_quant.let(**_filter("weight_", kwargs)) if weight_quant else None
+        bq = bias_quant.let(**_filter("bias_", kwargs)) if bias_quant else None
         iq = input_quant.let(**_filter("input_", kwargs)) if input_quant else None
         oq = output_quant.let(**_filter("output_", kwargs)) if output_quant else None
         self.weight_quant = WeightQuantProxy(wq, self.weight)
+        self.bias_quant = BiasQuantProxy(bq)
         self.input_quant = ActQuantProxy(iq, None)
         self.output_quant = ActQuantProxy(oq, None)
 
@@ -151,15 +239,35 @@ class _QuantWBIOL:
         return self.weight_quant(self.weight)
 
     def _forward(self, x, inner):
-        x = _unpack(x)
-        if self.input_quant.is_quant_enabled:
-            x = self.input_quant(x).value
-        w = self.quant_weight().value
-        out = inner(x, w, self.bias)
+        """forward_impl of the reference (nn/quant_layer.py:302-365): accumulator scale = weight scale x input scale,
+        accumulator bit-width from max_acc_bit_width, optional bias quantization against them"""
+        inp = _as_quant_tensor(x, self.training)
+        quant_input = self.input_quant(inp.value) if self.input_quant.is_quant_enabled else inp
+        quant_weight = self.quant_weight()
+        output_scale = output_bit_width = output_zero_point = output_signed = None
+        if quant_input.bit_width is not None and quant_weight.bit_width is not None:
+            output_bit_width = self.max_acc_bit_width(quant_input.bit_width, quant_weight.bit_width)
+        if quant_input.scale is not None and quant_weight.scale is not None:
+            shape = (1, -1) + (1,) * (quant_input.value.dim() - 2)            # compute_channel_view_shape(inp, 1)
+            output_scale = quant_weight.scale.view(shape) * quant_input.scale.view(shape)
+        if quant_input.signed is not None:
+            output_signed = bool(quant_input.signed or quant_weight.signed)
+        if self.bias is not None:
+            quant_bias = self.bias_quant(self.bias, output_scale, output_bit_width)
+            out = inner(quant_input.value, quant_weight.value, quant_bias.value)
+            if quant_bias.bit_width is not None and output_bit_width is not None:
+                output_bit_width = torch.where(quant_bias.bit_width > output_bit_width, quant_bias.bit_width,
+                                               output_bit_width) + 1
+        else:
+            out = inner(quant_input.value, quant_weight.value, None)
+        if self.return_quant_tensor and not self.output_quant.is_quant_enabled and quant_input.zero_point is not None:
+            output_zero_point = quant_input.zero_point
         if self.output_quant.is_quant_enabled:
             q = self.output_quant(out)
             return q if self.return_quant_tensor else q.value
-        return QuantTensor(out) if self.return_quant_tensor else out
+        if self.return_quant_tensor:
+            return QuantTensor(out, output_scale, output_zero_point, output_bit_width, output_signed, self.training)
+        return out
 
 
 class QuantLinear(_QuantWBIOL, nn.Linear):
@@ -168,9 +276,13 @@ class QuantLinear(_QuantWBIOL, nn.Linear):
     def __init__(self, in_features, out_features, bias=True, weight_quant=Int8WeightPerTensorFloat, bias_quant=None,
                  input_quant=None, output_quant=None, return_quant_tensor=False, **kwargs):
         nn.Linear.__init__(self, in_features, out_features, bias)
-        if bias_quant is not None:
-            raise NotImplementedError("bias quantizers need the input scale (SURVEY.md §8f rank 2)")
-        self._init_quant(weight_quant, input_quant, output_quant, return_quant_tensor, kwargs)
+        self._init_quant(weight_quant, bias_quant, input_quant, output_quant, return_quant_tensor, kwargs)
+
+    def max_acc_bit_width(self, input_bit_width, weight_bit_width):
+        """nn/quant_linear.py:68-73"""
+        max_input_val = max_int(bit_width=input_bit_width, signed=False, narrow_range=False)
+        max_fc_val = self.weight_quant.max_uint_value(weight_bit_width)
+        return ceil_ste(torch.log2(max_input_val * max_fc_val * self.in_features))
 
     def forward(self, x):
         return self._forward(x, F.linear)
@@ -183,10 +295,48 @@ class QuantConv2d(_QuantWBIOL, nn.Conv2d):
                  weight_quant=Int8WeightPerTensorFloat, bias_quant=None, input_quant=None, output_quant=None,
                  return_quant_tensor=False, **kwargs):
         nn.Conv2d.__init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
-        if bias_quant is not None:
-            raise NotImplementedError("bias quantizers need the input scale (SURVEY.md §8f rank 2)")
-        self._init_quant(weight_quant, input_quant, output_quant, return_quant_tensor, kwargs)
+        self._init_quant(weight_quant, bias_quant, input_quant, output_quant, return_quant_tensor, kwargs)
+
+    def max_acc_bit_width(self, input_bit_width, weight_bit_width):
+        """nn/quant_conv.py:199-206"""
+        max_uint_input = max_int(bit_width=input_bit_width, signed=False, narrow_range=False)
+        max_kernel_val = self.weight_quant.max_uint_value(weight_bit_width)
+        group_size = self.out_channels // self.groups
+        kernel_size = self.kernel_size[0] * self.kernel_size[1]
+        return ceil_ste(torch.log2(max_uint_input * max_kernel_val * kernel_size * group_size))
 
     def forward(self, x):
         return self._forward(
             x, lambda a, w, b: F.conv2d(a, w, b, self.stride, self.padding, self.dilation, self.groups))
+
+
+class QuantAvgPool2d(nn.AvgPool2d):
+    """nn/quant_avg_pool.py:21-73: average pool on a QuantTensor, the sum rescaled back to integers and its extra
+    bits truncated (``TruncTo8bit`` by default; ``bit_width=...`` refines it)"""
+
+    def __init__(self, kernel_size, stride=None, trunc_quant=TruncTo8bit, return_quant_tensor=True, **kwargs):
+        nn.AvgPool2d.__init__(self, kernel_size=kernel_size, stride=stride)
+        self.return_quant_tensor = return_quant_tensor
+        tq = trunc_quant.let(**{k[len("trunc_"):] if k.startswith("trunc_") else k: v for k, v in kwargs.items()}) \
+            if trunc_quant else None
+        self.trunc_quant = TruncQuantProxy(tq)
+
+    @property
+    def _avg_scaling(self):
+        if isinstance(self.kernel_size, tuple):
+            return self.kernel_size[0] * self.kernel_size[1]
+        return self.kernel_size * self.kernel_size
+
+    def max_acc_bit_width(self, input_bit_width):
+        max_uint_input = max_int(bit_width=input_bit_width, signed=False, narrow_range=False)
+        return ceil_ste(torch.log2(max_uint_input * self._avg_scaling))
+
+    def forward(self, x):
+        x = _as_quant_tensor(x, self.training)
+        x = x.set(value=nn.AvgPool2d.forward(self, x.value))
+        if self.trunc_quant.is_quant_enabled:
+            assert x.is_not_none, "QuantAvgPool2d needs a QuantTensor input (value, scale, zero-point, bit-width, sign)"
+            x = x.set(value=x.value * self._avg_scaling)           # remove the averaging: back to a sum of integers
+            x = x.set(bit_width=self.max_acc_bit_width(x.bit_width))
+            x = self.trunc_quant(x)
+        return x if self.return_quant_tensor else x.value

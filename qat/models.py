@@ -5,9 +5,9 @@
                    nn/quant_conv.py:129), every ReLU -> QuantReLU (default Uint8ActPerTensorFloat,
                    nn/quant_activation.py:18), Linear -> QuantLinear (the reference has no ResNet-18)
 * ``mobilenet_v1`` src/brevitas_examples/imagenet_classification/models/mobilenetv1.py:76-184 with
-                   CommonIntWeightPerChannelQuant / CommonUintActQuant (models/common.py:10-47); the truncating
-                   average pool and the integer bias of the classifier need the input scale and
-                   run un-quantized here -- stated wherever a number from this model is reported.
+                   CommonIntWeightPerChannelQuant / CommonUintActQuant (models/common.py:10-47), QuantTensor-carrying
+                   activations, the truncating ``QuantAvgPool2d`` and the ``IntBias`` classifier (accumulator scale and
+                   bit-width from the input QuantTensor), as in the reference.
 """
 from functools import reduce
 from operator import mul
@@ -15,8 +15,8 @@ from operator import mul
 import torch
 from torch import nn
 
-from brevitas_b200.nn import QuantConv2d, QuantIdentity, QuantLinear, QuantReLU
-from brevitas_b200.quant import (ActQuantizer, Int8WeightPerTensorFloat, Uint8ActPerTensorFloatMaxInit,
+from brevitas_b200.nn import QuantAvgPool2d, QuantConv2d, QuantIdentity, QuantLinear, QuantReLU
+from brevitas_b200.quant import (ActQuantizer, IntBias, Int8WeightPerTensorFloat, Uint8ActPerTensorFloatMaxInit,
                                  WeightQuantizer)
 
 
@@ -220,7 +220,8 @@ class ConvBlock(nn.Module):
         self.bn = nn.BatchNorm2d(out_channels, eps=bn_eps)
         self.activation = QuantReLU(act_quant=CommonUintActQuant, bit_width=act_bit_width,
                                     per_channel_broadcastable_shape=(1, out_channels, 1, 1),
-                                    scaling_per_output_channel=activation_scaling_per_channel)
+                                    scaling_per_output_channel=activation_scaling_per_channel,
+                                    return_quant_tensor=True)
 
     def forward(self, x):
         return self.activation(self.bn(self.conv(x)))
@@ -259,9 +260,9 @@ class MobileNetV1(nn.Module):
                 stage.add_module(f'unit{j + 1}', DwsConvBlock(cin, cout, stride, bit_width, per_channel))
                 cin = cout
             self.features.add_module(f'stage{i + 1}', stage)
-        self.final_pool = nn.AvgPool2d(7, 1)            # QuantAvgPool2d (trunc) in the reference: next-tier, see module doc
-        self.output = QuantLinear(cin, num_classes, bias=True, weight_quant=CommonIntWeightPerTensorQuant,
-                                  weight_bit_width=bit_width)
+        self.final_pool = QuantAvgPool2d(kernel_size=7, stride=1, bit_width=bit_width)
+        self.output = QuantLinear(cin, num_classes, bias=True, bias_quant=IntBias,
+                                  weight_quant=CommonIntWeightPerTensorQuant, weight_bit_width=bit_width)
 
     def forward(self, x):
         x = self.final_pool(self.features(x))

@@ -101,9 +101,49 @@ def test_mobilenet_v1_step_and_learned_per_channel_scales():
     s = m.features.init_block.activation.act_quant.fused_activation_quant_proxy.tensor_quant.scaling_impl
     assert s.value.shape == (1, 32, 1, 1) and s.value.grad is not None
     a = m.features.init_block.activation(m.features.init_block.bn(m.features.init_block.conv(x)))
+    assert a.is_not_none and a.signed is False and float(a.bit_width) == 4.0      # QuantTensor, as in the reference
+    a = a.value
     thr = 2 ** s.value.detach()
     codes = a / (thr / 15.0)
     assert float((codes - codes.round()).abs().max()) < 1e-3 and float(codes.max()) <= 15.001 and float(codes.min()) >= 0
+
+
+def test_avg_pool_trunc_and_int_bias_wiring():
+    """QuantReLU(return_quant_tensor) -> QuantAvgPool2d(trunc) -> QuantLinear(bias_quant=IntBias): the tail of the
+    reference's MobileNetV1 (mobilenetv1.py:153-159) against the formulas of nn/quant_avg_pool.py:55-73,
+    nn/quant_layer.py:302-345 and nn/quant_linear.py:68-73 written out with plain torch ops."""
+    import math
+    import torch.nn.functional as F
+    from brevitas_b200.nn import QuantAvgPool2d, QuantLinear, QuantReLU
+    from brevitas_b200.quant import IntBias
+    from qat.models import CommonIntWeightPerTensorQuant, CommonUintActQuant
+    torch.manual_seed(3)
+    act = QuantReLU(act_quant=CommonUintActQuant, bit_width=4, per_channel_broadcastable_shape=(1, 8, 1, 1),
+                    scaling_per_output_channel=False, return_quant_tensor=True).cuda()
+    pool = QuantAvgPool2d(kernel_size=7, stride=1, bit_width=4).cuda()
+    fc = QuantLinear(8, 5, bias=True, bias_quant=IntBias, weight_quant=CommonIntWeightPerTensorQuant,
+                     weight_bit_width=4).cuda()
+    with torch.no_grad():
+        fc.bias.copy_(torch.randn(5) * 0.7)
+    x = (torch.randn(3, 8, 7, 7, device="cuda") * 3).requires_grad_(True)
+    q = act(x)
+    s_in = q.scale
+    assert float(q.bit_width) == 4.0 and float(q.zero_point) == 0.0
+    p = pool(q)
+    # reference formulas: sum of integers -> 10-bit accumulator (ceil(log2(15 * 49))) -> drop 6 LSBs with floor
+    acc_bits = math.ceil(math.log2(15 * 49))
+    summed = F.avg_pool2d(q.value, 7, 1) * 49
+    expect = torch.floor(torch.round(summed / s_in) / 2.0 ** (acc_bits - 4)) * s_in
+    assert torch.equal(p.value, expect) and float(p.bit_width) == 4.0 and p.scale is s_in
+    out = fc(p.view(3, -1))
+    wq = fc.quant_weight()
+    out_scale = wq.scale.view(1, -1) * s_in.view(1, -1)
+    acc_bits_fc = math.ceil(math.log2(15 * 7 * 8))                           # max_uint_value(4 bits, narrow) = 7
+    lo, hi = -2.0 ** (acc_bits_fc - 1), 2.0 ** (acc_bits_fc - 1) - 1
+    bias_q = torch.clamp(torch.round(fc.bias / out_scale.view(-1)), lo, hi) * out_scale.view(-1)
+    assert torch.equal(out, F.linear(p.value.view(3, -1), wq.value, bias_q))
+    out.sum().backward()
+    assert x.grad is not None and fc.bias.grad is not None and torch.isfinite(x.grad).all()
 
 
 def test_per_token_dynamic_quantizer_full_size():
