@@ -52,6 +52,38 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _dense(t: torch.Tensor) -> torch.Tensor:
+    """Row-major OR channels-last dense tensors are used as they are: the element-wise kernels only need x, the
+    gradient and the output to share one dense layout, and the per-row kernels only need dim 0 to be the slowest
+    dimension in memory (true for both).  Anything else is made contiguous."""
+    if t.is_contiguous():
+        return t
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    if t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d):
+        return t
+    return t.contiguous()
+
+
+def _like(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """the gradient laid out exactly like x (a copy only if autograd handed it over in another layout)"""
+    if g.shape == x.shape and g.stride() == x.stride():
+        return g
+    if x.is_contiguous():
+        return g.contiguous()
+    out = torch.empty_like(x)
+    out.copy_(g)
+    return out
+
+
+def _dense_for_scale(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """channels-last x is only usable with one scale or a scale per dim-0 slice ([O,1,1,1]); a [1,C,1,1] scale
+    indexes the logical NCHW order"""
+    if scale.numel() == 1 or all(d == 1 for d in scale.shape[-(x.dim() - 1):]) and scale.dim() == x.dim():
+        return _dense(x)
+    return _c(x)
+
+
 def _launch(dev, name, *args):
     global launch_count
     launch_count += 1
@@ -164,7 +196,7 @@ def scalar_clamp_min(x, min_val: float):
 
 def int_quant_fwd(x, scale, zero_point: float, qmin: float, qmax: float, round_mode: int, want_codes=False):
     dev = _check_cuda(x, scale)
-    x, scale = _c(x), _c(scale)
+    x, scale = _dense_for_scale(x, scale), _c(scale)
     inner, count, sdt = _scale_args(x, scale)
     y = torch.empty_like(x)
     codes = torch.empty_like(x) if want_codes else None
@@ -175,7 +207,8 @@ def int_quant_fwd(x, scale, zero_point: float, qmin: float, qmax: float, round_m
 
 def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, want_gscale):
     dev = _check_cuda(gy, x, scale)
-    gy, x, scale = _c(gy), _c(x), _c(scale)
+    x, scale = _dense_for_scale(x, scale), _c(scale)
+    gy = _like(gy, x)
     inner, count, sdt = _scale_args(x, scale)
     gx = torch.empty_like(x)
     gs = torch.empty(count, dtype=torch.float32, device=dev) if want_gscale else None
@@ -189,7 +222,7 @@ def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, 
 def rows_absmax_int_quant_fwd(x, rows, cols, scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode,
                               want_absmax=False):
     dev = _check_cuda(x)
-    x = _c(x)
+    x = _dense(x) if (x.dim() >= 1 and x.shape[0] == rows) else _c(x)     # rows must be dim-0 slices to keep a layout
     assert rows * cols == x.numel()
     y = torch.empty_like(x)
     scale = torch.empty(rows, dtype=x.dtype, device=dev)
@@ -202,7 +235,8 @@ def rows_absmax_int_quant_fwd(x, rows, cols, scaling_min_val, int_threshold, zer
 def rows_absmax_int_quant_bwd(gy, x, scale, gscale, rows, cols, int_threshold, zero_point, qmin, qmax, round_mode,
                               clamp_mode):
     dev = _check_cuda(gy, x, scale, gscale)
-    gy, x, scale = _c(gy), _c(x), _c(scale)
+    x = _dense(x) if (x.dim() >= 1 and x.shape[0] == rows) else _c(x)
+    gy, scale = _like(gy, x), _c(scale)
     if gscale is not None:
         gscale = _c(gscale)
     gx = torch.empty_like(x)
@@ -218,7 +252,7 @@ def _workspace(dev):
 
 def tensor_absmax_int_quant_fwd(x, scale_dtype, scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode):
     dev = _check_cuda(x)
-    x = _c(x)
+    x = _dense(x)
     y = torch.empty_like(x)
     scale = torch.empty((), dtype=scale_dtype, device=dev)
     absmax = torch.empty((), dtype=x.dtype, device=dev)
@@ -232,7 +266,8 @@ def tensor_absmax_int_quant_fwd(x, scale_dtype, scaling_min_val, int_threshold, 
 def tensor_absmax_int_quant_bwd(gy, x, scale, absmax, gscale, int_threshold, zero_point, qmin, qmax, round_mode,
                                 clamp_mode):
     dev = _check_cuda(gy, x, scale, absmax, gscale)
-    gy, x = _c(gy), _c(x)
+    x = _dense(x)
+    gy = _like(gy, x)
     gx = torch.empty_like(x)
     ws = _workspace(dev)
     _launch(dev, "bvb_tensor_absmax_int_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), absmax.data_ptr(),

@@ -266,7 +266,14 @@ class MeanLearnedSigmaStd(nn.Module):
 
 def absmax_plan(stats_impl: nn.Module, view_impl: nn.Module, x: Tensor) -> Optional[AbsMaxPlan]:
     """Return the fused geometry when (view, AbsMax) reduces contiguous trailing elements of ``x``."""
-    if type(stats_impl) is not AbsMax or not x.is_contiguous() or x.numel() == 0:
+    if type(stats_impl) is not AbsMax or x.numel() == 0:
+        return None
+    # channels-last tensors keep dim 0 as the slowest dimension in memory: whole-tensor and per-dim-0-slice statistics
+    # (and the element-wise quantization) do not care about the order inside a slice
+    row_major = x.is_contiguous()
+    dense = row_major or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)) \
+        or (x.dim() == 5 and x.is_contiguous(memory_format=torch.channels_last_3d))
+    if not dense:
         return None
     dim = stats_impl.stats_reduce_dim
     if type(view_impl) is fw.OverTensorView and dim is None:
@@ -276,6 +283,8 @@ def absmax_plan(stats_impl: nn.Module, view_impl: nn.Module, x: Tensor) -> Optio
             return AbsMaxPlan('rows', x.shape[0], x.numel() // x.shape[0])
     if type(view_impl) is fw.OverBatchOverTensorView and dim in (1, -1) and x.dim() >= 1:
         return AbsMaxPlan('rows', x.shape[0], x.numel() // x.shape[0])
+    if not row_major:
+        return None
     if type(view_impl) is fw.OverBatchOverOutputChannelView and dim in (2, -1) and x.dim() >= 2:
         rows = x.shape[0] * x.shape[1]
         return AbsMaxPlan('rows', rows, x.numel() // rows)

@@ -125,7 +125,7 @@ def train_step(model, raw_model, x, y, loss_fn, opt):
     return loss
 
 
-def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False):
+def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False, channels_last=False):
     """returns a dict with samples/s (all ranks), ms/step, kernel-launch count per step of OUR kernels"""
     import brevitas_b200  # noqa: F401
     from brevitas_b200 import _kernels as K
@@ -144,7 +144,7 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
         # if that is not the legacy default stream, so the whole life of the model runs on a side stream
         torch.cuda.set_stream(torch.cuda.Stream(device))
     torch.manual_seed(1234)                               # identical initial weights on every rank
-    raw, loss_fn, spec = build(name, device, collect_stats_steps)
+    raw, loss_fn, spec = build(name, device, collect_stats_steps, channels_last=channels_last)
     model = raw
     if world > 1 and not graph:
         model = nn.parallel.DistributedDataParallel(raw, device_ids=[local], gradient_as_bucket_view=True,
@@ -152,6 +152,8 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
     opt = make_optimizer(raw, spec, capturable=graph)
     model.train()
     batches = [make_batch(spec, batch, device, 100 + rank * 7 + i) for i in range(2)]
+    if channels_last:       # NHWC end to end: cuDNN's native layout, and the fake-quant kernels take it in place
+        batches = [(x.contiguous(memory_format=torch.channels_last), y) for x, y in batches]
     # warm-up runs past the statistics-collection phase of the activation quantizers (steady state)
     for i in range(max(warmup, collect_stats_steps + 2)):
         loss = train_step(model, raw, *batches[i % 2], loss_fn, opt)
@@ -185,6 +187,7 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
     return {"model": name, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
             "samples_per_s": round(world * batch / (ms * 1e-3), 1), "fakequant_launches_per_step": launches,
             "final_loss": round(loss_val, 4), "dtype": "f32", "data": "synthetic",
+            "memory_format": "channels_last" if channels_last else "contiguous",
             "phase": f"steady state (after {collect_stats_steps} collect steps)",
             "step": "one CUDA graph (fwd+loss+bwd+allreduce+optimizer)" if graph else "eager launches"
                     + (" + DDP bucketed NCCL all-reduce" if world > 1 else "")}
@@ -198,10 +201,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--collect-stats-steps", type=int, default=2)
     ap.add_argument("--graph", action="store_true", help="capture the whole step in a CUDA graph")
+    ap.add_argument("--channels-last", action="store_true", help="NHWC activations and conv weights")
     a = ap.parse_args()
     os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
     os.environ.setdefault("NCCL_IB_DISABLE", "1")
-    res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps, graph=a.graph)
+    res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps, graph=a.graph, channels_last=a.channels_last)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(res))
     import torch.distributed as dist

@@ -339,6 +339,43 @@ def test_host_pipeline_matches_device_path(K, rows, cols, chunk, dtype):
         weight_fake_quant_fwd_bwd_host(hx.cuda(), hg.cuda())
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_channels_last_layouts(K, dtype):
+    """channels-last activations (one scale) and conv weights (a scale per output channel, fused abs-max) go through
+    the kernels in place -- no NCHW copy -- and give the bits of the row-major call, in the caller's layout."""
+    T = TDT[dtype]
+    x = torch.from_numpy(rand_np((4, 16, 9, 9), 31, 20.0)).to(T).cuda()
+    g = torch.from_numpy(rand_np((4, 16, 9, 9), 32, 1.0)).to(T).cuda()
+    s = torch.tensor(0.21, device="cuda").to(T)
+    xcl, gcl = x.contiguous(memory_format=torch.channels_last), g.contiguous(memory_format=torch.channels_last)
+    y, ycl = K.int_quant_fwd(x, s, 0.0, 0.0, 255.0, 0), K.int_quant_fwd(xcl, s, 0.0, 0.0, 255.0, 0)
+    assert ycl.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, ycl)
+    (gx, gs), (gxcl, gscl) = K.int_quant_bwd(g, x, s, 0.0, 0.0, 255.0, 0, 1, True), K.int_quant_bwd(g, xcl, s, 0.0, 0.0, 255.0, 0, 1, True)
+    assert gxcl.is_contiguous(memory_format=torch.channels_last) and torch.equal(gx, gxcl)      # row-major g, CL x
+    assert torch.equal(gx, K.int_quant_bwd(gcl, xcl, s, 0.0, 0.0, 255.0, 0, 1, True)[0])
+    assert abs(float(gs) - float(gscl)) <= 1e-3 * (abs(float(gs)) + 1.0)
+    # a [1,C,1,1] scale indexes the logical NCHW order: the wrapper falls back to a row-major copy
+    sc = (torch.rand(1, 16, 1, 1, device="cuda") * 0.2 + 0.1).to(T)
+    assert torch.equal(K.int_quant_fwd(x, sc, 0.0, -128.0, 127.0, 0), K.int_quant_fwd(xcl, sc, 0.0, -128.0, 127.0, 0))
+    # conv weight [O, I, kh, kw]: rows are dim-0 slices in both layouts
+    w = torch.from_numpy(rand_np((24, 16, 3, 3), 33, 0.3)).to(T).cuda()
+    gw = torch.from_numpy(rand_np((24, 16, 3, 3), 34, 1.0)).to(T).cuda()
+    wcl = w.contiguous(memory_format=torch.channels_last)
+    y, sc_r, _ = K.rows_absmax_int_quant_fwd(w, 24, 144, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+    ycl, sc_c, _ = K.rows_absmax_int_quant_fwd(wcl, 24, 144, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+    assert ycl.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, ycl) and torch.equal(sc_r, sc_c)
+    gx = K.rows_absmax_int_quant_bwd(gw, w, sc_r, None, 24, 144, 127.0, 0.0, -127.0, 127.0, 0, 0)
+    gxcl = K.rows_absmax_int_quant_bwd(gw, wcl, sc_c, None, 24, 144, 127.0, 0.0, -127.0, 127.0, 0, 0)
+    # the element receiving the abs-max gradient is the FIRST maximum in memory order: identical unless a row has ties
+    amax = w.abs().reshape(24, -1).amax(dim=1).view(24, 1, 1, 1)
+    off = w.abs() != amax
+    assert torch.equal(torch.where(off, gx, torch.zeros_like(gx)), torch.where(off, gxcl, torch.zeros_like(gx)))
+    assert torch.allclose(gx.float(), gxcl.float(), rtol=2e-2, atol=2e-2)
+    y, st, am = K.tensor_absmax_int_quant_fwd(w, torch.float32, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+    ycl, stc, _ = K.tensor_absmax_int_quant_fwd(wcl, torch.float32, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+    assert torch.equal(y, ycl) and torch.equal(st, stc)
+
+
 def test_fp32_scalar_scale_with_lowp_input(K):
     """fp32 quantizer modules fed bf16 activations: ATen's mul/div keep the fp32 0-dim scale in opmath"""
     x = torch.randn(4099, generator=torch.Generator().manual_seed(3)).mul(20).to(torch.bfloat16)
