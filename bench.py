@@ -472,7 +472,7 @@ def main():
         qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
         qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
         if world > 1 or args.qat_all:
-            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3)            # BASELINE.json configs[4]
+            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True)   # BASELINE.json configs[4]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -506,7 +506,7 @@ def main():
         "e2e": {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4,
                 "d2h_bytes_per_step": n * 4 + ROWS * 4, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
                 "api": "brevitas_b200.host_pipeline.weight_fake_quant_fwd_bwd_host (C-ABI bvb_host_rows_fakequant_fwd_bwd): "
-                       "pinned host W and G in, dW and scales out, 16 row chunks pipelined over 3 streams",
+                       "pinned host W and G in, dW and scales out, 8 row chunks pipelined over 3 streams",
                 "module_api": {"value": round(e2e_module_val, 2), "ms_per_step": round(e2e_module_ms, 3),
                                "api": "RescalingIntQuant(w) + autograd backward with whole-tensor H2D / D2H copies"}},
         "gpu_launches": launches,

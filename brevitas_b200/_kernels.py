@@ -76,12 +76,31 @@ def _like(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _is_channels_last(x: torch.Tensor) -> bool:
+    return (not x.is_contiguous()) and ((x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)) or
+                                        (x.dim() == 5 and x.is_contiguous(memory_format=torch.channels_last_3d)))
+
+
+def _is_dim1_channel_scale(x: torch.Tensor, scale: torch.Tensor) -> bool:
+    return (scale.dim() == x.dim() and x.dim() >= 3 and scale.shape[1] == x.shape[1]
+            and scale.numel() == scale.shape[1])
+
+
 def _dense_for_scale(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
-    """channels-last x is only usable with one scale or a scale per dim-0 slice ([O,1,1,1]); a [1,C,1,1] scale
-    indexes the logical NCHW order"""
-    if scale.numel() == 1 or all(d == 1 for d in scale.shape[-(x.dim() - 1):]) and scale.dim() == x.dim():
+    """channels-last x is used in place with one scale, a scale per dim-0 slice ([O,1,1,1]) or a scale per channel
+    ([1,C,1,1]: element i of the NHWC memory uses scale[i % C]); other patterns index the logical NCHW order"""
+    if scale.numel() == 1 or (scale.dim() == x.dim() and all(d == 1 for d in scale.shape[1:])):
         return _dense(x)
+    if _is_channels_last(x) and _is_dim1_channel_scale(x, scale):
+        return x
     return _c(x)
+
+
+def _scale_pattern(x: torch.Tensor, scale: torch.Tensor):
+    inner, count, sdt = _scale_args(x, scale)
+    if _is_channels_last(x) and scale.numel() > 1 and _is_dim1_channel_scale(x, scale):
+        inner, count = 1, scale.numel()           # memory order is N, H, W, C
+    return inner, count, sdt
 
 
 def _launch(dev, name, *args):
@@ -197,7 +216,7 @@ def scalar_clamp_min(x, min_val: float):
 def int_quant_fwd(x, scale, zero_point: float, qmin: float, qmax: float, round_mode: int, want_codes=False):
     dev = _check_cuda(x, scale)
     x, scale = _dense_for_scale(x, scale), _c(scale)
-    inner, count, sdt = _scale_args(x, scale)
+    inner, count, sdt = _scale_pattern(x, scale)
     y = torch.empty_like(x)
     codes = torch.empty_like(x) if want_codes else None
     _launch(dev, "bvb_int_quant_fwd", x.data_ptr(), scale.data_ptr(), y.data_ptr(), _ptr(codes), x.numel(), inner,
@@ -209,7 +228,7 @@ def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, 
     dev = _check_cuda(gy, x, scale)
     x, scale = _dense_for_scale(x, scale), _c(scale)
     gy = _like(gy, x)
-    inner, count, sdt = _scale_args(x, scale)
+    inner, count, sdt = _scale_pattern(x, scale)
     gx = torch.empty_like(x)
     gs = torch.empty(count, dtype=torch.float32, device=dev) if want_gscale else None
     _launch(dev, "bvb_int_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), gx.data_ptr(), _ptr(gs),

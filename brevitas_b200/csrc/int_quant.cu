@@ -374,6 +374,91 @@ __global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------
+// provided scale per CHANNEL of a channels-last tensor (NHWC activations with a [1,C,1,1] scale: the learned
+// per-channel activation scales of MobileNetV1): element i uses scale[i % C].  Every 16-byte vector spans V
+// consecutive channels, and with C | blockDim * V a thread meets the SAME V channels at every grid-stride step: the
+// V divisor set-ups are hoisted out of the loop like a row's single one, and d(scale) is accumulated in V registers,
+// reduced through shared memory, then C atomics per CTA.
+// ------------------------------------------------------------------------------------------------------
+constexpr int CL_THREADS = 256;
+constexpr int CL_UNROLL = 4;
+constexpr int CL_MAX_C = 2048;
+
+template <typename T, int RM, bool BWD>
+__global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
+        const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ out,
+        T* __restrict__ codes, float* gscale_out, int64_t nvec, int C, int masked, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ float sacc[BWD ? CL_MAX_C : 1];
+    const bool want_gs = BWD && gscale_out != nullptr;
+    const int c0 = (int)(((int64_t)threadIdx.x * V) % C);
+    if (want_gs) {
+        for (int c = threadIdx.x; c < C; c += CL_THREADS) sacc[c] = 0.f;
+        __syncthreads();
+    }
+    float sv[V];
+    {
+        const uint4 qs = *reinterpret_cast<const uint4*>(scale + c0);      // c0 is a multiple of V: 16-byte aligned
+        DT<T>::unpack(qs, sv);
+    }
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const uint4* gv = reinterpret_cast<const uint4*>(BWD ? gy : x);
+    uint4* ov = reinterpret_cast<uint4*>(out);
+    uint4* cv = reinterpret_cast<uint4*>(codes);
+    const int64_t stride = (int64_t)gridDim.x * CL_THREADS;
+    for (int64_t v0 = (int64_t)blockIdx.x * CL_THREADS + threadIdx.x; v0 < nvec; v0 += stride * CL_UNROLL) {
+        uint4 qx[CL_UNROLL], qg[CL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < CL_UNROLL; ++u) {
+            const int64_t v = v0 + (int64_t)u * stride;
+            if (v < nvec) {
+                qx[u] = ldg_stream(xv + v);
+                if (BWD) qg[u] = ldg_stream(gv + v);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CL_UNROLL; ++u) {
+            const int64_t v = v0 + (int64_t)u * stride;
+            if (v < nvec) {
+                float ex[V], eo[V], ek[V];
+                DT<T>::unpack(qx[u], ex);
+                if (BWD) {
+                    float eg[V];
+                    DT<T>::unpack(qg[u], eg);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const DivBy dv(sv[i], DT<T>::MUL_DIV_EXACT);      // loop-invariant per thread: hoisted by the compiler
+                        eo[i] = bwd_elem<T, RM>(eg[i], ex[i], dv, dv.approx_recip(), p, masked, want_gs, acc[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const DivBy dv(sv[i], DT<T>::MUL_DIV_EXACT);
+                        float t1, t3, t5;
+                        to_int_chain<T, RM>(ex[i], dv, p, t1, t3, t5);
+                        float t6 = fsub(t5, p.zp);
+                        if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
+                        eo[i] = fmul(t6, dv.b);
+                        ek[i] = t5;
+                    }
+                    if (codes) stg_stream(cv + v, DT<T>::pack(ek));
+                }
+                stg_stream(ov + v, DT<T>::pack(eo));
+            }
+        }
+    }
+    if (want_gs) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) atomicAdd(&sacc[c0 + i], acc[i]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += CL_THREADS) atomicAdd(gscale_out + c, sacc[c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // fused per-row abs-max + quant-dequant, TMA-staged (the C2 / C3 headline kernel)
 // dynamic smem: [0,64) mbarriers | [64,192) reduction scratch | [256, ...) `stages` row buffers
 // ------------------------------------------------------------------------------------------------------
@@ -1058,6 +1143,15 @@ static int launch_int_quant_fwd(const void* x, const void* scale, void* y, void*
             nullptr, (const T*)x, (const T*)scale, (T*)y, (T*)codes, nullptr, nplanes, inner, count, group, pv, 0, p);
         return check_launch("bvb_int_quant_fwd");
     }
+    if (smode == 1 && inner == 1 && vec_ok && aligned16(scale) && count <= CL_MAX_C && (count % V) == 0 &&
+        ((int64_t)CL_THREADS * V) % count == 0 && (n % count) == 0 && n >= (int64_t)CL_THREADS * V) {
+        // channels-last tensor, one scale per channel
+        const int64_t nv = n / V;
+        unsigned grid = stream_grid(nv, CL_THREADS * CL_UNROLL);
+        int_quant_chanlast_kernel<T, RM, false><<<grid, CL_THREADS, 0, st>>>(
+            nullptr, (const T*)x, (const T*)scale, (T*)y, (T*)codes, nullptr, nv, (int)count, 0, p);
+        return check_launch("bvb_int_quant_fwd");
+    }
     if (smode == 1 && (inner % V) != 0) vec_ok = false;
     if (vec_ok) nvec = n / V;
     if (nvec > 0) {
@@ -1144,6 +1238,14 @@ static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale
         int_quant_planes_kernel<T, RM, true><<<(unsigned)grid, PL_THREADS, 0, st>>>(
             (const T*)gy, (const T*)x, (const T*)scale, (T*)gx, nullptr, gscale_out, nplanes, inner, count, group, pv,
             masked, p);
+        return check_launch("bvb_int_quant_bwd");
+    }
+    if (smode == 1 && inner == 1 && vec_ok && aligned16(scale) && count <= CL_MAX_C && (count % V) == 0 &&
+        ((int64_t)CL_THREADS * V) % count == 0 && (n % count) == 0 && n >= (int64_t)CL_THREADS * V) {
+        const int64_t nv = n / V;
+        unsigned grid = stream_grid(nv, CL_THREADS * CL_UNROLL);
+        int_quant_chanlast_kernel<T, RM, true><<<grid, CL_THREADS, 0, st>>>(
+            (const T*)gy, (const T*)x, (const T*)scale, (T*)gx, nullptr, gscale_out, nv, (int)count, masked, p);
         return check_launch("bvb_int_quant_bwd");
     }
     if (smode == 1 && (inner % V) != 0) vec_ok = false;

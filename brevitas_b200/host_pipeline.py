@@ -47,8 +47,8 @@ def weight_fake_quant_fwd_bwd_host(w: torch.Tensor, grad_out: torch.Tensor, *, b
     tag = _DTYPES[w.dtype]
     qmin, qmax = int_range(signed, narrow_range, bit_width, torch.float32)
     int_thr = float(-qmin if (signed and not narrow_range) else qmax)
-    if chunk_rows is None:                      # ~16 chunks: fill/drain of the pipeline costs about 1/16 of the copies
-        chunk_rows = max(1, (rows + 15) // 16)
+    if chunk_rows is None:                      # 8 chunks (measured 7.58 ms on C2; 4: 7.81, 16: 7.71, 32: 8.21, 64: 9.37)
+        chunk_rows = max(1, (rows + 7) // 8)
     pin = torch.cuda.is_available()
     out_grad = torch.empty(w.shape, dtype=w.dtype, pin_memory=pin) if out_grad is None else out_grad
     out_scale = torch.empty((rows,) + (1,) * (w.dim() - 1), dtype=w.dtype, pin_memory=pin) if out_scale is None else out_scale

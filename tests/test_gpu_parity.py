@@ -354,9 +354,21 @@ def test_channels_last_layouts(K, dtype):
     assert gxcl.is_contiguous(memory_format=torch.channels_last) and torch.equal(gx, gxcl)      # row-major g, CL x
     assert torch.equal(gx, K.int_quant_bwd(gcl, xcl, s, 0.0, 0.0, 255.0, 0, 1, True)[0])
     assert abs(float(gs) - float(gscl)) <= 1e-3 * (abs(float(gs)) + 1.0)
-    # a [1,C,1,1] scale indexes the logical NCHW order: the wrapper falls back to a row-major copy
-    sc = (torch.rand(1, 16, 1, 1, device="cuda") * 0.2 + 0.1).to(T)
-    assert torch.equal(K.int_quant_fwd(x, sc, 0.0, -128.0, 127.0, 0), K.int_quant_fwd(xcl, sc, 0.0, -128.0, 127.0, 0))
+    # a [1,C,1,1] scale on NHWC memory is "scale[i % C]": int_quant_chanlast_kernel (hoisted per-thread divisors)
+    for cch, hw in ((16, 9), (64, 5), (24, 4)):          # 24 does not divide 256*V for fp32: row-major fallback
+        xc = torch.from_numpy(rand_np((3, cch, hw, hw + 3), 35, 20.0)).to(T).cuda()
+        gc = torch.from_numpy(rand_np((3, cch, hw, hw + 3), 36, 1.0)).to(T).cuda()
+        sc = (torch.rand(1, cch, 1, 1, device="cuda") * 0.2 + 0.1).to(T)
+        xccl = xc.contiguous(memory_format=torch.channels_last)
+        yr, kr = K.int_quant_fwd(xc, sc, 0.0, 0.0, 255.0, 0, want_codes=True)
+        yc, kc = K.int_quant_fwd(xccl, sc, 0.0, 0.0, 255.0, 0, want_codes=True)
+        assert torch.equal(yr, yc) and torch.equal(kr, kc)
+        gxr, gsr = K.int_quant_bwd(gc, xc, sc, 0.0, 0.0, 255.0, 0, 1, True)
+        gxc, gsc = K.int_quant_bwd(gc, xccl, sc, 0.0, 0.0, 255.0, 0, 1, True)
+        assert torch.equal(gxr, gxc)
+        assert torch.allclose(gsr, gsc, rtol=1e-3 if dtype == "f32" else 5e-2, atol=1e-2)
+        yo = O.int_quant_forward(host(xc), host(sc), 0.0, 0.0, 255.0, "round", dtype)
+        assert_bits_equal(host(yc), yo, "channels-last per-channel vs oracle")
     # conv weight [O, I, kh, kw]: rows are dim-0 slices in both layouts
     w = torch.from_numpy(rand_np((24, 16, 3, 3), 33, 0.3)).to(T).cuda()
     gw = torch.from_numpy(rand_np((24, 16, 3, 3), 34, 1.0)).to(T).cuda()
