@@ -104,28 +104,42 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
         const uint32_t prefix = s_prefix;
         const T* xr = x + row * cols;
         uint32_t* myh = sh[warp];
-        // every lane of a warp runs the same trip count (bounds are rounded up to the block), so the
-        // warp-wide primitives below always see a full, converged warp
+        // Pass 0 counts every element: plain shared atomics on the warp's private histogram (the hardware serialises
+        // same-bin lanes; measured faster than match_any aggregation, whose cost is paid per element).  Later passes
+        // count only the keys below the resolved prefix -- a small minority for the high percentiles this is used
+        // for -- so a warp first votes and skips the histogram update when no lane has a candidate.
         auto visit = [&](float v, bool valid) {
-            uint32_t key = KeyTraits<T>::key(v);
-            bool take = valid && ((pass == 0) || ((key >> (shift + 8)) == prefix));
-            uint32_t bin = take ? ((key >> shift) & 0xffu) : (0x100u + (uint32_t)lane);
-            // warp-aggregated shared atomics: one add per distinct bin per warp instruction
-            uint32_t peers = __match_any_sync(0xffffffffu, bin);
-            if (take && lane == __ffs(peers) - 1) atomicAdd(&myh[bin], (uint32_t)__popc(peers));
+            const uint32_t key = KeyTraits<T>::key(v);
+            if (pass == 0) {
+                if (valid) atomicAdd(&myh[key >> shift], 1u);
+            } else {
+                const bool take = valid && ((key >> (shift + 8)) == prefix);
+                if (__any_sync(0xffffffffu, take)) {
+                    if (take) atomicAdd(&myh[(key >> shift) & 0xffu], 1u);
+                }
+            }
         };
         const int64_t nvec = vec_ok ? cols / V : 0;
         const uint4* xv = reinterpret_cast<const uint4*>(xr);
         const int64_t gstride = (int64_t)gridDim.x * KTH_THREADS;
-        for (int64_t b0 = (int64_t)blockIdx.x * KTH_THREADS; b0 < nvec; b0 += gstride) {
-            const int64_t v0 = b0 + threadIdx.x;
-            const bool valid = v0 < nvec;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (valid) q = ldg_stream(xv + v0);
-            float e[V];
-            DT<T>::unpack(q, e);
+        // KTH_UNROLL independent 16-byte loads in flight per thread; every lane of a warp runs the same trip count
+        // (bounds are rounded up to the block), so the warp votes above always see a full, converged warp
+        for (int64_t b0 = (int64_t)blockIdx.x * KTH_THREADS; b0 < nvec; b0 += gstride * KTH_UNROLL) {
+            uint4 q[KTH_UNROLL];
+            bool ok[KTH_UNROLL];
 #pragma unroll
-            for (int i = 0; i < V; ++i) visit(e[i], valid);
+            for (int u = 0; u < KTH_UNROLL; ++u) {
+                const int64_t v0 = b0 + (int64_t)u * gstride + threadIdx.x;
+                ok[u] = v0 < nvec;
+                q[u] = ok[u] ? ldg_stream(xv + v0) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < KTH_UNROLL; ++u) {
+                float e[V];
+                DT<T>::unpack(q[u], e);
+#pragma unroll
+                for (int i = 0; i < V; ++i) visit(e[i], ok[u]);
+            }
         }
         for (int64_t b0 = nvec * V + (int64_t)blockIdx.x * KTH_THREADS; b0 < cols; b0 += gstride) {
             const int64_t j = b0 + threadIdx.x;

@@ -50,6 +50,9 @@ def main():
         "act_f32_scalar_fwd": (lambda i: K.int_quant_fwd(W[i % NS], s0f, 0.0, 0.0, 255.0, 0), R * C * 8),
         "act_f32_scalar_bwd_gs": (lambda i: K.int_quant_bwd(G[i % 2], W[i % NS], s0f, 0.0, 0.0, 255.0, 0, 1, True), R * C * 12),
         "w_f32_rows_provided_fwd": (lambda i: K.int_quant_fwd(W[i % NS], sch.view(R, 1), 0.0, -127.0, 127.0, 0), R * C * 8),
+        # AbsPercentile (99.999 %) over a whole activation tensor: 4 (fp32) / 2 (bf16) reads by construction
+        "abs_percentile_f32": (lambda i: K.abs_kth_value_rows(W[i % NS].reshape(-1), 1, R * C, int(0.99999 * R * C + 0.5)), R * C * 16),
+        "abs_percentile_bf16": (lambda i: K.abs_kth_value_rows(X[i % NS].reshape(-1), 1, T * D, int(0.99999 * T * D + 0.5)), T * D * 4),
     }
     only = [s for s in a.only.split(",") if s]
     period = 6                                    # lcm of the input rotations above
