@@ -573,6 +573,42 @@ __global__ void rows_fwd_generic_kernel(const T* __restrict__ x, T* __restrict__
     }
 }
 
+// per-row abs-max alone (AbsMax(dim) outside a fused quantizer: AbsMaxAve / AbsMaxL2, statistics over several
+// tracked parameters): 128-bit loads, 4 in flight per thread, sign-split integer maxima; a warp per short row, the
+// CTA per long row.  (The element-wise generic kernel above ran at 1.9 TB/s.)
+constexpr int AMR_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(AMR_THREADS) absmax_rows_vec_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                                       int64_t rows, int64_t row_vecs, int group) {
+    __shared__ uint32_t red[32];
+    const int lane = threadIdx.x & 31;
+    const int gid = (group == 32) ? (threadIdx.x >> 5) : 0;
+    const int gtid = (group == 32) ? lane : threadIdx.x;
+    const int groups_per_cta = AMR_THREADS / group;
+    for (int64_t row = (int64_t)blockIdx.x * groups_per_cta + gid; row < rows; row += (int64_t)gridDim.x * groups_per_cta) {
+        const uint4* xv = reinterpret_cast<const uint4*>(x) + row * row_vecs;
+        AbsMaxAcc<T> am;
+        for (int64_t v0 = gtid; v0 < row_vecs; v0 += (int64_t)group * 4) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t v = v0 + (int64_t)u * group;
+                q[u] = (v < row_vecs) ? ldg_stream(xv + v) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) am.add(q[u]);
+        }
+        uint32_t m = am.result();
+        if (group == 32) {
+            m = warp_max_u32(m);
+        } else {
+            m = block_max_u32(m, red);
+        }
+        if (gtid == 0) out[row] = DT<T>::from_f(DT<T>::bits_to_f(m));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // per-row backward with gradient through the abs-max (streaming: 2R + 1W, then a one-element fix-up)
 // ------------------------------------------------------------------------------------------------------
@@ -1604,6 +1640,17 @@ extern "C" int bvb_absmax_rows(const void* x, void* out, int64_t rows, int64_t c
     if (!x || !out) return fail(BVB_EINVAL, "bvb_absmax_rows: null pointer");
     QParams p = make_qparams(0.f, 0.f, 0.f, dtype);
     BVB_DISPATCH_DTYPE(dtype, {
+        constexpr int V = DT<T>::VEC;
+        if (aligned16(x) && (cols % V) == 0) {
+            const int64_t row_vecs = cols / V;
+            const int group = cols * (int64_t)sizeof(T) <= 4096 ? 32 : AMR_THREADS;
+            int64_t grid = (rows + (AMR_THREADS / group) - 1) / (AMR_THREADS / group);
+            const int64_t cap = (int64_t)sm_count() * 8;
+            if (grid > cap) grid = cap;
+            absmax_rows_vec_kernel<T><<<(unsigned)grid, AMR_THREADS, 0, (cudaStream_t)stream>>>(
+                (const T*)x, (T*)out, rows, row_vecs, group);
+            return check_launch("bvb_absmax_rows");
+        }
         int threads = cols >= 4096 ? 512 : (cols >= 512 ? 256 : 64);
         int64_t grid = rows;
         int64_t cap = (int64_t)sm_count() * (2048 / threads);
