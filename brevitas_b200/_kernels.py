@@ -213,26 +213,29 @@ def scalar_clamp_min(x, min_val: float):
 
 # ---- IntQuant with a provided scale ------------------------------------------------------------------------
 
-def int_quant_fwd(x, scale, zero_point: float, qmin: float, qmax: float, round_mode: int, want_codes=False):
+def int_quant_fwd(x, scale, zero_point: float, qmin: float, qmax: float, round_mode: int, want_codes=False,
+                  pre_relu=False):
     dev = _check_cuda(x, scale)
     x, scale = _dense_for_scale(x, scale), _c(scale)
     inner, count, sdt = _scale_pattern(x, scale)
     y = torch.empty_like(x)
     codes = torch.empty_like(x) if want_codes else None
-    _launch(dev, "bvb_int_quant_fwd", x.data_ptr(), scale.data_ptr(), y.data_ptr(), _ptr(codes), x.numel(), inner,
-            count, sdt, zero_point, qmin, qmax, round_mode, dtype_tag(x), _stream(dev))
+    _launch(dev, "bvb_relu_int_quant_fwd" if pre_relu else "bvb_int_quant_fwd", x.data_ptr(), scale.data_ptr(),
+            y.data_ptr(), _ptr(codes), x.numel(), inner, count, sdt, zero_point, qmin, qmax, round_mode, dtype_tag(x),
+            _stream(dev))
     return (y, codes) if want_codes else y
 
 
-def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, want_gscale):
+def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, want_gscale, pre_relu=False):
     dev = _check_cuda(gy, x, scale)
     x, scale = _dense_for_scale(x, scale), _c(scale)
     gy = _like(gy, x)
     inner, count, sdt = _scale_pattern(x, scale)
     gx = torch.empty_like(x)
     gs = torch.empty(count, dtype=torch.float32, device=dev) if want_gscale else None
-    _launch(dev, "bvb_int_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), gx.data_ptr(), _ptr(gs),
-            x.numel(), inner, count, sdt, zero_point, qmin, qmax, round_mode, clamp_mode, dtype_tag(x), _stream(dev))
+    _launch(dev, "bvb_relu_int_quant_bwd" if pre_relu else "bvb_int_quant_bwd", gy.data_ptr(), x.data_ptr(),
+            scale.data_ptr(), gx.data_ptr(), _ptr(gs), x.numel(), inner, count, sdt, zero_point, qmin, qmax, round_mode,
+            clamp_mode, dtype_tag(x), _stream(dev))
     return gx, gs
 
 

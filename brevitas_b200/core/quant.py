@@ -202,6 +202,29 @@ class RescalingIntQuant(nn.Module):
             thr = None
         return 0.0, qmin, qmax, modes[0], modes[1], thr
 
+    def forward_pre_relu(self, x: Tensor) -> Optional[Tuple[Tensor, Tensor, Tensor, Tensor]]:
+        """``self(torch.relu(x))`` in ONE kernel (``relu_int_quant``: the ReLU's own read + write pass and its
+        backward pass disappear), or None when the configuration does not allow it: the threshold must not depend on
+        the activation (learned / constant scale, or runtime statistics past their collection phase), the range
+        inputs must be construction-time constants and there must be no quantization delay."""
+        if not x.is_cuda or type(self.int_quant.delay_wrapper.delay_impl) is not _NoDelay:
+            return None
+        independent = getattr(self.scaling_impl, 'input_independent', None)
+        if independent is None or not independent():
+            return None
+        bit_width = self.msb_clamp_bit_width_impl()
+        cfg = self._host_config(bit_width.dtype)
+        if cfg is None:
+            return None
+        zp, qmin, qmax, rm, cm, _ = cfg
+        threshold = self.scaling_impl(x)                    # x is ignored (input independent)
+        scale = threshold / self.int_scaling_impl(bit_width)
+        if not (scale.dtype == x.dtype or (scale.numel() == 1 and scale.dtype == torch.float32)):
+            return None
+        zero_point = self.zero_point_impl(x, scale, bit_width)
+        y = torch.ops.brevitas_b200.relu_int_quant(x, scale, zp, qmin, qmax, rm, cm)
+        return y, scale, zero_point, bit_width
+
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         bit_width = self.msb_clamp_bit_width_impl()
         cfg = self._host_config(bit_width.dtype) if x.is_cuda else None

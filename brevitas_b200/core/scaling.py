@@ -77,6 +77,10 @@ class ConstScaling(nn.Module):
     def forward(self, placeholder: Tensor) -> Tensor:
         return self.restrict_clamp_scaling(self.value())
 
+    def input_independent(self) -> bool:
+        """the threshold does not look at the tensor being quantized (lets QuantReLU fuse the ReLU into the kernel)"""
+        return True
+
 
 class ParameterScaling(nn.Module):
     """Learned threshold (standalone.py:75-152)."""
@@ -97,6 +101,9 @@ class ParameterScaling(nn.Module):
 
     def forward(self, placeholder: Tensor) -> Tensor:
         return abs_binary_sign_grad(self.restrict_clamp_scaling(self.value))
+
+    def input_independent(self) -> bool:
+        return True
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
@@ -154,6 +161,10 @@ class ParameterFromRuntimeStatsScaling(nn.Module):
             inplace_tensor_mul(self.value.detach(), self.buffer)
             self.counter = self.counter + 1
         return abs_binary_sign_grad(self.clamp_scaling(self.restrict_scaling(self.value)))
+
+    def input_independent(self) -> bool:
+        """true once the collection phase is over (or in eval mode): the statistics input is ignored"""
+        return (not self.training) or self.counter >= self.collect_stats_steps
 
     def forward(self, stats_input: Tensor) -> Tensor:
         if self.training:

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
                 int64_t v = base + (int64_t)u * ST_THREADS;
                 if (v < nvec) {
                     uint4 kq, yq;
+                    if (p.pre_relu) q[u] = relu_vec<T>(q[u]);
                     if (smode != 0) {      // scale index constant within a vector (literal formulation)
                         const ScaleCtx<T> cxv(DT<T>::to_f(scale[(v / inner_v) % count]), true, p, false);
                         yq = qdq_vec<T, RM, VM_LITERAL>(q[u], cxv, p, codes ? &kq : nullptr);
@@ -86,7 +87,9 @@ __global__ void int_quant_fwd_scalar_kernel(const T* x, const T* scale, T* y, T*
     for (int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float s = count == 1 ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[(i / inner) % count]);
         float t1, t3, t5;
-        to_int_chain<T, RM>(DT<T>::to_f(x[i]), DivBy(s), p, t1, t3, t5);
+        float xe = DT<T>::to_f(x[i]);
+        if (p.pre_relu) xe = relu_f(xe);
+        to_int_chain<T, RM>(xe, DivBy(s), p, t1, t3, t5);
         float t6 = fsub(t5, p.zp);
         if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
         y[i] = DT<T>::from_f(fmul(t6, s));
@@ -248,9 +251,13 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_bwd_kernel(
                             acc = 0.f;
                             acc_idx = idx;
                         }
-                        stg_stream(ov + v, bwd_vec<T, RM, VM_LITERAL>(qg[u], qx[u], cxv, p, masked, want_gs, acc));
+                        uint4 o = bwd_vec<T, RM, VM_LITERAL>(qg[u], p.pre_relu ? relu_vec<T>(qx[u]) : qx[u], cxv, p, masked,
+                                                             want_gs, acc);
+                        stg_stream(ov + v, p.pre_relu ? relu_grad_vec<T>(o, qx[u]) : o);
                     } else {
-                        stg_stream(ov + v, bwd_vec<T, RM, MODE>(qg[u], qx[u], cx0, p, masked, want_gs, acc));
+                        uint4 o = bwd_vec<T, RM, MODE>(qg[u], p.pre_relu ? relu_vec<T>(qx[u]) : qx[u], cx0, p, masked, want_gs,
+                                                       acc);
+                        stg_stream(ov + v, p.pre_relu ? relu_grad_vec<T>(o, qx[u]) : o);
                     }
                 }
             }
@@ -277,7 +284,10 @@ __global__ void int_quant_bwd_scalar_kernel(const T* gy, const T* x, const T* sc
         float s = count == 1 ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[idx]);
         float acc = 0.f;
         const DivBy dv(s);
-        float r = bwd_elem<T, RM>(DT<T>::to_f(gy[i]), DT<T>::to_f(x[i]), dv, dv.approx_recip(), p, masked, want_gs, acc);
+        const float x0 = DT<T>::to_f(x[i]);
+        float r = bwd_elem<T, RM>(DT<T>::to_f(gy[i]), p.pre_relu ? relu_f(x0) : x0, dv, dv.approx_recip(), p, masked, want_gs,
+                                  acc);
+        if (p.pre_relu && x0 <= 0.f) r = 0.f;
         gx[i] = DT<T>::from_f(r);
         if (want_gs) atomicAdd(gscale_out + idx, acc);
     }
@@ -335,9 +345,12 @@ __global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
                         const int64_t v = v0 + (int64_t)u * group;
                         if (v < nv) {
                             if (BWD) {
-                                stg_stream(ov + v, bwd_vec<T, RM, MODE>(qg[u], qx[u], cx, p, masked, want_gs, acc));
+                                uint4 o = bwd_vec<T, RM, MODE>(qg[u], p.pre_relu ? relu_vec<T>(qx[u]) : qx[u], cx, p, masked,
+                                                               want_gs, acc);
+                                stg_stream(ov + v, p.pre_relu ? relu_grad_vec<T>(o, qx[u]) : o);
                             } else {
                                 uint4 kq;
+                                if (p.pre_relu) qx[u] = relu_vec<T>(qx[u]);
                                 const uint4 yq = qdq_vec<T, RM, MODE>(qx[u], cx, p, cv ? &kq : nullptr);
                                 stg_stream(ov + v, yq);
                                 if (cv) stg_stream(cv + v, kq);
@@ -348,10 +361,12 @@ __global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
             });
         } else {
             for (int64_t j = gtid; j < inner; j += group) {
-                float ex[1] = {DT<T>::to_f(x[base + j])};
+                const float x0 = DT<T>::to_f(x[base + j]);
+                float ex[1] = {p.pre_relu ? relu_f(x0) : x0};
                 if (BWD) {
                     float eg[1] = {DT<T>::to_f(gy[base + j])};
                     bwd_n<T, RM, 1>(eg, ex, cx.dv, cx.inv_s, p, masked, want_gs, acc);
+                    if (p.pre_relu && x0 <= 0.f) eg[0] = 0.f;
                     out[base + j] = DT<T>::from_f(eg[0]);
                 } else {
                     float k[1];
@@ -424,6 +439,8 @@ __global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
             const int64_t v = v0 + (int64_t)u * stride;
             if (v < nvec) {
                 float ex[V], eo[V], ek[V];
+                const uint4 qx0 = qx[u];
+                if (p.pre_relu) qx[u] = relu_vec<T>(qx[u]);
                 DT<T>::unpack(qx[u], ex);
                 if (BWD) {
                     float eg[V];
@@ -446,7 +463,9 @@ __global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
                     }
                     if (codes) stg_stream(cv + v, DT<T>::pack(ek));
                 }
-                stg_stream(ov + v, DT<T>::pack(eo));
+                uint4 o = DT<T>::pack(eo);
+                if (BWD && p.pre_relu) o = relu_grad_vec<T>(o, qx0);
+                stg_stream(ov + v, o);
             }
         }
     }
@@ -931,9 +950,12 @@ __global__ void scaled_bwd_tma_kernel(const T* __restrict__ gy, const T* __restr
                 const int nv = min(tile_vecs, rv - v_base);
                 const uint4* gbuf = reinterpret_cast<const uint4*>(ring + (size_t)s * 2u * tile_bytes);
                 const uint4* xbuf = gbuf + tile_vecs;
-                for (int v = ctid; v < nv; v += nct)
-                    stg_stream(ov + v0 + v_base + v,
-                               bwd_vec<T, RM, MODE>(lds128(gbuf + v), lds128(xbuf + v), cx, p, masked, want_gs, acc));
+                for (int v = ctid; v < nv; v += nct) {
+                    const uint4 qx = lds128(xbuf + v);
+                    uint4 o = bwd_vec<T, RM, MODE>(lds128(gbuf + v), p.pre_relu ? relu_vec<T>(qx) : qx, cx, p, masked,
+                                                   want_gs, acc);
+                    stg_stream(ov + v0 + v_base + v, p.pre_relu ? relu_grad_vec<T>(o, qx) : o);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
             }
@@ -1123,6 +1145,7 @@ static inline QParams make_qparams(float zero_point, float qmin, float qmax, int
     p.qmax = round_to_dtype(qmax, dtype);
     p.zp = round_to_dtype(zero_point, dtype);
     p.zp_nonzero = (zero_point != 0.f) ? 1 : 0;
+    p.pre_relu = 0;
     p.pk_ok = p.pk_lo_zero = p.pk_lo = p.pk_hi = p.pk_lo_pre = p.pk_thr_lo = p.pk_thr_hi = 0;
     if (dtype == BVB_F32 || zero_point != 0.f) return p;
     // magic-number rounding range: fp16 adds 1536 in fp16 ([-512, 511] keeps the sum in the ulp-1 binade), bf16 adds
@@ -1514,36 +1537,74 @@ extern "C" int bvb_debug_packed_constants(float zero_point, float qmin, float qm
     return BVB_OK;
 }
 
-extern "C" int bvb_int_quant_fwd(const void* x, const void* scale, void* y, void* codes_out, int64_t n,
-                                 int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,
-                                 float qmax, int round_mode, int dtype, void* stream) {
-    BVB_CHECK_COMMON("bvb_int_quant_fwd", n)
-    BVB_CHECK_SCALE_DTYPE("bvb_int_quant_fwd")
+static int int_quant_fwd_entry(const char* name, const void* x, const void* scale, void* y, void* codes_out, int64_t n,
+                               int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,
+                               float qmax, int round_mode, int dtype, int pre_relu, void* stream) {
+    if (n < 0) return fail(BVB_EINVAL, "%s: negative size", name);
+    if (!(qmin <= qmax)) return fail(BVB_EINVAL, "%s: qmin must be <= qmax", name);
+    const int scale_f32 = (scale_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;
+    if (scale_dtype != dtype && !(scale_f32 && scale_count == 1))
+        return fail(BVB_EUNSUPPORTED, "%s: scale dtype must equal the tensor dtype, or be fp32 with one element", name);
     if (n == 0) return BVB_OK;
-    if (!x || !scale || !y) return fail(BVB_EINVAL, "bvb_int_quant_fwd: null pointer");
-    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "bvb_int_quant_fwd: bad scale broadcast pattern");
+    if (!x || !scale || !y) return fail(BVB_EINVAL, "%s: null pointer", name);
+    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "%s: bad scale broadcast pattern", name);
     QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    p.pre_relu = pre_relu;
     BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_FWD(round_mode, zero_point == 0.f, return (launch_int_quant_fwd<T, RM>(
         x, scale, y, codes_out, n, scale_inner, scale_count, scale_f32, p, 0, (cudaStream_t)stream))));
     return BVB_OK;
 }
 
-extern "C" int bvb_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out, int64_t n,
-                                 int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,
-                                 float qmax, int round_mode, int clamp_mode, int dtype, void* stream) {
-    BVB_CHECK_COMMON("bvb_int_quant_bwd", n)
-    BVB_CHECK_SCALE_DTYPE("bvb_int_quant_bwd")
-    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "bvb_int_quant_bwd: bad scale broadcast pattern");
+static int int_quant_bwd_entry(const char* name, const void* gy, const void* x, const void* scale, void* gx,
+                               float* gscale_out, int64_t n, int64_t scale_inner, int64_t scale_count, int scale_dtype,
+                               float zero_point, float qmin, float qmax, int round_mode, int clamp_mode, int dtype,
+                               int pre_relu, void* stream) {
+    if (n < 0) return fail(BVB_EINVAL, "%s: negative size", name);
+    if (!(qmin <= qmax)) return fail(BVB_EINVAL, "%s: qmin must be <= qmax", name);
+    const int scale_f32 = (scale_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;
+    if (scale_dtype != dtype && !(scale_f32 && scale_count == 1))
+        return fail(BVB_EUNSUPPORTED, "%s: scale dtype must equal the tensor dtype, or be fp32 with one element", name);
+    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "%s: bad scale broadcast pattern", name);
     if (n == 0) {
         if (gscale_out) cudaMemsetAsync(gscale_out, 0, sizeof(float) * (size_t)scale_count, (cudaStream_t)stream);
         return BVB_OK;
     }
-    if (!gy || !x || !scale || !gx) return fail(BVB_EINVAL, "bvb_int_quant_bwd: null pointer");
+    if (!gy || !x || !scale || !gx) return fail(BVB_EINVAL, "%s: null pointer", name);
     QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    p.pre_relu = pre_relu;
     const int masked = clamp_mode == BVB_CLAMP_MASKED;
     BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_MODE_BWD(round_mode, zero_point == 0.f, masked, return (launch_int_quant_bwd<T, RM>(
         gy, x, scale, gx, gscale_out, n, scale_inner, scale_count, scale_f32, p, masked, (cudaStream_t)stream))));
     return BVB_OK;
+}
+
+extern "C" int bvb_int_quant_fwd(const void* x, const void* scale, void* y, void* codes_out, int64_t n,
+                                 int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,
+                                 float qmax, int round_mode, int dtype, void* stream) {
+    return int_quant_fwd_entry("bvb_int_quant_fwd", x, scale, y, codes_out, n, scale_inner, scale_count, scale_dtype,
+                               zero_point, qmin, qmax, round_mode, dtype, 0, stream);
+}
+
+extern "C" int bvb_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out, int64_t n,
+                                 int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point, float qmin,
+                                 float qmax, int round_mode, int clamp_mode, int dtype, void* stream) {
+    return int_quant_bwd_entry("bvb_int_quant_bwd", gy, x, scale, gx, gscale_out, n, scale_inner, scale_count, scale_dtype,
+                               zero_point, qmin, qmax, round_mode, clamp_mode, dtype, 0, stream);
+}
+
+extern "C" int bvb_relu_int_quant_fwd(const void* x, const void* scale, void* y, void* codes_out, int64_t n,
+                                      int64_t scale_inner, int64_t scale_count, int scale_dtype, float zero_point,
+                                      float qmin, float qmax, int round_mode, int dtype, void* stream) {
+    return int_quant_fwd_entry("bvb_relu_int_quant_fwd", x, scale, y, codes_out, n, scale_inner, scale_count, scale_dtype,
+                               zero_point, qmin, qmax, round_mode, dtype, 1, stream);
+}
+
+extern "C" int bvb_relu_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out,
+                                      int64_t n, int64_t scale_inner, int64_t scale_count, int scale_dtype,
+                                      float zero_point, float qmin, float qmax, int round_mode, int clamp_mode, int dtype,
+                                      void* stream) {
+    return int_quant_bwd_entry("bvb_relu_int_quant_bwd", gy, x, scale, gx, gscale_out, n, scale_inner, scale_count,
+                               scale_dtype, zero_point, qmin, qmax, round_mode, clamp_mode, dtype, 1, stream);
 }
 
 extern "C" int bvb_rows_absmax_int_quant_fwd(const void* x, void* y, void* scale_out, void* absmax_out,

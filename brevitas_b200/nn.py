@@ -156,6 +156,11 @@ class FusedActivationQuantProxy(nn.Module):
         self.tensor_quant = tensor_quant
 
     def forward(self, x):
+        if type(self.activation_impl) is nn.ReLU and self.tensor_quant is not None:
+            fused = getattr(self.tensor_quant, 'forward_pre_relu', None)
+            out = fused(x) if fused is not None else None
+            if out is not None:                 # ReLU folded into the quantizer kernel (forward and backward)
+                return out
         x = self.activation_impl(x)
         if self.tensor_quant is None:
             return x, None, None, None

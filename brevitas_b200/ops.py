@@ -204,6 +204,48 @@ def _int_quant_bwd(ctx, gy):
 torch.library.register_autograd(f"{FQ_NS}::int_quant", _int_quant_bwd, setup_context=_int_quant_setup, lib=_FQ)
 
 
+# ---- ReLU fused in front of IntQuant (QuantReLU = nn.ReLU + act quantizer, proxy/runtime_quant.py:73-84) ----------
+_FQ.define("relu_int_quant(Tensor x, Tensor scale, float zero_point, float qmin, float qmax, int round_mode, "
+           "int clamp_mode) -> Tensor")
+_FQ.define("relu_int_quant_backward(Tensor gy, Tensor x, Tensor scale, float zero_point, float qmin, float qmax, "
+           "int round_mode, int clamp_mode, bool want_gscale) -> (Tensor, Tensor)")
+
+
+def _relu_int_quant_cuda(x, scale, zp, qmin, qmax, rm, cm):
+    return K.int_quant_fwd(x, scale, zp, qmin, qmax, rm, pre_relu=True)
+
+
+def _relu_int_quant_backward_cuda(gy, x, scale, zp, qmin, qmax, rm, cm, want_gscale):
+    gx, gs = K.int_quant_bwd(gy, x, scale, zp, qmin, qmax, rm, cm, want_gscale, pre_relu=True)
+    if gs is None:
+        gs = torch.empty(0, dtype=torch.float32, device=x.device)
+    return gx, gs
+
+
+_FQ.impl("relu_int_quant", _relu_int_quant_cuda, "CUDA")
+_FQ.impl("relu_int_quant", _no_cpu("relu_int_quant"), "CPU")
+_FQ.impl("relu_int_quant_backward", _relu_int_quant_backward_cuda, "CUDA")
+_FQ.impl("relu_int_quant_backward", _no_cpu("relu_int_quant_backward"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::relu_int_quant", lambda x, s, zp, a, b, rm, cm: torch.empty_like(x), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::relu_int_quant_backward",
+    lambda gy, x, s, zp, a, b, rm, cm, want: (torch.empty_like(x), torch.empty(max(1, s.numel()) if want else 0,
+                                                                                dtype=torch.float32, device=x.device)),
+    lib=_FQ)
+
+
+def _relu_int_quant_bwd(ctx, gy):
+    x, scale = ctx.saved_tensors
+    zp, qmin, qmax, rm, cm = ctx.q
+    want_gs = ctx.needs_input_grad[1]
+    gx, gs = torch.ops.brevitas_b200.relu_int_quant_backward(gy.to(x.dtype), x, scale, zp, qmin, qmax, rm, cm, want_gs)
+    return (gx if ctx.needs_input_grad[0] else None, _reduce_gscale(gs, scale) if want_gs else None,
+            None, None, None, None, None)
+
+
+torch.library.register_autograd(f"{FQ_NS}::relu_int_quant", _relu_int_quant_bwd, setup_context=_int_quant_setup, lib=_FQ)
+
+
 # ---- fused per-row abs-max + IntQuant ----------------------------------------------------------------------
 _FQ.define("rows_absmax_int_quant(Tensor x, int rows, int cols, float scaling_min_val, float int_threshold, "
            "float zero_point, float qmin, float qmax, int round_mode, int clamp_mode) -> (Tensor, Tensor, Tensor)")

@@ -105,6 +105,18 @@ int bvb_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx
                       float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
                       int dtype, void* stream);
 
+/* QuantReLU fused with its quantizer (FusedActivationQuantProxy: activation_impl = nn.ReLU, then tensor_quant;
+ * src/brevitas/proxy/runtime_quant.py:73-84, nn/quant_activation.py:14-31): y = int_quant(relu(x)) in ONE pass, and
+ * gx = int_quant_bwd(gy, relu(x)) * [not (x <= 0)] (ATen's threshold_backward) in one pass -- saves the ReLU's
+ * read + write forward and its two reads + one write backward.  Same arguments as the two calls above.        */
+int bvb_relu_int_quant_fwd(const void* x, const void* scale, void* y, void* codes_out, int64_t n,
+                           int64_t scale_inner, int64_t scale_count, int scale_dtype,
+                           float zero_point, float qmin, float qmax, int round_mode, int dtype, void* stream);
+int bvb_relu_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, float* gscale_out, int64_t n,
+                           int64_t scale_inner, int64_t scale_count, int scale_dtype,
+                           float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
+                           int dtype, void* stream);
+
 /* ---- 3. RescalingIntQuant with abs-max statistics, fused (src/brevitas/core/quant/int.py:156-163 over
  *         core/scaling/runtime.py:19-102, core/stats/stats_op.py:129-141) ----------------------------------
  * Per row of a [rows, cols] view (OverOutputChannelView / OverBatchOverOutputChannelView + AbsMax(dim)):

@@ -388,6 +388,56 @@ def test_channels_last_layouts(K, dtype):
     assert torch.equal(y, ycl) and torch.equal(st, stc)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,sshape,cl", [((5000,), (), False), ((1 << 20,), (), False), ((6, 16, 9, 9), (1, 16, 1, 1), False),
+                                             ((6, 16, 9, 9), (1, 16, 1, 1), True), ((600, 2048), (600, 1), False),
+                                             ((4, 8, 33), (4, 8, 1), False)])
+def test_relu_fused_into_quantizer(K, shape, sshape, cl, dtype):
+    """bvb_relu_int_quant_{fwd,bwd} (QuantReLU: nn.ReLU folded into its quantizer kernel) == int_quant(torch.relu(x))
+    followed by ATen's ReLU backward, bit for bit, on every provided-scale kernel variant (streaming, planes, TMA ring,
+    channels-last, scalar fallbacks), with -0.0 / NaN / +-inf among the inputs."""
+    T = TDT[dtype]
+    x = O.rnd(rand_np(shape, 41, 20.0), dtype)
+    flat = x.reshape(-1)
+    flat[:6] = [0.0, -0.0, np.nan, np.inf, -np.inf, -1e-30]
+    g = torch.from_numpy(O.rnd(rand_np(shape, 42, 1.0), dtype)).to(T).cuda()
+    s = torch.from_numpy(O.rnd(np.abs(rand_np(sshape, 43, 0.3)) + 0.05, dtype)).reshape(sshape).to(T).cuda()
+    xd = torch.from_numpy(x).to(T).cuda()
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    for qmin, qmax, cm in ((0.0, 255.0, 1), (0.0, 15.0, 0)):
+        yf = K.int_quant_fwd(xd, s, 0.0, qmin, qmax, 0, pre_relu=True)
+        xr = torch.relu(xd)
+        yr = K.int_quant_fwd(xr, s, 0.0, qmin, qmax, 0)
+        assert_bits_equal(host(yf), host(yr), "forward")
+        gxf, gsf = K.int_quant_bwd(g, xd, s, 0.0, qmin, qmax, 0, cm, True, pre_relu=True)
+        gq, gsr = K.int_quant_bwd(g, xr, s, 0.0, qmin, qmax, 0, cm, True)
+        gxr = torch.where(xd <= 0, torch.zeros_like(gq), gq)          # threshold_backward: zero where x <= 0
+        assert_bits_equal(host(gxf), host(gxr), "gradient")
+        ok = torch.isfinite(gsr) & torch.isfinite(gsf)
+        assert torch.allclose(gsf[ok], gsr[ok], rtol=1e-3 if dtype == "f32" else 6e-2, atol=1e-2)
+
+
+def test_quant_relu_module_fusion_matches_unfused():
+    """QuantReLU with a learned scale: the fused proxy path and the literal ReLU -> tensor_quant path agree exactly"""
+    from brevitas_b200.nn import QuantReLU
+    from brevitas_b200.quant import Uint8ActPerTensorFloatMaxInit
+    torch.manual_seed(0)
+    act = QuantReLU(act_quant=Uint8ActPerTensorFloatMaxInit, max_val=6.0, bit_width=4, return_quant_tensor=True).cuda()
+    x1 = (torch.randn(8, 16, 12, 12, device="cuda") * 3).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    proxy = act.act_quant.fused_activation_quant_proxy
+    q1 = act(x1)
+    q1.value.square().sum().backward()
+    g_scale_fused = proxy.tensor_quant.scaling_impl.value.grad.clone()
+    proxy.tensor_quant.scaling_impl.value.grad = None
+    y2, s2, zp2, bw2 = proxy.tensor_quant(torch.relu(x2))            # the unfused composition
+    y2.square().sum().backward()
+    assert torch.equal(q1.value, y2) and torch.equal(q1.scale, s2)
+    assert torch.equal(x1.grad, x2.grad)
+    assert torch.allclose(g_scale_fused, proxy.tensor_quant.scaling_impl.value.grad, rtol=1e-4, atol=1e-4)
+
+
 def test_fp32_scalar_scale_with_lowp_input(K):
     """fp32 quantizer modules fed bf16 activations: ATen's mul/div keep the fp32 0-dim scale in opmath"""
     x = torch.randn(4099, generator=torch.Generator().manual_seed(3)).mul(20).to(torch.bfloat16)
