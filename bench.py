@@ -466,13 +466,17 @@ def main():
         from qat.train import run as qat_run
         os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
         os.environ.setdefault("NCCL_IB_DISABLE", "1")
-        # BASELINE.json configs[3]; NHWC end to end (cuDNN's native layout; the fake-quant kernels take it in place)
-        qat["resnet18_int8"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True)
-        qat["resnet18_int8_nchw"] = qat_run("resnet18", args.qat_batch, 10, 3)
+        # BASELINE.json configs[3]; NHWC end to end (cuDNN's native layout; the fake-quant kernels take it in place), ReLU
+        # folded into the quantizer kernels, the whole step (fwd + loss + bwd + gradient all-reduce + SGD) as ONE CUDA graph
+        qat["resnet18_int8"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True, graph=True)
+        qat["resnet18_int8_eager_ddp"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True)
+        qat["resnet18_int8_nchw_eager"] = qat_run("resnet18", args.qat_batch, 10, 3)
         qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
         qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
         if world > 1 or args.qat_all:
-            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True)   # BASELINE.json configs[4]
+            # BASELINE.json configs[4]: ~1100 small launches per step, host-bound when launched eagerly
+            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True, graph=True)
+            qat["mobilenet_v1_4b_eager_ddp"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
