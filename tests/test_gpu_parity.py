@@ -528,6 +528,42 @@ def test_lowp_exhaustive(K, dtype, qmin, qmax):
     assert_bits_equal(host(y), yo, "fused y")
 
 
+def test_more_than_2_31_elements(K):
+    """maximum sizes: 2^31 + 4099 bf16 elements (4.3 GB per tensor) through the streaming forward, the TMA
+    provided-scale backward and the fused per-row kernels; slices on both sides of the 2^31 boundary and at the tail
+    must equal what small calls on the same data produce (64-bit indexing end to end)."""
+    n = (1 << 31) + 4099
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    g = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for t in (x, g):
+        for a in range(0, n, 1 << 28):
+            t[a:a + (1 << 28)] = torch.randn(min(1 << 28, n - a), device="cuda", generator=gen).to(torch.bfloat16) * 20
+    s = torch.tensor(0.37, device="cuda", dtype=torch.bfloat16)
+    y = K.int_quant_fwd(x, s, 0.0, -128.0, 127.0, 0)
+    gx, gs = K.int_quant_bwd(g, x, s, 0.0, -128.0, 127.0, 0, 1, True)
+    spans = [(0, 70000), ((1 << 31) - 40000, (1 << 31) + 4000), (n - 5003, n)]
+    for a, b in spans:
+        ys = K.int_quant_fwd(x[a:b].clone(), s, 0.0, -128.0, 127.0, 0)
+        gxs, _ = K.int_quant_bwd(g[a:b].clone(), x[a:b].clone(), s, 0.0, -128.0, 127.0, 0, 1, True)
+        assert torch.equal(y[a:b], ys) and torch.equal(gx[a:b], gxs), (a, b)
+    assert torch.isfinite(gs).all()
+    del y, gx
+    rows, cols = (1 << 20) + 2, 2048                       # 2^31 + 4096 elements as [rows, 2048]
+    xr, gr = x[:rows * cols], g[:rows * cols]
+    yr, sc, _ = K.rows_absmax_int_quant_fwd(xr, rows, cols, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+    gxr = K.rows_absmax_int_quant_bwd(gr, xr, sc, None, rows, cols, 127.0, 0.0, -127.0, 127.0, 0, 0)
+    for r0 in (0, (1 << 20) - 3):
+        sl = slice(r0 * cols, (r0 + 5) * cols)
+        y5, s5, _ = K.rows_absmax_int_quant_fwd(xr[sl].clone(), 5, cols, 1e-10, 127.0, 0.0, -127.0, 127.0, 0)
+        g5 = K.rows_absmax_int_quant_bwd(gr[sl].clone(), xr[sl].clone(), s5, None, 5, cols, 127.0, 0.0, -127.0, 127.0, 0, 0)
+        assert torch.equal(yr[sl], y5) and torch.equal(sc[r0:r0 + 5], s5)
+        assert torch.allclose(gxr[sl].float(), g5.float(), rtol=2e-2, atol=2e-2)
+        first = torch.zeros(5 * cols, dtype=torch.bool, device="cuda")
+        first[torch.arange(5, device="cuda") * cols + xr[sl].view(5, cols).abs().argmax(dim=1)] = True
+        assert torch.equal(torch.where(first, 0, gxr[sl].float()), torch.where(first, 0, g5.float()))
+
+
 def test_empty_and_errors(K):
     e = torch.empty(0, device="cuda")
     assert K.int_quant_fwd(e, torch.tensor(1.0, device="cuda"), 0.0, -1.0, 1.0, 0).numel() == 0
