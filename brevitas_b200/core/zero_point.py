@@ -26,7 +26,9 @@ class ZeroZeroPoint(nn.Module):
 
 
 class _ScaleShiftZeroPoint(nn.Module):
-    """``zero_point / scale + min_int``, optionally rounded and clamped to the integer range (zero_point.py:38-54)."""
+    """Turns a real-valued offset into the quantizer's zero-point: ``offset / scale + min_int``, or -- with
+    ``quantize_zero_point`` -- that value rounded and clamped by the quantizer's own ``to_int`` so it is a valid
+    integer code (zero_point.py:38-54)."""
 
     def __init__(self, int_quant: nn.Module, quantize_zero_point: bool) -> None:
         super().__init__()
@@ -34,83 +36,99 @@ class _ScaleShiftZeroPoint(nn.Module):
         self.quantize_zero_point = quantize_zero_point
 
     def forward(self, zero_point: Tensor, scale: Tensor, bit_width: Tensor) -> Tensor:
-        min_int = self.int_quant.min_int(bit_width)
-        if self.quantize_zero_point:
-            out = self.int_quant.to_int(scale, min_int, bit_width, zero_point)
-        else:
-            out = zero_point / scale + min_int
-        return out
+        lowest_code = self.int_quant.min_int(bit_width)
+        if not self.quantize_zero_point:
+            return zero_point / scale + lowest_code
+        return self.int_quant.to_int(scale, lowest_code, bit_width, zero_point)
 
 
-class StatsFromParameterZeroPoint(nn.Module):
-    """Zero-point from a statistic of the tracked parameters, e.g. ``-min(w)`` (zero_point.py:57-82)."""
+class _OffsetZeroPoint(nn.Module):
+    """Shared tail of the asymmetric zero-points: a real-valued offset (statistic, collected buffer or learned
+    parameter) goes through ``_ScaleShiftZeroPoint``; missing-key policy for the optional ``value`` parameter."""
+
+    def __init__(self, int_quant: nn.Module, quantize_zero_point: bool) -> None:
+        super().__init__()
+        self.scale_shift_zero_point = _ScaleShiftZeroPoint(int_quant, quantize_zero_point)
+
+    def _to_codes(self, offset: Tensor, scale: Tensor, bit_width: Tensor) -> Tensor:
+        return self.scale_shift_zero_point(offset, scale, bit_width)
+
+    @staticmethod
+    def _forgive_missing_value(prefix: str, missing_keys) -> None:
+        key = prefix + 'value'
+        if IGNORE_MISSING_KEYS and key in missing_keys:
+            missing_keys.remove(key)
+
+
+class StatsFromParameterZeroPoint(_OffsetZeroPoint):
+    """Offset = minus a statistic of the tracked parameters, e.g. ``-min(w)`` (zero_point.py:57-82)."""
 
     def __init__(self, int_quant: nn.Module, quantize_zero_point: bool, zero_point_stats_input_view_shape_impl: nn.Module,
                  zero_point_stats_input_concat_dim: int, zero_point_stats_impl: nn.Module,
                  zero_point_shape: Tuple[int, ...], tracked_parameter_list: List[Parameter]) -> None:
-        super().__init__()
+        super().__init__(int_quant, quantize_zero_point)
         self.parameter_list_stats = _ParameterListStats(
             zero_point_stats_impl, zero_point_shape, zero_point_stats_input_view_shape_impl,
             zero_point_stats_input_concat_dim, tracked_parameter_list)
-        self.scale_shift_zero_point = _ScaleShiftZeroPoint(int_quant, quantize_zero_point)
 
     def forward(self, x: Tensor, scale: Tensor, bit_width: Tensor) -> Tensor:
-        stats = self.parameter_list_stats()
-        return self.scale_shift_zero_point(-stats, scale, bit_width)
+        return self._to_codes(-self.parameter_list_stats(), scale, bit_width)
 
 
-class ParameterFromRuntimeZeroPoint(nn.Module):
-    """Collect a runtime statistic for ``collect_stats_steps`` steps, then learn it (zero_point.py:85-186)."""
+class ParameterFromRuntimeZeroPoint(_OffsetZeroPoint):
+    """A runtime statistic for ``collect_stats_steps`` training steps (kept as a running average in ``buffer``), then
+    a learned parameter initialised from it (zero_point.py:85-186).  Three phases, driven by ``counter``:
+    collecting (< steps), hand-over (== steps: the buffer is added into ``value`` once), learned (> steps)."""
 
     def __init__(self, collect_stats_steps: int, int_quant: nn.Module, quantize_zero_point: bool,
                  zero_point_stats_impl: nn.Module, zero_point_shape: Tuple[int, ...],
                  zero_point_stats_input_view_shape_impl: nn.Module,
                  zero_point_stats_momentum: Optional[float] = DEFAULT_MOMENTUM) -> None:
-        super().__init__()
+        super().__init__(int_quant, quantize_zero_point)
         assert collect_stats_steps > 0, 'Steps should be more than 0'
         self.collect_stats_steps = collect_stats_steps
         self.counter: int = 0
         self.zero_point_shape = zero_point_shape
-        self.stats_input_view_shape_impl = zero_point_stats_input_view_shape_impl
         self.momentum = zero_point_stats_momentum
+        self.stats_input_view_shape_impl = zero_point_stats_input_view_shape_impl
+        self.zero_point_stats_impl = zero_point_stats_impl
         self.value = Parameter(torch.full(zero_point_shape, 0.0))
         self.register_buffer('buffer', torch.full(zero_point_shape, 0.0))
-        self.zero_point_stats_impl = zero_point_stats_impl
-        self.scale_shift_zero_point = _ScaleShiftZeroPoint(int_quant, quantize_zero_point)
 
-    def training_forward(self, x: Tensor) -> Tensor:
-        if self.counter < self.collect_stats_steps:
-            stats_input = self.stats_input_view_shape_impl(x)
-            stats = self.zero_point_stats_impl(stats_input)
-            stats = stats.view(self.zero_point_shape)
-            new_counter = self.counter + 1
-            if self.counter == 0:
-                inplace_tensor_add(self.buffer, stats.detach())
-            else:
-                inplace_momentum_update(self.buffer, stats.detach(), self.momentum, self.counter, new_counter)
-            self.counter = new_counter
-            out = stats + 0. * self.value
-        elif self.counter == self.collect_stats_steps:
-            inplace_tensor_add(self.value.detach(), self.buffer)
-            self.counter = self.counter + 1
-            out = self.value
+    def _observe(self, x: Tensor) -> Tensor:
+        """one collection step: statistic of this batch, folded into the running buffer"""
+        stats = self.zero_point_stats_impl(self.stats_input_view_shape_impl(x)).view(self.zero_point_shape)
+        seen = self.counter
+        if seen == 0:
+            inplace_tensor_add(self.buffer, stats.detach())
         else:
-            out = self.value
-        return out
+            inplace_momentum_update(self.buffer, stats.detach(), self.momentum, seen, seen + 1)
+        self.counter = seen + 1
+        return stats + 0. * self.value            # keeps `value` in the autograd graph (DDP sees it used)
+
+    def training_forward(self, x) -> Tensor:
+        if self.counter < self.collect_stats_steps:
+            return self._observe(x)
+        if self.counter == self.collect_stats_steps:        # hand-over, exactly once
+            inplace_tensor_add(self.value.detach(), self.buffer)
+            self.counter += 1
+        return self.value
 
     def forward(self, x: Tensor, scale: Tensor, bit_width: Tensor) -> Tensor:
         if self.training:
-            out = self.training_forward(x)
+            offset = self.training_forward(x)
+        elif self.counter <= self.collect_stats_steps:
+            offset = self.buffer
         else:
-            out = self.buffer if self.counter <= self.collect_stats_steps else self.value
-        out = abs_binary_sign_grad(out)
-        return self.scale_shift_zero_point(out, scale, bit_width)
+            offset = self.value
+        return self._to_codes(abs_binary_sign_grad(offset), scale, bit_width)
 
     def state_dict(self, *args, destination=None, prefix='', keep_vars=False):
+        """the running buffer never appears; before the hand-over it is what gets saved as ``value``"""
         out = super().state_dict(*args, destination=destination, prefix=prefix, keep_vars=keep_vars)
-        del out[prefix + 'buffer']
+        out.pop(prefix + 'buffer')
         if self.counter == 0:
-            del out[prefix + 'value']
+            out.pop(prefix + 'value')
         elif self.counter <= self.collect_stats_steps:
             out[prefix + 'value'] = self.buffer
         return out
@@ -119,43 +137,33 @@ class ParameterFromRuntimeZeroPoint(nn.Module):
                               error_msgs):
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
-        value_key, buffer_key, training_key = prefix + 'value', prefix + 'buffer', prefix + 'training'
-        if buffer_key in missing_keys:
-            missing_keys.remove(buffer_key)
-        if training_key in missing_keys:
-            missing_keys.remove(training_key)
-        if value_key not in missing_keys:
-            self.counter = self.collect_stats_steps + 1
-        if IGNORE_MISSING_KEYS and value_key in missing_keys:
-            missing_keys.remove(value_key)
+        for never_saved in (prefix + 'buffer', prefix + 'training'):
+            if never_saved in missing_keys:
+                missing_keys.remove(never_saved)
+        if prefix + 'value' not in missing_keys:
+            self.counter = self.collect_stats_steps + 1          # a loaded value ends the collection phase
+        self._forgive_missing_value(prefix, missing_keys)
 
 
-class ParameterZeroPoint(nn.Module):
-    """Learned zero-point (zero_point.py:189-226)."""
+class ParameterZeroPoint(_OffsetZeroPoint):
+    """Learned offset (zero_point.py:189-226)."""
 
     def __init__(self, zero_point_init: Union[float, Tensor], int_quant: nn.Module, quantize_zero_point: bool,
                  zero_point_shape: Optional[Tuple[int, ...]] = None) -> None:
-        super().__init__()
-        if (isinstance(zero_point_init, Tensor) and zero_point_shape is not None
-                and zero_point_init.shape != SCALAR_SHAPE and zero_point_init.shape != zero_point_shape):
-            raise RuntimeError("zero_point_init.shape is non-scalar and != from zero_point_shape.")
-        if isinstance(zero_point_init, Tensor):
-            zero_point_init = zero_point_init.detach()
-        else:
-            zero_point_init = torch.tensor(zero_point_init)
-        if zero_point_init.shape == SCALAR_SHAPE and zero_point_shape is not None:
-            zero_point_init = torch.full(zero_point_shape, zero_point_init)
-        self.value = Parameter(zero_point_init)
-        self.scale_shift_zero_point = _ScaleShiftZeroPoint(int_quant, quantize_zero_point)
+        super().__init__(int_quant, quantize_zero_point)
+        init = zero_point_init.detach() if isinstance(zero_point_init, Tensor) else torch.tensor(zero_point_init)
+        if zero_point_shape is not None:
+            if init.shape == SCALAR_SHAPE:
+                init = torch.full(zero_point_shape, init)
+            elif init.shape != zero_point_shape:
+                raise RuntimeError("zero_point_init.shape is non-scalar and != from zero_point_shape.")
+        self.value = Parameter(init)
 
     def forward(self, x: Tensor, scale: Tensor, bit_width: Tensor) -> Tensor:
-        out = abs_binary_sign_grad(self.value)
-        return self.scale_shift_zero_point(out, scale, bit_width)
+        return self._to_codes(abs_binary_sign_grad(self.value), scale, bit_width)
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
-        value_key = prefix + 'value'
-        if IGNORE_MISSING_KEYS and value_key in missing_keys:
-            missing_keys.remove(value_key)
+        self._forgive_missing_value(prefix, missing_keys)
