@@ -992,21 +992,23 @@ __global__ void __launch_bounds__(ST_THREADS) absmax_tensor_kernel(
     __shared__ uint32_t red[32];
     const int64_t nvec = vec_ok ? n / V : 0;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
-    const int64_t chunk = ST_THREADS * ST_UNROLL;
-    const int64_t nchunks = (nvec + chunk - 1) / chunk;
-    uint32_t m = 0;
-    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const int64_t base = c * chunk + threadIdx.x;
-        uint4 q[ST_UNROLL];
+    // every CTA reduces ONE contiguous, equally sized slice (a grid-stride loop over 16 KB chunks left some CTAs with
+    // 5 chunks and others with 4: a 20 % tail on a read-only kernel), 8 independent 16-byte loads in flight per thread
+    const int64_t per_cta = (nvec + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per_cta;
+    const int64_t hi = lo + per_cta < nvec ? lo + per_cta : nvec;
+    AbsMaxAcc<T> am;
+    for (int64_t b = lo + threadIdx.x; b < hi; b += (int64_t)ST_THREADS * 8) {
+        uint4 q[8];
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) {
-            int64_t v = base + (int64_t)u * ST_THREADS;
-            q[u] = (v < nvec) ? ldg_stream(xv + v) : make_uint4(0, 0, 0, 0);
+        for (int u = 0; u < 8; ++u) {
+            const int64_t v = b + (int64_t)u * ST_THREADS;
+            q[u] = (v < hi) ? ldg_stream(xv + v) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) m = DT<T>::absmax_acc(m, q[u]);
+        for (int u = 0; u < 8; ++u) am.add(q[u]);
     }
-    m = DT<T>::absmax_fold(m);
+    uint32_t m = am.result();
     // widen to fp32 bit ordering so that all dtypes share the same workspace encoding
     uint32_t mf = __float_as_uint(DT<T>::bits_to_f(m));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
