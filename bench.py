@@ -471,6 +471,10 @@ def main():
         qat["resnet18_int8"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True, graph=True)
         qat["resnet18_int8_eager_ddp"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True)
         qat["resnet18_int8_nchw_eager"] = qat_run("resnet18", args.qat_batch, 10, 3)
+        # the first 300 steps of the default activation quantizers collect an exact 99.999th percentile of every
+        # activation tensor (AbsPercentile, radix select): step time while collecting (SURVEY.md §8d C4 "warm-up")
+        qat["resnet18_int8_collecting_stats"] = qat_run("resnet18", args.qat_batch, 6, 3, collect_stats_steps=10 ** 6,
+                                                        channels_last=True)
         qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
         qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
         if world > 1 or args.qat_all:

@@ -19,18 +19,27 @@ constexpr int KTH_UNROLL = 4;
 constexpr int KTH_BINS = 256;
 
 template <typename T> struct KeyTraits;
+// Digit layout, most significant first.  The FIRST digit is the whole 8-bit exponent, so that from the second pass on
+// only the elements in the answer's binade are candidates (with byte-aligned digits the first one holds just the top
+// 7 exponent bits -- two binades -- and the second pass still histograms a large part of the tensor).
 template <> struct KeyTraits<float> {
     static constexpr int PASSES = 4;
+    __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 23 : (pass == 1 ? 15 : (pass == 2 ? 7 : 0)); }
+    __device__ __forceinline__ static int width(int pass) { return pass == 3 ? 7 : 8; }
     __device__ __forceinline__ static uint32_t key(float v) { return __float_as_uint(v) & 0x7fffffffu; }
     __device__ __forceinline__ static float value(uint32_t k) { return __uint_as_float(k); }
 };
 template <> struct KeyTraits<__nv_bfloat16> {
     static constexpr int PASSES = 2;
+    __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 7 : 0; }      // exponent | 7-bit mantissa
+    __device__ __forceinline__ static int width(int pass) { return pass == 0 ? 8 : 7; }
     __device__ __forceinline__ static uint32_t key(float v) { return (__float_as_uint(v) >> 16) & 0x7fffu; }
     __device__ __forceinline__ static float value(uint32_t k) { return __uint_as_float(k << 16); }
 };
 template <> struct KeyTraits<__half> {
     static constexpr int PASSES = 2;
+    __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 8 : 0; }      // 15-bit key: 7 | 8 bits
+    __device__ __forceinline__ static int width(int pass) { return pass == 0 ? 7 : 8; }
     __device__ __forceinline__ static uint32_t key(float v) { return (uint32_t)(__half_as_ushort(__float2half_rn(v)) & 0x7fffu); }
     __device__ __forceinline__ static float value(uint32_t k) {
         __half_raw r; r.x = (unsigned short)k; return __half2float(__half(r));
@@ -39,6 +48,7 @@ template <> struct KeyTraits<__half> {
 
 // Resolve the digits fixed by passes [0, upto) for one row.  Executed by warp 0 of a block; returns
 // (prefix, remaining k) to every lane.  hist counts are exact, so the walk is deterministic.
+template <typename T>
 __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, int64_t row, int upto, int64_t k,
                                             uint32_t& prefix, int64_t& krem) {
     const int lane = threadIdx.x & 31;
@@ -78,7 +88,7 @@ __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, 
         }
         bin = __shfl_sync(0xffffffffu, bin, src);
         before = __shfl_sync(0xffffffffu, before, src);
-        prefix = (prefix << 8) | (uint32_t)bin;
+        prefix = (prefix << KeyTraits<T>::width(q)) | (uint32_t)bin;
         krem -= before;
     }
 }
@@ -88,16 +98,17 @@ template <typename T>
 __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                 int vec_ok, int pass, int64_t k, uint32_t* hist) {
     constexpr int V = DT<T>::VEC;
-    constexpr int P = KeyTraits<T>::PASSES;
     __shared__ uint32_t sh[KTH_THREADS / 32][KTH_BINS];
     __shared__ uint32_t s_prefix;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int shift = 8 * (P - 1 - pass);
+    const int shift = KeyTraits<T>::shift(pass);
+    const uint32_t digit_mask = (1u << KeyTraits<T>::width(pass)) - 1u;
+    const int prefix_shift = shift + KeyTraits<T>::width(pass);      // the bits above this digit are the resolved prefix
     for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
         for (int i = threadIdx.x; i < (KTH_THREADS / 32) * KTH_BINS; i += KTH_THREADS) (&sh[0][0])[i] = 0;
         if (warp == 0) {
             uint32_t prefix; int64_t krem;
-            kth_resolve(hist, rows, row, pass, k, prefix, krem);
+            kth_resolve<T>(hist, rows, row, pass, k, prefix, krem);
             if (lane == 0) s_prefix = prefix;
         }
         __syncthreads();
@@ -113,9 +124,9 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
             if (pass == 0) {
                 if (valid) atomicAdd(&myh[key >> shift], 1u);
             } else {
-                const bool take = valid && ((key >> (shift + 8)) == prefix);
+                const bool take = valid && ((key >> prefix_shift) == prefix);
                 if (__any_sync(0xffffffffu, take)) {
-                    if (take) atomicAdd(&myh[(key >> shift) & 0xffu], 1u);
+                    if (take) atomicAdd(&myh[(key >> shift) & digit_mask], 1u);
                 }
             }
         };
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_final_kernel(const T* __restr
     for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
         if (warp == 0) {
             uint32_t prefix; int64_t krem;
-            kth_resolve(hist, rows, row, P, k, prefix, krem);
+            kth_resolve<T>(hist, rows, row, P, k, prefix, krem);
             if (lane == 0) s_key = prefix;
         }
         __syncthreads();
@@ -214,7 +225,8 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     dim3 grid((unsigned)gx, (unsigned)gy);
     for (int pass = 0; pass < P; ++pass)
         kth_hist_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist);
-    kth_final_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out);
+    const dim3 fgrid(index_out ? (unsigned)gx : 1u, (unsigned)gy);      // the value alone needs one CTA per row
+    kth_final_kernel<T><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out);
     return check_launch("bvb_abs_kth_value_rows");
 }
 

@@ -158,7 +158,8 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
     if channels_last:       # NHWC end to end: cuDNN's native layout, and the fake-quant kernels take it in place
         batches = [(x.contiguous(memory_format=torch.channels_last), y) for x, y in batches]
     # warm-up runs past the statistics-collection phase of the activation quantizers (steady state)
-    for i in range(max(warmup, collect_stats_steps + 2)):
+    collecting = collect_stats_steps > 10000           # measure the statistics-collection phase itself
+    for i in range(warmup if collecting else max(warmup, collect_stats_steps + 2)):
         loss = train_step(model, raw, *batches[i % 2], loss_fn, opt)
     torch.cuda.synchronize()
     if graph:
@@ -191,7 +192,8 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
             "samples_per_s": round(world * batch / (ms * 1e-3), 1), "fakequant_launches_per_step": launches,
             "final_loss": round(loss_val, 4), "dtype": "f32", "data": "synthetic",
             "memory_format": "channels_last" if channels_last else "contiguous",
-            "phase": f"steady state (after {collect_stats_steps} collect steps)",
+            "phase": "collecting activation statistics (AbsPercentile every step)" if collecting
+                     else f"steady state (after {collect_stats_steps} collect steps)",
             "step": "one CUDA graph (fwd+loss+bwd+allreduce+optimizer)" if graph else "eager launches"
                     + (" + DDP bucketed NCCL all-reduce" if world > 1 else "")}
 
