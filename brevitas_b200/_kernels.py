@@ -239,6 +239,28 @@ def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, 
     return gx, gs
 
 
+_INT_OUT = {torch.int8: (_lib.OUT_I8, -128.0, 127.0), torch.uint8: (_lib.OUT_U8, 0.0, 255.0),
+            torch.int32: (_lib.OUT_I32, -2147483648.0, 2147483520.0)}
+
+
+def int_quant_to_int(x, scale, zero_point: float, qmin: Optional[float], qmax: Optional[float], round_mode: int,
+                     out_dtype=torch.int8):
+    """integer codes clamp(round(x / scale + zero_point), qmin, qmax) in a real integer dtype (qmin / qmax None: the
+    output dtype's own limits, i.e. the conversion of an already quantized tensor)"""
+    dev = _check_cuda(x, scale)
+    try:
+        kind, lo, hi = _INT_OUT[out_dtype]
+    except KeyError:
+        raise RuntimeError(f"brevitas_b200: integer export supports int8, uint8 and int32, got {out_dtype}")
+    x, scale = _dense_for_scale(x, scale), _c(scale)
+    inner, count, sdt = _scale_pattern(x, scale)
+    out = torch.empty_like(x, dtype=out_dtype)
+    _launch(dev, "bvb_int_quant_to_int", x.data_ptr(), scale.data_ptr(), out.data_ptr(), x.numel(), inner, count, sdt,
+            zero_point, lo if qmin is None else qmin, hi if qmax is None else qmax, round_mode, kind, dtype_tag(x),
+            _stream(dev))
+    return out
+
+
 # ---- fused abs-max + quant --------------------------------------------------------------------------------
 
 def rows_absmax_int_quant_fwd(x, rows, cols, scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode,

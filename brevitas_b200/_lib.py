@@ -18,6 +18,7 @@ F32, BF16, F16 = 0, 1, 2
 OK, EINVAL, EUNSUPPORTED, ECUDA = 0, 1, 2, 3
 ROUND, FLOOR, CEIL, ROUND_TO_ZERO, DPU_ROUND = 0, 1, 2, 3, 4
 CLAMP_STE, CLAMP_MASKED = 0, 1
+OUT_I8, OUT_U8, OUT_I32 = 0, 1, 2
 
 _P, _I, _L, _F, _D = c_void_p, c_int, c_int64, c_float, c_double
 _UNARY = [_P, _P, _L, _I, _P]
@@ -47,6 +48,7 @@ SIGNATURES = {
     "bvb_scalar_clamp_min_ste_impl": (c_int, [_P, _P, _L, _D, _I, _P]),
     "bvb_int_quant_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _P]),
     "bvb_int_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _I, _P]),
+    "bvb_int_quant_to_int": (c_int, [_P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _I, _P]),
     "bvb_relu_int_quant_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _P]),
     "bvb_relu_int_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _I, _P]),
     "bvb_rows_absmax_int_quant_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _I, _I, _P]),

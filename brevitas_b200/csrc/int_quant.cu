@@ -478,6 +478,78 @@ __global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------
+// integer export: clamp(round(x / scale + zero_point), qmin, qmax) stored in a real integer dtype
+// (IntQuant.to_int + the cast of QuantTensor.int(), quant_tensor/__init__.py:174-187).  1 read of T, 1 write of
+// 1 or 4 bytes per element.  OUT: int8_t / uint8_t / int32_t.  The codes are integer-valued floats inside the
+// output range by construction, so the conversion is exact; NaN codes are stored as 0 (cvt.rni semantics).
+// ------------------------------------------------------------------------------------------------------
+template <typename OUT> struct IntPack;
+template <> struct IntPack<int32_t> {
+    template <int N> __device__ __forceinline__ static void store(int32_t* dst, const int (&c)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) *reinterpret_cast<int4*>(dst + i) = make_int4(c[i], c[i + 1], c[i + 2], c[i + 3]);
+    }
+};
+template <typename B> struct IntPack8 {
+    template <int N> __device__ __forceinline__ static void store(B* dst, const int (&c)[N]) {
+        uint32_t w[N / 4];
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i)
+            w[i] = (uint32_t)(c[4 * i] & 0xff) | ((uint32_t)(c[4 * i + 1] & 0xff) << 8) |
+                   ((uint32_t)(c[4 * i + 2] & 0xff) << 16) | ((uint32_t)(c[4 * i + 3] & 0xff) << 24);
+        if (N == 4) *reinterpret_cast<uint32_t*>(dst) = w[0];
+        else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[N / 4 - 1]);
+    }
+};
+template <> struct IntPack<int8_t> : IntPack8<int8_t> {};
+template <> struct IntPack<uint8_t> : IntPack8<uint8_t> {};
+
+template <typename T, int RM, typename OUT>
+__global__ void __launch_bounds__(ST_THREADS) to_int_kernel(const T* __restrict__ x, const T* __restrict__ scale,
+                                                            OUT* __restrict__ out, int64_t n, int64_t nvec, int64_t inner,
+                                                            int64_t count, int scale_f32, QParams p) {
+    constexpr int V = DT<T>::VEC;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const int64_t stride = (int64_t)gridDim.x * ST_THREADS;
+    float s_one = 1.f;
+    if (count == 1) s_one = load_scale0<T>(scale, scale_f32);
+    const DivBy dv_one(s_one);
+    for (int64_t v0 = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; v0 < nvec; v0 += stride * ST_UNROLL) {
+        uint4 q[ST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            const int64_t v = v0 + (int64_t)u * stride;
+            if (v < nvec) q[u] = ldg_stream(xv + v);
+        }
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+            const int64_t v = v0 + (int64_t)u * stride;
+            if (v < nvec) {
+                // the host only takes this path when a vector never straddles two scales (inner % V == 0 or one scale)
+                const DivBy dv = count == 1 ? dv_one : DivBy(DT<T>::to_f(scale[((v * V) / inner) % count]));
+                float e[V];
+                int c[V];
+                DT<T>::unpack(q[u], e);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    float t1, t3, t5;
+                    to_int_chain<T, RM>(e[i], dv, p, t1, t3, t5);
+                    c[i] = __float2int_rn(t5);
+                }
+                IntPack<OUT>::template store<V>(out + v * V, c);
+            }
+        }
+    }
+    // ragged tail / generic broadcast: element-wise
+    for (int64_t i = nvec * V + (int64_t)blockIdx.x * ST_THREADS + threadIdx.x; i < n; i += stride) {
+        const float s = count == 1 ? s_one : DT<T>::to_f(scale[(i / inner) % count]);
+        float t1, t3, t5;
+        to_int_chain<T, RM>(DT<T>::to_f(x[i]), DivBy(s), p, t1, t3, t5);
+        out[i] = (OUT)__float2int_rn(t5);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // fused per-row abs-max + quant-dequant, TMA-staged (the C2 / C3 headline kernel)
 // dynamic smem: [0,64) mbarriers | [64,192) reduction scratch | [256, ...) `stages` row buffers
 // ------------------------------------------------------------------------------------------------------
@@ -1607,6 +1679,44 @@ extern "C" int bvb_relu_int_quant_bwd(const void* gy, const void* x, const void*
                                       void* stream) {
     return int_quant_bwd_entry("bvb_relu_int_quant_bwd", gy, x, scale, gx, gscale_out, n, scale_inner, scale_count,
                                scale_dtype, zero_point, qmin, qmax, round_mode, clamp_mode, dtype, 1, stream);
+}
+
+extern "C" int bvb_int_quant_to_int(const void* x, const void* scale, void* out, int64_t n, int64_t scale_inner,
+                                    int64_t scale_count, int scale_dtype, float zero_point, float qmin, float qmax,
+                                    int round_mode, int out_kind, int dtype, void* stream) {
+    if (n < 0) return fail(BVB_EINVAL, "bvb_int_quant_to_int: negative size");
+    if (!(qmin <= qmax)) return fail(BVB_EINVAL, "bvb_int_quant_to_int: qmin must be <= qmax");
+    if (out_kind < BVB_OUT_I8 || out_kind > BVB_OUT_I32) return fail(BVB_EINVAL, "bvb_int_quant_to_int: unknown output kind %d", out_kind);
+    const float lo_rep = out_kind == BVB_OUT_I8 ? -128.f : (out_kind == BVB_OUT_U8 ? 0.f : -2147483648.f);
+    const float hi_rep = out_kind == BVB_OUT_I8 ? 127.f : (out_kind == BVB_OUT_U8 ? 255.f : 2147483520.f);
+    if (qmin < lo_rep || qmax > hi_rep)
+        return fail(BVB_EINVAL, "bvb_int_quant_to_int: range [%g, %g] does not fit the output dtype", qmin, qmax);
+    const int scale_f32 = (scale_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;
+    if (scale_dtype != dtype && !(scale_f32 && scale_count == 1))
+        return fail(BVB_EUNSUPPORTED, "bvb_int_quant_to_int: scale dtype must equal the tensor dtype, or be fp32 with one element");
+    if (n == 0) return BVB_OK;
+    if (!x || !scale || !out) return fail(BVB_EINVAL, "bvb_int_quant_to_int: null pointer");
+    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "bvb_int_quant_to_int: bad scale broadcast pattern");
+    QParams p = make_qparams(zero_point, qmin, qmax, dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, {
+        constexpr int V = DT<T>::VEC;
+        const int out_bytes = out_kind == BVB_OUT_I32 ? 4 : 1;
+        const bool vec_ok = aligned16(x) && ((reinterpret_cast<uintptr_t>(out) & (uintptr_t)(V * out_bytes > 16 ? 15 : V * out_bytes - 1)) == 0) &&
+                            (scale_count == 1 || (scale_inner % V) == 0);
+        const int64_t nvec = vec_ok ? n / V : 0;
+        const unsigned grid = stream_grid(vec_ok ? nvec + 1 : n, ST_THREADS * ST_UNROLL);
+        if (out_kind == BVB_OUT_I8)
+            to_int_kernel<T, RM, int8_t><<<grid, ST_THREADS, 0, st>>>((const T*)x, (const T*)scale, (int8_t*)out, n, nvec,
+                                                                      scale_inner, scale_count, scale_f32, p);
+        else if (out_kind == BVB_OUT_U8)
+            to_int_kernel<T, RM, uint8_t><<<grid, ST_THREADS, 0, st>>>((const T*)x, (const T*)scale, (uint8_t*)out, n, nvec,
+                                                                       scale_inner, scale_count, scale_f32, p);
+        else
+            to_int_kernel<T, RM, int32_t><<<grid, ST_THREADS, 0, st>>>((const T*)x, (const T*)scale, (int32_t*)out, n, nvec,
+                                                                       scale_inner, scale_count, scale_f32, p);
+    }));
+    return check_launch("bvb_int_quant_to_int");
 }
 
 extern "C" int bvb_rows_absmax_int_quant_fwd(const void* x, void* y, void* scale_out, void* absmax_out,

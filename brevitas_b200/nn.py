@@ -55,6 +55,23 @@ class QuantTensor(NamedTuple):
     def size(self, *args, **kwargs):
         return self.value.size(*args, **kwargs)
 
+    def int(self, float_datatype: bool = False) -> Tensor:
+        """integer representation ``round(value / scale + zero_point)`` (quant_tensor/__init__.py:174-187): int8 for
+        signed <= 8 bits, uint8 for unsigned <= 8 bits, int32 otherwise -- one export kernel (1 read + 1 byte write)
+        instead of div, add, round, cast.  A tensor-valued non-zero zero-point takes the literal sequence."""
+        if not self.is_not_none:
+            raise RuntimeError("QuantTensor not valid.")
+        narrow = float(self.bit_width) <= 8.0
+        dtype = (torch.int8 if self.signed else torch.uint8) if narrow else torch.int32
+        scalar_zp = self.zero_point.numel() == 1
+        if float_datatype or not self.value.is_cuda or not scalar_zp:
+            from .core.quant import scalar_div
+            from .function.ops_ste import round_ste
+            int_value = round_ste(scalar_div(self.value, self.scale) + self.zero_point)
+            return int_value if float_datatype else int_value.to(dtype)
+        return torch.ops.brevitas_b200.int_quant_to_int(self.value.detach(), self.scale.detach(), float(self.zero_point),
+                                                        None, None, 0, dtype)
+
     @property
     def shape(self):
         return self.value.shape

@@ -204,6 +204,15 @@ def _int_quant_bwd(ctx, gy):
 torch.library.register_autograd(f"{FQ_NS}::int_quant", _int_quant_bwd, setup_context=_int_quant_setup, lib=_FQ)
 
 
+# ---- integer export (IntQuant.to_int + cast; QuantTensor.int(), quant_tensor/__init__.py:174-187) -------------------
+_FQ.define("int_quant_to_int(Tensor x, Tensor scale, float zero_point, float? qmin, float? qmax, int round_mode, "
+           "ScalarType out_dtype) -> Tensor")
+_FQ.impl("int_quant_to_int", lambda x, s, zp, a, b, rm, dt: K.int_quant_to_int(x, s, zp, a, b, rm, dt), "CUDA")
+_FQ.impl("int_quant_to_int", _no_cpu("int_quant_to_int"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::int_quant_to_int",
+                            lambda x, s, zp, a, b, rm, dt: torch.empty_like(x, dtype=dt), lib=_FQ)
+
+
 # ---- ReLU fused in front of IntQuant (QuantReLU = nn.ReLU + act quantizer, proxy/runtime_quant.py:73-84) ----------
 _FQ.define("relu_int_quant(Tensor x, Tensor scale, float zero_point, float qmin, float qmax, int round_mode, "
            "int clamp_mode) -> Tensor")

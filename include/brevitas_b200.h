@@ -105,6 +105,18 @@ int bvb_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx
                       float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
                       int dtype, void* stream);
 
+/* Integer export: the codes clamp(round(x / scale + zero_point), qmin, qmax) of IntQuant.to_int (int_base.py:64-76) stored
+ * in a REAL integer dtype -- what QuantTensor.int() (src/brevitas/quant_tensor/__init__.py:174-187) and the export
+ * handlers produce with a round + cast over the dequantized value.  out_kind: BVB_OUT_I8 / BVB_OUT_U8 / BVB_OUT_I32; the
+ * range must fit it.  Pass qmin / qmax = the dtype's own limits to convert an already quantized tensor (value / scale
+ * + zero_point is integral there, the clamp is a no-op).  1 read of T + 1 write of 1 (4) bytes per element.            */
+#define BVB_OUT_I8 0
+#define BVB_OUT_U8 1
+#define BVB_OUT_I32 2
+int bvb_int_quant_to_int(const void* x, const void* scale, void* out, int64_t n, int64_t scale_inner, int64_t scale_count,
+                         int scale_dtype, float zero_point, float qmin, float qmax, int round_mode, int out_kind,
+                         int dtype, void* stream);
+
 /* QuantReLU fused with its quantizer (FusedActivationQuantProxy: activation_impl = nn.ReLU, then tensor_quant;
  * src/brevitas/proxy/runtime_quant.py:73-84, nn/quant_activation.py:14-31): y = int_quant(relu(x)) in ONE pass, and
  * gx = int_quant_bwd(gy, relu(x)) * [not (x <= 0)] (ATen's threshold_backward) in one pass -- saves the ReLU's

@@ -438,6 +438,42 @@ def test_quant_relu_module_fusion_matches_unfused():
     assert torch.allclose(g_scale_fused, proxy.tensor_quant.scaling_impl.value.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_integer_export(K, dtype):
+    """bvb_int_quant_to_int: IntQuant.to_int stored as int8 / uint8 / int32, against the golden codes of the reference
+    and against the float codes of the fused kernel; scalar, per-row, per-channel and ragged / unaligned cases;
+    QuantTensor.int() of a layer output."""
+    T = TDT[dtype]
+    for name, out_dt in (("s8n_round_ste_scalar", torch.int8), ("u8_round_masked_scalar", torch.uint8),
+                         ("u8_round_masked_scalar_zp", torch.uint8), ("s4n_floor_ste_rows", torch.int8),
+                         ("u4n_rtz_masked_chan", torch.uint8), ("s8_dpu_masked_chan_zp", torch.int32)):
+        c = case("int_quant", f"int_quant/{name}/{dtype}/")
+        signed, narrow, bits, zp = [float(v) for v in c["meta"]]
+        rm, _ = INT_CASES[name]
+        qmin, qmax = O.min_int(bool(signed), bool(narrow), bits), O.max_int(bool(signed), bool(narrow), bits)
+        x, s = dev(c["x"], dtype), dev(c["scale"], dtype)
+        got = K.int_quant_to_int(x, s, zp, qmin, qmax, RM[rm], out_dt)
+        ref = np.nan_to_num(c["codes"], nan=0.0)
+        assert got.dtype == out_dt and np.array_equal(got.cpu().numpy().astype(np.float64), ref), name
+    x = torch.from_numpy(O.rnd(rand_np((37, 1003), 51, 30.0), dtype)).to(T).cuda()
+    for s in (torch.tensor(0.3, device="cuda").to(T), (torch.rand(37, 1, device="cuda") * 0.3 + 0.1).to(T)):
+        _, codes = K.int_quant_fwd(x, s, 0.0, -128.0, 127.0, 0, want_codes=True)
+        for xx in (x, x.reshape(-1)[3:].reshape(-1)) if s.numel() == 1 else (x,):       # unaligned view
+            ref = codes if xx is x else K.int_quant_fwd(xx.contiguous(), s, 0.0, -128.0, 127.0, 0, want_codes=True)[1]
+            for out_dt in (torch.int8, torch.int32):
+                got = K.int_quant_to_int(xx, s, 0.0, -128.0, 127.0, 0, out_dt)
+                assert torch.equal(got.to(torch.float32), ref.float())
+    if dtype == "f32":
+        from brevitas_b200.nn import QuantReLU
+        from brevitas_b200.quant import Uint8ActPerTensorFloatMaxInit
+        act = QuantReLU(act_quant=Uint8ActPerTensorFloatMaxInit, max_val=6.0, return_quant_tensor=True).cuda()
+        q = act(torch.randn(4, 8, 6, 6, device="cuda") * 3)
+        codes = q.int()
+        assert codes.dtype == torch.uint8
+        assert torch.equal(codes.float(), torch.round(q.value.detach() / q.scale.detach()))
+        assert torch.equal(q.int(float_datatype=True).detach(), codes.float())
+
+
 def test_fp32_scalar_scale_with_lowp_input(K):
     """fp32 quantizer modules fed bf16 activations: ATen's mul/div keep the fp32 0-dim scale in opmath"""
     x = torch.randn(4099, generator=torch.Generator().manual_seed(3)).mul(20).to(torch.bfloat16)
