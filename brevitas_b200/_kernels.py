@@ -239,6 +239,40 @@ def int_quant_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, 
     return gx, gs
 
 
+def _zpt_args(x, scale, zero_point):
+    if zero_point.numel() != scale.numel():
+        raise RuntimeError("brevitas_b200: a tensor zero-point must have the broadcast pattern of the scale")
+    inner, count, sdt = _scale_args(x, scale)
+    zdt = dtype_tag(zero_point)
+    if zero_point.dtype != x.dtype and not (zero_point.dtype == torch.float32 and count == 1):
+        raise RuntimeError("brevitas_b200: zero-point dtype must equal the input dtype (or be fp32 with one element)")
+    return inner, count, sdt, zdt
+
+
+def int_quant_zpt_fwd(x, scale, zero_point, qmin: float, qmax: float, round_mode: int):
+    """IntQuant with a tensor-valued zero-point (same broadcast pattern as the scale)"""
+    dev = _check_cuda(x, scale, zero_point)
+    x, scale, zero_point = _c(x), _c(scale), _c(zero_point)
+    inner, count, sdt, zdt = _zpt_args(x, scale, zero_point)
+    y = torch.empty_like(x)
+    _launch(dev, "bvb_int_quant_zpt_fwd", x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), y.data_ptr(), x.numel(),
+            inner, count, sdt, zdt, qmin, qmax, round_mode, dtype_tag(x), _stream(dev))
+    return y
+
+
+def int_quant_zpt_bwd(gy, x, scale, zero_point, qmin, qmax, round_mode, clamp_mode, want_grads):
+    dev = _check_cuda(gy, x, scale, zero_point)
+    gy, x, scale, zero_point = _c(gy), _c(x), _c(scale), _c(zero_point)
+    inner, count, sdt, zdt = _zpt_args(x, scale, zero_point)
+    gx = torch.empty_like(x)
+    gs = torch.empty(count, dtype=torch.float32, device=dev) if want_grads else None
+    gz = torch.empty(count, dtype=torch.float32, device=dev) if want_grads else None
+    _launch(dev, "bvb_int_quant_zpt_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(),
+            gx.data_ptr(), _ptr(gs), _ptr(gz), x.numel(), inner, count, sdt, zdt, qmin, qmax, round_mode, clamp_mode,
+            dtype_tag(x), _stream(dev))
+    return gx, gs, gz
+
+
 _INT_OUT = {torch.int8: (_lib.OUT_I8, -128.0, 127.0), torch.uint8: (_lib.OUT_U8, 0.0, 255.0),
             torch.int32: (_lib.OUT_I32, -2147483648.0, 2147483520.0)}
 

@@ -48,6 +48,8 @@ SIGNATURES = {
     "bvb_scalar_clamp_min_ste_impl": (c_int, [_P, _P, _L, _D, _I, _P]),
     "bvb_int_quant_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _P]),
     "bvb_int_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _I, _P]),
+    "bvb_int_quant_zpt_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _I, _F, _F, _I, _I, _P]),
+    "bvb_int_quant_zpt_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _F, _F, _I, _I, _I, _P]),
     "bvb_int_quant_to_int": (c_int, [_P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _I, _P]),
     "bvb_relu_int_quant_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _P]),
     "bvb_relu_int_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _I, _P]),

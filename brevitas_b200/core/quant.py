@@ -151,6 +151,18 @@ class IntQuant(nn.Module):
         y = torch.ops.brevitas_b200.int_quant(x, scale, zero_point, qmin, qmax, modes[0], modes[1])
         return self.delay_wrapper(x, y)
 
+    def forward_fused_zpt(self, scale: Tensor, zero_point: Tensor, qmin: float, qmax: float, x: Tensor) -> Optional[Tensor]:
+        """One kernel with a TENSOR zero-point that has the scale's shape (asymmetric quantizers); gradients flow to x,
+        scale and zero-point.  None if not applicable."""
+        modes = self.kernel_modes()
+        if modes is None or zero_point.shape != scale.shape:
+            return None
+        for t in (scale, zero_point):
+            if t.dtype != x.dtype and not (t.numel() == 1 and t.dtype == torch.float32):
+                return None
+        y = torch.ops.brevitas_b200.int_quant_zpt(x, scale, zero_point, qmin, qmax, modes[0], modes[1])
+        return self.delay_wrapper(x, y)
+
     def forward(self, scale: Tensor, zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
         if (x.is_cuda and zero_point.numel() == 1 and bit_width.numel() == 1 and not zero_point.requires_grad
                 and not bit_width.requires_grad and not torch.cuda.is_current_stream_capturing()):
@@ -185,8 +197,7 @@ class RescalingIntQuant(nn.Module):
         """(zero_point, qmin, qmax, round_mode, clamp_mode, int_threshold or None) when every range input is a
         construction-time constant; None otherwise (-> literal reference sequence)."""
         iq = self.int_quant
-        if type(iq) is not IntQuant or type(self.zero_point_impl) is not ZeroZeroPoint \
-                or type(self.msb_clamp_bit_width_impl) is not BitWidthConst:
+        if type(iq) is not IntQuant or type(self.msb_clamp_bit_width_impl) is not BitWidthConst:
             return None
         modes = iq.kernel_modes()
         if modes is None:
@@ -200,7 +211,9 @@ class RescalingIntQuant(nn.Module):
             thr = _int_threshold('po2', isi.signed, False, bw, bw_dtype)
         else:
             thr = None
-        return 0.0, qmin, qmax, modes[0], modes[1], thr
+        # zero-point: the constant 0.0, or None = tensor-valued (computed by zero_point_impl, fused as a device operand)
+        zp = 0.0 if type(self.zero_point_impl) is ZeroZeroPoint else None
+        return zp, qmin, qmax, modes[0], modes[1], thr
 
     def forward_pre_relu(self, x: Tensor) -> Optional[Tuple[Tensor, Tensor, Tensor, Tensor]]:
         """``self(torch.relu(x))`` in ONE kernel (``relu_int_quant``: the ReLU's own read + write pass and its
@@ -217,6 +230,8 @@ class RescalingIntQuant(nn.Module):
         if cfg is None:
             return None
         zp, qmin, qmax, rm, cm, _ = cfg
+        if zp is None:
+            return None
         threshold = self.scaling_impl(x)                    # x is ignored (input independent)
         scale = threshold / self.int_scaling_impl(bit_width)
         if not (scale.dtype == x.dtype or (scale.numel() == 1 and scale.dtype == torch.float32)):
@@ -238,6 +253,16 @@ class RescalingIntQuant(nn.Module):
             y = self.int_quant(scale, zero_point, bit_width, x)
             return y, scale, zero_point, bit_width
         zp, qmin, qmax, rm, cm, int_thr = cfg
+        if zp is None:
+            # asymmetric: scale and zero-point from their (statistics-sized) implementations, the tensor itself through
+            # ONE kernel with the zero-point as a device operand; its backward returns d(scale) and d(zero_point)
+            threshold = self.scaling_impl(x)
+            scale = threshold / self.int_scaling_impl(bit_width)
+            zero_point = self.zero_point_impl(x, scale, bit_width)
+            y = self.int_quant.forward_fused_zpt(scale, zero_point, qmin, qmax, x)
+            if y is None:
+                y = self.int_quant(scale, zero_point, bit_width, x)
+            return y, scale, zero_point, bit_width
         plan_fn = getattr(self.scaling_impl, 'fused_stats_plan', None)
         plan = plan_fn(x) if (plan_fn is not None and int_thr is not None) else None
         if plan is not None:

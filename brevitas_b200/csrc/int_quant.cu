@@ -478,6 +478,115 @@ __global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------
+// provided scale AND a tensor-valued zero-point (asymmetric quantizers: StatsFromParameterZeroPoint,
+// ParameterFromRuntimeZeroPoint, ParameterZeroPoint -- the ShiftedUint8* quantizers): element i uses
+// scale[(i / inner) % count] and zero_point[(i / inner) % count].  A group of threads owns a plane of `inner`
+// elements (for one scale the tensor is cut into planes of ZP_CHUNK elements); the backward also reduces
+//   d(scale)      = sum g*(q - zp) - d*((x/s)/s)
+//   d(zero_point) = sum (d - g*s)            (the clamp mask removes d, the "- zp" of the dequantization always counts)
+// per plane.  Literal op sequence (the zero-point steps need their own roundings in 16-bit dtypes).
+// ------------------------------------------------------------------------------------------------------
+constexpr int ZP_CHUNK = 16384;
+
+template <typename T, int RM, bool BWD>
+__global__ void __launch_bounds__(PL_THREADS) int_quant_zpt_kernel(
+        const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, const T* __restrict__ zero_point,
+        T* __restrict__ out, float* gscale_out, float* gzp_out, int64_t n, int64_t inner, int64_t count, int scale_f32,
+        int zp_f32, int masked, QParams p0) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ float red[32];
+    const int64_t nplanes = (n + inner - 1) / inner;
+    const bool want_g = BWD && gscale_out != nullptr;
+    for (int64_t pl = blockIdx.x; pl < nplanes; pl += gridDim.x) {
+        const int64_t sidx = pl % count;
+        const float s = count == 1 ? load_scale0<T>(scale, scale_f32) : DT<T>::to_f(scale[sidx]);
+        QParams p = p0;
+        // a 0-dim fp32 zero-point next to a 16-bit tensor is rounded to the tensor dtype by ATen's add / sub
+        p.zp = DT<T>::rnd(count == 1 ? load_scale0<T>(zero_point, zp_f32) : DT<T>::to_f(zero_point[sidx]));
+        p.zp_nonzero = 1;
+        const DivBy dv(s);
+        const float inv_s = dv.approx_recip();
+        const int64_t base = pl * inner;
+        const int64_t len = (n - base < inner) ? (n - base) : inner;
+        float acc_s = 0.f, acc_z = 0.f;
+        const bool vec = ((reinterpret_cast<uintptr_t>(x + base) | reinterpret_cast<uintptr_t>(out + base) |
+                           (BWD ? reinterpret_cast<uintptr_t>(gy + base) : 0)) & 15u) == 0;
+        const int64_t nv = vec ? len / V : 0;
+        const uint4* xv = reinterpret_cast<const uint4*>(x + base);
+        const uint4* gv = reinterpret_cast<const uint4*>(BWD ? gy + base : x + base);
+        uint4* ov = reinterpret_cast<uint4*>(out + base);
+        auto one = [&](float g, float xe) -> float {
+            if (!BWD) return quant_dequant<T, RM>(xe, dv, p);
+            const float gsv = DT<T>::rnd(fmul(g, dv.b));
+            float t1, t3, t5;
+            to_int_chain<T, RM>(xe, dv, p, t1, t3, t5);
+            float d = gsv;
+            if (masked) d = (!(t3 > p.qmax) && !(t3 < p.qmin)) ? gsv : 0.f;
+            if (want_g) {
+                const float t6 = DT<T>::rnd(fsub(t5, p.zp));
+                acc_s = fmaf(g, t6, acc_s);
+                acc_s = fmaf(-d, t1 * inv_s, acc_s);
+                acc_z += d - gsv;
+            }
+            return dv(d);
+        };
+        for (int64_t v0 = threadIdx.x; v0 < nv; v0 += (int64_t)PL_THREADS * PL_UNROLL) {
+            uint4 qx[PL_UNROLL], qg[PL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PL_UNROLL; ++u) {
+                const int64_t v = v0 + (int64_t)u * PL_THREADS;
+                if (v < nv) {
+                    qx[u] = ldg_stream(xv + v);
+                    if (BWD) qg[u] = ldg_stream(gv + v);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PL_UNROLL; ++u) {
+                const int64_t v = v0 + (int64_t)u * PL_THREADS;
+                if (v < nv) {
+                    float ex[V], eg[V];
+                    DT<T>::unpack(qx[u], ex);
+                    if (BWD) DT<T>::unpack(qg[u], eg);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) ex[i] = one(BWD ? eg[i] : 0.f, ex[i]);
+                    stg_stream(ov + v, DT<T>::pack(ex));
+                }
+            }
+        }
+        for (int64_t j = nv * V + threadIdx.x; j < len; j += PL_THREADS)
+            out[base + j] = DT<T>::from_f(one(BWD ? DT<T>::to_f(gy[base + j]) : 0.f, DT<T>::to_f(x[base + j])));
+        if (want_g) {
+            const float ts = block_sum_f(acc_s, red);
+            const float tz = block_sum_f(acc_z, red);
+            if (threadIdx.x == 0) {
+                atomicAdd(gscale_out + sidx, ts);
+                atomicAdd(gzp_out + sidx, tz);
+            }
+        }
+    }
+}
+
+template <typename T, int RM, bool BWD>
+static int launch_int_quant_zpt(const void* gy, const void* x, const void* scale, const void* zp, void* out,
+                                float* gscale_out, float* gzp_out, int64_t n, int64_t inner, int64_t count, int scale_f32,
+                                int zp_f32, int masked, const QParams& p, cudaStream_t st) {
+    if (BWD && gscale_out) {
+        cudaError_t e = cudaMemsetAsync(gscale_out, 0, sizeof(float) * (size_t)count, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(gzp_out, 0, sizeof(float) * (size_t)count, st);
+        if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_int_quant_zpt_bwd: memset: %s", cudaGetErrorString(e));
+    }
+    const int64_t plane = count == 1 ? (int64_t)ZP_CHUNK : inner;
+    const int64_t nplanes = (n + plane - 1) / plane;
+    int64_t grid = nplanes;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    int_quant_zpt_kernel<T, RM, BWD><<<(unsigned)grid, PL_THREADS, 0, st>>>(
+        (const T*)gy, (const T*)x, (const T*)scale, (const T*)zp, (T*)out, gscale_out, gzp_out, n, plane, count, scale_f32,
+        zp_f32, masked, p);
+    return check_launch(BWD ? "bvb_int_quant_zpt_bwd" : "bvb_int_quant_zpt_fwd");
+}
+
+// ------------------------------------------------------------------------------------------------------
 // integer export: clamp(round(x / scale + zero_point), qmin, qmax) stored in a real integer dtype
 // (IntQuant.to_int + the cast of QuantTensor.int(), quant_tensor/__init__.py:174-187).  1 read of T, 1 write of
 // 1 or 4 bytes per element.  OUT: int8_t / uint8_t / int32_t.  The codes are integer-valued floats inside the
@@ -1679,6 +1788,61 @@ extern "C" int bvb_relu_int_quant_bwd(const void* gy, const void* x, const void*
                                       void* stream) {
     return int_quant_bwd_entry("bvb_relu_int_quant_bwd", gy, x, scale, gx, gscale_out, n, scale_inner, scale_count,
                                scale_dtype, zero_point, qmin, qmax, round_mode, clamp_mode, dtype, 1, stream);
+}
+
+static int zpt_check(const char* name, int64_t n, int64_t scale_inner, int64_t scale_count, int scale_dtype, int zp_dtype,
+                     int dtype, float qmin, float qmax, int* scale_f32, int* zp_f32) {
+    if (n < 0) return fail(BVB_EINVAL, "%s: negative size", name);
+    if (!(qmin <= qmax)) return fail(BVB_EINVAL, "%s: qmin must be <= qmax", name);
+    if (scale_inner < 1 || scale_count < 1) return fail(BVB_EINVAL, "%s: bad scale broadcast pattern", name);
+    if (scale_count > 1 && n % scale_inner != 0) return fail(BVB_EINVAL, "%s: size is not a multiple of the plane size", name);
+    *scale_f32 = (scale_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;
+    *zp_f32 = (zp_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;
+    if ((scale_dtype != dtype && !(*scale_f32 && scale_count == 1)) || (zp_dtype != dtype && !(*zp_f32 && scale_count == 1)))
+        return fail(BVB_EUNSUPPORTED, "%s: scale / zero-point dtype must equal the tensor dtype, or be fp32 with one element", name);
+    return BVB_OK;
+}
+
+extern "C" int bvb_int_quant_zpt_fwd(const void* x, const void* scale, const void* zero_point, void* y, int64_t n,
+                                     int64_t scale_inner, int64_t scale_count, int scale_dtype, int zp_dtype, float qmin,
+                                     float qmax, int round_mode, int dtype, void* stream) {
+    int scale_f32 = 0, zp_f32 = 0;
+    int rc = zpt_check("bvb_int_quant_zpt_fwd", n, scale_inner, scale_count, scale_dtype, zp_dtype, dtype, qmin, qmax,
+                       &scale_f32, &zp_f32);
+    if (rc != BVB_OK) return rc;
+    if (n == 0) return BVB_OK;
+    if (!x || !scale || !zero_point || !y) return fail(BVB_EINVAL, "bvb_int_quant_zpt_fwd: null pointer");
+    QParams p = make_qparams(1.f, qmin, qmax, dtype);          // non-zero zero-point: literal formulation
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_zpt<T, RM, false>(
+        nullptr, x, scale, zero_point, y, nullptr, nullptr, n, scale_inner, scale_count, scale_f32, zp_f32, 0, p,
+        (cudaStream_t)stream))));
+    return BVB_OK;
+}
+
+extern "C" int bvb_int_quant_zpt_bwd(const void* gy, const void* x, const void* scale, const void* zero_point, void* gx,
+                                     float* gscale_out, float* gzp_out, int64_t n, int64_t scale_inner,
+                                     int64_t scale_count, int scale_dtype, int zp_dtype, float qmin, float qmax,
+                                     int round_mode, int clamp_mode, int dtype, void* stream) {
+    int scale_f32 = 0, zp_f32 = 0;
+    int rc = zpt_check("bvb_int_quant_zpt_bwd", n, scale_inner, scale_count, scale_dtype, zp_dtype, dtype, qmin, qmax,
+                       &scale_f32, &zp_f32);
+    if (rc != BVB_OK) return rc;
+    if ((gscale_out == nullptr) != (gzp_out == nullptr))
+        return fail(BVB_EINVAL, "bvb_int_quant_zpt_bwd: pass both gradient outputs or neither");
+    if (n == 0) {
+        if (gscale_out) {
+            cudaMemsetAsync(gscale_out, 0, sizeof(float) * (size_t)scale_count, (cudaStream_t)stream);
+            cudaMemsetAsync(gzp_out, 0, sizeof(float) * (size_t)scale_count, (cudaStream_t)stream);
+        }
+        return BVB_OK;
+    }
+    if (!gy || !x || !scale || !zero_point || !gx) return fail(BVB_EINVAL, "bvb_int_quant_zpt_bwd: null pointer");
+    QParams p = make_qparams(1.f, qmin, qmax, dtype);
+    const int masked = clamp_mode == BVB_CLAMP_MASKED;
+    BVB_DISPATCH_DTYPE(dtype, BVB_DISPATCH_ROUND(round_mode, return (launch_int_quant_zpt<T, RM, true>(
+        gy, x, scale, zero_point, gx, gscale_out, gzp_out, n, scale_inner, scale_count, scale_f32, zp_f32, masked, p,
+        (cudaStream_t)stream))));
+    return BVB_OK;
 }
 
 extern "C" int bvb_int_quant_to_int(const void* x, const void* scale, void* out, int64_t n, int64_t scale_inner,

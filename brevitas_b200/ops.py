@@ -204,6 +204,52 @@ def _int_quant_bwd(ctx, gy):
 torch.library.register_autograd(f"{FQ_NS}::int_quant", _int_quant_bwd, setup_context=_int_quant_setup, lib=_FQ)
 
 
+# ---- IntQuant with a tensor-valued zero-point (asymmetric quantizers) -----------------------------------------------
+_FQ.define("int_quant_zpt(Tensor x, Tensor scale, Tensor zero_point, float qmin, float qmax, int round_mode, "
+           "int clamp_mode) -> Tensor")
+_FQ.define("int_quant_zpt_backward(Tensor gy, Tensor x, Tensor scale, Tensor zero_point, float qmin, float qmax, "
+           "int round_mode, int clamp_mode, bool want_grads) -> (Tensor, Tensor, Tensor)")
+
+
+def _int_quant_zpt_backward_cuda(gy, x, scale, zp, qmin, qmax, rm, cm, want):
+    gx, gs, gz = K.int_quant_zpt_bwd(gy, x, scale, zp, qmin, qmax, rm, cm, want)
+    if gs is None:
+        gs = torch.empty(0, dtype=torch.float32, device=x.device)
+        gz = torch.empty(0, dtype=torch.float32, device=x.device)
+    return gx, gs, gz
+
+
+_FQ.impl("int_quant_zpt", lambda x, s, z, a, b, rm, cm: K.int_quant_zpt_fwd(x, s, z, a, b, rm), "CUDA")
+_FQ.impl("int_quant_zpt", _no_cpu("int_quant_zpt"), "CPU")
+_FQ.impl("int_quant_zpt_backward", _int_quant_zpt_backward_cuda, "CUDA")
+_FQ.impl("int_quant_zpt_backward", _no_cpu("int_quant_zpt_backward"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::int_quant_zpt", lambda x, s, z, a, b, rm, cm: torch.empty_like(x), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::int_quant_zpt_backward",
+    lambda gy, x, s, z, a, b, rm, cm, w: (torch.empty_like(x), x.new_empty(s.numel() if w else 0, dtype=torch.float32),
+                                          x.new_empty(s.numel() if w else 0, dtype=torch.float32)),
+    lib=_FQ)
+
+
+def _int_quant_zpt_setup(ctx, inputs, output):
+    x, scale, zp, qmin, qmax, rm, cm = inputs
+    ctx.save_for_backward(x, scale, zp)
+    ctx.q = (qmin, qmax, rm, cm)
+
+
+def _int_quant_zpt_bwd(ctx, gy):
+    x, scale, zp = ctx.saved_tensors
+    qmin, qmax, rm, cm = ctx.q
+    want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+    gx, gs, gz = torch.ops.brevitas_b200.int_quant_zpt_backward(gy.to(x.dtype), x, scale, zp, qmin, qmax, rm, cm, want)
+    return (gx if ctx.needs_input_grad[0] else None,
+            _reduce_gscale(gs, scale) if ctx.needs_input_grad[1] else None,
+            _reduce_gscale(gz, zp) if ctx.needs_input_grad[2] else None, None, None, None, None)
+
+
+torch.library.register_autograd(f"{FQ_NS}::int_quant_zpt", _int_quant_zpt_bwd, setup_context=_int_quant_zpt_setup, lib=_FQ)
+
+
 # ---- integer export (IntQuant.to_int + cast; QuantTensor.int(), quant_tensor/__init__.py:174-187) -------------------
 _FQ.define("int_quant_to_int(Tensor x, Tensor scale, float zero_point, float? qmin, float? qmax, int round_mode, "
            "ScalarType out_dtype) -> Tensor")

@@ -105,6 +105,19 @@ int bvb_int_quant_bwd(const void* gy, const void* x, const void* scale, void* gx
                       float zero_point, float qmin, float qmax, int round_mode, int clamp_mode,
                       int dtype, void* stream);
 
+/* IntQuant with a TENSOR-valued zero-point (asymmetric quantizers: src/brevitas/core/zero_point.py:38-226, the
+ * ShiftedUint8* quantizers of quant/shifted_scaled_int.py): zero_point has the broadcast pattern of scale (one element,
+ * or scale_count elements).  Same arithmetic as bvb_int_quant_fwd / bwd; the backward additionally returns
+ * d(loss)/d(zero_point) = sum over each region of m*(gy*s) - gy*s (fp32, zero-filled by the callee; pass both
+ * gradient outputs or neither).                                                                                  */
+int bvb_int_quant_zpt_fwd(const void* x, const void* scale, const void* zero_point, void* y, int64_t n,
+                          int64_t scale_inner, int64_t scale_count, int scale_dtype, int zp_dtype,
+                          float qmin, float qmax, int round_mode, int dtype, void* stream);
+int bvb_int_quant_zpt_bwd(const void* gy, const void* x, const void* scale, const void* zero_point, void* gx,
+                          float* gscale_out, float* gzp_out, int64_t n, int64_t scale_inner, int64_t scale_count,
+                          int scale_dtype, int zp_dtype, float qmin, float qmax, int round_mode, int clamp_mode,
+                          int dtype, void* stream);
+
 /* Integer export: the codes clamp(round(x / scale + zero_point), qmin, qmax) of IntQuant.to_int (int_base.py:64-76) stored
  * in a REAL integer dtype -- what QuantTensor.int() (src/brevitas/quant_tensor/__init__.py:174-187) and the export
  * handlers produce with a round + cast over the dequantized value.  out_kind: BVB_OUT_I8 / BVB_OUT_U8 / BVB_OUT_I32; the

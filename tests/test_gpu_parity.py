@@ -439,6 +439,44 @@ def test_quant_relu_module_fusion_matches_unfused():
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", ["u8_round_masked_scalar_zp", "s8_dpu_masked_chan_zp"])
+def test_tensor_zero_point_kernel(K, name, dtype):
+    """bvb_int_quant_zpt_{fwd,bwd}: the zero-point as a DEVICE operand with the scale's broadcast pattern.  Outputs and
+    element-wise gradients bit-exact against the reference's golden vectors (which used the same value as a Python
+    constant); d(scale) within the reduction tolerance; d(zero_point) against the closed form sum(m*d - d)."""
+    c = case("int_quant", f"int_quant/{name}/{dtype}/")
+    signed, narrow, bits, zp = [float(v) for v in c["meta"]]
+    rm, cm = INT_CASES[name]
+    qmin, qmax = O.min_int(bool(signed), bool(narrow), bits), O.max_int(bool(signed), bool(narrow), bits)
+    x, s, g = dev(c["x"], dtype), dev(c["scale"], dtype), dev(c["g"], dtype)
+    zpt = torch.full_like(s, zp)
+    y = K.int_quant_zpt_fwd(x, s, zpt, qmin, qmax, RM[rm])
+    assert_bits_equal(host(y), c["y"], "y")
+    gx, gs, gz = K.int_quant_zpt_bwd(g, x, s, zpt, qmin, qmax, RM[rm], CM[cm], True)
+    assert_bits_equal(host(gx), c["gx"], "gx")
+    gx2, none_s, none_z = K.int_quant_zpt_bwd(g, x, s, zpt, qmin, qmax, RM[rm], CM[cm], False)
+    assert none_s is None and none_z is None
+    assert_bits_equal(host(gx2), c["gx"], "gx without parameter gradients")
+    if np.isfinite(c["gscale"]).all():
+        _, gs_el = O.int_quant_backward(c["g"], c["x"], c["scale"], zp, qmin, qmax, rm, cm, dtype)
+        n = c["x"].size // max(1, c["gscale"].size)
+        mag = np.abs(gs_el).sum() / max(1, c["gscale"].size) + 1.0
+        close_sum(host(gs).reshape(c["gscale"].shape), c["gscale"], n, mag, dtype)
+    # d(zero_point): every element contributes m*d - d with d = rnd(g * s)  (0 inside the range, -d where clamped)
+    _, t1, t3, t5 = O.int_quant_chain(c["x"], c["scale"], zp, qmin, qmax, rm, dtype)
+    d = O.rnd(c["g"] * c["scale"], dtype).astype(np.float64)
+    clamped = (t3 > O.scalar_to(qmax, dtype)) | (t3 < O.scalar_to(qmin, dtype))
+    el = np.where(clamped & np.isfinite(d), -d, 0.0) if cm == "masked" else np.zeros_like(d)
+    el = np.where(np.isfinite(el), el, 0.0)              # +-inf inputs are ordinary clamped elements; NaN compares false
+    ref = np.zeros(max(1, c["scale"].size))
+    idx = np.broadcast_to(np.arange(ref.size).reshape(c["scale"].shape), c["x"].shape).reshape(-1)
+    np.add.at(ref, idx, el.reshape(-1))
+    fin = np.isfinite(host(gz)) & np.isfinite(ref)
+    tol = np.abs(el).sum() * 4 * ulp(dtype) + 1e-4
+    assert np.all(np.abs(host(gz).astype(np.float64)[fin] - ref[fin]) <= tol), (host(gz), ref)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_integer_export(K, dtype):
     """bvb_int_quant_to_int: IntQuant.to_int stored as int8 / uint8 / int32, against the golden codes of the reference
     and against the float codes of the fused kernel; scalar, per-row, per-channel and ragged / unaligned cases;
