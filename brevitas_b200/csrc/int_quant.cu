@@ -303,7 +303,7 @@ constexpr int PL_THREADS = 256;
 constexpr int PL_UNROLL = 4;
 
 template <typename T, int RM, bool BWD>
-__global__ void __launch_bounds__(PL_THREADS) int_quant_planes_kernel(
+__global__ void __launch_bounds__(PL_THREADS, BWD ? 2 : 4) int_quant_planes_kernel(
         const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ out,
         T* __restrict__ codes, float* gscale_out, int64_t nplanes, int64_t inner, int64_t count, int group,
         int vec_ok, int masked, QParams p) {
