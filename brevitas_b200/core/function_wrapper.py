@@ -120,7 +120,13 @@ class PermuteDims(nn.Module):
 
 
 class OverTensorView(nn.Module):
+    """Flat view for whole-tensor statistics (function_wrapper/shape.py:30-45).  Every whole-tensor statistic (max, min,
+    mean, k-th value) is invariant under a permutation of the elements, so a channels-last tensor is flattened in its
+    MEMORY order -- a view -- instead of being copied into logical NCHW order first."""
+
     def forward(self, x: Tensor) -> Tensor:
+        if x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+            return x.permute(0, 2, 3, 1).reshape(-1)
         return x.reshape(F_shape.over_tensor(x))
 
 

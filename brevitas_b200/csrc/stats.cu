@@ -8,7 +8,9 @@
 //                             (fp32: 4 passes, bf16/fp16: 2 passes) instead of a sort.
 //   bvb_running_stats_update  _RuntimeStats.forward   src/brevitas/core/stats/stats_wrapper.py:56-65
 //
-// Workspace layout for the select (uint32 words): hist[pass][row][256].
+// Workspace layout for the select: uint32 hist[4][rows][256], then (8-byte aligned) int64 first_index[rows][256]: the
+// smallest element index seen per bin of the LAST digit, recorded during the last pass so that locating the k-th
+// value's position (needed by the backward) costs no extra scan of the tensor.
 #include "common.cuh"
 #include "host.cuh"
 
@@ -96,7 +98,8 @@ __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, 
 // one radix pass: histogram digit `pass` of the keys whose higher digits equal the resolved prefix
 template <typename T>
 __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
-                                                                int vec_ok, int pass, int64_t k, uint32_t* hist) {
+                                                                int vec_ok, int pass, int64_t k, uint32_t* hist,
+                                                                unsigned long long* first_index) {
     constexpr int V = DT<T>::VEC;
     __shared__ uint32_t sh[KTH_THREADS / 32][KTH_BINS];
     __shared__ uint32_t s_prefix;
@@ -119,14 +122,19 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
         // same-bin lanes; measured faster than match_any aggregation, whose cost is paid per element).  Later passes
         // count only the keys below the resolved prefix -- a small minority for the high percentiles this is used
         // for -- so a warp first votes and skips the histogram update when no lane has a candidate.
-        auto visit = [&](float v, bool valid) {
+        unsigned long long* fi = first_index ? first_index + row * KTH_BINS : nullptr;   // non-null in the last pass only
+        auto visit = [&](float v, bool valid, int64_t j) {
             const uint32_t key = KeyTraits<T>::key(v);
             if (pass == 0) {
                 if (valid) atomicAdd(&myh[key >> shift], 1u);
             } else {
                 const bool take = valid && ((key >> prefix_shift) == prefix);
                 if (__any_sync(0xffffffffu, take)) {
-                    if (take) atomicAdd(&myh[(key >> shift) & digit_mask], 1u);
+                    if (take) {
+                        const uint32_t bin = (key >> shift) & digit_mask;
+                        atomicAdd(&myh[bin], 1u);
+                        if (fi) atomicMin(fi + bin, (unsigned long long)j);
+                    }
                 }
             }
         };
@@ -149,13 +157,13 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
                 float e[V];
                 DT<T>::unpack(q[u], e);
 #pragma unroll
-                for (int i = 0; i < V; ++i) visit(e[i], ok[u]);
+                for (int i = 0; i < V; ++i) visit(e[i], ok[u], (b0 + (int64_t)u * gstride + threadIdx.x) * V + i);
             }
         }
         for (int64_t b0 = nvec * V + (int64_t)blockIdx.x * KTH_THREADS; b0 < cols; b0 += gstride) {
             const int64_t j = b0 + threadIdx.x;
             const bool valid = j < cols;
-            visit(valid ? DT<T>::to_f(xr[j]) : 0.f, valid);
+            visit(valid ? DT<T>::to_f(xr[j]) : 0.f, valid, j);
         }
         __syncthreads();
         uint32_t* gh = hist + ((int64_t)pass * rows + row) * KTH_BINS;
@@ -173,7 +181,8 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
 template <typename T>
 __global__ void __launch_bounds__(KTH_THREADS) kth_final_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                  int64_t k, const uint32_t* hist, T* out,
-                                                                 long long* index_out) {
+                                                                 long long* index_out,
+                                                                 const unsigned long long* first_index) {
     constexpr int P = KeyTraits<T>::PASSES;
     __shared__ uint32_t s_key;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,18 +195,9 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_final_kernel(const T* __restr
         __syncthreads();
         const uint32_t key = s_key;
         if (blockIdx.x == 0 && threadIdx.x == 0) out[row] = DT<T>::from_f(KeyTraits<T>::value(key));
-        if (index_out) {
-            const T* xr = x + row * cols;
-            long long best = 0x7fffffffffffffffLL;
-            for (int64_t j = (int64_t)blockIdx.x * KTH_THREADS + threadIdx.x; j < cols; j += (int64_t)gridDim.x * KTH_THREADS) {
-                if (KeyTraits<T>::key(DT<T>::to_f(xr[j])) == key) { best = j; break; }   // ascending per thread
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                long long t = __shfl_xor_sync(0xffffffffu, best, o);
-                best = t < best ? t : best;
-            }
-            if (lane == 0 && best != 0x7fffffffffffffffLL) atomicMin(index_out + row, best);
+        if (index_out && blockIdx.x == 0 && threadIdx.x == 0) {
+            const uint32_t last_bin = key & ((1u << KeyTraits<T>::width(P - 1)) - 1u);
+            index_out[row] = (long long)first_index[row * KTH_BINS + last_bin];
         }
         __syncthreads();
     }
@@ -209,10 +209,11 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     constexpr int P = KeyTraits<T>::PASSES;
     constexpr int V = DT<T>::VEC;
     uint32_t* hist = (uint32_t*)workspace;
+    unsigned long long* first_index = (unsigned long long*)(hist + (size_t)4 * (size_t)rows * KTH_BINS);
     cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)P * (size_t)rows * KTH_BINS, st);
     if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_abs_kth_value_rows: memset: %s", cudaGetErrorString(e));
     if (index_out) {
-        e = cudaMemsetAsync(index_out, 0x7f, sizeof(int64_t) * (size_t)rows, st);
+        e = cudaMemsetAsync(first_index, 0xff, sizeof(unsigned long long) * (size_t)rows * KTH_BINS, st);
         if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_abs_kth_value_rows: memset: %s", cudaGetErrorString(e));
     }
     const int vec_ok = (aligned16(x) && (cols % V) == 0) ? 1 : 0;
@@ -224,9 +225,11 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)gy);
     for (int pass = 0; pass < P; ++pass)
-        kth_hist_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist);
-    const dim3 fgrid(index_out ? (unsigned)gx : 1u, (unsigned)gy);      // the value alone needs one CTA per row
-    kth_final_kernel<T><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out);
+        kth_hist_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist,
+                                                         (index_out && pass == P - 1) ? first_index : nullptr);
+    const dim3 fgrid(1u, (unsigned)gy);                                  // one CTA per row resolves the last digit
+    kth_final_kernel<T><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out,
+                                                       first_index);
     return check_launch("bvb_abs_kth_value_rows");
 }
 
@@ -252,7 +255,7 @@ using namespace bvb;
 
 extern "C" int64_t bvb_kth_workspace_bytes(int64_t rows) {
     if (rows < 1) rows = 1;
-    return (int64_t)sizeof(uint32_t) * 4 * rows * KTH_BINS;
+    return (int64_t)sizeof(uint32_t) * 4 * rows * KTH_BINS + (int64_t)sizeof(unsigned long long) * rows * KTH_BINS;
 }
 
 extern "C" int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols,

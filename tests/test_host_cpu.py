@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     loaded = _lib.load()
     assert loaded.bvb_version() == 100
     assert loaded.bvb_workspace_bytes() >= 64 * 1024
-    assert loaded.bvb_kth_workspace_bytes(3) == 4 * 4 * 3 * 256
+    assert loaded.bvb_kth_workspace_bytes(3) == 4 * 4 * 3 * 256 + 8 * 3 * 256     # histograms + first-index table
 
 
 def test_header_cites_reference_lines():
