@@ -172,6 +172,32 @@ def int_quant_backward(g, x, scale, zero_point, qmin, qmax, round_mode="round", 
     return gx, gs
 
 
+# ---- QuantReLU with the ReLU folded in (proxy/runtime_quant.py:73-84: activation_impl = nn.ReLU, then tensor_quant) ----
+def relu_int_quant_forward(x, scale, zero_point, qmin, qmax, round_mode="round", dtype="f32"):
+    """int_quant(torch.relu(x)); torch.relu keeps NaN and maps -0.0 to +0.0"""
+    x = np.asarray(x, dtype=F32)
+    r = np.where(np.isnan(x), x, np.maximum(x, F32(0.0))).astype(F32)
+    r = np.where(r == 0, F32(0.0), r).astype(F32)
+    return int_quant_forward(r, scale, zero_point, qmin, qmax, round_mode, dtype)
+
+
+def relu_int_quant_backward(g, x, scale, zero_point, qmin, qmax, round_mode="round", clamp_mode="masked", dtype="f32"):
+    """(gx, gscale_elementwise) of int_quant(relu(x)): the quantizer's backward at relu(x), then ATen's
+    threshold_backward, which zeroes the gradient where x <= 0 (NaN inputs keep it)"""
+    x = np.asarray(x, dtype=F32)
+    r = np.where(np.isnan(x), x, np.maximum(x, F32(0.0))).astype(F32)
+    gq, gs = int_quant_backward(g, r, scale, zero_point, qmin, qmax, round_mode, clamp_mode, dtype)
+    with np.errstate(invalid="ignore"):
+        dead = x <= 0
+    return np.where(dead, F32(0.0), gq).astype(F32), gs
+
+
+# ---- integer export (QuantTensor.int(), quant_tensor/__init__.py:174-187; IntQuant.to_int + cast) -------------------
+def int_quant_to_int(x, scale, zero_point, qmin, qmax, round_mode="round", dtype="f32", out_dtype=np.int8):
+    codes = int_quant_chain(x, scale, zero_point, qmin, qmax, round_mode, dtype)[3]
+    return np.nan_to_num(codes, nan=0.0).astype(np.int64).astype(out_dtype)
+
+
 # ---- scale from abs-max statistics (core/stats/stats_op.py:129-141, core/scaling/runtime.py:50-72,
 #      core/restrict_val.py:22-42, core/quant/int.py:156-163) -----------------------------------------------------
 def absmax_rows(x2d):

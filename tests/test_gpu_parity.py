@@ -414,6 +414,11 @@ def test_relu_fused_into_quantizer(K, shape, sshape, cl, dtype):
         gq, gsr = K.int_quant_bwd(g, xr, s, 0.0, qmin, qmax, 0, cm, True)
         gxr = torch.where(xd <= 0, torch.zeros_like(gq), gq)          # threshold_backward: zero where x <= 0
         assert_bits_equal(host(gxf), host(gxr), "gradient")
+        # ... and against the oracle's restatement of the fused op
+        cmn = "masked" if cm == 1 else "ste"
+        assert_bits_equal(host(yf), O.relu_int_quant_forward(host(xd), host(s), 0.0, qmin, qmax, "round", dtype), "fwd vs oracle")
+        gxo, _ = O.relu_int_quant_backward(host(g), host(xd), host(s), 0.0, qmin, qmax, "round", cmn, dtype)
+        assert_bits_equal(host(gxf), gxo, "bwd vs oracle")
         ok = torch.isfinite(gsr) & torch.isfinite(gsf)
         assert torch.allclose(gsf[ok], gsr[ok], rtol=1e-3 if dtype == "f32" else 6e-2, atol=1e-2)
 
