@@ -22,8 +22,8 @@ from .core.quant import (BinaryQuant, ClampedBinaryQuant, IntQuant, PrescaledRes
 from .core.restrict_val import FloatRestrictValue, LogFloatRestrictValue, PowerOfTwoRestrictValue
 from .core.scaling import (ConstScaling, IntScaling, ParameterFromRuntimeStatsScaling, ParameterScaling,
                            PowerOfTwoIntScaling, RuntimeStatsScaling, StatsFromParameterScaling)
-from .core.stats import AbsMax, AbsMinMax, AbsPercentile, NegativeMinOrZero
-from .core.zero_point import StatsFromParameterZeroPoint, ZeroZeroPoint
+from .core.stats import AbsMax, AbsMinMax, AbsPercentile, NegativeMinOrZero, NegativePercentileOrZero, PercentileInterval
+from .core.zero_point import ParameterFromRuntimeZeroPoint, StatsFromParameterZeroPoint, ZeroZeroPoint
 
 SCALING_STATS_REDUCE_DIM = 1
 
@@ -337,3 +337,31 @@ class ShiftedUint8WeightPerTensorFloat(WeightQuantizer):
 
 class ShiftedUint8WeightPerChannelFloat(ShiftedUint8WeightPerTensorFloat):
     scaling_per_output_channel = True
+
+
+class ShiftedUint8ActPerTensorFloat(ActQuantizer):
+    """quant/shifted_scaled_int.py:19-42 = ShiftedParamFromPercentileUintQuant + ParamFromRuntimePercentileIntervalScaling:
+    scale from the [0.001, 99.999] percentile interval and zero-point from the low percentile, both collected for
+    ``collect_stats_steps`` steps and then learned."""
+    narrow_range = False
+    signed = False
+    bit_width = 8
+    scaling_min_val = 1e-10
+    high_percentile_q = 99.999
+    low_percentile_q = 0.001
+    collect_stats_steps = 300
+    quantize_zero_point = True
+
+    @classmethod
+    def tensor_quant(cls) -> nn.Module:
+        iq = IntQuant(narrow_range=cls.narrow_range, signed=cls.signed,
+                      float_to_int_impl=_FLOAT_TO_INT[cls.float_to_int_impl_type](), tensor_clamp_impl=fw.TensorClamp(),
+                      quant_delay_steps=cls.quant_delay_steps)
+        scaling = ParameterFromRuntimeStatsScaling(
+            cls.collect_stats_steps, PercentileInterval(cls.low_percentile_q, cls.high_percentile_q, None),
+            fw.OverTensorView(), (), cls._restrict(), cls.scaling_stats_momentum, cls.scaling_min_val)
+        zero_point = ParameterFromRuntimeZeroPoint(
+            cls.collect_stats_steps, iq, cls.quantize_zero_point, NegativePercentileOrZero(cls.low_percentile_q, None), (),
+            fw.OverTensorView(), cls.scaling_stats_momentum)
+        return RescalingIntQuant(int_quant=iq, scaling_impl=scaling, int_scaling_impl=cls._int_scaling(),
+                                 zero_point_impl=zero_point, bit_width_impl=BitWidthConst(int(cls.bit_width)))

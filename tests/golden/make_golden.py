@@ -466,13 +466,51 @@ def gen_widen(out):
     out["widen/parameter_zero_point/zp"] = npf(pz(xa, sc8, bw8))
 
 
+def gen_shifted_act(out):
+    """ShiftedUint8ActPerTensorFloat wiring (quant/shifted_scaled_int.py:19-42 = ShiftedParamFromPercentileUintQuant +
+    ParamFromRuntimePercentileIntervalScaling): scale and zero-point are runtime statistics for `collect` steps, then
+    learned parameters; masked clamp.  3 collection steps, 2 learned steps (gradients reach both parameters), eval."""
+    from brevitas.core import function_wrapper as fw
+    from brevitas.core.bit_width import BitWidthConst
+    from brevitas.core.quant import IntQuant, RescalingIntQuant
+    from brevitas.core.restrict_val import FloatRestrictValue
+    from brevitas.core.scaling import IntScaling, ParameterFromRuntimeStatsScaling
+    from brevitas.core.stats import NegativePercentileOrZero, PercentileInterval
+    from brevitas.core.zero_point import ParameterFromRuntimeZeroPoint
+    collect = 3
+    iq = IntQuant(narrow_range=False, signed=False, float_to_int_impl=fw.RoundSte(), tensor_clamp_impl=fw.TensorClamp())
+    tq = RescalingIntQuant(
+        iq, ParameterFromRuntimeStatsScaling(collect, PercentileInterval(5.0, 95.0, None), fw.OverTensorView(), (),
+                                             FloatRestrictValue(), 0.1, 1e-10),
+        IntScaling(False, False),
+        ParameterFromRuntimeZeroPoint(collect, iq, True, NegativePercentileOrZero(5.0, None), (), fw.OverTensorView(), 0.1),
+        BitWidthConst(8))
+    tq.train()
+    for step in range(6):
+        if step == 5:
+            tq.eval()
+        x = (make_input((6, 40), 200 + step, 1.5, False) + 0.4).requires_grad_(True)
+        g = make_input((6, 40), 300 + step, 1.0, False)
+        y, scale, zp, bw = tq(x)
+        for prm in (tq.scaling_impl.value, tq.zero_point_impl.value):
+            prm.grad = None
+        (y * g).sum().backward()
+        k = f"shifted_act/step{step}/"
+        out[k + "x"], out[k + "g"], out[k + "y"], out[k + "gx"] = npf(x), npf(g), npf(y), npf(x.grad)
+        out[k + "scale"], out[k + "zero_point"] = npf(scale), npf(zp)
+        gs, gz = tq.scaling_impl.value.grad, tq.zero_point_impl.value.grad
+        out[k + "g_scale_value"] = npf(gs) if gs is not None else np.zeros((), np.float32)
+        out[k + "g_zp_value"] = npf(gz) if gz is not None else np.zeros((), np.float32)
+        out[k + "scale_value"], out[k + "zp_value"] = npf(tq.scaling_impl.value), npf(tq.zero_point_impl.value)
+
+
 def main():
     import_reference()
     torch.manual_seed(123456)
     groups = {"ste": gen_ste, "int_quant": gen_int_quant, "weight_stats": gen_weight_stats,
               "runtime_token": gen_runtime_token, "binary": gen_binary, "percentile": gen_percentile,
               "param_from_stats": gen_param_from_stats, "int_tables": gen_int_tables, "kat": gen_docstring_kats,
-              "widen": gen_widen}
+              "widen": gen_widen, "shifted_act": gen_shifted_act}
     only = sys.argv[1:]
     if only:
         groups = {k: v for k, v in groups.items() if k in only}

@@ -240,3 +240,37 @@ def test_learned_bit_width_and_zero_points():
     assert_bits_equal(host(zpm(xa, sc8, bw8)), d["widen/runtime_zero_point/zp_eval"], "eval")
     pz = ParameterZeroPoint(-0.37, iq, True, None).cuda()
     assert_bits_equal(host(pz(xa, sc8, bw8)), d["widen/parameter_zero_point/zp"], "learned zero point")
+
+
+def test_shifted_uint8_act_quantizer_collect_then_learn():
+    """ShiftedUint8ActPerTensorFloat (quant/shifted_scaled_int.py:19-42): 3 collection steps, 2 learned steps, eval.  The
+    tensor goes through the zero-point-operand kernel; from step 3 on its d(scale) / d(zero_point) reach the two
+    learned parameters through the reference's own tiny ops."""
+    from brevitas_b200.quant import ShiftedUint8ActPerTensorFloat
+    d = load("shifted_act")
+    tq = ShiftedUint8ActPerTensorFloat.let(collect_stats_steps=3, high_percentile_q=95.0, low_percentile_q=5.0).tensor_quant().cuda()
+    tq.train()
+    for step in range(6):
+        if step == 5:
+            tq.eval()
+        k = f"shifted_act/step{step}/"
+        x = dev(d[k + "x"], "f32").requires_grad_(True)
+        y, scale, zp, bw = tq(x)
+        for prm in (tq.scaling_impl.value, tq.zero_point_impl.value):
+            prm.grad = None
+        (y * dev(d[k + "g"], "f32")).sum().backward()
+        assert_bits_equal(host(scale), d[k + "scale"], f"scale, step {step}")
+        assert_bits_equal(host(zp), d[k + "zero_point"], f"zero point, step {step}")
+        assert_bits_equal(host(y), d[k + "y"], f"y, step {step}")
+        assert_bits_equal(host(tq.scaling_impl.value), d[k + "scale_value"], f"scale parameter, step {step}")
+        assert_bits_equal(host(tq.zero_point_impl.value), d[k + "zp_value"], f"zero-point parameter, step {step}")
+        if step < 3:
+            # collecting: the percentile statistics route gradient to single elements of x (tie-free here)
+            close(host(x.grad), d[k + "gx"], "f32", k=64.0, what=f"gx, step {step}")
+        else:
+            assert_bits_equal(host(x.grad), d[k + "gx"], f"gx, step {step}")
+            gs, gz = tq.scaling_impl.value.grad, tq.zero_point_impl.value.grad
+            xs = np.abs(d[k + "g"]) * (np.abs(d[k + "x"]) / d[k + "scale"] + 256.0)
+            tol = 1e-5 * float(xs.sum()) + 1e-4
+            assert abs(float(gs) - float(d[k + "g_scale_value"])) <= tol, (step, float(gs), d[k + "g_scale_value"])
+            assert abs(float(gz) - float(d[k + "g_zp_value"])) <= tol, (step, float(gz), d[k + "g_zp_value"])
