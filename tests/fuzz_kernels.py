@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Randomised differential test of the C-ABI kernels against the numpy oracle (run on the GPU box):
+"""Test infrastructure (lives under tests/ because it uses the oracle).  Randomised differential test of the C-ABI
+kernels against the numpy oracle (run on the GPU box):
 random shapes (aligned / ragged / tiny / wide rows), dtypes, scale layouts (scalar, per row, NCHW channel, NHWC
 channel, per token), ranges, round and clamp modes, with and without the fused ReLU / tensor zero-point / integer export.
-    python tools/fuzz.py --cases 400 --seed 0
+    python tests/fuzz_kernels.py --cases 400 --seed 0
 Exits non-zero on the first mismatch and prints the case."""
 import argparse
 import os
@@ -13,7 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import brevitas_b200  # noqa: E402,F401
 from brevitas_b200 import _kernels as K  # noqa: E402
 from golden_util import assert_bits_equal  # noqa: E402
