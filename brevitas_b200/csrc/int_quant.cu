@@ -106,12 +106,12 @@ __device__ __forceinline__ float bwd_elem(float g, float x, const DivBy& dv, flo
     float gsv = DT<T>::rnd(fmul(g, dv.b));               // d y / d t6 : grad * scale
     float d = gsv;
     if (masked || want_gs) {
-        float t1, t3, t5;
-        to_int_chain<T, RM>(x, dv, p, t1, t3, t5);
-        if (masked) {
-            bool m = !(t3 > p.qmax) && !(t3 < p.qmin);   // torch.where backward of both clamp stages
-            d = m ? gsv : 0.f;
-        }
+        const float t1 = DT<T>::rnd(dv(x));
+        float t2 = fadd(t1, p.zp);
+        if (DT<T>::LOWP && p.zp_nonzero) t2 = DT<T>::rnd(t2);
+        const float t3 = float_to_int<T, RM>(t2);
+        const float t5 = minmax_clamp(t3, p.qmin, p.qmax);      // see bwd_n: sign of zero invisible, mask = "unchanged"
+        if (masked) d = (t3 < t5 || t3 > t5) ? 0.f : gsv;       // torch.where backward of both clamp stages
         if (want_gs) {
             float t6 = fsub(t5, p.zp);
             // d(scale) = g * t6  -  d * ((x / s) / s); order-dependent sum => fp32 accumulation,
@@ -138,14 +138,20 @@ __device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], cons
         DT<T>::template rnd_n<N>(t1);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            float t3, t5;
             const float t1r = t1[i];
-            to_int_from_t1<T, RM>(t1r, p, t3, t5);
-            const float dfull = d[i];
-            if (masked) {
-                const bool m = !(t3 > p.qmax) && !(t3 < p.qmin);
-                d[i] = m ? dfull : 0.f;
+            float t2;
+            if (RM & RM_ZP0) {
+                t2 = fadd(t1r, 0.f);
+            } else {
+                t2 = fadd(t1r, p.zp);
+                if (DT<T>::LOWP && p.zp_nonzero) t2 = DT<T>::rnd(t2);
             }
+            const float t3 = float_to_int<T, RM>(t2);
+            // the clamped code only feeds the d(scale) sum here (a zero's sign is invisible), and the clamp mask
+            // "not (t3 > qmax) and not (t3 < qmin)" is "the clamp left t3 unchanged, or t3 is NaN": one ordered
+            // not-equal compare instead of two compares on the bounds
+            const float t5 = minmax_clamp(t3, p.qmin, p.qmax);
+            if (masked) d[i] = (t3 < t5 || t3 > t5) ? 0.f : d[i];
             if (want_gs) {
                 const float t6 = (RM & RM_ZP0) ? t5 : fsub(t5, p.zp);
                 gs_acc = fmaf(eg[i], t6, gs_acc);
