@@ -422,9 +422,14 @@ __global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
         const uint4 qs = *reinterpret_cast<const uint4*>(scale + c0);      // c0 is a multiple of V: 16-byte aligned
         DT<T>::unpack(qs, sv);
     }
-    float acc[V];
+    float acc[V], inv_s[V];
+    DivBy dvs[V];                                   // the thread's V divisor set-ups, built once
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int i = 0; i < V; ++i) {
+        acc[i] = 0.f;
+        dvs[i] = DivBy(sv[i], DT<T>::MUL_DIV_EXACT);
+        inv_s[i] = dvs[i].approx_recip();
+    }
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     const uint4* gv = reinterpret_cast<const uint4*>(BWD ? gy : x);
     uint4* ov = reinterpret_cast<uint4*>(out);
@@ -452,19 +457,16 @@ __global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
                     float eg[V];
                     DT<T>::unpack(qg[u], eg);
 #pragma unroll
-                    for (int i = 0; i < V; ++i) {
-                        const DivBy dv(sv[i], DT<T>::MUL_DIV_EXACT);      // loop-invariant per thread: hoisted by the compiler
-                        eo[i] = bwd_elem<T, RM>(eg[i], ex[i], dv, dv.approx_recip(), p, masked, want_gs, acc[i]);
-                    }
+                    for (int i = 0; i < V; ++i)
+                        eo[i] = bwd_elem<T, RM>(eg[i], ex[i], dvs[i], inv_s[i], p, masked, want_gs, acc[i]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < V; ++i) {
-                        const DivBy dv(sv[i], DT<T>::MUL_DIV_EXACT);
                         float t1, t3, t5;
-                        to_int_chain<T, RM>(ex[i], dv, p, t1, t3, t5);
+                        to_int_chain<T, RM>(ex[i], dvs[i], p, t1, t3, t5);
                         float t6 = fsub(t5, p.zp);
                         if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
-                        eo[i] = fmul(t6, dv.b);
+                        eo[i] = fmul(t6, dvs[i].b);
                         ek[i] = t5;
                     }
                     if (codes) stg_stream(cv + v, DT<T>::pack(ek));
