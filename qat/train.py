@@ -128,7 +128,7 @@ def train_step(model, raw_model, x, y, loss_fn, opt):
     return loss
 
 
-def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False, channels_last=False):
+def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False, channels_last=False, dtype="f32"):
     """returns a dict with samples/s (all ranks), ms/step, kernel-launch count per step of OUR kernels"""
     import brevitas_b200  # noqa: F401
     from brevitas_b200 import _kernels as K
@@ -148,6 +148,9 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
         torch.cuda.set_stream(torch.cuda.Stream(device))
     torch.manual_seed(1234)                               # identical initial weights on every rank
     raw, loss_fn, spec = build(name, device, collect_stats_steps, channels_last=channels_last)
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[dtype]
+    if tdt != torch.float32:
+        raw = raw.to(tdt)               # parameters, buffers and activations in bf16: the packed 16-bit kernels
     model = raw
     if world > 1 and not graph:
         model = nn.parallel.DistributedDataParallel(raw, device_ids=[local], gradient_as_bucket_view=True,
@@ -157,6 +160,8 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
     batches = [make_batch(spec, batch, device, 100 + rank * 7 + i) for i in range(2)]
     if channels_last:       # NHWC end to end: cuDNN's native layout, and the fake-quant kernels take it in place
         batches = [(x.contiguous(memory_format=torch.channels_last), y) for x, y in batches]
+    if tdt != torch.float32:
+        batches = [(x.to(tdt), y if y.dtype == torch.int64 else y.to(tdt)) for x, y in batches]
     # warm-up runs past the statistics-collection phase of the activation quantizers (steady state)
     collecting = collect_stats_steps > 10000           # measure the statistics-collection phase itself
     for i in range(warmup if collecting else max(warmup, collect_stats_steps + 2)):
@@ -190,7 +195,7 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
         ms = float(t.item())
     return {"model": name, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
             "samples_per_s": round(world * batch / (ms * 1e-3), 1), "fakequant_launches_per_step": launches,
-            "final_loss": round(loss_val, 4), "dtype": "f32", "data": "synthetic",
+            "final_loss": round(loss_val, 4), "dtype": dtype, "data": "synthetic",
             "memory_format": "channels_last" if channels_last else "contiguous",
             "phase": "collecting activation statistics (AbsPercentile every step)" if collecting
                      else f"steady state (after {collect_stats_steps} collect steps)",
@@ -207,10 +212,12 @@ def main():
     ap.add_argument("--collect-stats-steps", type=int, default=2)
     ap.add_argument("--graph", action="store_true", help="capture the whole step in a CUDA graph")
     ap.add_argument("--channels-last", action="store_true", help="NHWC activations and conv weights")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     a = ap.parse_args()
     os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
     os.environ.setdefault("NCCL_IB_DISABLE", "1")
-    res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps, graph=a.graph, channels_last=a.channels_last)
+    res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps, graph=a.graph, channels_last=a.channels_last,
+              dtype=a.dtype)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(res))
     import torch.distributed as dist
