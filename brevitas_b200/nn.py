@@ -93,9 +93,9 @@ def _as_quant_tensor(x: Union[Tensor, QuantTensor], training: bool) -> QuantTens
 class WeightQuantProxy(nn.Module):
     """proxy/parameter_quant.py:65-89: owns ``tensor_quant`` for one layer's weight"""
 
-    def __init__(self, quantizer: Optional[Type[WeightQuantizer]], weight: nn.Parameter):
+    def __init__(self, quantizer: Optional[Type[WeightQuantizer]], weight: nn.Parameter, output_channel_dim: int = 0):
         super().__init__()
-        self.tensor_quant = quantizer.tensor_quant(weight) if quantizer is not None else None
+        self.tensor_quant = quantizer.tensor_quant(weight, output_channel_dim) if quantizer is not None else None
         self.signed = quantizer.signed if quantizer is not None else None
         self.is_narrow_range = bool(quantizer.narrow_range) if quantizer is not None else False
 
@@ -252,7 +252,7 @@ class _QuantWBIOL:
         bq = bias_quant.let(**_filter("bias_", kwargs)) if bias_quant else None
         iq = input_quant.let(**_filter("input_", kwargs)) if input_quant else None
         oq = output_quant.let(**_filter("output_", kwargs)) if output_quant else None
-        self.weight_quant = WeightQuantProxy(wq, self.weight)
+        self.weight_quant = WeightQuantProxy(wq, self.weight, getattr(self, "output_channel_dim", 0))
         self.bias_quant = BiasQuantProxy(bq)
         self.input_quant = ActQuantProxy(iq, None)
         self.output_quant = ActQuantProxy(oq, None)
@@ -362,3 +362,51 @@ class QuantAvgPool2d(nn.AvgPool2d):
             x = x.set(bit_width=self.max_acc_bit_width(x.bit_width))
             x = self.trunc_quant(x)
         return x if self.return_quant_tensor else x.value
+
+
+class QuantConv1d(_QuantWBIOL, nn.Conv1d):
+    """nn/quant_conv.py:22-113"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 weight_quant=Int8WeightPerTensorFloat, bias_quant=None, input_quant=None, output_quant=None,
+                 return_quant_tensor=False, **kwargs):
+        nn.Conv1d.__init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+        self._init_quant(weight_quant, bias_quant, input_quant, output_quant, return_quant_tensor, kwargs)
+
+    def max_acc_bit_width(self, input_bit_width, weight_bit_width):
+        max_uint_input = max_int(bit_width=input_bit_width, signed=False, narrow_range=False)
+        max_kernel_val = self.weight_quant.max_uint_value(weight_bit_width)
+        group_size = self.out_channels // self.groups
+        return ceil_ste(torch.log2(max_uint_input * max_kernel_val * self.kernel_size[0] * group_size))
+
+    def forward(self, x):
+        return self._forward(
+            x, lambda a, w, b: F.conv1d(a, w, b, self.stride, self.padding, self.dilation, self.groups))
+
+
+class QuantConvTranspose2d(_QuantWBIOL, nn.ConvTranspose2d):
+    """nn/quant_convtranspose.py: output channels live in dim 1 of the weight ``[in, out / groups, kh, kw]``: per-channel
+    statistics see a permuted view, the scale has shape ``[1, out, 1, 1]``"""
+    output_channel_dim = 1
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1, bias=True,
+                 dilation=1, weight_quant=Int8WeightPerTensorFloat, bias_quant=None, input_quant=None, output_quant=None,
+                 return_quant_tensor=False, **kwargs):
+        nn.ConvTranspose2d.__init__(self, in_channels, out_channels, kernel_size, stride, padding, output_padding, groups,
+                                    bias, dilation)
+        self._init_quant(weight_quant, bias_quant, input_quant, output_quant, return_quant_tensor, kwargs)
+
+    def max_acc_bit_width(self, input_bit_width, weight_bit_width):
+        """nn/quant_convtranspose.py:193-201: overlapping kernel patches per output position"""
+        max_uint_input = max_int(bit_width=input_bit_width, signed=False, narrow_range=False)
+        max_kernel_val = self.weight_quant.max_uint_value(weight_bit_width)
+        group_size = self.out_channels // self.groups
+        overlap = 1
+        for k, st in zip(self.kernel_size, self.stride):
+            overlap *= max(round(k / st), 1)
+        return ceil_ste(torch.log2(max_uint_input * max_kernel_val * overlap * group_size))
+
+    def forward(self, x):
+        return self._forward(
+            x, lambda a, w, b: F.conv_transpose2d(a, w, b, self.stride, self.padding, self.output_padding, self.groups,
+                                                  self.dilation))

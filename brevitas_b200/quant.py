@@ -105,12 +105,14 @@ class WeightQuantizer(Quantizer):
         qt = cls._quant_type()
         if qt == "FP":
             return None
-        if output_channel_dim != 0:
-            raise NotImplementedError("output channels must be dim 0 (Linear / Conv weights)")
         # scaling shape / view / reduce dim: quant/solver/common.py:131-165, parameter.py:137-160
         if cls.scaling_per_output_channel:
-            shape = (weight.shape[0],) + (1,) * (weight.dim() - 1)
-            view, reduce_dim, concat = fw.OverOutputChannelView(cls.scaling_stats_permute_dims), SCALING_STATS_REDUCE_DIM, 1
+            shape = tuple(weight.shape[d] if d == output_channel_dim else 1 for d in range(weight.dim()))
+            permute = cls.scaling_stats_permute_dims
+            if permute is None and output_channel_dim != 0:
+                # transposed convolutions keep their output channels in dim 1: the statistics see them first
+                permute = (output_channel_dim,) + tuple(d for d in range(weight.dim()) if d != output_channel_dim)
+            view, reduce_dim, concat = fw.OverOutputChannelView(permute), SCALING_STATS_REDUCE_DIM, 1
         else:
             shape = ()
             view, reduce_dim, concat = fw.OverTensorView(), None, 0
@@ -127,8 +129,8 @@ class WeightQuantizer(Quantizer):
             # learned scale initialised from the weight statistics (parameter.py:37-61): a one-off, construction-time
             # reduction of a (still host-resident or device) parameter -- not part of the training hot path
             with torch.no_grad():
-                w2 = weight.detach().reshape(weight.shape[0], -1) if cls.scaling_per_output_channel \
-                    else weight.detach().reshape(1, -1)
+                w2 = weight.detach().movedim(output_channel_dim, 0).reshape(weight.shape[output_channel_dim], -1) \
+                    if cls.scaling_per_output_channel else weight.detach().reshape(1, -1)
                 init = w2.abs().max(dim=1)[0].view(shape).clone()
                 if cls.scaling_min_val:
                     init = init.clamp_min(cls.scaling_min_val)

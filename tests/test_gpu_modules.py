@@ -267,3 +267,52 @@ def test_int_quant_roundtrip_every_integer(B):
                         y = iq(s, z, bw, x)
                         assert torch.isclose(y, x).all()
                         assert torch.equal(iq.to_int(s, z, bw, x), ints)
+
+
+def _literal_weight_quant(w, reduce_dims, bits=8):
+    """the reference chain op by op in torch: AbsMax stats -> / int_threshold -> round/clamp with the STE"""
+    thr = 2.0 ** (bits - 1) - 1
+    scale = w.detach().abs().amax(dim=reduce_dims, keepdim=True).clamp_min(1e-10) / thr
+    q = torch.clamp(torch.round(w.detach() / scale), -thr, thr) * scale
+    return w + (q - w).detach(), scale
+
+
+@pytest.mark.parametrize("per_channel", [False, True])
+def test_conv_transpose2d_and_conv1d_layers(B, per_channel):
+    """nn/quant_convtranspose.py, nn/quant_conv.py:22-113: output channels in dim 1 of a transposed-conv weight --
+    per-channel statistics over the permuted view, scale shape [1, O, 1, 1]; values, scales and gradients against
+    the literal torch composition"""
+    from brevitas_b200 import nn as qnn
+    from brevitas_b200.quant import Int8WeightPerChannelFloat, Int8WeightPerTensorFloat
+    wq = Int8WeightPerChannelFloat if per_channel else Int8WeightPerTensorFloat
+    torch.manual_seed(3)
+    layer = qnn.QuantConvTranspose2d(6, 10, 3, stride=2, padding=1, bias=True, weight_quant=wq).cuda()
+    qt = layer.quant_weight()
+    ref_w, ref_s = _literal_weight_quant(layer.weight, (0, 2, 3) if per_channel else (0, 1, 2, 3))
+    assert qt.scale.shape == ((1, 10, 1, 1) if per_channel else ())
+    assert torch.equal(qt.scale.reshape(-1), ref_s.reshape(-1))
+    assert torch.equal(qt.value, ref_w)
+    x = torch.randn(4, 6, 9, 9, device="cuda", requires_grad=True)
+    out = layer(x)
+    ref_out = torch.nn.functional.conv_transpose2d(x, ref_w, layer.bias, 2, 1)
+    # same weights bit for bit; the transposed convolution itself (cuDNN backward-data) may reorder its sums
+    torch.testing.assert_close(out, ref_out, rtol=1e-4, atol=1e-5)
+    g = torch.randn_like(out)
+    gw, = torch.autograd.grad(out, layer.weight, g, retain_graph=True)
+    gw_ref, = torch.autograd.grad(ref_out, layer.weight, g)
+    # the STE passes the weight gradient through everywhere except the arg-max elements, which also collect d(scale)
+    argmax = (layer.weight.detach().abs() == layer.weight.detach().abs().amax(
+        dim=(0, 2, 3) if per_channel else (0, 1, 2, 3), keepdim=True))
+    torch.testing.assert_close(gw[~argmax], gw_ref[~argmax], rtol=1e-4, atol=1e-5)
+    assert int(argmax.sum()) == (10 if per_channel else 1)
+
+    c1 = qnn.QuantConv1d(5, 7, 4, padding=2, weight_quant=wq).cuda()
+    q1 = c1.quant_weight()
+    r1, s1 = _literal_weight_quant(c1.weight, (1, 2) if per_channel else (0, 1, 2))
+    assert q1.scale.shape == ((7, 1, 1) if per_channel else ())
+    assert torch.equal(q1.value, r1) and torch.equal(q1.scale.reshape(-1), s1.reshape(-1))
+    x1 = torch.randn(3, 5, 33, device="cuda")
+    torch.testing.assert_close(c1(x1), torch.nn.functional.conv1d(x1, r1, c1.bias, 1, 2), rtol=1e-4, atol=1e-5)
+    eight = torch.tensor(8.0, device="cuda")
+    assert int(c1.max_acc_bit_width(eight, eight)) == 21      # ceil(log2(255*255*4*7))
+    assert int(layer.max_acc_bit_width(eight, eight)) == 22   # ceil(log2(255*255*(2*2)*10))

@@ -268,3 +268,15 @@ def test_widened_modules_mirror_reference_trees():
     # CPU tensors are rejected by every kernel-backed op (no CPU fallback)
     with pytest.raises(RuntimeError):
         shifted(w)
+
+
+def test_transposed_conv_and_conv1d_layers_construct():
+    """nn/quant_convtranspose.py: output channels in dim 1 -> scale shape [1, O, 1, 1] and a permuting stats view"""
+    import brevitas_b200  # noqa: F401
+    from brevitas_b200 import nn as qnn
+    from brevitas_b200.quant import Int8WeightPerChannelFloat
+    t = qnn.QuantConvTranspose2d(6, 10, 3, stride=2, weight_quant=Int8WeightPerChannelFloat)
+    view = t.weight_quant.tensor_quant.scaling_impl.parameter_list_stats.first_tracked_param.view_shape_impl
+    assert tuple(view.permute_impl.permute_dims) == (1, 0, 2, 3)
+    c = qnn.QuantConv1d(5, 7, 4, weight_quant=Int8WeightPerChannelFloat)
+    assert type(c.weight_quant.tensor_quant).__name__ == "RescalingIntQuant"
