@@ -797,16 +797,15 @@ __global__ void __launch_bounds__(AMR_THREADS) absmax_rows_vec_kernel(const T* _
     for (int64_t row = (int64_t)blockIdx.x * groups_per_cta + gid; row < rows; row += (int64_t)gridDim.x * groups_per_cta) {
         const uint4* xv = reinterpret_cast<const uint4*>(x) + row * row_vecs;
         AbsMaxAcc<T> am;
-        for (int64_t v0 = gtid; v0 < row_vecs; v0 += (int64_t)group * 4) {
+        int64_t v0 = gtid;
+        for (; v0 + (int64_t)3 * group < row_vecs; v0 += (int64_t)group * 4) {      // full chunks: no predication
             uint4 q[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t v = v0 + (int64_t)u * group;
-                q[u] = (v < row_vecs) ? ldg_stream(xv + v) : make_uint4(0, 0, 0, 0);
-            }
+            for (int u = 0; u < 4; ++u) q[u] = ldg_stream(xv + v0 + (int64_t)u * group);
 #pragma unroll
             for (int u = 0; u < 4; ++u) am.add(q[u]);
         }
+        for (; v0 < row_vecs; v0 += group) am.add(ldg_stream(xv + v0));
         uint32_t m = am.result();
         if (group == 32) {
             m = warp_max_u32(m);
@@ -1187,16 +1186,15 @@ __global__ void __launch_bounds__(ST_THREADS) absmax_tensor_kernel(
     const int64_t lo = (int64_t)blockIdx.x * per_cta;
     const int64_t hi = lo + per_cta < nvec ? lo + per_cta : nvec;
     AbsMaxAcc<T> am;
-    for (int64_t b = lo + threadIdx.x; b < hi; b += (int64_t)ST_THREADS * 8) {
+    int64_t b = lo + threadIdx.x;
+    for (; b + (int64_t)7 * ST_THREADS < hi; b += (int64_t)ST_THREADS * 8) {      // full chunks: no predication
         uint4 q[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int64_t v = b + (int64_t)u * ST_THREADS;
-            q[u] = (v < hi) ? ldg_stream(xv + v) : make_uint4(0, 0, 0, 0);
-        }
+        for (int u = 0; u < 8; ++u) q[u] = ldg_stream(xv + b + (int64_t)u * ST_THREADS);
 #pragma unroll
         for (int u = 0; u < 8; ++u) am.add(q[u]);
     }
+    for (; b < hi; b += ST_THREADS) am.add(ldg_stream(xv + b));
     uint32_t m = am.result();
     // widen to fp32 bit ordering so that all dtypes share the same workspace encoding
     uint32_t mf = __float_as_uint(DT<T>::bits_to_f(m));
@@ -1372,6 +1370,17 @@ static inline unsigned stream_grid(int64_t nvec_or_n, int per_block) {
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (unsigned)b;
+}
+
+// Read-only statistic kernels (abs-max, radix-select histograms).  tools/readbench.cu: a bare read pass over 180 MB
+// takes 30.8 us with exactly 1024 resident threads per SM and 34.7-35.0 us with 512 or 2048, whatever the unroll depth
+// (profiles/sweeps/r01w_readbench.log); with the statistic's own arithmetic on top the optimum moves to 5-6 CTAs of
+// 256 threads per SM (tools/statbench.py, profiles/sweeps/r01w_statbench.log).  One wave, contiguous work per CTA.
+unsigned stat_grid(int64_t blocks_wanted, int default_per_sm) {
+    const int per_sm = tuning().stream_ctas_per_sm > 0 ? tuning().stream_ctas_per_sm : default_per_sm;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    int64_t b = blocks_wanted < cap ? blocks_wanted : cap;
+    return (unsigned)(b < 1 ? 1 : b);
 }
 
 template <typename T, int RM>
@@ -1699,7 +1708,7 @@ static int launch_absmax_tensor(const void* x, int64_t n, void* ws, void* scale_
     if (e != cudaSuccess) return fail(BVB_ECUDA, "absmax_tensor: memset: %s", cudaGetErrorString(e));
     int vec_ok = aligned16(x) ? 1 : 0;
     int64_t work = vec_ok ? (n / V + 1) : n;
-    unsigned grid = stream_grid(work, ST_THREADS * ST_UNROLL);
+    unsigned grid = stat_grid((work + ST_THREADS * 8 - 1) / (ST_THREADS * 8), 5);
     absmax_tensor_kernel<T><<<grid, ST_THREADS, 0, st>>>((const T*)x, n, vec_ok, (uint32_t*)ws, (T*)scale_out,
                                                          (T*)absmax_out, min_val, has_min, int_thr, scale_f32);
     return check_launch("absmax_tensor");
@@ -1989,9 +1998,7 @@ extern "C" int bvb_absmax_rows(const void* x, void* out, int64_t rows, int64_t c
         if (aligned16(x) && (cols % V) == 0) {
             const int64_t row_vecs = cols / V;
             const int group = cols * (int64_t)sizeof(T) <= 4096 ? 32 : AMR_THREADS;
-            int64_t grid = (rows + (AMR_THREADS / group) - 1) / (AMR_THREADS / group);
-            const int64_t cap = (int64_t)sm_count() * 8;
-            if (grid > cap) grid = cap;
+            const int64_t grid = stat_grid((rows + (AMR_THREADS / group) - 1) / (AMR_THREADS / group), 6);
             absmax_rows_vec_kernel<T><<<(unsigned)grid, AMR_THREADS, 0, (cudaStream_t)stream>>>(
                 (const T*)x, (T*)out, rows, row_vecs, group);
             return check_launch("bvb_absmax_rows");

@@ -10,7 +10,13 @@
 //
 // Workspace layout for the select: uint32 hist[4][rows][256], then (8-byte aligned) int64 first_index[rows][256]: the
 // smallest element index seen per bin of the LAST digit, recorded during the last pass so that locating the k-th
-// value's position (needed by the backward) costs no extra scan of the tensor.
+// value's position (needed by the backward) costs no extra scan of the tensor.  For rows <= KTH_COMPACT_ROWS a
+// candidate buffer follows: uint32 count[rows] (256 bytes), uint32 keys[rows][KTH_COMPACT_CAP], int64
+// index[rows][KTH_COMPACT_CAP].  As soon as a histogram shows that at most KTH_COMPACT_CAP elements still share the
+// resolved prefix, the next pass copies those candidates (key, element index) aside while it scans, and every later
+// pass reads the copy instead of the tensor: a 99.999th percentile of an fp32 tensor costs two reads of the tensor
+// instead of four.  The decision is a pure function of the (exact) histograms, so every CTA of every pass takes the
+// same one without any flag.
 #include "common.cuh"
 #include "host.cuh"
 
@@ -19,6 +25,9 @@ namespace bvb {
 constexpr int KTH_THREADS = 256;
 constexpr int KTH_UNROLL = 4;
 constexpr int KTH_BINS = 256;
+constexpr int KTH_COMPACT_ROWS = 4;
+constexpr uint32_t KTH_COMPACT_CAP = 1u << 20;
+constexpr int KTH_NO_COMPACT = 99;
 
 template <typename T> struct KeyTraits;
 // Digit layout, most significant first.  The FIRST digit is the whole 8-bit exponent, so that from the second pass on
@@ -50,12 +59,15 @@ template <> struct KeyTraits<__half> {
 
 // Resolve the digits fixed by passes [0, upto) for one row.  Executed by warp 0 of a block; returns
 // (prefix, remaining k) to every lane.  hist counts are exact, so the walk is deterministic.
+// compact_at (optional): 1 + the first pass whose selected bin holds <= cap elements = the pass that copies the
+// candidates aside (KTH_NO_COMPACT if there is none among the resolved passes).
 template <typename T>
 __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, int64_t row, int upto, int64_t k,
-                                            uint32_t& prefix, int64_t& krem) {
+                                            uint32_t& prefix, int64_t& krem, uint32_t cap = 0, int* compact_at = nullptr) {
     const int lane = threadIdx.x & 31;
     prefix = 0;
     krem = k;
+    int cat = KTH_NO_COMPACT;
     for (int q = 0; q < upto; ++q) {
         const uint32_t* h = hist + ((int64_t)q * rows + row) * KTH_BINS;
         // each lane owns 8 consecutive bins
@@ -77,32 +89,42 @@ __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, 
         int src = who ? (__ffs(who) - 1) : 31;
         int bin = 0;
         int64_t before = excl;
+        uint32_t pop = 0;
         if (lane == src) {
             int64_t run = excl;
             bin = 7;
             before = excl + mine - c[7];
+            pop = c[7];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (krem <= run + c[j]) { bin = j; before = run; break; }
+                if (krem <= run + c[j]) { bin = j; before = run; pop = c[j]; break; }
                 run += c[j];
             }
             bin += lane * 8;
         }
         bin = __shfl_sync(0xffffffffu, bin, src);
         before = __shfl_sync(0xffffffffu, before, src);
+        pop = __shfl_sync(0xffffffffu, pop, src);
+        if (cat == KTH_NO_COMPACT && pop <= cap) cat = q + 1;
         prefix = (prefix << KeyTraits<T>::width(q)) | (uint32_t)bin;
         krem -= before;
     }
+    if (compact_at) *compact_at = cat;
 }
 
 // one radix pass: histogram digit `pass` of the keys whose higher digits equal the resolved prefix
 template <typename T>
 __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                 int vec_ok, int pass, int64_t k, uint32_t* hist,
-                                                                unsigned long long* first_index) {
+                                                                unsigned long long* first_index, uint32_t cap,
+                                                                uint32_t* ccount, uint32_t* ckeys,
+                                                                unsigned long long* cidx) {
     constexpr int V = DT<T>::VEC;
+    constexpr int P = KeyTraits<T>::PASSES;
+    constexpr bool CAN_COMPACT = P >= 3;       // 2-digit keys: the copying pass would be the last one
     __shared__ uint32_t sh[KTH_THREADS / 32][KTH_BINS];
     __shared__ uint32_t s_prefix;
+    __shared__ int s_mode;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int shift = KeyTraits<T>::shift(pass);
     const uint32_t digit_mask = (1u << KeyTraits<T>::width(pass)) - 1u;
@@ -110,14 +132,22 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
     for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
         for (int i = threadIdx.x; i < (KTH_THREADS / 32) * KTH_BINS; i += KTH_THREADS) (&sh[0][0])[i] = 0;
         if (warp == 0) {
-            uint32_t prefix; int64_t krem;
-            kth_resolve<T>(hist, rows, row, pass, k, prefix, krem);
-            if (lane == 0) s_prefix = prefix;
+            uint32_t prefix; int64_t krem; int cat;
+            kth_resolve<T>(hist, rows, row, pass, k, prefix, krem, cap, &cat);
+            if (lane == 0) {
+                s_prefix = prefix;
+                // 0: scan the tensor   1: scan it and copy the candidates aside   2: scan the copy made by pass `cat`
+                s_mode = cat < pass ? 2 : ((cat == pass && pass < P - 1) ? 1 : 0);
+                if (pass == 0 && blockIdx.x == 0 && ccount) ccount[row] = 0;
+            }
         }
         __syncthreads();
         const uint32_t prefix = s_prefix;
+        const int mode = CAN_COMPACT ? s_mode : 0;
         const T* xr = x + row * cols;
         uint32_t* myh = sh[warp];
+        uint32_t* ck = ckeys + (size_t)row * cap;
+        unsigned long long* ci = cidx + (size_t)row * cap;
         // Pass 0 counts every element: plain shared atomics on the warp's private histogram (the hardware serialises
         // same-bin lanes; measured faster than match_any aggregation, whose cost is paid per element).  Later passes
         // count only the keys below the resolved prefix -- a small minority for the high percentiles this is used
@@ -135,16 +165,55 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
                         atomicAdd(&myh[bin], 1u);
                         if (fi) atomicMin(fi + bin, (unsigned long long)j);
                     }
+                    if (CAN_COMPACT && mode == 1) {          // warp-aggregated append; the total is known to fit (it is the bin's count)
+                        const uint32_t m = __ballot_sync(0xffffffffu, take);
+                        const int leader = __ffs(m) - 1;
+                        uint32_t base = 0;
+                        if (lane == leader) base = atomicAdd(ccount + row, (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (take) {
+                            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                            ck[slot] = key;
+                            ci[slot] = (unsigned long long)j;
+                        }
+                    }
                 }
             }
         };
-        const int64_t nvec = vec_ok ? cols / V : 0;
+        if (CAN_COMPACT && mode == 2) {
+            const uint32_t cnt = ccount[row];
+            for (uint32_t b0 = blockIdx.x * KTH_THREADS; b0 < cnt; b0 += gridDim.x * KTH_THREADS) {
+                const uint32_t i = b0 + threadIdx.x;
+                if (i < cnt) {
+                    const uint32_t key = ck[i];
+                    if ((key >> prefix_shift) == prefix) {
+                        const uint32_t bin = (key >> shift) & digit_mask;
+                        atomicAdd(&myh[bin], 1u);
+                        if (fi) atomicMin(fi + bin, ci[i]);
+                    }
+                }
+            }
+        }
+        const int64_t nvec = (mode == 2) ? 0 : (vec_ok ? cols / V : 0);
+        const int64_t scan_end = (mode == 2) ? 0 : cols;
         const uint4* xv = reinterpret_cast<const uint4*>(xr);
         const int64_t gstride = (int64_t)gridDim.x * KTH_THREADS;
         // KTH_UNROLL independent 16-byte loads in flight per thread; every lane of a warp runs the same trip count
         // (bounds are rounded up to the block), so the warp votes above always see a full, converged warp
         for (int64_t b0 = (int64_t)blockIdx.x * KTH_THREADS; b0 < nvec; b0 += gstride * KTH_UNROLL) {
             uint4 q[KTH_UNROLL];
+            if (b0 + (int64_t)(KTH_UNROLL - 1) * gstride + KTH_THREADS <= nvec) {     // CTA-uniform: no predication
+#pragma unroll
+                for (int u = 0; u < KTH_UNROLL; ++u) q[u] = ldg_stream(xv + b0 + (int64_t)u * gstride + threadIdx.x);
+#pragma unroll
+                for (int u = 0; u < KTH_UNROLL; ++u) {
+                    float e[V];
+                    DT<T>::unpack(q[u], e);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) visit(e[i], true, (b0 + (int64_t)u * gstride + threadIdx.x) * V + i);
+                }
+                continue;
+            }
             bool ok[KTH_UNROLL];
 #pragma unroll
             for (int u = 0; u < KTH_UNROLL; ++u) {
@@ -160,7 +229,7 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
                 for (int i = 0; i < V; ++i) visit(e[i], ok[u], (b0 + (int64_t)u * gstride + threadIdx.x) * V + i);
             }
         }
-        for (int64_t b0 = nvec * V + (int64_t)blockIdx.x * KTH_THREADS; b0 < cols; b0 += gstride) {
+        for (int64_t b0 = nvec * V + (int64_t)blockIdx.x * KTH_THREADS; b0 < scan_end; b0 += gstride) {
             const int64_t j = b0 + threadIdx.x;
             const bool valid = j < cols;
             visit(valid ? DT<T>::to_f(xr[j]) : 0.f, valid, j);
@@ -203,6 +272,10 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_final_kernel(const T* __restr
     }
 }
 
+static inline int64_t kth_base_bytes(int64_t rows) {
+    return (int64_t)sizeof(uint32_t) * 4 * rows * KTH_BINS + (int64_t)sizeof(unsigned long long) * rows * KTH_BINS;
+}
+
 template <typename T>
 static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
                       void* workspace, cudaStream_t st) {
@@ -220,13 +293,20 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     const int64_t work = vec_ok ? cols / V : cols;
     int64_t gx = (work + (int64_t)KTH_THREADS * KTH_UNROLL - 1) / ((int64_t)KTH_THREADS * KTH_UNROLL);
     int64_t gy = rows < 65535 ? rows : 65535;
-    const int64_t cap = (int64_t)sm_count() * 8;
-    if (gx * gy > cap) gx = (cap + gy - 1) / gy;
+    const int64_t wave = (int64_t)stat_grid((int64_t)1 << 40, 5);       // CTAs of one wave (tools/statbench.py)
+    if (gx * gy > wave) gx = (wave + gy - 1) / gy;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)gy);
+    // candidate buffer (see the layout at the top); only worth it when there are passes left after the copying one
+    const uint32_t cap = (P >= 3 && rows <= KTH_COMPACT_ROWS) ? KTH_COMPACT_CAP : 0u;
+    unsigned char* cbase = (unsigned char*)workspace + kth_base_bytes(rows);
+    uint32_t* ccount = cap ? (uint32_t*)cbase : nullptr;
+    uint32_t* ckeys = (uint32_t*)(cbase + 256);
+    unsigned long long* cidx = (unsigned long long*)(cbase + 256 + sizeof(uint32_t) * (size_t)rows * KTH_COMPACT_CAP);
     for (int pass = 0; pass < P; ++pass)
         kth_hist_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist,
-                                                         (index_out && pass == P - 1) ? first_index : nullptr);
+                                                         (index_out && pass == P - 1) ? first_index : nullptr, cap,
+                                                         ccount, ckeys, cidx);
     const dim3 fgrid(1u, (unsigned)gy);                                  // one CTA per row resolves the last digit
     kth_final_kernel<T><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out,
                                                        first_index);
@@ -255,7 +335,9 @@ using namespace bvb;
 
 extern "C" int64_t bvb_kth_workspace_bytes(int64_t rows) {
     if (rows < 1) rows = 1;
-    return (int64_t)sizeof(uint32_t) * 4 * rows * KTH_BINS + (int64_t)sizeof(unsigned long long) * rows * KTH_BINS;
+    int64_t bytes = kth_base_bytes(rows);
+    if (rows <= KTH_COMPACT_ROWS) bytes += 256 + (int64_t)rows * KTH_COMPACT_CAP * (sizeof(uint32_t) + sizeof(unsigned long long));
+    return bytes;
 }
 
 extern "C" int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols,

@@ -156,6 +156,46 @@ def test_percentile_golden(K):
     assert got == [float(i) for i in range(1, 11)]
 
 
+def _kth_check(K, x, rows, cols, k):
+    """value and position against torch on the same GPU (exact: a selection, no arithmetic); the position must be the
+    smallest index holding the k-th smallest |x|"""
+    val, idx = K.abs_kth_value_rows(x, rows, cols, k, want_index=True)
+    a = x.view(rows, cols).abs()
+    ref = a.float().kthvalue(k, dim=1)[0].to(x.dtype)
+    assert torch.equal(val, ref), (val, ref)
+    first = torch.stack([(a[r] == ref[r]).nonzero()[0, 0] for r in range(rows)])
+    assert torch.equal(idx, first), (idx, first)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_percentile_candidate_buffer_regimes(K, dtype):
+    """the radix select copies the surviving candidates aside once a histogram shows at most 2^20 of them
+    (csrc/stats.cu): after the first digit (high percentile), after the second (median of 6M values: > 2^20 share the
+    binade), never (more than 2^20 copies of the answer itself), and per row for up to 4 rows"""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 6_000_000
+    x = torch.randn(n, device="cuda", generator=g).to(dtype)
+    for q in (99.999, 99.9, 50.0, 1.0):
+        _kth_check(K, x, 1, n, O.percentile_k(q, n))
+    _kth_check(K, x, 1, n, 1)
+    _kth_check(K, x, 1, n, n)
+    dup = x.clone()
+    dup[::3] = 0.75                      # 2M copies of one value, which is also the median region's answer
+    dup[1::3] = -0.75
+    _kth_check(K, dup, 1, n, n // 2)
+    _kth_check(K, torch.full((n,), -2.5, device="cuda", dtype=dtype), 1, n, n // 3)
+    relu = torch.relu(x)                 # > half exact zeros: the low percentiles resolve to 0 with 3M duplicates
+    _kth_check(K, relu, 1, n, O.percentile_k(10.0, n))
+    _kth_check(K, relu, 1, n, O.percentile_k(99.99, n))
+    rows = x[: 3 * 1_500_000]
+    _kth_check(K, rows, 3, 1_500_000, O.percentile_k(99.99, 1_500_000))
+    _kth_check(K, rows, 3, 1_500_000, O.percentile_k(40.0, 1_500_000))
+    many = x[: 6 * 1_000_000]            # > 4 rows: no candidate buffer
+    _kth_check(K, many, 6, 1_000_000, O.percentile_k(99.9, 1_000_000))
+    ragged = x[1: 1 + 3 * 1_000_001]     # unaligned rows: scalar path
+    _kth_check(K, ragged, 3, 1_000_001, O.percentile_k(99.999, 1_000_001))
+
+
 STE_C = {"round_ste": "bvb_round_ste_impl", "ceil_ste": "bvb_ceil_ste_impl", "floor_ste": "bvb_floor_ste_impl",
          "binary_sign_ste": "bvb_binary_sign_ste_impl", "ternary_sign_ste": "bvb_ternary_sign_ste_impl",
          "round_to_zero_ste": "bvb_round_to_zero_ste_impl", "dpu_round_ste": "bvb_dpu_round_ste_impl",

@@ -23,7 +23,9 @@ def test_library_exports_every_declared_symbol():
     loaded = _lib.load()
     assert loaded.bvb_version() == 100
     assert loaded.bvb_workspace_bytes() >= 64 * 1024
-    assert loaded.bvb_kth_workspace_bytes(3) == 4 * 4 * 3 * 256 + 8 * 3 * 256     # histograms + first-index table
+    base = 4 * 4 * 3 * 256 + 8 * 3 * 256                                            # histograms + first-index table
+    assert loaded.bvb_kth_workspace_bytes(3) == base + 256 + 3 * (1 << 20) * 12     # + candidate buffer (rows <= 4)
+    assert loaded.bvb_kth_workspace_bytes(5) == 4 * 4 * 5 * 256 + 8 * 5 * 256
 
 
 def test_header_cites_reference_lines():
