@@ -41,6 +41,45 @@ def check_sum(got, el, idx, count, dtype, what):
     assert np.all(np.abs(got[ok] - ref[ok]) <= tol[ok]), (what, got[:4], ref[:4])
 
 
+def fuzz_stats(rng, dtype, case):
+    """the reductions behind the scale statistics: k-th smallest |x| with its first position (AbsPercentile), abs-max
+    per row / per tensor -- selections, so exact whatever the dtype; NaN sorts above +inf like torch.kthvalue / max"""
+    T = TDT[dtype]
+    rows = int(rng.choice([1, 1, 2, 3, 4, 5, 9]))
+    cols = int(rng.choice([1, 5, 250, 4096, 10007, 262144, 1_200_000 if rows <= 3 else 70001]))
+    x = O.rnd((rng.standard_normal((rows, cols)) * rng.choice([1e-3, 1.0, 300.0])).astype(np.float32), dtype)
+    mode = rng.choice(["plain", "dup", "relu", "special", "const"])
+    if mode == "dup":
+        x[:, :: int(rng.integers(2, 5))] = x[0, 0]
+    elif mode == "relu":
+        x = np.maximum(x, 0.0)
+    elif mode == "const":
+        x[:] = x[0, 0]
+    elif mode == "special" and cols >= 8:
+        x[:, :6] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30]
+        x = O.rnd(x, dtype)
+    k = int(rng.choice([1, cols, int(rng.integers(1, cols + 1)), O.percentile_k(99.999, cols) or 1, O.percentile_k(99.9, cols) or 1]))
+    desc = f"case {case}: {dtype} stats rows={rows} cols={cols} mode={mode} k={k}"
+    try:
+        xd = torch.from_numpy(x).to(T).cuda()
+        val, idx = K.abs_kth_value_rows(xd, rows, cols, k, want_index=True)
+        a = np.abs(x)
+        keys = np.where(np.isnan(a), np.float32(np.inf), a).view(np.uint32).astype(np.int64) + np.isnan(a)   # NaN last
+        order = np.sort(keys, axis=1, kind="stable")[:, k - 1]
+        ref = np.take_along_axis(a, np.argmax(keys == order[:, None], axis=1)[:, None], axis=1)[:, 0]
+        assert_bits_equal(host(val), ref, "kth value")
+        assert np.array_equal(idx.cpu().numpy(), np.argmax(keys == order[:, None], axis=1)), "kth first index"
+        amax_keys = keys.max(axis=1)
+        ref_rows = np.take_along_axis(a, np.argmax(keys == amax_keys[:, None], axis=1)[:, None], axis=1)[:, 0]
+        assert_bits_equal(host(K.absmax_rows(xd, rows, cols)), ref_rows, "absmax rows")
+        flat = keys.reshape(-1)
+        assert_bits_equal(host(K.absmax_tensor(xd)).reshape(1), a.reshape(-1)[np.argmax(flat == flat.max())].reshape(1),
+                          "absmax tensor")
+    except Exception:
+        print("FAILED", desc)
+        raise
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=300)
@@ -50,7 +89,7 @@ def main():
     for case in range(a.cases):
         dtype = rng.choice(["f32", "bf16", "f16"])
         T = TDT[dtype]
-        kind = rng.choice(["flat", "rows", "nchw", "nhwc", "token", "fused_rows", "fused_tensor"])
+        kind = rng.choice(["flat", "rows", "nchw", "nhwc", "token", "fused_rows", "fused_tensor", "stats"])
         rm = rng.choice(["round", "round", "round", "floor", "ceil", "round_to_zero", "dpu_round"])
         cm = rng.choice(["ste", "masked"])
         qmin, qmax = [(-127.0, 127.0), (-128.0, 127.0), (0.0, 255.0), (-8.0, 7.0), (0.0, 15.0), (-1.0, 1.0)][rng.integers(6)]
@@ -69,6 +108,9 @@ def main():
         else:
             shape = (int(rng.choice([1, 9, 1023, 100003])),)
             sshape = ()
+        if kind == "stats":
+            fuzz_stats(rng, dtype, case)
+            continue
         x = O.rnd((rng.standard_normal(shape) * rng.choice([0.3, 5.0, 60.0])).astype(np.float32), dtype)
         g = O.rnd(rng.standard_normal(shape).astype(np.float32), dtype)
         flat = x.reshape(-1)
