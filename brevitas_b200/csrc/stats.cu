@@ -12,8 +12,8 @@
 // smallest element index seen per bin of the LAST digit, recorded during the last pass so that locating the k-th
 // value's position (needed by the backward) costs no extra scan of the tensor.  For rows <= KTH_COMPACT_ROWS a
 // candidate buffer follows: uint32 count[rows] (256 bytes), uint32 keys[rows][KTH_COMPACT_CAP], int64
-// index[rows][KTH_COMPACT_CAP].  As soon as a histogram shows that at most KTH_COMPACT_CAP elements still share the
-// resolved prefix, the next pass copies those candidates (key, element index) aside while it scans, and every later
+// index[rows][KTH_COMPACT_CAP].  As soon as a histogram shows that at most min(KTH_COMPACT_CAP, cols / 8) elements still
+// share the resolved prefix, the next pass copies those candidates (key, element index) aside while it scans, and every later
 // pass reads the copy instead of the tensor: a 99.999th percentile of an fp32 tensor costs two reads of the tensor
 // instead of four.  The decision is a pure function of the (exact) histograms, so every CTA of every pass takes the
 // same one without any flag.
@@ -25,8 +25,8 @@ namespace bvb {
 constexpr int KTH_THREADS = 256;
 constexpr int KTH_UNROLL = 4;
 constexpr int KTH_BINS = 256;
-constexpr int KTH_COMPACT_ROWS = 4;
-constexpr uint32_t KTH_COMPACT_CAP = 1u << 20;
+constexpr int KTH_COMPACT_ROWS = 2;
+constexpr uint32_t KTH_COMPACT_CAP = 1u << 22;
 constexpr int KTH_NO_COMPACT = 99;
 
 template <typename T> struct KeyTraits;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, 
 
 // one radix pass: histogram digit `pass` of the keys whose higher digits equal the resolved prefix
 template <typename T>
-__global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
+__global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                 int vec_ok, int pass, int64_t k, uint32_t* hist,
                                                                 unsigned long long* first_index, uint32_t cap,
                                                                 uint32_t* ccount, uint32_t* ckeys,
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_hist_kernel(const T* __restri
         const int mode = CAN_COMPACT ? s_mode : 0;
         const T* xr = x + row * cols;
         uint32_t* myh = sh[warp];
-        uint32_t* ck = ckeys + (size_t)row * cap;
-        unsigned long long* ci = cidx + (size_t)row * cap;
+        uint32_t* ck = ckeys + (size_t)row * KTH_COMPACT_CAP;
+        unsigned long long* ci = cidx + (size_t)row * KTH_COMPACT_CAP;
         // Pass 0 counts every element: plain shared atomics on the warp's private histogram (the hardware serialises
         // same-bin lanes; measured faster than match_any aggregation, whose cost is paid per element).  Later passes
         // count only the keys below the resolved prefix -- a small minority for the high percentiles this is used
@@ -298,7 +298,9 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)gy);
     // candidate buffer (see the layout at the top); only worth it when there are passes left after the copying one
-    const uint32_t cap = (P >= 3 && rows <= KTH_COMPACT_ROWS) ? KTH_COMPACT_CAP : 0u;
+    // ... and when the candidates are a small part of the row (copying costs 12 bytes per candidate)
+    uint32_t cap = (P >= 3 && rows <= KTH_COMPACT_ROWS) ? KTH_COMPACT_CAP : 0u;
+    if ((int64_t)cap > cols / 8) cap = (uint32_t)(cols / 8);
     unsigned char* cbase = (unsigned char*)workspace + kth_base_bytes(rows);
     uint32_t* ccount = cap ? (uint32_t*)cbase : nullptr;
     uint32_t* ckeys = (uint32_t*)(cbase + 256);

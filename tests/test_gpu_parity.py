@@ -169,9 +169,9 @@ def _kth_check(K, x, rows, cols, k):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_percentile_candidate_buffer_regimes(K, dtype):
-    """the radix select copies the surviving candidates aside once a histogram shows at most 2^20 of them
-    (csrc/stats.cu): after the first digit (high percentile), after the second (median of 6M values: > 2^20 share the
-    binade), never (more than 2^20 copies of the answer itself), and per row for up to 4 rows"""
+    """the radix select copies the surviving candidates aside once a histogram shows at most min(2^22, cols / 8) of
+    them (csrc/stats.cu): after the first digit (high percentile), after the second (median of 6M values: a quarter of
+    them share the binade), never (2M copies of the answer itself), and per row for up to 2 rows"""
     g = torch.Generator(device="cuda").manual_seed(5)
     n = 6_000_000
     x = torch.randn(n, device="cuda", generator=g).to(dtype)
@@ -187,10 +187,11 @@ def test_percentile_candidate_buffer_regimes(K, dtype):
     relu = torch.relu(x)                 # > half exact zeros: the low percentiles resolve to 0 with 3M duplicates
     _kth_check(K, relu, 1, n, O.percentile_k(10.0, n))
     _kth_check(K, relu, 1, n, O.percentile_k(99.99, n))
-    rows = x[: 3 * 1_500_000]
+    _kth_check(K, x, 2, 3_000_000, O.percentile_k(99.99, 3_000_000))
+    _kth_check(K, x, 2, 3_000_000, O.percentile_k(40.0, 3_000_000))
+    rows = x[: 3 * 1_500_000]            # > 2 rows: no candidate buffer
     _kth_check(K, rows, 3, 1_500_000, O.percentile_k(99.99, 1_500_000))
-    _kth_check(K, rows, 3, 1_500_000, O.percentile_k(40.0, 1_500_000))
-    many = x[: 6 * 1_000_000]            # > 4 rows: no candidate buffer
+    many = x[: 6 * 1_000_000]
     _kth_check(K, many, 6, 1_000_000, O.percentile_k(99.9, 1_000_000))
     ragged = x[1: 1 + 3 * 1_000_001]     # unaligned rows: scalar path
     _kth_check(K, ragged, 3, 1_000_001, O.percentile_k(99.999, 1_000_001))

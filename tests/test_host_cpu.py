@@ -24,8 +24,8 @@ def test_library_exports_every_declared_symbol():
     assert loaded.bvb_version() == 100
     assert loaded.bvb_workspace_bytes() >= 64 * 1024
     base = 4 * 4 * 3 * 256 + 8 * 3 * 256                                            # histograms + first-index table
-    assert loaded.bvb_kth_workspace_bytes(3) == base + 256 + 3 * (1 << 20) * 12     # + candidate buffer (rows <= 4)
-    assert loaded.bvb_kth_workspace_bytes(5) == 4 * 4 * 5 * 256 + 8 * 5 * 256
+    assert loaded.bvb_kth_workspace_bytes(3) == base
+    assert loaded.bvb_kth_workspace_bytes(2) == 4 * 4 * 2 * 256 + 8 * 2 * 256 + 256 + 2 * (1 << 22) * 12   # + candidates
 
 
 def test_header_cites_reference_lines():
