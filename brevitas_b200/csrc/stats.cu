@@ -17,6 +17,8 @@
 // pass reads the copy instead of the tensor: a 99.999th percentile of an fp32 tensor costs two reads of the tensor
 // instead of four.  The decision is a pure function of the (exact) histograms, so every CTA of every pass takes the
 // same one without any flag.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host.cuh"
 
@@ -153,28 +155,47 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
         // count only the keys below the resolved prefix -- a small minority for the high percentiles this is used
         // for -- so a warp first votes and skips the histogram update when no lane has a candidate.
         unsigned long long* fi = first_index ? first_index + row * KTH_BINS : nullptr;   // non-null in the last pass only
-        auto visit = [&](float v, bool valid, int64_t j) {
-            const uint32_t key = KeyTraits<T>::key(v);
+        // NV elements of one thread (a 16-byte vector, or one element of a ragged tail) at element index j0.  ONE warp
+        // vote per vector decides whether any lane holds a candidate at all; everything behind it is rare.
+        auto visit = [&](const float* v, auto nv_tag, bool valid, int64_t j0) {
+            constexpr int NV = decltype(nv_tag)::value;
+            uint32_t key[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) key[i] = KeyTraits<T>::key(v[i]);
             if (pass == 0) {
-                if (valid) atomicAdd(&myh[key >> shift], 1u);
-            } else {
-                const bool take = valid && ((key >> prefix_shift) == prefix);
-                if (__any_sync(0xffffffffu, take)) {
-                    if (take) {
-                        const uint32_t bin = (key >> shift) & digit_mask;
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) atomicAdd(&myh[key[i] >> shift], 1u);
+                }
+                return;
+            }
+            bool take[NV];
+            bool mine = false;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                take[i] = valid && ((key[i] >> prefix_shift) == prefix);
+                mine = mine || take[i];
+            }
+            if (__any_sync(0xffffffffu, mine)) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    if (take[i]) {
+                        const uint32_t bin = (key[i] >> shift) & digit_mask;
                         atomicAdd(&myh[bin], 1u);
-                        if (fi) atomicMin(fi + bin, (unsigned long long)j);
+                        if (fi) atomicMin(fi + bin, (unsigned long long)(j0 + i));
                     }
-                    if (CAN_COMPACT && mode == 1) {          // warp-aggregated append; the total is known to fit (it is the bin's count)
-                        const uint32_t m = __ballot_sync(0xffffffffu, take);
-                        const int leader = __ffs(m) - 1;
-                        uint32_t base = 0;
-                        if (lane == leader) base = atomicAdd(ccount + row, (uint32_t)__popc(m));
-                        base = __shfl_sync(0xffffffffu, base, leader);
-                        if (take) {
-                            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
-                            ck[slot] = key;
-                            ci[slot] = (unsigned long long)j;
+                    if (CAN_COMPACT && mode == 1) {   // warp-aggregated append; the total is known to fit (the bin's count)
+                        const uint32_t m = __ballot_sync(0xffffffffu, take[i]);
+                        if (m) {
+                            const int leader = __ffs(m) - 1;
+                            uint32_t base = 0;
+                            if (lane == leader) base = atomicAdd(ccount + row, (uint32_t)__popc(m));
+                            base = __shfl_sync(0xffffffffu, base, leader);
+                            if (take[i]) {
+                                const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                                ck[slot] = key[i];
+                                ci[slot] = (unsigned long long)(j0 + i);
+                            }
                         }
                     }
                 }
@@ -209,8 +230,7 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
                 for (int u = 0; u < KTH_UNROLL; ++u) {
                     float e[V];
                     DT<T>::unpack(q[u], e);
-#pragma unroll
-                    for (int i = 0; i < V; ++i) visit(e[i], true, (b0 + (int64_t)u * gstride + threadIdx.x) * V + i);
+                    visit(e, std::integral_constant<int, V>{}, true, (b0 + (int64_t)u * gstride + threadIdx.x) * V);
                 }
                 continue;
             }
@@ -225,14 +245,14 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
             for (int u = 0; u < KTH_UNROLL; ++u) {
                 float e[V];
                 DT<T>::unpack(q[u], e);
-#pragma unroll
-                for (int i = 0; i < V; ++i) visit(e[i], ok[u], (b0 + (int64_t)u * gstride + threadIdx.x) * V + i);
+                visit(e, std::integral_constant<int, V>{}, ok[u], (b0 + (int64_t)u * gstride + threadIdx.x) * V);
             }
         }
         for (int64_t b0 = nvec * V + (int64_t)blockIdx.x * KTH_THREADS; b0 < scan_end; b0 += gstride) {
             const int64_t j = b0 + threadIdx.x;
             const bool valid = j < cols;
-            visit(valid ? DT<T>::to_f(xr[j]) : 0.f, valid, j);
+            const float e1 = valid ? DT<T>::to_f(xr[j]) : 0.f;
+            visit(&e1, std::integral_constant<int, 1>{}, valid, j);
         }
         __syncthreads();
         uint32_t* gh = hist + ((int64_t)pass * rows + row) * KTH_BINS;
