@@ -405,77 +405,191 @@ constexpr int CL_THREADS = 256;
 constexpr int CL_UNROLL = 4;
 constexpr int CL_MAX_C = 2048;
 
+// one vector of the channels-last kernels through the literal op sequence with the divisors rebuilt on the spot: the
+// never-taken branch of the packed variant, kept out of line so that it costs the hot loop no registers
+template <typename T> struct ClSlow { uint4 o, k; float dacc[DT<T>::VEC]; };
 template <typename T, int RM, bool BWD>
+__device__ __noinline__ ClSlow<T> chanlast_slow_vec(uint4 qx, uint4 qg, uint4 qs, QParams p, int masked_rt, bool want_gs) {
+    constexpr int V = DT<T>::VEC;
+    ClSlow<T> r;
+    float ex[V], eg[V], sv[V], eo[V], ek[V];
+    DT<T>::unpack(qx, ex);
+    DT<T>::unpack(qg, eg);
+    DT<T>::unpack(qs, sv);
+#pragma unroll 1
+    for (int i = 0; i < V; ++i) {
+        const DivBy d(sv[i], DT<T>::MUL_DIV_EXACT);
+        float a = 0.f;
+        if (BWD) {
+            eo[i] = bwd_elem<T, RM>(eg[i], ex[i], d, d.approx_recip(), p, masked_rt, want_gs, a);
+            ek[i] = 0.f;
+        } else {
+            float t1, t3, t5;
+            to_int_chain<T, RM>(ex[i], d, p, t1, t3, t5);
+            float t6 = fsub(t5, p.zp);
+            if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
+            eo[i] = fmul(t6, d.b);
+            ek[i] = t5;
+        }
+        r.dacc[i] = a;
+    }
+    r.o = DT<T>::pack(eo);
+    r.k = DT<T>::pack(ek);
+    return r;
+}
+
+// PK: packed-pair formulation (qdq_vec / bwd_vec) with one scale per LANE, for bf16 with the default quantizers when
+// the host knows the bounds qualify (QParams::pk_ok): the thread keeps V reciprocals and V/2 packed scale pairs instead
+// of V full divisor set-ups.  A thread whose scales leave the exact multiply-by-reciprocal window (|s| outside
+// [2^-40, 2^40)) rebuilds the literal divisor per element instead -- correct, slow, and never seen in practice.
+template <typename T, int RM, bool BWD, bool PK = false>
 __global__ void __launch_bounds__(CL_THREADS) int_quant_chanlast_kernel(
         const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ out,
-        T* __restrict__ codes, float* gscale_out, int64_t nvec, int C, int masked, QParams p) {
+        T* __restrict__ codes, float* gscale_out, int64_t nvec, int C, int masked_rt, QParams p) {
     constexpr int V = DT<T>::VEC;
+    constexpr int NDV = PK ? 1 : V;
     __shared__ float sacc[BWD ? CL_MAX_C : 1];
     const bool want_gs = BWD && gscale_out != nullptr;
+    const bool masked = (RM & RM_MASK_KNOWN) ? ((RM & RM_MASKED) != 0) : (masked_rt != 0);
+    (void)masked;
     const int c0 = (int)(((int64_t)threadIdx.x * V) % C);
     if (want_gs) {
         for (int c = threadIdx.x; c < C; c += CL_THREADS) sacc[c] = 0.f;
         __syncthreads();
     }
-    float sv[V];
+    const uint4 qs = *reinterpret_cast<const uint4*>(scale + c0);          // c0 is a multiple of V: 16-byte aligned
+    float acc[V], inv_s[V];                         // PK: inv_s doubles as the exact reciprocal
+    DivBy dvs[NDV];                                 // !PK: the thread's V divisor set-ups, built once
+    bool lanes_ok = true;
     {
-        const uint4 qs = *reinterpret_cast<const uint4*>(scale + c0);      // c0 is a multiple of V: 16-byte aligned
+        float sv[V];
         DT<T>::unpack(qs, sv);
-    }
-    float acc[V], inv_s[V];
-    DivBy dvs[V];                                   // the thread's V divisor set-ups, built once
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        acc[i] = 0.f;
-        dvs[i] = DivBy(sv[i], DT<T>::MUL_DIV_EXACT);
-        inv_s[i] = dvs[i].approx_recip();
+        for (int i = 0; i < V; ++i) {
+            acc[i] = 0.f;
+            const DivBy d(sv[i], DT<T>::MUL_DIV_EXACT);
+            inv_s[i] = d.approx_recip();
+            lanes_ok = lanes_ok && d.mul_only != 0u;
+            if constexpr (!PK) dvs[i] = d;
+        }
     }
+    const uint32_t s2[4] = {qs.x, qs.y, qs.z, qs.w};                        // PK: the scales as packed pairs of T
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     const uint4* gv = reinterpret_cast<const uint4*>(BWD ? gy : x);
     uint4* ov = reinterpret_cast<uint4*>(out);
     uint4* cv = reinterpret_cast<uint4*>(codes);
-    const int64_t stride = (int64_t)gridDim.x * CL_THREADS;
-    for (int64_t v0 = (int64_t)blockIdx.x * CL_THREADS + threadIdx.x; v0 < nvec; v0 += stride * CL_UNROLL) {
-        uint4 qx[CL_UNROLL], qg[CL_UNROLL];
+
+    auto literal = [&](const uint4& qx, const uint4& qg, int64_t v) -> uint4 {
+        if constexpr (PK) {
+            const ClSlow<T> r = chanlast_slow_vec<T, RM, BWD>(qx, qg, qs, p, masked_rt, want_gs);
 #pragma unroll
-        for (int u = 0; u < CL_UNROLL; ++u) {
-            const int64_t v = v0 + (int64_t)u * stride;
-            if (v < nvec) {
-                qx[u] = ldg_stream(xv + v);
-                if (BWD) qg[u] = ldg_stream(gv + v);
-            }
-        }
+            for (int i = 0; i < V; ++i) acc[i] += r.dacc[i];
+            if (!BWD && codes) stg_stream(cv + v, r.k);
+            return r.o;
+        } else {
+            float ex[V], eo[V], ek[V];
+            DT<T>::unpack(qx, ex);
+            if (BWD) {
+                float eg[V];
+                DT<T>::unpack(qg, eg);
 #pragma unroll
-        for (int u = 0; u < CL_UNROLL; ++u) {
-            const int64_t v = v0 + (int64_t)u * stride;
-            if (v < nvec) {
-                float ex[V], eo[V], ek[V];
-                const uint4 qx0 = qx[u];
-                if (p.pre_relu) qx[u] = relu_vec<T>(qx[u]);
-                DT<T>::unpack(qx[u], ex);
-                if (BWD) {
-                    float eg[V];
-                    DT<T>::unpack(qg[u], eg);
+                for (int i = 0; i < V; ++i)
+                    eo[i] = bwd_elem<T, RM>(eg[i], ex[i], dvs[i], inv_s[i], p, masked_rt, want_gs, acc[i]);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < V; ++i)
-                        eo[i] = bwd_elem<T, RM>(eg[i], ex[i], dvs[i], inv_s[i], p, masked, want_gs, acc[i]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < V; ++i) {
-                        float t1, t3, t5;
-                        to_int_chain<T, RM>(ex[i], dvs[i], p, t1, t3, t5);
-                        float t6 = fsub(t5, p.zp);
-                        if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
-                        eo[i] = fmul(t6, dvs[i].b);
-                        ek[i] = t5;
-                    }
-                    if (codes) stg_stream(cv + v, DT<T>::pack(ek));
+                for (int i = 0; i < V; ++i) {
+                    float t1, t3, t5;
+                    to_int_chain<T, RM>(ex[i], dvs[i], p, t1, t3, t5);
+                    float t6 = fsub(t5, p.zp);
+                    if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
+                    eo[i] = fmul(t6, dvs[i].b);
+                    ek[i] = t5;
                 }
-                uint4 o = DT<T>::pack(eo);
-                if (BWD && p.pre_relu) o = relu_grad_vec<T>(o, qx0);
-                stg_stream(ov + v, o);
+                if (codes) stg_stream(cv + v, DT<T>::pack(ek));
             }
+            return DT<T>::pack(eo);
         }
+    };
+
+    auto body = [&](uint4 qx, const uint4& qg, int64_t v) {
+        const uint4 qx0 = qx;
+        if (p.pre_relu) qx = relu_vec<T>(qx);
+        uint4 o;
+        if constexpr (PK) {
+            if (lanes_ok) {
+                float ex[V], t1[V];
+                DT<T>::unpack(qx, ex);
+#pragma unroll
+                for (int i = 0; i < V; ++i) t1[i] = fmul(ex[i], inv_s[i]);             // x / s (exact after the rounding)
+                if constexpr (!BWD) {
+                    uint32_t w[V / 2], k[V / 2];
+#pragma unroll
+                    for (int j = 0; j < V / 2; ++j) {
+                        const uint32_t t2 = DT<T>::p_add(DT<T>::pack2(t1[2 * j], t1[2 * j + 1]), 0u);
+                        const uint32_t c = DT<T>::p_max_nan(DT<T>::p_min_nan(t2, p.pk_hi), p.pk_lo_pre);
+                        uint32_t r = DT<T>::p_rint(c);
+                        if (p.pk_lo_zero) r &= ~DT<T>::p_lt_mask(r, 0u);
+                        k[j] = r;
+                        w[j] = DT<T>::p_mul(r, s2[j]);
+                    }
+                    if (codes) stg_stream(cv + v, make_uint4(k[0], k[1], k[2], k[3]));
+                    o = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+                    const uint32_t qgw[4] = {qg.x, qg.y, qg.z, qg.w};
+                    float gxe[V];
+#pragma unroll
+                    for (int j = 0; j < V / 2; ++j) {
+                        uint32_t d = DT<T>::p_mul(qgw[j], s2[j]);                          // rnd_T(grad * scale)
+                        const uint32_t t1p = DT<T>::pack2(t1[2 * j], t1[2 * j + 1]);
+                        const uint32_t t2 = DT<T>::p_add(t1p, 0u);
+                        if (masked) d &= ~(DT<T>::p_gt_mask(t2, p.pk_thr_hi) | DT<T>::p_lt_mask(t2, p.pk_thr_lo));
+                        float d0, d1;
+                        DT<T>::p_unpack(d, d0, d1);
+                        if (want_gs) {
+                            const uint32_t c = DT<T>::p_max_nan(DT<T>::p_min_nan(t2, p.pk_hi), p.pk_lo);
+                            float k0, k1, g0, g1, a0, a1;
+                            DT<T>::p_rint_f(c, k0, k1);                                    // t6 (zero-point is 0)
+                            DT<T>::p_unpack(qgw[j], g0, g1);
+                            DT<T>::p_unpack(t1p, a0, a1);
+                            acc[2 * j] = fmaf(g0, k0, acc[2 * j]);
+                            acc[2 * j] = fmaf(-d0, fmul(a0, inv_s[2 * j]), acc[2 * j]);
+                            acc[2 * j + 1] = fmaf(g1, k1, acc[2 * j + 1]);
+                            acc[2 * j + 1] = fmaf(-d1, fmul(a1, inv_s[2 * j + 1]), acc[2 * j + 1]);
+                        }
+                        gxe[2 * j] = fmul(d0, inv_s[2 * j]);                               // grad / scale
+                        gxe[2 * j + 1] = fmul(d1, inv_s[2 * j + 1]);
+                    }
+                    o = DT<T>::pack(gxe);
+                }
+            } else {
+                o = literal(qx, qg, v);
+            }
+        } else {
+            o = literal(qx, qg, v);
+        }
+        if (BWD && p.pre_relu) o = relu_grad_vec<T>(o, qx0);
+        stg_stream(ov + v, o);
+    };
+
+    // grid-stride over vectors; stride * V is a multiple of C, so a thread keeps its V channels.  Full chunks issue
+    // all their loads before the first use (no predication), the ragged end goes one vector at a time.
+    constexpr int U = BWD ? CL_UNROLL / 2 : CL_UNROLL;       // the backward loads two vectors per step
+    const int64_t stride = (int64_t)gridDim.x * CL_THREADS;
+    int64_t v0 = (int64_t)blockIdx.x * CL_THREADS + threadIdx.x;
+    for (; v0 - threadIdx.x + (int64_t)(U - 1) * stride + CL_THREADS <= nvec; v0 += stride * U) {
+        uint4 qx[U], qg[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            qx[u] = ldg_stream(xv + v0 + (int64_t)u * stride);
+            qg[u] = BWD ? ldg_stream(gv + v0 + (int64_t)u * stride) : qx[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) body(qx[u], qg[u], v0 + (int64_t)u * stride);
+    }
+    for (; v0 < nvec; v0 += stride) {
+        const uint4 qx1 = ldg_stream(xv + v0);
+        const uint4 qg1 = BWD ? ldg_stream(gv + v0) : qx1;
+        body(qx1, qg1, v0);
     }
     if (want_gs) {
 #pragma unroll
@@ -1383,6 +1497,23 @@ unsigned stat_grid(int64_t blocks_wanted, int default_per_sm) {
     return (unsigned)(b < 1 ? 1 : b);
 }
 
+// channels-last per-channel kernels: ONE resident wave (every CTA pays V divisor set-ups and, in the backward, C atomics;
+// tools/clbench.py: 63.5 us with the 3 CTAs/SM the backward's registers allow, 78 us with a grid of 4/SM = 1.33 waves)
+template <typename K>
+static unsigned chanlast_grid(K kernel, int64_t nvec) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CL_THREADS, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 2;
+    }
+    if (occ > 4) occ = 4;                                   // 1024 threads per SM
+    if (tuning().stream_ctas_per_sm > 0) occ = tuning().stream_ctas_per_sm;
+    int64_t b = (nvec + CL_THREADS - 1) / CL_THREADS;
+    const int64_t cap = (int64_t)sm_count() * occ;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
 template <typename T, int RM>
 static int launch_int_quant_fwd(const void* x, const void* scale, void* y, void* codes, int64_t n,
                                 int64_t inner, int64_t count, int scale_f32, const QParams& p, int reverse,
@@ -1406,8 +1537,16 @@ static int launch_int_quant_fwd(const void* x, const void* scale, void* y, void*
         ((int64_t)CL_THREADS * V) % count == 0 && (n % count) == 0 && n >= (int64_t)CL_THREADS * V) {
         // channels-last tensor, one scale per channel
         const int64_t nv = n / V;
-        unsigned grid = stream_grid(nv, CL_THREADS * CL_UNROLL);
-        int_quant_chanlast_kernel<T, RM, false><<<grid, CL_THREADS, 0, st>>>(
+        if constexpr (PackedPath<T, RM>::value && DT<T>::MUL_DIV_EXACT) {
+            if (p.pk_ok) {
+                const unsigned grid = chanlast_grid(int_quant_chanlast_kernel<T, RM, false, true>, nv);
+                int_quant_chanlast_kernel<T, RM, false, true><<<grid, CL_THREADS, 0, st>>>(
+                    nullptr, (const T*)x, (const T*)scale, (T*)y, (T*)codes, nullptr, nv, (int)count, 0, p);
+                return check_launch("bvb_int_quant_fwd");
+            }
+        }
+        const unsigned grid = chanlast_grid(int_quant_chanlast_kernel<T, RM, false, false>, nv);
+        int_quant_chanlast_kernel<T, RM, false, false><<<grid, CL_THREADS, 0, st>>>(
             nullptr, (const T*)x, (const T*)scale, (T*)y, (T*)codes, nullptr, nv, (int)count, 0, p);
         return check_launch("bvb_int_quant_fwd");
     }
@@ -1502,8 +1641,16 @@ static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale
     if (smode == 1 && inner == 1 && vec_ok && aligned16(scale) && count <= CL_MAX_C && (count % V) == 0 &&
         ((int64_t)CL_THREADS * V) % count == 0 && (n % count) == 0 && n >= (int64_t)CL_THREADS * V) {
         const int64_t nv = n / V;
-        unsigned grid = stream_grid(nv, CL_THREADS * CL_UNROLL);
-        int_quant_chanlast_kernel<T, RM, true><<<grid, CL_THREADS, 0, st>>>(
+        if constexpr (PackedPath<T, RM>::value && DT<T>::MUL_DIV_EXACT) {
+            if (p.pk_ok) {
+                const unsigned grid = chanlast_grid(int_quant_chanlast_kernel<T, RM, true, true>, nv);
+                int_quant_chanlast_kernel<T, RM, true, true><<<grid, CL_THREADS, 0, st>>>(
+                    (const T*)gy, (const T*)x, (const T*)scale, (T*)gx, nullptr, gscale_out, nv, (int)count, masked, p);
+                return check_launch("bvb_int_quant_bwd");
+            }
+        }
+        const unsigned grid = chanlast_grid(int_quant_chanlast_kernel<T, RM, true, false>, nv);
+        int_quant_chanlast_kernel<T, RM, true, false><<<grid, CL_THREADS, 0, st>>>(
             (const T*)gy, (const T*)x, (const T*)scale, (T*)gx, nullptr, gscale_out, nv, (int)count, masked, p);
         return check_launch("bvb_int_quant_bwd");
     }

@@ -640,6 +640,28 @@ def test_lowp_exhaustive(K, dtype, qmin, qmax):
     gxo, _ = O.int_quant_backward(g.reshape(8, 8192), xr.float().numpy(), srow, 0.0, qmin, qmax, "round", "masked", dtype)
     gx, _ = K.int_quant_bwd(dev(g.reshape(8, 8192), dtype), xr.cuda(), dev(srow, dtype), 0.0, qmin, qmax, 0, 1, True)
     assert_bits_equal(host(gx), gxo, "rows provided gx")
+    # one scale per channel of a channels-last tensor (packed per-lane variant of int_quant_chanlast_kernel in bf16):
+    # [1, 16, 64, 64] NHWC holds all 2^16 patterns, pattern i under scale[i % 16]; one scale outside the exact
+    # multiply-by-reciprocal window sends its threads through the out-of-line literal branch
+    sch = np.array([1.0, 0.25, 0.0371, 3.0, 0.5, 0.11, 2.0, 0.9, 1.7e-3, 40.0, 2.0 ** -7, 0.61, 7.0, 0.013, 1.0e-13, 0.3],
+                   dtype=np.float32)
+    if dtype == "f16":
+        sch[14] = 6.1e-5
+    sch = O.rnd(sch, dtype)
+    xn = allx.view(1, 64, 64, 16).permute(0, 3, 1, 2)          # NCHW view of NHWC memory
+    gn = torch.from_numpy(g).to(tdt).view(1, 64, 64, 16).permute(0, 3, 1, 2)
+    assert xn.is_contiguous(memory_format=torch.channels_last)
+    sn = sch.reshape(1, 16, 1, 1)
+    yo = O.int_quant_forward(xn.float().numpy(), sn, 0.0, qmin, qmax, "round", dtype)
+    co = O.int_quant_chain(xn.float().numpy(), sn, 0.0, qmin, qmax, "round", dtype)
+    y, codes = K.int_quant_fwd(xn.cuda(), dev(sn, dtype), 0.0, qmin, qmax, 0, want_codes=True)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert_bits_equal(host(y), yo, "channels-last y")
+    assert_bits_equal(host(codes), co[-1] if isinstance(co, tuple) else co, "channels-last codes")
+    for cm in ("ste", "masked"):
+        gxo, _ = O.int_quant_backward(gn.float().numpy(), xn.float().numpy(), sn, 0.0, qmin, qmax, "round", cm, dtype)
+        gx, _ = K.int_quant_bwd(gn.cuda(), xn.cuda(), dev(sn, dtype), 0.0, qmin, qmax, 0, CM[cm], True)
+        assert_bits_equal(host(gx), gxo, f"channels-last gx {cm}")
     finite = torch.where(torch.isfinite(xr.float()), xr, torch.ones((), dtype=tdt)).contiguous()
     thr = max(abs(qmin), abs(qmax))
     yo, so, _ = O.rows_absmax_int_quant_forward(finite.float().numpy(), 1e-10, thr, 0.0, qmin, qmax, "round", dtype)
