@@ -228,6 +228,20 @@ class QuantReLU(_QuantActLayer):
         super().__init__(nn.ReLU(), act_quant, input_quant, return_quant_tensor, **kwargs)
 
 
+class QuantSigmoid(_QuantActLayer):
+    """nn/quant_activation.py:32-47 (default quantizer Uint8ActPerTensorFloat)"""
+
+    def __init__(self, act_quant=Uint8ActPerTensorFloat, input_quant=None, return_quant_tensor=False, **kwargs):
+        super().__init__(nn.Sigmoid(), act_quant, input_quant, return_quant_tensor, **kwargs)
+
+
+class QuantTanh(_QuantActLayer):
+    """nn/quant_activation.py:50-65 (default quantizer Int8ActPerTensorFloat)"""
+
+    def __init__(self, act_quant=Int8ActPerTensorFloat, input_quant=None, return_quant_tensor=False, **kwargs):
+        super().__init__(nn.Tanh(), act_quant, input_quant, return_quant_tensor, **kwargs)
+
+
 class QuantIdentity(_QuantActLayer):
     """nn/quant_activation.py:82-101 (default quantizer Int8ActPerTensorFloat)"""
 
@@ -409,4 +423,29 @@ class QuantConvTranspose2d(_QuantWBIOL, nn.ConvTranspose2d):
     def forward(self, x):
         return self._forward(
             x, lambda a, w, b: F.conv_transpose2d(a, w, b, self.stride, self.padding, self.output_padding, self.groups,
+                                                  self.dilation))
+
+
+class QuantConvTranspose1d(_QuantWBIOL, nn.ConvTranspose1d):
+    """nn/quant_convtranspose.py:22-111: weight ``[in, out / groups, k]``, output channels in dim 1"""
+    output_channel_dim = 1
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1, bias=True,
+                 dilation=1, weight_quant=Int8WeightPerTensorFloat, bias_quant=None, input_quant=None, output_quant=None,
+                 return_quant_tensor=False, **kwargs):
+        nn.ConvTranspose1d.__init__(self, in_channels, out_channels, kernel_size, stride, padding, output_padding, groups,
+                                    bias, dilation)
+        self._init_quant(weight_quant, bias_quant, input_quant, output_quant, return_quant_tensor, kwargs)
+
+    def max_acc_bit_width(self, input_bit_width, weight_bit_width):
+        """nn/quant_convtranspose.py:104-111"""
+        max_uint_input = max_int(bit_width=input_bit_width, signed=False, narrow_range=False)
+        max_kernel_val = self.weight_quant.max_uint_value(weight_bit_width)
+        group_size = self.out_channels // self.groups
+        overlap = max(round(self.kernel_size[0] / self.stride[0]), 1)
+        return ceil_ste(torch.log2(max_uint_input * max_kernel_val * overlap * group_size))
+
+    def forward(self, x):
+        return self._forward(
+            x, lambda a, w, b: F.conv_transpose1d(a, w, b, self.stride, self.padding, self.output_padding, self.groups,
                                                   self.dilation))

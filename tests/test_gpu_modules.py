@@ -272,7 +272,9 @@ def test_int_quant_roundtrip_every_integer(B):
 def _literal_weight_quant(w, reduce_dims, bits=8):
     """the reference chain op by op in torch: AbsMax stats -> / int_threshold -> round/clamp with the STE"""
     thr = 2.0 ** (bits - 1) - 1
-    scale = w.detach().abs().amax(dim=reduce_dims, keepdim=True).clamp_min(1e-10) / thr
+    # a TENSOR divisor like the reference's int_scaling_impl(bit_width): ATen divides IEEE-exactly by a device tensor but
+    # multiplies by a rounded reciprocal when the divisor is a Python scalar
+    scale = w.detach().abs().amax(dim=reduce_dims, keepdim=True).clamp_min(1e-10) / torch.tensor(thr, device=w.device)
     q = torch.clamp(torch.round(w.detach() / scale), -thr, thr) * scale
     return w + (q - w).detach(), scale
 
@@ -316,3 +318,33 @@ def test_conv_transpose2d_and_conv1d_layers(B, per_channel):
     eight = torch.tensor(8.0, device="cuda")
     assert int(c1.max_acc_bit_width(eight, eight)) == 21      # ceil(log2(255*255*4*7))
     assert int(layer.max_acc_bit_width(eight, eight)) == 22   # ceil(log2(255*255*(2*2)*10))
+
+
+def test_sigmoid_tanh_and_conv_transpose1d_layers(B):
+    """nn/quant_activation.py:32-65, nn/quant_convtranspose.py:22-111: activation then the quantizer with a learned scale
+    (eval mode of a freshly built layer uses the collected buffer); values against the literal torch composition"""
+    from brevitas_b200 import nn as qnn
+    from brevitas_b200.quant import Int8WeightPerChannelFloat
+    torch.manual_seed(7)
+    x = torch.randn(4, 33, device="cuda") * 3
+    for layer, act, signed in ((qnn.QuantSigmoid(return_quant_tensor=True), torch.sigmoid, False),
+                               (qnn.QuantTanh(return_quant_tensor=True), torch.tanh, True)):
+        layer = layer.cuda().train()
+        q = layer(x)
+        a = act(x)
+        scale = q.scale
+        lo, hi = (-128.0, 127.0) if signed else (0.0, 255.0)
+        ref = torch.clamp(torch.round(a / scale), lo, hi) * scale
+        assert torch.equal(q.value, ref) and q.signed is signed and int(q.bit_width) == 8
+        # 99.999th percentile of |act(x)| over 132 values = their maximum, divided by the int threshold
+        thr = 128.0 if signed else 255.0
+        assert torch.allclose(scale, a.abs().max() / thr, rtol=1e-6)
+    t = qnn.QuantConvTranspose1d(6, 10, 4, stride=2, weight_quant=Int8WeightPerChannelFloat).cuda()
+    qt = t.quant_weight()
+    ref_w, ref_s = _literal_weight_quant(t.weight, (0, 2))
+    assert qt.scale.shape == (1, 10, 1)
+    assert torch.equal(qt.scale.reshape(-1), ref_s.reshape(-1)) and torch.equal(qt.value, ref_w)
+    xin = torch.randn(3, 6, 17, device="cuda")
+    torch.testing.assert_close(t(xin), torch.nn.functional.conv_transpose1d(xin, ref_w, t.bias, 2), rtol=1e-4, atol=1e-5)
+    eight = torch.tensor(8.0, device="cuda")
+    assert int(t.max_acc_bit_width(eight, eight)) == 21      # ceil(log2(255*255*2*10))
