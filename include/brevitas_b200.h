@@ -204,8 +204,10 @@ int bvb_absmax_rows(const void* x, void* out, int64_t rows, int64_t cols, int dt
 /* AbsMax(None) -> out[1] (T) */
 int bvb_absmax_tensor(const void* x, void* out, int64_t n, int dtype, void* workspace, void* stream);
 /* AbsPercentile (stats_op.py:41-66): k-th smallest (1-indexed) of |x| over each row of a [rows, cols] view
- * (rows = 1: flat).  out[rows] (T); index_out (nullable, int64[rows]) = an index attaining it.
- * Exact radix select; workspace >= bvb_kth_workspace_bytes(rows).                                       */
+ * (rows = 1: flat).  out[rows] (T); index_out (nullable, int64[rows]) = the SMALLEST index attaining it.
+ * Exact radix select; workspace >= bvb_kth_workspace_bytes(rows) bytes of device scratch, contents irrelevant on
+ * entry (histograms, a first-index table and, for rows <= 2, a 48 MiB per row buffer the surviving candidates are
+ * copied to once few enough are left, so that a high percentile of an fp32 tensor costs two reads instead of four). */
 int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
                            int dtype, void* workspace, void* stream);
 int64_t bvb_kth_workspace_bytes(int64_t rows);
