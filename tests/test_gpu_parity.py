@@ -670,6 +670,34 @@ def test_lowp_exhaustive(K, dtype, qmin, qmax):
     assert_bits_equal(host(y), yo, "fused y")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dpu_round_exhaustive(K, dtype):
+    """dpu_round_ste (ops_ste.py dpu_round_ste / function/ops.py dpu_round): the kernels use a one-FRND formulation of
+    where((x < 0) & (x - floor(x) == 0.5), ceil(x), round(x)); all 2^16 bf16 / fp16 inputs, and for fp32 every negative
+    and positive half-integer up to 2^17 with its two neighbours, signed zeros, infinities and NaN, against the
+    literal torch expression evaluated in the tensor's dtype on the same GPU"""
+    tdt = TDT[dtype]
+    if dtype == "f32":
+        half = torch.arange(0, 1 << 17, dtype=torch.float32) + 0.5
+        cand = torch.cat([half, -half, torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), -8388607.5,
+                                                      8388607.5, -1e-45, -3.0e38, 16777216.0])])
+        bits = cand.view(torch.int32)
+        x = torch.cat([(bits + k).view(torch.float32) for k in (-1, 0, 1)]).cuda()
+    else:
+        x = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(tdt).cuda()
+    frac = x - torch.floor(x)
+    ref = torch.where((x < 0) & (frac == 0.5), torch.ceil(x), torch.round(x))
+    got = K.unary("bvb_dpu_round_ste_impl", x)
+    assert_bits_equal(host(got), host(ref), "dpu_round")
+    # the same rounding inside the quantizer kernel: scale 1, wide range -> codes are dpu_round(x) where finite and in range
+    xs = x[torch.isfinite(x.float()) & (x.float().abs() < 30000)].contiguous()
+    one = torch.ones((), device="cuda", dtype=tdt)
+    y = K.int_quant_fwd(xs, one, 0.0, -32768.0, 32767.0, 4)
+    fr = xs - torch.floor(xs)
+    refq = torch.where((xs < 0) & (fr == 0.5), torch.ceil(xs), torch.round(xs))
+    assert torch.equal(y.float() + 0.0, refq.float() + 0.0)          # "+ 0" : the chain's "+ zero_point" turns -0 into +0
+
+
 def test_more_than_2_31_elements(K):
     """maximum sizes: 2^31 + 4099 bf16 elements (4.3 GB per tensor) through the streaming forward, the TMA
     provided-scale backward and the fused per-row kernels; slices on both sides of the 2^31 boundary and at the tail
