@@ -101,6 +101,46 @@ __device__ __forceinline__ float binary_bwd_elem(float g, float x, float s, bool
     return d;
 }
 
+// One 16-byte vector of the backward in packed-pair arithmetic (bf16 / fp16, ONE positive finite scale stored in T --
+// the learned / constant scalar scales of the binary quantizers): grad*scale is one HMUL2 (the fp32 product of two T
+// values is exact, hence a single rounding like rnd_T(g*s)), the clamp masks are two packed compares (for s > 0 the
+// low test "clamp_hi(x) < -s" is "x < -s"), clamped lanes become +0 by masking, and d(scale) adds
+// g*sign_b(x) (sign flipped where x < 0, times 0 where x is NaN: sign_b(NaN) = 0) + d[x > s] - d[x < -s] in fp32.
+// Element-wise results are bit-identical to binary_bwd_elem; the d(scale) sum only changes its summation order.
+template <typename T, bool CLAMPED>
+__device__ __forceinline__ uint4 binary_bwd_vec_packed(const uint4& qg, const uint4& qx, uint32_t s2, uint32_t ns2,
+                                                       bool want_gs, float& acc) {
+    const uint32_t g[4] = {qg.x, qg.y, qg.z, qg.w};
+    const uint32_t x[4] = {qx.x, qx.y, qx.z, qx.w};
+    uint32_t o[4];
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t d = DT<T>::p_mul(g[j], s2);
+        uint32_t hi = 0u, lo = 0u;
+        if (CLAMPED) {
+            hi = DT<T>::p_gt_mask(x[j], s2);
+            lo = DT<T>::p_lt_mask(x[j], ns2);
+        }
+        o[j] = d & ~(hi | lo);
+        if (want_gs) {
+            const uint32_t neg = DT<T>::p_lt_mask(x[j], 0u);
+            const uint32_t nan = DT<T>::p_gtu_mask(x[j], x[j]);
+            float t0, t1;
+            DT<T>::p_unpack(g[j] ^ (neg & 0x80008000u), t0, t1);
+            if (nan & 0xffffu) t0 = fmul(t0, 0.f);                  // g * sign_b(NaN) = g * 0 (NaN for an infinite g)
+            if (nan >> 16) t1 = fmul(t1, 0.f);
+            a0 += t0; a1 += t1;
+            if (CLAMPED) {
+                DT<T>::p_unpack((d & (hi | lo)) ^ (lo & 0x80008000u), t0, t1);
+                a0 += t0; a1 += t1;
+            }
+        }
+    }
+    if (want_gs) acc += a0 + a1;
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <typename T, bool CLAMPED>
 __global__ void __launch_bounds__(BQ_THREADS) binary_quant_bwd_kernel(
         const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ scale, T* __restrict__ gx,
@@ -117,6 +157,13 @@ __global__ void __launch_bounds__(BQ_THREADS) binary_quant_bwd_kernel(
     if (smode == 0) s0 = load_scale0<T>(scale, scale_f32);
     float acc = 0.f;
     int64_t acc_idx = -1;
+    bool packed = false;
+    uint32_t s2 = 0u, ns2 = 0u;
+    if constexpr (DT<T>::LOWP) {
+        packed = smode == 0 && !scale_f32 && s0 > 0.f && s0 < __int_as_float(0x7f800000);
+        s2 = DT<T>::pack2(s0, s0);
+        ns2 = DT<T>::pack2(-s0, -s0);
+    }
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const int64_t base = c * chunk + threadIdx.x;
         uint4 qg[BQ_UNROLL], qx[BQ_UNROLL];
@@ -124,6 +171,16 @@ __global__ void __launch_bounds__(BQ_THREADS) binary_quant_bwd_kernel(
         for (int u = 0; u < BQ_UNROLL; ++u) {
             int64_t v = base + (int64_t)u * BQ_THREADS;
             if (v < nvec) { qg[u] = ldg_stream(gv + v); qx[u] = ldg_stream(xv + v); }
+        }
+        if constexpr (DT<T>::LOWP) {
+            if (packed) {
+#pragma unroll
+                for (int u = 0; u < BQ_UNROLL; ++u) {
+                    const int64_t v = base + (int64_t)u * BQ_THREADS;
+                    if (v < nvec) stg_stream(ov + v, binary_bwd_vec_packed<T, CLAMPED>(qg[u], qx[u], s2, ns2, want_gs, acc));
+                }
+                continue;
+            }
         }
 #pragma unroll
         for (int u = 0; u < BQ_UNROLL; ++u) {

@@ -139,6 +139,34 @@ def test_binary_golden(K, qname, sname, dtype):
         close_sum(host(gs).reshape(c["gvalue"].shape), c["gvalue"], n, np.abs(c["g"]).sum() / c["gvalue"].size + 1, dtype)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("clamped", [False, True])
+def test_binary_backward_lowp_exhaustive(K, clamped, dtype):
+    """the 16-bit backward of BinaryQuant / ClampedBinaryQuant with one positive scale runs in packed-pair arithmetic
+    (csrc/binary_quant.cu binary_bwd_vec_packed): ALL 2^16 input patterns (+-0, denormals, +-inf, NaNs) x scales,
+    element-wise gradients bit-exact against the oracle, d(scale) within the reduction tolerance; a negative scale and
+    an fp32 scalar scale take the literal branch of the same kernel"""
+    tdt = TDT[dtype]
+    allx = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(tdt)
+    x = allx.float().numpy()
+    g = O.rnd(rand_np((65536,), 17, 1.0), dtype)
+    for sv in (1.0, 0.37, 2.5, 1.7e-3, -0.5):
+        s = O.rnd(np.float32(sv), dtype)
+        gxo, gs_el = O.binary_quant_backward(g, x, s, clamped, dtype)
+        gx, gs = K.binary_quant_bwd(dev(g, dtype), allx.cuda(), dev(np.asarray(s), dtype), clamped, True)
+        assert_bits_equal(host(gx), gxo, f"gx scale={sv}")
+        fin = np.isfinite(x)
+        xf = torch.from_numpy(np.where(fin, x, 1.0)).to(tdt).cuda()
+        _, gs = K.binary_quant_bwd(dev(g, dtype), xf, dev(np.asarray(s), dtype), clamped, True)
+        _, gs_ref = O.binary_quant_backward(g, host(xf), s, clamped, dtype)
+        mag = float(np.abs(gs_ref).sum()) + 1.0
+        assert abs(float(gs) - float(gs_ref.sum())) <= mag * (65536 * 2.0 ** -21 + 16 * ulp(dtype))
+    s32 = torch.tensor(0.37, device="cuda")                         # fp32 0-dim scale next to a 16-bit tensor
+    gx32, _ = K.binary_quant_bwd(dev(g, dtype), allx.cuda(), s32, clamped, True)
+    gxo, _ = O.binary_quant_backward(g, x, np.float32(0.37), clamped, dtype)
+    assert_bits_equal(host(gx32), gxo, "gx fp32 scale")
+
+
 def test_percentile_golden(K):
     d = load("percentile")
     for q in (99.999, 99.9, 90.0, 50.0, 1.0):
