@@ -10,10 +10,10 @@ fwd 1R+1W = 8 B/elem, bwd 2R+1W = 12 B/elem -> 20 B/elem x 45,088,768 = 901.8 MB
   e2e       the same metric through the public module API (RescalingIntQuant + autograd) with HOST pinned
             buffers: H2D of weight and incoming gradient, D2H of the weight gradient and scales, every step
   roofline  dominant kernel (backward) algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline   the oracle's ATen port of the reference chain (oracle/torch_port.py) on the host cores, on a
-            bounded row sample of the same workload
+  cpu_baseline   the UNMODIFIED reference (oracle/_ref, placed by oracle/make_ref.py): brevitas.nn.QuantLinear with
+            Int8WeightPerChannelFloat, quant_weight() + autograd on the host cores, the same full-size weight
 
-`--impl reference` times only that CPU path (kind "port": /root/reference cannot travel to the GPU box).
+`--impl reference` times only that CPU path (kind "reference"), same config, every step the full weight.
 N > 1 (torchrun): the path shards trivially (independent weights) -> every rank runs its own replica of the
 workload, no data-path collective ("scaling": "weak"); value = units of all ranks / max-over-ranks time.
 """
@@ -31,6 +31,7 @@ if ROOT not in sys.path:
 
 ROWS, COLS = 4096, 11008
 FWD_B, BWD_B = 8, 12          # algorithmic bytes per element, fp32
+NSETS = 4                     # rotating (W, G) input sets, > L2 in total
 METRIC = "int8_per_channel_weight_fakequant_fwd_bwd_GBps"
 
 
@@ -118,56 +119,113 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_port_step(torch, P, w, g):
-    """one fwd+bwd of the reference op chain on the host cores (oracle/torch_port.py)"""
-    w.grad = None
-    y, scale, _, _ = P.rescaling_int_quant_absmax(w, "rows", 8, True, True, 1e-10, "round", True)
-    y.backward(g)
-    return w.grad
+def workload_config():
+    """the ``config`` object, identical in both arms (the driver compares them)"""
+    n = ROWS * COLS
+    return {"workload": f"C2 (BASELINE.json configs[1]): int8 per-output-channel weight fake-quant fwd + STE bwd, "
+                        f"{ROWS}x{COLS} fp32, one weight per rank (Int8WeightPerChannelFloat)",
+            "algorithmic_bytes_per_step": n * (FWD_B + BWD_B),
+            "l2": f"inputs rotate over {NSETS} (W,G) sets of 2x{n * 4 // 2**20} MiB (> 126 MB L2)"}
 
 
-def cpu_baseline(torch, sample_rows, reps):
-    from oracle import torch_port as P
-    torch.set_num_threads(os.cpu_count() or 1)
-    gen = torch.Generator().manual_seed(0)
-    w = torch.randn(sample_rows, COLS, generator=gen).requires_grad_(True)
-    g = torch.randn(sample_rows, COLS, generator=gen)
-    cpu_port_step(torch, P, w, g)                     # warm-up
+def load_reference():
+    """Import the UNMODIFIED reference (oracle/_ref/src, placed by oracle/make_ref.py; /root/reference/src in the build
+    container) on its own Python STE backend.  None of this repository's kernels or modules are involved: only the
+    clean-room stand-in for the absent third-party `dependencies` package (wiring, no arithmetic) is put on the path
+    when the real one is not installed."""
+    os.environ.setdefault("BREVITAS_JIT", "0")
+    for cand in (os.path.join(ROOT, "oracle", "_ref", "src"), "/root/reference/src"):
+        if os.path.isdir(os.path.join(cand, "brevitas")):
+            if cand not in sys.path:
+                sys.path.insert(0, cand)
+            break
+    else:
+        raise RuntimeError("reference not found: run `python oracle/make_ref.py` where /root/reference exists")
+    try:
+        import dependencies  # noqa: F401
+    except ImportError:
+        sys.path.append(os.path.join(ROOT, "brevitas_b200", "_compat"))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import brevitas.nn as qnn
+        from brevitas.quant import Int8WeightPerChannelFloat
+    import brevitas.function.ops_ste as ops_ste
+    import brevitas
+    assert ops_ste.fn_prefix is brevitas, "the reference arm must run the reference's own Python STE backend"
+    return qnn, Int8WeightPerChannelFloat
+
+
+class ReferenceC2:
+    """BASELINE config 2 through the reference's public API: ``QuantLinear(11008, 4096, weight_quant=
+    Int8WeightPerChannelFloat).quant_weight()`` (nn/mixin/parameter.py:54-55 -> proxy/parameter_quant.py:83-89 ->
+    core/quant/int.py:156-163) + autograd backward, full 4096 x 11008 fp32 weight, on the host cores."""
+
+    def __init__(self, torch, rows=ROWS, device="cpu"):
+        qnn, quant = load_reference()
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.torch, self.rows = torch, rows
+        gen = torch.Generator().manual_seed(0)
+        self.layer = qnn.QuantLinear(COLS, rows, False, weight_quant=quant)
+        with torch.no_grad():
+            self.layer.weight.copy_(torch.randn(rows, COLS, generator=gen))
+        self.g = torch.randn(rows, COLS, generator=gen).to(device)
+        self.layer.to(device)
+        tq = self.layer.weight_quant.tensor_quant
+        assert type(tq).__module__ == "brevitas.core.quant.int", type(tq)
+
+    def step(self):
+        self.layer.weight.grad = None
+        qw = self.layer.quant_weight()
+        qw.value.backward(self.g)
+        return self.layer.weight.grad
+
+    def describe(self, t):
+        return (f"full {self.rows}x{COLS} fp32 weight per step, fwd+bwd, the reference's own brevitas.nn.QuantLinear."
+                f"quant_weight() + autograd on {self.torch.get_num_threads()} host threads ({t * 1e3:.0f} ms/step)")
+
+
+def cpu_baseline(torch, reps):
+    """the reference itself on the host cores, same workload (bounded: reps x ~0.2-1 s)"""
+    ref = ReferenceC2(torch)
+    ref.step()
+    ref.step()
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_port_step(torch, P, w, g)
+        ref.step()
         ts.append(time.perf_counter() - t0)
     t = sorted(ts)[len(ts) // 2]
-    gbps = sample_rows * COLS * (FWD_B + BWD_B) / t / 1e9
-    return {"value": round(gbps, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample_rows} of {ROWS} rows x {COLS} fp32, fwd+bwd, median of {reps} "
-                      f"(oracle/torch_port.py: the reference's ATen op chain; {t * 1e3:.1f} ms)"}, t
+    gbps = ROWS * COLS * (FWD_B + BWD_B) / t / 1e9
+    return {"value": round(gbps, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": ref.describe(t) + f", median of {reps}"}, t
 
 
 def cpu_tfc_baseline(torch):
-    """BASELINE.json configs[0]: bnn_pynq TFC 2W2A fwd+bwd, batch 256, on the host cores (oracle/ref_models.py)"""
-    from oracle import ref_models as R
+    """BASELINE.json configs[0]: bnn_pynq TFC 2W2A QAT fwd+bwd on a synthetic 28x28 batch of 256, on the host cores, the
+    reference's own model (brevitas_examples/bnn_pynq/models/FC.py:19-69) and loss (models/losses.py:9-31)"""
+    load_reference()
+    from brevitas_examples.bnn_pynq.models import model_with_cfg
+    from brevitas_examples.bnn_pynq.models.losses import SqrHingeLoss
     torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model, _ = model_with_cfg("tfc_2w2a", False)
+    model.train()
+    crit = SqrHingeLoss()
     g = torch.Generator().manual_seed(0)
-    sizes = [(64, 784), (64, 64), (64, 64), (10, 64)]
-    ws = [(torch.rand(s, generator=g) * 2 - 1).requires_grad_(True) for s in sizes]
-    bn = [(torch.ones(64, requires_grad=True), torch.zeros(64, requires_grad=True), torch.zeros(64), torch.ones(64))
-          for _ in range(3)]
-    tn = (torch.ones(1, requires_grad=True), torch.zeros(1, requires_grad=True))
     x = torch.rand(256, 1, 28, 28, generator=g)
     y = torch.full((256, 10), -1.0)
     y.scatter_(1, torch.randint(0, 10, (256, 1), generator=g), 1.0)
     ts = []
     for i in range(25):
-        for w in ws:
-            w.grad = None
+        model.zero_grad(set_to_none=True)
         t0 = time.perf_counter()
-        R.sqr_hinge(R.tfc_forward(x, ws, bn, tn), y).backward()
+        crit(model(x), y).backward()
         ts.append(time.perf_counter() - t0)
     t = sorted(ts[5:])[10]
     return {"samples_per_s": round(256 / t, 1), "ms_per_step": round(t * 1e3, 3), "cores": torch.get_num_threads(),
-            "kind": "port", "what": "TFC 2W2A fwd+bwd (no optimizer step), batch 256, oracle/ref_models.py"}
+            "kind": "reference", "what": "TFC 2W2A fwd+bwd (no optimizer step), batch 256, brevitas_examples.bnn_pynq "
+                                         "model_with_cfg('tfc_2w2a') unmodified, Python STE backend"}
 
 
 def run_reference(args):
@@ -175,27 +233,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # each "step" = a bounded sample (512 rows) of the workload; K steps after W warm-ups
-    sample_rows = 512
-    from oracle import torch_port as P
-    torch.set_num_threads(os.cpu_count() or 1)
-    gen = torch.Generator().manual_seed(0)
-    w = torch.randn(sample_rows, COLS, generator=gen).requires_grad_(True)
-    g = torch.randn(sample_rows, COLS, generator=gen)
+    ref = ReferenceC2(torch)
     for _ in range(args.warmup):
-        cpu_port_step(torch, P, w, g)
+        ref.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_step(torch, P, w, g)
+        ref.step()
     dt = (time.perf_counter() - t0) / args.steps
-    gbps = sample_rows * COLS * (FWD_B + BWD_B) / dt / 1e9
-    sample = f"{sample_rows} of {ROWS} rows x {COLS} fp32 per step, fwd+bwd (oracle/torch_port.py, ATen on host cores)"
+    step_bytes = ROWS * COLS * (FWD_B + BWD_B)
+    gbps = step_bytes / dt / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": round(gbps, 3), "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2: int8 per-output-channel weight fake-quant fwd + STE bwd, {ROWS}x{COLS} fp32"},
-            "cpu_baseline": {"value": round(gbps, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
+            "config": workload_config(),
+            "cpu_baseline": {"value": round(gbps, 3), "unit": "GB/s", "cores": torch.get_num_threads(),
+                             "kind": "reference", "sample": ref.describe(dt)},
             "e2e": {"value": round(gbps, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     args.emit(line)
@@ -209,7 +261,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the bf16 / per-token / per-tensor extra kernels")
-    ap.add_argument("--cpu-rows", type=int, default=512)
     ap.add_argument("--no-qat", action="store_true", help="skip the QAT-step workloads")
     ap.add_argument("--qat-all", action="store_true", help="also run MobileNetV1 at N=1")
     ap.add_argument("--qat-batch", type=int, default=256, help="per-GPU batch of the ResNet-18 QAT step")
@@ -247,7 +298,6 @@ def main():
     step_bytes = n * (FWD_B + BWD_B)
 
     # ---- inputs: NSETS rotating (W, G) pairs so no step finds its inputs in the 126 MB L2 ---------------------
-    NSETS = 4
     gen = torch.Generator(device=dev).manual_seed(rank)
     Ws = [torch.randn(ROWS, COLS, device=dev, generator=gen) for _ in range(NSETS)]
     Gs = [torch.randn(ROWS, COLS, device=dev, generator=gen) for _ in range(NSETS)]
@@ -447,16 +497,6 @@ def main():
         extras["act_bf16_learned_scale_fwd"] = {"ms": round(ms, 4), "GBps": gb(T * C * 4, ms)}
         ms = timeit(lambda i: K.int_quant_bwd(GX[i % 2], X[i % 4], s0, 0.0, 0.0, 255.0, 0, 1, True))
         extras["act_bf16_learned_scale_bwd"] = {"ms": round(ms, 4), "GBps": gb(T * C * 6, ms)}
-        # eager PyTorch composition of the same chain on the same GPU (what a Brevitas user gets on a B200 today)
-        from oracle import torch_port as P
-        wt = Ws[0].clone().requires_grad_(True)
-
-        def eager(i):
-            wt.grad = None
-            yy, ss, _, _ = P.rescaling_int_quant_absmax(wt, "rows", 8, True, True, 1e-10, "round", True)
-            yy.backward(Gs[0])
-        ms = timeit(eager, reps=5, graph=False)
-        extras["c2_f32_eager_aten_same_gpu_fwd_bwd"] = {"ms": round(ms, 3), "GBps_algorithmic": gb(step_bytes, ms)}
 
     # ---- QAT step (north star: data-parallel QAT across 1/2/4/8 GPUs, NCCL gradient all-reduce) ---------------------
     qat = {}
@@ -485,19 +525,36 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return 0
-    cpu, _ = cpu_baseline(torch, args.cpu_rows, 5)
+    from brevitas_b200.binding import uninstall
+    uninstall()              # the CPU baselines run the pure reference (its own Python backend and core classes)
+    cpu, _ = cpu_baseline(torch, 5)
+    if not args.no_extras:
+        # the reference itself on the SAME GPU (its Python STE backend on eager ATen): what a Brevitas user gets on a
+        # B200 today; a baseline leg like cpu_baseline, device-timed
+        gref = ReferenceC2(torch, device=dev)
+        for _ in range(3):
+            gref.step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            gref.step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        extras["c2_f32_reference_eager_aten_same_gpu_fwd_bwd"] = {
+            "ms": round(ms, 3), "GBps_algorithmic": round(step_bytes / (ms * 1e-3) / 1e9, 1),
+            "what": "unmodified brevitas.nn.QuantLinear.quant_weight() + backward on cuda (Python STE backend, ATen kernels)"}
+        del gref
     if not args.no_qat:
         qat["tfc_2w2a_cpu_port"] = cpu_tfc_baseline(torch)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2 (BASELINE.json configs[1]): int8 per-output-channel weight fake-quant fwd + STE bwd, "
-                               f"{ROWS}x{COLS} fp32, one weight per rank",
-                   "algorithmic_bytes_per_step": step_bytes,
-                   "l2": f"inputs rotate over {NSETS} (W,G) sets of 2x{n * 4 // 2**20} MiB (> 126 MB L2)",
-                   "percent_of_hbm_peak": round(100 * value / world / peak, 1), "hbm_peak_gbs": peak,
-                   "hbm_peak_source": peak_src, "percent_of_nominal_8TBps": round(100 * value / world / 8000, 1)},
+        "config": workload_config(),
+        "hbm": {"percent_of_hbm_peak": round(100 * value / world / peak, 1), "hbm_peak_gbs": peak,
+                "hbm_peak_source": peak_src, "percent_of_nominal_8TBps": round(100 * value / world / 8000, 1)},
         "roofline": {"bound": "hbm", "kernel": "rows_bwd_tma_kernel<float,ROUND|ZP0|STE> (STE backward + grad through abs-max)",
                      "achieved": round(bwd_gbps, 1), "peak": peak, "unit": "GB/s", "frac": round(bwd_gbps / peak, 4),
                      "traffic": ncu_traffic("rows_bwd_tma_kernel<float"),

@@ -14,3 +14,4 @@ _lib.load()          # fail loudly at import when the native library is missing
 from . import ops  # noqa: E402,F401  (registers torch.ops.autograd_ste_ops.* and torch.ops.brevitas_b200.*)
 from . import function  # noqa: E402,F401
 from . import core  # noqa: E402,F401
+from .binding import install, uninstall  # noqa: E402,F401  (binds an unmodified Brevitas installation to the kernels)

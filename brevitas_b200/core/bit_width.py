@@ -2,6 +2,8 @@
 parameter (:101-141) and the clamp on an incoming accumulator bit-width (const.py:43-78 ``MsbClampBitWidth``).
 Bit-widths are 0-dim tensors; everything here is a handful of scalar ops on the STE kernels."""
 import torch
+
+from .. import config
 from torch import Tensor, nn
 from torch.nn import Parameter
 
@@ -11,7 +13,6 @@ from .utils import StatelessBuffer
 MIN_INT_BIT_WIDTH = 2
 NON_ZERO_EPSILON = 1e-6
 REMOVE_ZERO_BIT_WIDTH = 0.1
-IGNORE_MISSING_KEYS = False
 
 
 class BitWidthConst(nn.Module):
@@ -64,7 +65,7 @@ class BitWidthParameter(nn.Module):
             del state_dict[key]
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
-        if IGNORE_MISSING_KEYS and key in missing_keys:
+        if config.IGNORE_MISSING_KEYS and key in missing_keys:
             missing_keys.remove(key)
 
 
@@ -94,7 +95,7 @@ class RemoveBitwidthParameter(nn.Module):
             del state_dict[key]
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
-        if IGNORE_MISSING_KEYS and key in missing_keys:
+        if config.IGNORE_MISSING_KEYS and key in missing_keys:
             missing_keys.remove(key)
 
 

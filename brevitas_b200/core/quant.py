@@ -88,13 +88,13 @@ def scalar_mul(x: Tensor, s: Tensor) -> Tensor:
 def int_range(signed: bool, narrow_range: bool, bit_width: int, dtype: torch.dtype) -> Tuple[float, float]:
     """(min_int, max_int) as the reference computes them from a 0-dim ``bit_width`` tensor of ``dtype``
     (function/ops.py:133-191), evaluated once on the host so the fused kernels need no device read-back."""
-    bw = torch.tensor(float(bit_width), dtype=dtype)
+    bw = torch.tensor(float(bit_width), dtype=dtype, device='cpu')
     return float(min_int(signed, narrow_range, bw)), float(max_int(signed, narrow_range, bw))
 
 
 @lru_cache(maxsize=None)
 def _int_threshold(kind: str, signed: bool, narrow_range: bool, bit_width: int, dtype: torch.dtype) -> float:
-    bw = torch.tensor(float(bit_width), dtype=dtype)
+    bw = torch.tensor(float(bit_width), dtype=dtype, device='cpu')
     if kind == 'int':
         impl = IntScaling(signed, narrow_range)
     else:

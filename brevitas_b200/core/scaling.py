@@ -9,6 +9,8 @@ while the statistics over full tensors run on the sm_100a kernels or are fused i
 from typing import List, Optional, Tuple, Union
 
 import torch
+
+from .. import config
 from torch import Tensor, nn
 from torch.nn import Parameter
 
@@ -113,7 +115,7 @@ class ParameterScaling(nn.Module):
             state_dict[value_key] = state_dict.pop(retro)
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
-        if _stats.IGNORE_MISSING_KEYS and value_key in missing_keys:
+        if config.IGNORE_MISSING_KEYS and value_key in missing_keys:
             missing_keys.remove(value_key)
 
 
@@ -199,7 +201,7 @@ class ParameterFromRuntimeStatsScaling(nn.Module):
             missing_keys.remove(training_key)
         if value_key not in missing_keys:
             self.counter = self.collect_stats_steps + 1     # a loaded value ends the collection phase
-        if _stats.IGNORE_MISSING_KEYS and value_key in missing_keys:
+        if config.IGNORE_MISSING_KEYS and value_key in missing_keys:
             missing_keys.remove(value_key)
 
 
@@ -219,7 +221,7 @@ class _AffineRescaling(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
         for key in (prefix + 'affine_weight', prefix + 'affine_bias'):
-            if _stats.IGNORE_MISSING_KEYS and key in missing_keys:
+            if config.IGNORE_MISSING_KEYS and key in missing_keys:
                 missing_keys.remove(key)
 
 

@@ -10,6 +10,8 @@ import math
 from typing import List, NamedTuple, Optional, Tuple
 
 import torch
+
+from .. import config
 from torch import Tensor, nn
 
 from .. import ops as _ops  # noqa: F401
@@ -17,7 +19,6 @@ from . import function_wrapper as fw
 
 DEFAULT_MOMENTUM = 0.1
 SCALAR_SHAPE = ()
-IGNORE_MISSING_KEYS = False   # mirrors brevitas.config.IGNORE_MISSING_KEYS
 
 
 class AbsMaxPlan(NamedTuple):
@@ -260,7 +261,7 @@ class MeanLearnedSigmaStd(nn.Module):
                 state_dict[value_key] = state_dict.pop(retro_key)
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
-        if IGNORE_MISSING_KEYS and value_key in missing_keys:
+        if config.IGNORE_MISSING_KEYS and value_key in missing_keys:
             missing_keys.remove(value_key)
 
 
@@ -347,7 +348,7 @@ class _RuntimeStats(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
         key = prefix + 'running_stats'
-        if IGNORE_MISSING_KEYS and key in missing_keys:
+        if config.IGNORE_MISSING_KEYS and key in missing_keys:
             missing_keys.remove(key)
         training_key = prefix + 'training'
         if training_key in missing_keys:

@@ -6,11 +6,13 @@ which take the resulting zero-point."""
 from typing import List, Optional, Tuple, Union
 
 import torch
+
+from .. import config
 from torch import Tensor, nn
 from torch.nn import Parameter
 
 from ..function.ops_ste import abs_binary_sign_grad
-from .stats import DEFAULT_MOMENTUM, IGNORE_MISSING_KEYS, SCALAR_SHAPE, _ParameterListStats
+from .stats import DEFAULT_MOMENTUM, SCALAR_SHAPE, _ParameterListStats
 from .utils import StatelessBuffer, inplace_momentum_update, inplace_tensor_add
 
 __all__ = ['ZeroZeroPoint', 'StatsFromParameterZeroPoint', 'ParameterFromRuntimeZeroPoint', 'ParameterZeroPoint']
@@ -56,7 +58,7 @@ class _OffsetZeroPoint(nn.Module):
     @staticmethod
     def _forgive_missing_value(prefix: str, missing_keys) -> None:
         key = prefix + 'value'
-        if IGNORE_MISSING_KEYS and key in missing_keys:
+        if config.IGNORE_MISSING_KEYS and key in missing_keys:
             missing_keys.remove(key)
 
 

@@ -296,7 +296,7 @@ def gen_docstring_kats(out):
     from brevitas.core.quant import BinaryQuant, ClampedBinaryQuant, IntQuant, RescalingIntQuant
     from brevitas.core.scaling import ConstScaling, IntScaling
     from brevitas.core.zero_point import ZeroZeroPoint
-    inp = torch.Tensor([0.042, -0.053, 0.31, -0.44])
+    inp = torch.tensor([0.042, -0.053, 0.31, -0.44])
     iq = IntQuant(narrow_range=True, signed=True)                                 # int_base.py:33-38
     out["kat/int_quant/x"] = npf(inp)
     out["kat/int_quant/y"] = npf(iq(torch.tensor(0.01), torch.tensor(0.), torch.tensor(4.), inp))
@@ -305,13 +305,13 @@ def gen_docstring_kats(out):
     y, s, z, b = rq(inp)
     out["kat/rescaling/y"], out["kat/rescaling/scale"] = npf(y), npf(s)
     bq = BinaryQuant(ConstScaling(0.1))                                            # binary.py:33-43
-    binp = torch.Tensor([0.04, -0.6, 3.3])
+    binp = torch.tensor([0.04, -0.6, 3.3])
     out["kat/binary/x"] = npf(binp)
     out["kat/binary/y"] = npf(bq(binp)[0])
     cq = ClampedBinaryQuant(ConstScaling(0.1))                                     # binary.py:84-97
     ci = binp.clone().requires_grad_(True)
     cy = cq(ci)[0]
-    cy.backward(torch.Tensor([1.0, 1.0, 1.0]))
+    cy.backward(torch.tensor([1.0, 1.0, 1.0]))
     out["kat/clamped_binary/y"], out["kat/clamped_binary/gx"] = npf(cy), npf(ci.grad)
 
 
@@ -376,7 +376,7 @@ def gen_widen(out):
     # docstring KAT (int.py:33-47)
     iq = IntQuant(narrow_range=True, signed=True)
     kat = PrescaledRestrictIntQuantWithInputBitWidth(iq, fw.Identity())
-    yk, _, _, bwk = kat(torch.Tensor([0.042, -0.053, 0.31, -0.44]), torch.tensor(0.01), torch.tensor(4.))
+    yk, _, _, bwk = kat(torch.tensor([0.042, -0.053, 0.31, -0.44]), torch.tensor(0.01), torch.tensor(4.))
     out["widen/kat/prescaled/y"], out["widen/kat/prescaled/bw"] = npf(yk), npf(bwk)
     # ---- C. TruncIntQuant (QuantAvgPool2d): 12-bit accumulator values truncated to 8 bits ----
     for dname, dt in DT.items():
@@ -393,7 +393,7 @@ def gen_widen(out):
     # ---- D. DecoupledIntQuant ----
     dq = DecoupledIntQuant(narrow_range=True, signed=True)
     yk = dq(torch.tensor(0.02), torch.tensor(0.), torch.tensor(0.01), torch.tensor(0.), torch.tensor(4.),
-            torch.Tensor([0.042, -0.053, 0.31, -0.44]))           # docstring KAT (int_base.py:118-125)
+            torch.tensor([0.042, -0.053, 0.31, -0.44]))           # docstring KAT (int_base.py:118-125)
     out["widen/kat/decoupled/y"] = npf(yk)
     for dname, dt in DT.items():
         xd = make_input((7, 29), 71, 3.0, with_edges=False).to(dt)
@@ -409,7 +409,7 @@ def gen_widen(out):
         out[k + "g_pre_scale"], out[k + "g_scale"] = npf(ps.grad), npf(sc.grad)
     # ---- E. TernaryQuant ----
     tk = TernaryQuant(ParameterScaling(1.0), 0.5)
-    out["widen/kat/ternary/y"] = npf(tk(torch.Tensor([0.04, -0.6, 3.3]))[0])       # docstring KAT (ternary.py:34-38)
+    out["widen/kat/ternary/y"] = npf(tk(torch.tensor([0.04, -0.6, 3.3]))[0])       # docstring KAT (ternary.py:34-38)
     for dname, dt in DT.items():
         xq = make_input((9, 31), 81, 1.0, with_edges=True).to(dt)
         gq = make_input((9, 31), 82, 1.0, False).to(dt)

@@ -29,7 +29,7 @@ def host(t):
 
 
 def close(got, ref, n, mag, dtype):
-    tol = mag * (n * 2.0 ** -21 + 4 * ulp(dtype)) + 1e-6
+    tol = mag * (8.0 * np.sqrt(n) * 2.0 ** -24 + 4 * ulp(dtype)) + 1e-6     # see test_gpu_parity.close_sum
     both_nan = np.isnan(got) & np.isnan(ref)
     assert np.all(both_nan | (np.abs(got - ref) <= tol)), (got, ref, tol)
 

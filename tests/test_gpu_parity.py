@@ -46,7 +46,11 @@ def host(t):
 
 
 def close_sum(got, ref, n, mag, dtype):
-    tol = mag * (n * 2.0 ** -21 + 4 * ulp(dtype)) + 1e-6
+    """Two fp32 sums of the same n terms in different orders (``mag``: sum of |terms|, or a bound on it): each differs
+    from the exact sum by about sqrt(n) * 2^-24 * mag in the random-walk model (observed: 2.4e-6 at n = 11008, SURVEY
+    probe D.6); 8x margin, plus the final rounding to the tensor dtype (4 ulp).  The whole-tensor tests in
+    test_gpu_reference_binding.py check the same quantities against an fp64 sum."""
+    tol = mag * (8.0 * np.sqrt(n) * 2.0 ** -24 + 4 * ulp(dtype)) + 1e-6
     both_nan = np.isnan(got) & np.isnan(ref)
     assert np.all(both_nan | (np.abs(got - ref) <= tol)), (got, ref, tol)
 
