@@ -186,6 +186,7 @@ def install(reference_path: Optional[str] = None, fuse: bool = True):
     from . import config
     if not _state["installed"]:
         _set(ops_ste, "fn_prefix", torch)
+        _set(brevitas, "NATIVE_STE_BACKEND_LOADED", True)       # a native STE backend IS loaded: this library
         config.IGNORE_MISSING_KEYS = ref_config.IGNORE_MISSING_KEYS
         _state["installed"] = True
     if fuse and not _state["fused"]:

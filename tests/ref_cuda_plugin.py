@@ -1,0 +1,13 @@
+"""pytest plugin (test infrastructure): run the REFERENCE's own CPU-written tests on the GPU, unchanged.  Every tensor
+a test, fixture or hypothesis strategy creates from non-tensor arguments is moved to ``cuda`` (``ref_util.FactoryToCuda``),
+so modules and inputs built inside the tests live on the device and flow through ``torch.ops.autograd_ste_ops.*`` /
+the fused ``tensor_quant`` modules that ``brevitas_b200.install()`` bound."""
+import pytest
+
+from ref_util import FactoryToCuda
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_protocol(item, nextitem):
+    with FactoryToCuda():
+        yield
