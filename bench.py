@@ -510,16 +510,15 @@ def main():
         # folded into the quantizer kernels, the whole step (fwd + loss + bwd + gradient all-reduce + SGD) as ONE CUDA graph
         qat["resnet18_int8"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True, graph=True)
         qat["resnet18_int8_eager_ddp"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True)
-        qat["resnet18_int8_nchw_eager"] = qat_run("resnet18", args.qat_batch, 10, 3)
         # the first 300 steps of the default activation quantizers collect an exact 99.999th percentile of every
         # activation tensor (AbsPercentile, radix select): step time while collecting (SURVEY.md §8d C4 "warm-up")
         qat["resnet18_int8_collecting_stats"] = qat_run("resnet18", args.qat_batch, 6, 3, collect_stats_steps=10 ** 6,
                                                         channels_last=True)
         qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
         qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
+        # BASELINE.json configs[4]: ~1100 small launches per step, host-bound when launched eagerly
+        qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True, graph=True)
         if world > 1 or args.qat_all:
-            # BASELINE.json configs[4]: ~1100 small launches per step, host-bound when launched eagerly
-            qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True, graph=True)
             qat["mobilenet_v1_4b_eager_ddp"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True)
     if rank != 0:
         if dist is not None:
@@ -579,6 +578,22 @@ def main():
         "qat_step": qat,
         "extras": extras,
     }
+    if qat:
+        # LAST key of the line (survives a truncated tail): the data-parallel QAT step at this N, compact
+        def compact(r):
+            ro = r["roofline"]
+            out = {"samples_per_s": r["samples_per_s"], "ms_per_step": r["ms_per_step"], "per_gpu_batch": r["per_gpu_batch"],
+                   "roofline_bound_ms": ro["bound_ms"], "frac_of_bound": ro["frac_of_bound"],
+                   "serial_bound_ms": ro["serial_bound_ms"], "frac_of_serial_bound": ro["frac_of_serial_bound"],
+                   "compute_ms": ro["compute_ms"], "hbm_ms": ro["hbm_ms"], "nvlink_ms": ro["nvlink_ms"]}
+            if r.get("allreduce"):
+                out["allreduce_bytes"] = r["allreduce"]["bytes"]
+                out["allreduce_ms_alone"] = r["allreduce"]["ms_alone"]
+            return out
+        line["qat_scaling"] = {"n_gpus": world, "scaling": "weak (fixed per-GPU batch)",
+                               "resnet18_int8": compact(qat["resnet18_int8"]),
+                               "mobilenet_v1_4b": compact(qat["mobilenet_v1_4b"]),
+                               "tfc_2w2a": compact(qat["tfc_2w2a_cuda_graph"])}
     args.emit(line)
     if dist is not None:
         dist.destroy_process_group()

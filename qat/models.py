@@ -62,8 +62,11 @@ class TensorNorm(nn.Module):
             mean = x.mean()
             unbias_var = x.var(unbiased=True)
             biased_var = x.var(unbiased=False)
-            self.running_mean = (1 - self.momentum) * self.running_mean + self.momentum * mean.detach()
-            self.running_var = (1 - self.momentum) * self.running_var + self.momentum * unbias_var.detach()
+            # in place: a CUDA-graph replay must mutate the REGISTERED buffers (rebinding the attribute would leave
+            # replays writing a pool tensor nobody reads; same values as tensor_norm.py's out-of-place form)
+            with torch.no_grad():
+                self.running_mean.mul_(1 - self.momentum).add_(self.momentum * mean.detach())
+                self.running_var.mul_(1 - self.momentum).add_(self.momentum * unbias_var.detach())
             inv_std = 1 / (biased_var + self.eps).pow(0.5)
             return (x - mean) * inv_std * self.weight + self.bias
         return ((x - self.running_mean) / (self.running_var + self.eps).pow(0.5)) * self.weight + self.bias

@@ -55,19 +55,110 @@ def build(name: str, device, collect_stats_steps: int = 300, channels_last: bool
 def make_optimizer(model, spec, capturable=False):
     if spec["opt"] == "adam":
         return torch.optim.Adam(model.parameters(), lr=spec["lr"], capturable=capturable)
-    return torch.optim.SGD(model.parameters(), lr=spec["lr"], momentum=0.9, weight_decay=1e-4)
+    # graph mode: the fused multi-tensor SGD (one launch set per step instead of ~4 foreach launches per chunk)
+    return torch.optim.SGD(model.parameters(), lr=spec["lr"], momentum=0.9, weight_decay=1e-4, fused=bool(capturable))
+
+
+class FlatGrads:
+    """Every gradient is a view of ONE flat buffer, laid out in the order backward produces them (reverse parameter
+    order) and cut into buckets.  There is no gather before the all-reduce and no copy back after it: each bucket is
+    all-reduced IN PLACE (NCCL ``avg``) as soon as the last of its gradients has been accumulated, from a
+    post-accumulate hook, so the exchange overlaps the rest of the backward pass -- inside a CUDA graph the hook-time
+    fork / join on NCCL's stream becomes a parallel branch of the captured graph (SURVEY.md §5, §8e:
+    ``gradient_as_bucket_view`` semantics, without DDP's per-step Python reducer)."""
+
+    def __init__(self, params, world=1, dist=None, bucket_bytes=8 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.world, self.dist = world, dist
+        assert len({p.dtype for p in self.params}) == 1 and len({p.device for p in self.params}) == 1
+        order = list(reversed(self.params))
+        total = sum(p.numel() for p in order)
+        self.flat = torch.zeros(total, dtype=order[0].dtype, device=order[0].device)
+        self.buckets, self.bucket_of = [], {}          # [start, end, n_params]
+        off, start, count = 0, 0, 0
+        cap = max(1, bucket_bytes // self.flat.element_size())
+        for p in order:
+            n = p.numel()
+            view = self.flat[off:off + n]
+            if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+                g = view.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)   # NHWC like p
+            else:
+                g = view.view(p.shape)
+            p.grad = g
+            self.bucket_of[p] = len(self.buckets)
+            off += n
+            count += 1
+            if off - start >= cap:
+                self.buckets.append([start, off, count])
+                start, count = off, 0
+        if count:
+            self.buckets.append([start, off, count])
+        self.pending = [b[2] for b in self.buckets]
+        self.works = []
+        self.reduced = [False] * len(self.buckets)
+        self.allreduce_bytes = total * self.flat.element_size()
+        # NCCL averages inside the collective; other backends (gloo in the CPU tests) sum, then one divide
+        self.native_avg = world > 1 and dist.get_backend() == "nccl"
+        if world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def zero(self):
+        self.flat.zero_()                               # one memset instead of one per parameter
+        self.pending = [b[2] for b in self.buckets]
+        self.reduced = [False] * len(self.buckets)
+        self.works = []
+
+    def _launch(self, i):
+        s, e, _ = self.buckets[i]
+        self.reduced[i] = True
+        op = self.dist.ReduceOp.AVG if self.native_avg else self.dist.ReduceOp.SUM
+        self.works.append(self.dist.all_reduce(self.flat[s:e], op=op, async_op=True))
+
+    def _hook(self, p):
+        i = self.bucket_of[p]
+        self.pending[i] -= 1
+        if self.pending[i] == 0 and not self.reduced[i]:
+            self._launch(i)
+
+    def finish(self):
+        """after backward: buckets whose parameters took no gradient this step, then join every exchange"""
+        if self.world > 1:
+            for i, done in enumerate(self.reduced):
+                if not done:
+                    self._launch(i)
+            for w in self.works:
+                w.wait()
+            self.works = []
+            if not self.native_avg:
+                self.flat.div_(self.world)
+
+
+def assert_capturable(model):
+    """A CUDA graph replays device work only: host-side state that a step is supposed to advance would freeze at its
+    capture-time value.  Refuse to capture while any quantizer still counts steps on the host."""
+    for name, m in model.named_modules():
+        steps = getattr(m, "collect_stats_steps", None)
+        if steps is not None and hasattr(m, "counter") and m.training and int(m.counter) <= int(steps):
+            raise RuntimeError(f"{name}: still collecting statistics ({int(m.counter)} of {steps} steps); run the "
+                               "collection phase eagerly before capturing the step in a CUDA graph")
+        if getattr(m, "first_batch", False) and m.training:
+            raise RuntimeError(f"{name}: running statistics not initialised yet (first_batch); run one eager step first")
+        if int(getattr(m, "quant_delay_steps", 0) or 0) > 0:
+            raise RuntimeError(f"{name}: quantization delay still counting down ({m.quant_delay_steps}); not capturable")
 
 
 class GraphedStep:
-    """The whole training step (forward, loss, backward, gradient all-reduce, optimizer, weight clip) captured in
-    ONE CUDA graph: small models such as TFC are launch-bound (~150 kernels of a few microseconds per step), and the
-    C-ABI is capture-safe by construction (no allocation outside torch's caching allocator, no sync, current stream).
-    Data-parallel ranks exchange gradients with a captured NCCL all-reduce over one flat bucket."""
+    """The whole training step (forward, loss, backward, bucketed gradient all-reduce overlapped with backward,
+    optimizer, weight clip) captured in ONE CUDA graph: small models such as TFC are launch-bound (~150 kernels of a few
+    microseconds per step), and the C-ABI is capture-safe by construction (no allocation outside torch's caching
+    allocator, no sync, current stream)."""
 
-    def __init__(self, raw_model, loss_fn, opt, x, y, world=1, dist=None):
+    def __init__(self, raw_model, loss_fn, opt, x, y, world=1, dist=None, bucket_bytes=8 << 20):
         self.raw, self.loss_fn, self.opt, self.world, self.dist = raw_model, loss_fn, opt, world, dist
         self.x, self.y = x.clone(), y.clone()
-        self.params = [p for p in raw_model.parameters() if p.requires_grad]
+        assert_capturable(raw_model)
+        self.grads = FlatGrads(raw_model.parameters(), world, dist, bucket_bytes)
         from brevitas_b200 import _kernels as K
         for _ in range(3):                       # warm-up on the (non-default) current stream, see run()
             self._eager_step()
@@ -79,18 +170,10 @@ class GraphedStep:
         self.captured_launches = K.launch_count - before
 
     def _eager_step(self):
-        self.opt.zero_grad(set_to_none=False)
+        self.grads.zero()
         loss = self.loss_fn(self.raw(self.x), self.y)
         loss.backward()
-        if self.world > 1:
-            grads = [p.grad for p in self.params if p.grad is not None]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            self.dist.all_reduce(flat)
-            flat /= self.world
-            off = 0
-            for g in grads:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+        self.grads.finish()
         self.opt.step()
         if hasattr(self.raw, "clip_weights"):
             self.raw.clip_weights(-1, 1)
@@ -189,17 +272,39 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
     ms = e0.elapsed_time(e1) / steps
     launches = gstep.captured_launches if graph else (K.launch_count - l0) / steps
     loss_val = float(loss.detach())
+    allreduce = None
     if dist is not None:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {"model": name, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
+        if graph:
+            # the gradient exchange on its own (all buckets back to back, nothing to overlap with): what the step would
+            # pay if the exchange were exposed
+            flat, g = gstep.grads.flat, gstep.grads
+            dist.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(5):
+                for bs, be, _n in g.buckets:
+                    dist.all_reduce(flat[bs:be], op=dist.ReduceOp.AVG)
+            a1.record()
+            torch.cuda.synchronize()
+            ar_ms = a0.elapsed_time(a1) / 5
+            allreduce = {"bytes": g.allreduce_bytes, "buckets": len(g.buckets), "ms_alone": round(ar_ms, 3),
+                         "busbw_GBps": round(g.allreduce_bytes * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9, 1),
+                         "overlap": "bucket all-reduce launched from post-accumulate-grad hooks, joined before the optimizer; "
+                                    "a parallel branch of the captured graph"}
+    from qat import roofline as R
+    counts = R.account(raw, batches[0][0], optimizer_words=7 if spec["opt"] == "adam" else 5, world=world,
+                       dtype_bytes=2 if dtype == "bf16" else 4)
+    roof = R.roofline(counts, ms, dtype)
+    return {"model": name, "roofline": roof, "allreduce": allreduce, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
             "samples_per_s": round(world * batch / (ms * 1e-3), 1), "fakequant_launches_per_step": launches,
             "final_loss": round(loss_val, 4), "dtype": dtype, "data": "synthetic",
             "memory_format": "channels_last" if channels_last else "contiguous",
             "phase": "collecting activation statistics (AbsPercentile every step)" if collecting
                      else f"steady state (after {collect_stats_steps} collect steps)",
-            "step": "one CUDA graph (fwd+loss+bwd+allreduce+optimizer)" if graph else "eager launches"
+            "step": "one CUDA graph (fwd+loss+bwd+bucketed all-reduce overlapped with bwd+optimizer)" if graph else "eager launches"
                     + (" + DDP bucketed NCCL all-reduce" if world > 1 else "")}
 
 

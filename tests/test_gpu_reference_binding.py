@@ -402,15 +402,34 @@ def test_c3_whole_tensor_vs_reference(ref, heavy_tail):
         same = _bits(a[2]) == _bits(b[2])
         n_diff = int((~same).sum())
         assert n_diff <= B * T, f"step {step}: {n_diff} gradient elements differ (more than one per token)"
-        # the differing entries are arg-max entries; in bf16 the reference rounds the two large sums behind
-        # d(scale) (sum g*code and sum (g*s)*x/(s*s), each of magnitude S) to bf16 before they cancel, so the entry is
-        # only defined to a few bf16 ulps of S / 128 (the tight, fp64-referenced check of this kernel is the fp32 C2 test)
-        xa = x_host.cuda().float().abs()
+        # The differing entries must be arg-max entries (one per token): they carry sign(x) * Gs / 128 with
+        # Gs = sum g*code - sum m*(g*s)*x/(s*s).  The bf16 reference rounds every product and both sums to
+        # bf16 before they cancel, so its own value is only defined to ~sqrt(C) * 2^-9 * rms|g*code| / 128; the kernel
+        # accumulates Gs in fp32.  Both are therefore compared with an fp64 evaluation of Gs from the same bf16 inputs:
+        # the kernel to 4 bf16 ulps of the terms it adds, the reference (sanity of the checker) to its noise floor.
+        xd, gd = x_host.cuda(), g_host.cuda()
         ne = (~same).nonzero()
+        xa = xd.float().abs()
         assert bool((xa[ne[:, 0], ne[:, 1], ne[:, 2]] == xa.amax(dim=2)[ne[:, 0], ne[:, 1]]).all()), "not an arg-max"
-        codes = (a[0].float() / a[1].float())
-        S = torch.maximum((g_host.cuda().float() * codes).sum(dim=2).abs(),
-                          (g_host.cuda().float() * x_host.cuda().float() / a[1].float()).sum(dim=2).abs())
-        tol = 8 * 2.0 ** -8 * S / 128.0 + 2.0 ** -6 * b[2].float().abs().amax(dim=2) + 1e-3
-        d = (a[2].float() - b[2].float()).abs().amax(dim=2)
-        assert bool((d <= tol).all()), f"step {step}: arg-max gradient beyond tolerance: {float((d / tol).max()):.2f}x"
+        sc = a[1]                                                   # bf16 [B,T,1]
+        t3 = torch.round(xd / sc)
+        m = ((t3 <= 127) & (t3 >= -128)).double()
+        ew = (((gd * sc) / sc).float() * m.float())                 # element-wise part, per-op bf16 rounding like ATen
+        s64, g64, x64 = sc.double(), gd.double(), xd.double()
+        codes64 = torch.round(a[0].double() / s64)
+        t_a, t_b = g64 * codes64, m * (g64 * s64) * x64 / (s64 * s64)
+        gs64 = (t_a - t_b).sum(dim=2) / 128.0                        # [B,T]
+        r0, r1, r2 = ne[:, 0], ne[:, 1], ne[:, 2]
+        fix = torch.sign(x64[r0, r1, r2]) * gs64[r0, r1]
+        want_e = ew.double()[r0, r1, r2] + fix
+        mag = torch.maximum(want_e.abs(), torch.maximum(ew.double()[r0, r1, r2].abs(), fix.abs()))
+        err_k = (a[2].double()[r0, r1, r2] - want_e).abs()
+        lim_k = 4 * 2.0 ** -8 * mag + 1e-3
+        assert bool((err_k <= lim_k).all()), f"step {step}: kernel arg-max gradient {float((err_k / lim_k).max()):.2f}x its bound"
+        rms = (t_a * t_a).mean(dim=2).sqrt()[r0, r1]
+        big = torch.maximum(t_a.sum(dim=2).abs(), t_b.sum(dim=2).abs())[r0, r1]
+        lim_r = (8 * np.sqrt(C) * 2.0 ** -9 * rms + 4 * 2.0 ** -8 * big) / 128.0 + lim_k
+        err_r = (b[2].double()[r0, r1, r2] - want_e).abs()
+        assert bool((err_r <= lim_r).all()), f"step {step}: reference arg-max gradient {float((err_r / lim_r).max()):.2f}x its noise floor"
+        print(f"step {step}: {n_diff} arg-max entries differ from the bf16 reference; kernel max err/bound "
+              f"{float((err_k / lim_k).max()):.3f}, reference max err/floor {float((err_r / lim_r).max()):.3f}")

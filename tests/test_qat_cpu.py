@@ -127,3 +127,64 @@ def test_ddp_harness_gloo_world_size_2(tmp_path):
     r = torch.load(out)
     assert r["same_grad"] and r["same_weights"] and r["moved"] and r["clipped"]
     assert r["tmax"] == 2.0 and r["loss"] > 0
+
+
+def _flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qat.train import FlatGrads
+    torch.manual_seed(7)
+    model = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 8, 3, padding=1), nn.Flatten(),
+                          nn.Linear(8 * 6 * 6, 5)).to(memory_format=torch.channels_last)
+    unused = nn.Parameter(torch.ones(3))                   # takes no gradient: its bucket is reduced by finish()
+    params = list(model.parameters()) + [unused]
+    import copy
+    plain = copy.deepcopy(model)                             # same weights, ordinary .grad tensors, no exchange
+    fg = FlatGrads(params, world, dist, bucket_bytes=1024)   # several buckets
+    g = torch.Generator().manual_seed(50 + rank)
+    x = torch.randn(4, 3, 6, 6, generator=g).contiguous(memory_format=torch.channels_last)
+    res = []
+    for step in range(2):                                    # second step: zero() really clears, hooks re-arm
+        fg.zero()
+        model(x).square().sum().backward()
+        fg.finish()
+        plain.zero_grad(set_to_none=True)
+        plain(x).square().sum().backward()
+        local = [p.grad.detach().clone() for p in plain.parameters()] + [torch.zeros(3)]
+        res.append((local, [p.grad.detach().clone() for p in params]))
+    views_ok = all(p.grad.untyped_storage().data_ptr() == fg.flat.untyped_storage().data_ptr() for p in params)
+    strides_ok = all(p.grad.stride() == p.stride() for p in model.parameters())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [[t.tolist() for t in loc] for loc, _ in res])
+    if rank == 0:
+        ok = True
+        for step in range(2):
+            for i, p in enumerate(params):
+                mean = sum(torch.tensor(gathered[r][step][i]) for r in range(world)) / world
+                ok &= bool(torch.allclose(res[step][1][i], mean.view_as(p), atol=1e-6))
+        torch.save({"ok": ok, "views": views_ok, "strides": strides_ok, "buckets": len(fg.buckets),
+                    "bytes": fg.allreduce_bytes, "n": sum(p.numel() for p in params)}, out)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_buckets_gloo_world_size_2(tmp_path):
+    """qat.train.FlatGrads (the graph-mode data-parallel exchange): gradients are views of one buffer with the
+    parameters' own strides, every bucket is averaged over the ranks in place -- from the hooks during backward, or by
+    finish() for parameters that took no gradient -- and the next step starts from zeros."""
+    out = str(tmp_path / "flat.pt")
+    mp.spawn(_flat_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["ok"] and r["views"] and r["strides"] and r["buckets"] >= 3 and r["bytes"] == 4 * r["n"]
+
+
+def test_graph_capture_refused_while_host_state_still_advances():
+    from qat.train import assert_capturable
+    from brevitas_b200.quant import Uint8ActPerTensorFloat
+    from brevitas_b200.nn import QuantReLU
+    m = QuantReLU(collect_stats_steps=5).train()
+    with pytest.raises(RuntimeError, match="still collecting"):
+        assert_capturable(m)
+    m.act_quant.fused_activation_quant_proxy.tensor_quant.scaling_impl.counter = 6
+    assert_capturable(m)
+    m.eval()
+    assert_capturable(m)
