@@ -59,14 +59,10 @@ sys.exit(int(rc))
     return launches, tail
 
 
-def test_reference_function_tests_on_b200_ops():
-    launches, tail = run_suite(FUNCTION, fuse=False)
+def test_reference_function_and_core_tests_on_b200_ops():
+    launches, tail = run_suite(FUNCTION + CORE, fuse=False)
+    assert launches > 0, "the reference's tests never reached a B200 kernel"
     print(tail[-400:])
-
-
-def test_reference_core_tests_on_b200_ops():
-    launches, tail = run_suite(CORE, fuse=False)
-    assert launches > 0, "the reference's core tests never reached a B200 kernel"
 
 
 def test_reference_core_and_layer_tests_on_fused_classes():
