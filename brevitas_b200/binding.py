@@ -187,7 +187,7 @@ def install(reference_path: Optional[str] = None, fuse: bool = True):
     if not _state["installed"]:
         _set(ops_ste, "fn_prefix", torch)
         _set(brevitas, "NATIVE_STE_BACKEND_LOADED", True)       # a native STE backend IS loaded: this library
-        config.IGNORE_MISSING_KEYS = ref_config.IGNORE_MISSING_KEYS
+        config.bind(ref_config)
         _state["installed"] = True
     if fuse and not _state["fused"]:
         # everything that holds references to the core classes must be loaded before the sweep
@@ -210,6 +210,8 @@ def uninstall():
             setattr(holder, key, old)
         else:
             holder[key] = old
+    from . import config
+    config.bind(None)
     _state.update(installed=False, fused=False, table={})
 
 

@@ -123,22 +123,23 @@ def tfc(weight_bit_width=2, act_bit_width=2, in_bit_width=2):
 
 
 # ---- ResNet-18 ------------------------------------------------------------------------------------------------
-def _act(**kw):
-    return QuantReLU(**kw)
+class _MirrorLayers:
+    """layer namespace: this repository's mirror of brevitas.nn"""
+    QuantConv2d, QuantReLU, QuantLinear = QuantConv2d, QuantReLU, QuantLinear
 
 
 class BasicBlock(nn.Module):
     expansion = 1
 
-    def __init__(self, inplanes, planes, stride=1, downsample=None, act_kw=None):
+    def __init__(self, inplanes, planes, stride=1, downsample=None, act_kw=None, L=_MirrorLayers):
         super().__init__()
         act_kw = act_kw or {}
-        self.conv1 = QuantConv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.conv1 = L.QuantConv2d(inplanes, planes, 3, stride, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
-        self.relu1 = _act(**act_kw)
-        self.conv2 = QuantConv2d(planes, planes, 3, 1, 1, bias=False)
+        self.relu1 = L.QuantReLU(**act_kw)
+        self.conv2 = L.QuantConv2d(planes, planes, 3, 1, 1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
-        self.relu2 = _act(**act_kw)
+        self.relu2 = L.QuantReLU(**act_kw)
         self.downsample = downsample
 
     def forward(self, x):
@@ -151,12 +152,15 @@ class BasicBlock(nn.Module):
 
 
 class ResNet18(nn.Module):
-    def __init__(self, num_classes=1000, act_kw=None):
+    """``L``: the layer namespace -- the mirror (default) or the reference's own ``brevitas.nn`` (qat/ref_models.py)"""
+
+    def __init__(self, num_classes=1000, act_kw=None, L=_MirrorLayers):
         super().__init__()
         act_kw = act_kw or {}
-        self.conv1 = QuantConv2d(3, 64, 7, 2, 3, bias=False)
+        self.L = L
+        self.conv1 = L.QuantConv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
-        self.relu = _act(**act_kw)
+        self.relu = L.QuantReLU(**act_kw)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         self.inplanes = 64
         self.layer1 = self._make_layer(64, 2, 1, act_kw)
@@ -164,7 +168,7 @@ class ResNet18(nn.Module):
         self.layer3 = self._make_layer(256, 2, 2, act_kw)
         self.layer4 = self._make_layer(512, 2, 2, act_kw)
         self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
-        self.fc = QuantLinear(512, num_classes)
+        self.fc = L.QuantLinear(512, num_classes, True)
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
@@ -172,11 +176,12 @@ class ResNet18(nn.Module):
     def _make_layer(self, planes, blocks, stride, act_kw):
         downsample = None
         if stride != 1 or self.inplanes != planes:
-            downsample = nn.Sequential(QuantConv2d(self.inplanes, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
-        layers = [BasicBlock(self.inplanes, planes, stride, downsample, act_kw)]
+            downsample = nn.Sequential(self.L.QuantConv2d(self.inplanes, planes, 1, stride, bias=False),
+                                       nn.BatchNorm2d(planes))
+        layers = [BasicBlock(self.inplanes, planes, stride, downsample, act_kw, self.L)]
         self.inplanes = planes
         for _ in range(1, blocks):
-            layers.append(BasicBlock(planes, planes, act_kw=act_kw))
+            layers.append(BasicBlock(planes, planes, act_kw=act_kw, L=self.L))
         return nn.Sequential(*layers)
 
     def forward(self, x):

@@ -31,14 +31,26 @@ WORKLOADS = {
 }
 
 
-def build(name: str, device, collect_stats_steps: int = 300, channels_last: bool = False):
+def bind_reference(brevitas_src=None):
+    """``--frontend reference``: bind an (unmodified) Brevitas installation to the kernels.  ``brevitas_src``: a source
+    tree to import it from when it is not pip-installed (``$BREVITAS_SRC``)."""
+    import brevitas_b200
+    brevitas_b200.install(brevitas_src or os.environ.get("BREVITAS_SRC"), fuse=True)
+
+
+def build(name: str, device, collect_stats_steps: int = 300, channels_last: bool = False, frontend: str = "mirror"):
+    """``frontend``: "mirror" = this repository's re-statement of the layers (brevitas_b200.nn); "reference" = the
+    reference's own brevitas.nn / brevitas_examples model code after bind_reference()."""
     spec = WORKLOADS[name]
+    M = models
+    if frontend == "reference":
+        from qat import ref_models as M
     if name == "tfc":
-        model = models.tfc()
+        model = M.tfc()
     elif name == "resnet18":
-        model = models.resnet18(collect_stats_steps=collect_stats_steps)
+        model = M.resnet18(collect_stats_steps=collect_stats_steps)
     else:
-        model = models.mobilenet_v1()
+        model = M.mobilenet_v1()
     model = model.to(device)
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
@@ -211,9 +223,12 @@ def train_step(model, raw_model, x, y, loss_fn, opt):
     return loss
 
 
-def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False, channels_last=False, dtype="f32"):
+def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False, channels_last=False, dtype="f32",
+        frontend="mirror", brevitas_src=None):
     """returns a dict with samples/s (all ranks), ms/step, kernel-launch count per step of OUR kernels"""
     import brevitas_b200  # noqa: F401
+    if frontend == "reference":
+        bind_reference(brevitas_src)
     from brevitas_b200 import _kernels as K
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,7 +245,7 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
         # if that is not the legacy default stream, so the whole life of the model runs on a side stream
         torch.cuda.set_stream(torch.cuda.Stream(device))
     torch.manual_seed(1234)                               # identical initial weights on every rank
-    raw, loss_fn, spec = build(name, device, collect_stats_steps, channels_last=channels_last)
+    raw, loss_fn, spec = build(name, device, collect_stats_steps, channels_last=channels_last, frontend=frontend)
     tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[dtype]
     if tdt != torch.float32:
         raw = raw.to(tdt)               # parameters, buffers and activations in bf16: the packed 16-bit kernels
@@ -298,7 +313,8 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
     counts = R.account(raw, batches[0][0], optimizer_words=7 if spec["opt"] == "adam" else 5, world=world,
                        dtype_bytes=2 if dtype == "bf16" else 4)
     roof = R.roofline(counts, ms, dtype)
-    return {"model": name, "roofline": roof, "allreduce": allreduce, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
+    return {"model": name, "frontend": "unmodified brevitas.nn / brevitas_examples + brevitas_b200.install()"
+            if frontend == "reference" else "brevitas_b200.nn mirror", "roofline": roof, "allreduce": allreduce, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
             "samples_per_s": round(world * batch / (ms * 1e-3), 1), "fakequant_launches_per_step": launches,
             "final_loss": round(loss_val, 4), "dtype": dtype, "data": "synthetic",
             "memory_format": "channels_last" if channels_last else "contiguous",
@@ -318,11 +334,14 @@ def main():
     ap.add_argument("--graph", action="store_true", help="capture the whole step in a CUDA graph")
     ap.add_argument("--channels-last", action="store_true", help="NHWC activations and conv weights")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--frontend", default="mirror", choices=["mirror", "reference"],
+                    help="reference: the unmodified brevitas.nn / brevitas_examples models bound by brevitas_b200.install()")
+    ap.add_argument("--brevitas-src", default=None, help="source tree to import Brevitas from (default: installed / $BREVITAS_SRC)")
     a = ap.parse_args()
     os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
     os.environ.setdefault("NCCL_IB_DISABLE", "1")
     res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps, graph=a.graph, channels_last=a.channels_last,
-              dtype=a.dtype)
+              dtype=a.dtype, frontend=a.frontend, brevitas_src=a.brevitas_src)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(res))
     import torch.distributed as dist

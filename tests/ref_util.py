@@ -12,7 +12,7 @@ import sys
 
 import torch
 from torch.overrides import TorchFunctionMode
-from torch.utils._pytree import tree_flatten, tree_map
+from torch.utils._pytree import tree_flatten, tree_map, tree_unflatten
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -43,9 +43,17 @@ class FactoryToCuda(TorchFunctionMode):
         kwargs = kwargs or {}
         if func is torch.Tensor.numpy and args and args[0].is_cuda:        # tests written for CPU call x.numpy()
             return args[0].detach().cpu().numpy()
-        out = func(*args, **kwargs)
         if _has_tensor(args, kwargs):
-            return out
+            # an op mixing a device tensor with a host tensor that escaped the factories (torch.from_numpy, the legacy
+            # torch.Tensor(...) constructor): bring the host side over, as a test written for one device expects
+            flat, spec = tree_flatten((args, kwargs))
+            devs = {a.device.type for a in flat if isinstance(a, torch.Tensor)}
+            if devs == {"cpu", "cuda"} and getattr(func, "__name__", "") not in ("to", "cpu", "cuda", "copy_", "numpy"):
+                flat = [a.to(self.device) if isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dim() > 0 else a
+                        for a in flat]
+                args, kwargs = tree_unflatten(flat, spec)
+            return func(*args, **kwargs)
+        out = func(*args, **kwargs)
         return tree_map(lambda t: t.to(self.device) if isinstance(t, torch.Tensor) and t.device.type == "cpu" else t, out)
 
 

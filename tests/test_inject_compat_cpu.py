@@ -232,3 +232,25 @@ def test_mirror_constructors_match_the_reference_by_name():
         if a != b:
             bad.append((ref_cls.__name__, a, b))
     assert not bad, bad
+
+
+@needs_ref
+def test_config_flags_follow_the_reference_after_install():
+    """one config module, read at call time by every module kind, following brevitas.config once bound"""
+    import brevitas_b200
+    from brevitas_b200 import config
+    from brevitas_b200.binding import uninstall
+    uninstall()
+    assert config.IGNORE_MISSING_KEYS is False
+    brevitas_b200.install(reference_src(), fuse=False)
+    import brevitas.config as ref_config
+    old = ref_config.IGNORE_MISSING_KEYS
+    try:
+        ref_config.IGNORE_MISSING_KEYS = True
+        assert config.IGNORE_MISSING_KEYS is True
+        from brevitas_b200.core import bit_width, scaling, stats, zero_point
+        assert all(m.config is config for m in (bit_width, scaling, stats, zero_point))
+    finally:
+        ref_config.IGNORE_MISSING_KEYS = old
+        uninstall()
+    assert config.IGNORE_MISSING_KEYS is False
