@@ -520,6 +520,15 @@ def main():
         qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True, graph=True)
         if world > 1 or args.qat_all:
             qat["mobilenet_v1_4b_eager_ddp"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True)
+        # the same three workloads built by the REFERENCE's own, unmodified model code (brevitas.nn layers, injector,
+        # proxies, brevitas_examples models) after brevitas_b200.install(): the drop-in a Brevitas user gets.  The host
+        # framework is imported from the copy that travelled with the repository (a user has it pip-installed).
+        ref_src = os.environ.get("BREVITAS_SRC") or os.path.join(ROOT, "oracle", "_ref", "src")
+        if os.path.isdir(os.path.join(ref_src, "brevitas")):
+            fe = dict(frontend="reference", brevitas_src=ref_src)
+            qat["resnet18_int8_reference_frontend"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True, graph=True, **fe)
+            qat["mobilenet_v1_4b_reference_frontend"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True, graph=True, **fe)
+            qat["tfc_2w2a_reference_frontend"] = qat_run("tfc", 256, 200, 5, graph=True, **fe)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -594,6 +603,10 @@ def main():
                                "resnet18_int8": compact(qat["resnet18_int8"]),
                                "mobilenet_v1_4b": compact(qat["mobilenet_v1_4b"]),
                                "tfc_2w2a": compact(qat["tfc_2w2a_cuda_graph"])}
+        for k in ("resnet18_int8", "mobilenet_v1_4b", "tfc_2w2a"):
+            r = qat.get(k + "_reference_frontend")
+            if r is not None:
+                line["qat_scaling"][k]["unmodified_brevitas_nn_samples_per_s"] = r["samples_per_s"]
     args.emit(line)
     if dist is not None:
         dist.destroy_process_group()
