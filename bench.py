@@ -508,7 +508,7 @@ def main():
         os.environ.setdefault("NCCL_IB_DISABLE", "1")
         # BASELINE.json configs[3]; NHWC end to end (cuDNN's native layout; the fake-quant kernels take it in place), ReLU
         # folded into the quantizer kernels, the whole step (fwd + loss + bwd + gradient all-reduce + SGD) as ONE CUDA graph
-        qat["resnet18_int8"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True, graph=True)
+        qat["resnet18_int8"] = qat_run("resnet18", args.qat_batch, 20, 3, channels_last=True, graph=True)
         qat["resnet18_int8_eager_ddp"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True)
         # the first 300 steps of the default activation quantizers collect an exact 99.999th percentile of every
         # activation tensor (AbsPercentile, radix select): step time while collecting (SURVEY.md §8d C4 "warm-up")
@@ -517,7 +517,7 @@ def main():
         qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
         qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
         # BASELINE.json configs[4]: ~1100 small launches per step, host-bound when launched eagerly
-        qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True, graph=True)
+        qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 20, 3, channels_last=True, graph=True)
         if world > 1 or args.qat_all:
             qat["mobilenet_v1_4b_eager_ddp"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True)
         # the same three workloads built by the REFERENCE's own, unmodified model code (brevitas.nn layers, injector,
@@ -526,9 +526,11 @@ def main():
         ref_src = os.environ.get("BREVITAS_SRC") or os.path.join(ROOT, "oracle", "_ref", "src")
         if os.path.isdir(os.path.join(ref_src, "brevitas")):
             fe = dict(frontend="reference", brevitas_src=ref_src)
-            qat["resnet18_int8_reference_frontend"] = qat_run("resnet18", args.qat_batch, 10, 3, channels_last=True, graph=True, **fe)
-            qat["mobilenet_v1_4b_reference_frontend"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True, graph=True, **fe)
-            qat["tfc_2w2a_reference_frontend"] = qat_run("tfc", 256, 200, 5, graph=True, **fe)
+            qat["resnet18_int8_reference_frontend"] = qat_run("resnet18", args.qat_batch, 20, 3, channels_last=True, graph=True, **fe)
+            qat["mobilenet_v1_4b_reference_frontend"] = qat_run("mobilenet_v1", 128, 20, 3, channels_last=True, graph=True, **fe)
+            # the reference's FC.forward builds a tensor from a Python list every call (FC.py:66: a host-to-device copy),
+            # so its step cannot be captured in a CUDA graph: launched eagerly
+            qat["tfc_2w2a_reference_frontend"] = qat_run("tfc", 256, 30, 5, **fe)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

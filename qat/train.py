@@ -77,9 +77,15 @@ class FlatGrads:
     all-reduced IN PLACE (NCCL ``avg``) as soon as the last of its gradients has been accumulated, from a
     post-accumulate hook, so the exchange overlaps the rest of the backward pass -- inside a CUDA graph the hook-time
     fork / join on NCCL's stream becomes a parallel branch of the captured graph (SURVEY.md §5, §8e:
-    ``gradient_as_bucket_view`` semantics, without DDP's per-step Python reducer)."""
+    ``gradient_as_bucket_view`` semantics, without DDP's per-step Python reducer).
 
-    def __init__(self, params, world=1, dist=None, bucket_bytes=8 << 20):
+    Bucket size, measured on 2 x B200 (tools/ddp_probe.sh, profiles/r02_ddp_probe.md): NCCL kernels that run BESIDE the
+    backward kernels take SMs and HBM bandwidth from them, and these models' exchanges are short (0.07-0.12 ms for 17-47
+    MB), so small buckets cost more than their overlap hides: ResNet-18 20.54 / 20.40 / 20.16 ms per step with 1 / 8 /
+    64 MB buckets (19.95 ms without any exchange).  The default therefore keeps models of this size in ONE bucket
+    (launched by the hook of the last gradient); larger models split and overlap."""
+
+    def __init__(self, params, world=1, dist=None, bucket_bytes=64 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.world, self.dist = world, dist
         assert len({p.dtype for p in self.params}) == 1 and len({p.device for p in self.params}) == 1
@@ -124,6 +130,8 @@ class FlatGrads:
     def _launch(self, i):
         s, e, _ = self.buckets[i]
         self.reduced[i] = True
+        if os.environ.get("QAT_PROBE_NO_ALLREDUCE"):       # experiment knob: everything but the collective itself
+            return
         op = self.dist.ReduceOp.AVG if self.native_avg else self.dist.ReduceOp.SUM
         self.works.append(self.dist.all_reduce(self.flat[s:e], op=op, async_op=True))
 
@@ -166,7 +174,8 @@ class GraphedStep:
     microseconds per step), and the C-ABI is capture-safe by construction (no allocation outside torch's caching
     allocator, no sync, current stream)."""
 
-    def __init__(self, raw_model, loss_fn, opt, x, y, world=1, dist=None, bucket_bytes=8 << 20):
+    def __init__(self, raw_model, loss_fn, opt, x, y, world=1, dist=None, bucket_bytes=64 << 20):
+        bucket_bytes = int(float(os.environ.get("QAT_BUCKET_MB", bucket_bytes / (1 << 20))) * (1 << 20))
         self.raw, self.loss_fn, self.opt, self.world, self.dist = raw_model, loss_fn, opt, world, dist
         self.x, self.y = x.clone(), y.clone()
         assert_capturable(raw_model)
