@@ -279,7 +279,7 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
         step_fn = lambda i: gstep(*batches[i % 2])
     else:
         step_fn = lambda i: train_step(model, raw, *batches[i % 2], loss_fn, opt)
-    for i in range(3):
+    for i in range(10 if graph else 3):      # graph capture leaves the GPU idle for a while: replay past the clock ramp
         step_fn(i)
     torch.cuda.synchronize()
     if dist is not None:
