@@ -291,13 +291,24 @@ class _QuantWBIOL:
         if self.bias is not None:
             quant_bias = self.bias_quant(self.bias, output_scale, output_bit_width)
             out = inner(quant_input.value, quant_weight.value, quant_bias.value)
+            # a bias that is NOT quantized at the accumulator scale (a float bias, or a bias quantizer with its own
+            # scale) shifts the accumulator: it is carried as the output zero-point (quant_layer.py:337-341)
+            if output_scale is not None and (quant_bias.scale is None
+                                             or quant_bias.scale.data_ptr() != output_scale.data_ptr()):
+                output_zero_point = - quant_bias.value.view(shape) / output_scale
             if quant_bias.bit_width is not None and output_bit_width is not None:
                 output_bit_width = torch.where(quant_bias.bit_width > output_bit_width, quant_bias.bit_width,
                                                output_bit_width) + 1
         else:
             out = inner(quant_input.value, quant_weight.value, None)
-        if self.return_quant_tensor and not self.output_quant.is_quant_enabled and quant_input.zero_point is not None:
-            output_zero_point = quant_input.zero_point
+        if self.return_quant_tensor and not self.output_quant.is_quant_enabled:
+            # quant_layer.py:349-355 (the reference evaluates the two .any() on the host here, under the same condition)
+            checkable = not (quant_input.value.is_cuda and torch.cuda.is_current_stream_capturing())   # a host read
+            if checkable and quant_input.zero_point is not None and ((quant_input.zero_point != 0.0).any()
+                                                                     or (quant_weight.zero_point != 0.0).any()):
+                raise RuntimeError("Computing zero point of output accumulator not supported yet.")
+            elif quant_input.zero_point is not None and output_zero_point is None:
+                output_zero_point = quant_input.zero_point
         if self.output_quant.is_quant_enabled:
             q = self.output_quant(out)
             return q if self.return_quant_tensor else q.value

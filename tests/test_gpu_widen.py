@@ -274,3 +274,31 @@ def test_shifted_uint8_act_quantizer_collect_then_learn():
             tol = 1e-5 * float(xs.sum()) + 1e-4
             assert abs(float(gs) - float(d[k + "g_scale_value"])) <= tol, (step, float(gs), d[k + "g_scale_value"])
             assert abs(float(gz) - float(d[k + "g_zp_value"])) <= tol, (step, float(gz), d[k + "g_zp_value"])
+
+
+def test_layer_output_zero_point_follows_the_reference_bias_rule():
+    """nn/quant_layer.py:337-355: a bias that is not quantized at the accumulator scale becomes the output
+    zero-point -bias / (weight_scale * input_scale); non-zero input / weight zero-points are refused."""
+    from brevitas_b200.nn import QuantIdentity, QuantLinear
+    from brevitas_b200.quant import Int8ActPerTensorFloat, Int8Bias, ShiftedUint8ActPerTensorFloat
+    torch.manual_seed(0)
+    x = torch.randn(4, 16, device="cuda")
+    qin = QuantIdentity(act_quant=Int8ActPerTensorFloat, return_quant_tensor=True).cuda().train()
+    lin = QuantLinear(16, 8, bias=True, return_quant_tensor=True).cuda().train()            # float bias
+    out = lin(qin(x))
+    qi = qin(x)
+    acc_scale = lin.quant_weight().scale.view(1, -1) * qi.scale.view(1, -1)
+    assert torch.equal(out.scale, acc_scale)
+    assert torch.equal(out.zero_point, -lin.bias.view(1, -1) / acc_scale)
+    # (value / scale + zero_point) is then the integer accumulator WITHOUT the bias
+    acc = out.value / out.scale + out.zero_point
+    ref = torch.nn.functional.linear(qi.value, lin.quant_weight().value) / acc_scale
+    assert torch.allclose(acc, ref, atol=1e-2)
+    lin_q = QuantLinear(16, 8, bias=True, bias_quant=Int8Bias, return_quant_tensor=True).cuda().train()
+    out_q = lin_q(qin(x))                              # bias quantized AT the accumulator scale: no shift
+    assert torch.equal(out_q.zero_point, qi.zero_point)
+    shifted = QuantIdentity(act_quant=ShiftedUint8ActPerTensorFloat, return_quant_tensor=True, collect_stats_steps=1).cuda().train()
+    shifted(x)
+    shifted(x)
+    with pytest.raises(RuntimeError, match="zero point of output accumulator"):
+        lin(shifted(x - 3.0))
