@@ -11,7 +11,8 @@ from ctypes import c_double, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libbrevitas_b200.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+# tools/ sweeps point this at libbrevitas_b200_tuning.so (make TUNING=1), which adds bvb_set_tuning
+LIB_PATH = os.environ.get("BREVITAS_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 
 # dtype / mode tags of include/brevitas_b200.h
 F32, BF16, F16 = 0, 1, 2
@@ -28,12 +29,14 @@ SIGNATURES = {
     "bvb_version": (c_int, []),
     "bvb_last_error": (ctypes.c_char_p, []),
     "bvb_sm_count": (c_int, []),
-    "bvb_set_tuning": (None, [_I, _I, _I, _I, _I]),
     "bvb_selftest_div": (c_int, [c_float, ctypes.c_uint32, ctypes.c_uint64, _P, _P]),
     "bvb_selftest_lowp_div": (c_int, [_I, _P, _P]),
     "bvb_debug_packed_constants": (c_int, [_F, _F, _F, _I, _P]),
     "bvb_host_rows_fakequant_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _F, _F, _F, _F, _F, _I, _I, _I, _P, _L, _P]),
     "bvb_host_pipeline_workspace_bytes": (_L, [_L, _L, _L, _I, _I]),
+    "bvb_host_pipeline_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "bvb_host_pipeline_destroy": (c_int, [_P]),
+    "bvb_host_rows_fakequant_fwd_bwd_on": (c_int, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _F, _F, _F, _F, _I, _I, _I, _P, _L, _P]),
     "bvb_round_ste_impl": (c_int, _UNARY),
     "bvb_ceil_ste_impl": (c_int, _UNARY),
     "bvb_floor_ste_impl": (c_int, _UNARY),

@@ -22,7 +22,7 @@ int sm_count();
 struct Tuning {
     int rows_threads, rows_stages, rows_ctas_per_sm, stream_threads, stream_ctas_per_sm;
 };
-Tuning& tuning();
+const Tuning& tuning();      // all zero (= heuristics) in the product build; see lib.cu
 unsigned stat_grid(int64_t blocks_wanted, int default_per_sm);   // grid of a read-only statistic kernel (256-thread CTAs), int_quant.cu
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -9,6 +9,8 @@
 //
 // Replaces, for host-resident tensors, the same reference chain as bvb_rows_absmax_int_quant_{fwd,bwd}:
 // RescalingIntQuant.forward (src/brevitas/core/quant/int.py:156-163) + autograd through it.
+#include <new>
+
 #include "common.cuh"
 #include "host.cuh"
 
@@ -73,11 +75,58 @@ extern "C" int64_t bvb_host_pipeline_workspace_bytes(int64_t rows, int64_t cols,
             return fail(BVB_ECUDA, "bvb_host_rows_fakequant_fwd_bwd: %s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// A caller-owned set of the pipeline's three streams and its events, so that repeated calls do not create and destroy
+// 3 streams + 11 events each time.  The library itself still holds no state: the handle lives with the caller.
+extern "C" int bvb_host_pipeline_create(void** handle) {
+    if (!handle) return fail(BVB_EINVAL, "bvb_host_pipeline_create: null pointer");
+    Pipe* p = new (std::nothrow) Pipe();
+    if (!p) return fail(BVB_ECUDA, "bvb_host_pipeline_create: out of host memory");
+    cudaError_t e = p->create(HOST_SLOTS);
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(BVB_ECUDA, "bvb_host_pipeline_create: %s", cudaGetErrorString(e));
+    }
+    *handle = p;
+    return BVB_OK;
+}
+
+extern "C" int bvb_host_pipeline_destroy(void* handle) {
+    delete static_cast<Pipe*>(handle);      // the runtime defers stream / event destruction until their work drained
+    return BVB_OK;
+}
+
+static int host_rows_impl(Pipe& pp, const void* h_x, const void* h_gy, void* h_y, void* h_gx, void* h_scale,
+                          int64_t rows, int64_t cols, int64_t chunk_rows, float scaling_min_val, float int_threshold,
+                          float zero_point, float qmin, float qmax, int round_mode, int clamp_mode, int dtype,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+extern "C" int bvb_host_rows_fakequant_fwd_bwd_on(void* pipeline, const void* h_x, const void* h_gy, void* h_y, void* h_gx,
+                                                  void* h_scale, int64_t rows, int64_t cols, int64_t chunk_rows,
+                                                  float scaling_min_val, float int_threshold, float zero_point, float qmin,
+                                                  float qmax, int round_mode, int clamp_mode, int dtype, void* workspace,
+                                                  int64_t workspace_bytes, void* stream) {
+    if (!pipeline) return fail(BVB_EINVAL, "bvb_host_rows_fakequant_fwd_bwd_on: null pipeline handle");
+    return host_rows_impl(*static_cast<Pipe*>(pipeline), h_x, h_gy, h_y, h_gx, h_scale, rows, cols, chunk_rows,
+                          scaling_min_val, int_threshold, zero_point, qmin, qmax, round_mode, clamp_mode, dtype, workspace,
+                          workspace_bytes, stream);
+}
+
 extern "C" int bvb_host_rows_fakequant_fwd_bwd(const void* h_x, const void* h_gy, void* h_y, void* h_gx, void* h_scale,
                                                int64_t rows, int64_t cols, int64_t chunk_rows, float scaling_min_val,
                                                float int_threshold, float zero_point, float qmin, float qmax,
                                                int round_mode, int clamp_mode, int dtype, void* workspace,
                                                int64_t workspace_bytes, void* stream) {
+    Pipe pp;                                 // one-shot form: transient streams and events
+    cudaError_t e = pp.create(HOST_SLOTS);
+    if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_host_rows_fakequant_fwd_bwd: %s", cudaGetErrorString(e));
+    return host_rows_impl(pp, h_x, h_gy, h_y, h_gx, h_scale, rows, cols, chunk_rows, scaling_min_val, int_threshold,
+                          zero_point, qmin, qmax, round_mode, clamp_mode, dtype, workspace, workspace_bytes, stream);
+}
+
+static int host_rows_impl(Pipe& pp, const void* h_x, const void* h_gy, void* h_y, void* h_gx, void* h_scale,
+                          int64_t rows, int64_t cols, int64_t chunk_rows, float scaling_min_val, float int_threshold,
+                          float zero_point, float qmin, float qmax, int round_mode, int clamp_mode, int dtype,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
     if (rows < 0 || cols < 0) return fail(BVB_EINVAL, "bvb_host_rows_fakequant_fwd_bwd: negative size");
     if (rows == 0) return BVB_OK;
     if (cols == 0) return fail(BVB_EINVAL, "bvb_host_rows_fakequant_fwd_bwd: abs-max over an empty row is undefined");
@@ -98,8 +147,6 @@ extern "C" int bvb_host_rows_fakequant_fwd_bwd(const void* h_x, const void* h_gy
     unsigned char* d_scale = ws + per_slot * HOST_SLOTS;
     cudaStream_t user = (cudaStream_t)stream;
 
-    Pipe pp;
-    BVB_CUDA_OK(pp.create(HOST_SLOTS));
     // order the pipeline after whatever the caller enqueued before (the staging buffers may still be in use)
     BVB_CUDA_OK(cudaEventRecord(pp.start, user));
     BVB_CUDA_OK(cudaStreamWaitEvent(pp.in, pp.start, 0));

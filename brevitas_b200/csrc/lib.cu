@@ -37,10 +37,17 @@ int sm_count() {
     return cached_sms;
 }
 
-Tuning& tuning() {
-    static Tuning t = {0, 0, 0, 0, 0};
-    return t;
+#ifdef BVB_TUNING_BUILD
+// sweep build only (make TUNING=1 -> libbrevitas_b200_tuning.so): process-wide launch-geometry overrides
+static Tuning g_tuning = {0, 0, 0, 0, 0};
+const Tuning& tuning() { return g_tuning; }
+#else
+// product build: the heuristics are the only geometry source; nothing mutable lives in the library
+const Tuning& tuning() {
+    static const Tuning none = {0, 0, 0, 0, 0};
+    return none;
 }
+#endif
 
 // DivBy (common.cuh) against the compiler's IEEE division, over `count` consecutive numerator bit patterns
 __global__ void selftest_div_kernel(float divisor, uint32_t first_bits, unsigned long long count,
@@ -120,14 +127,11 @@ const char* bvb_last_error(void) { return bvb::err_buf(); }
 
 int bvb_sm_count(void) { return bvb::sm_count(); }
 
+#ifdef BVB_TUNING_BUILD
 void bvb_set_tuning(int rows_threads, int rows_stages, int rows_ctas_per_sm, int stream_threads, int stream_ctas_per_sm) {
-    bvb::Tuning& t = bvb::tuning();
-    t.rows_threads = rows_threads;
-    t.rows_stages = rows_stages;
-    t.rows_ctas_per_sm = rows_ctas_per_sm;
-    t.stream_threads = stream_threads;
-    t.stream_ctas_per_sm = stream_ctas_per_sm;
+    bvb::g_tuning = {rows_threads, rows_stages, rows_ctas_per_sm, stream_threads, stream_ctas_per_sm};
 }
+#endif
 
 int64_t bvb_workspace_bytes(void) { return 1 << 20; }
 

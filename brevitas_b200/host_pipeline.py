@@ -14,6 +14,18 @@ from ._kernels import _DTYPES
 from .core.quant import int_range
 
 _workspaces = {}
+_pipes = {}          # device -> C-ABI pipeline handle (3 streams + events), created once, owned here
+
+
+def _pipe(dev: torch.device):
+    import ctypes
+    h = _pipes.get(dev)
+    if h is None:
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.call("bvb_host_pipeline_create", ctypes.byref(h))
+        _pipes[dev] = h
+    return h
 
 
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
@@ -59,7 +71,7 @@ def weight_fake_quant_fwd_bwd_host(w: torch.Tensor, grad_out: torch.Tensor, *, b
     ws = _workspace(dev, int(need))
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
-        _lib.call("bvb_host_rows_fakequant_fwd_bwd", w.data_ptr(), grad_out.data_ptr(),
+        _lib.call("bvb_host_rows_fakequant_fwd_bwd_on", _pipe(dev), w.data_ptr(), grad_out.data_ptr(),
                   None if out_quantized is None else out_quantized.data_ptr(), out_grad.data_ptr(), out_scale.data_ptr(),
                   rows, cols, chunk_rows, float(scaling_min_val), int_thr, 0.0, float(qmin), float(qmax), _lib.ROUND,
                   _lib.CLAMP_MASKED if masked_clamp else _lib.CLAMP_STE, tag, ws.data_ptr(), ws.numel(),

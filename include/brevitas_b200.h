@@ -46,9 +46,12 @@ int bvb_version(void);
 const char* bvb_last_error(void);
 /* number of SMs of the current device (cached per device), used for grid sizing */
 int bvb_sm_count(void);
-/* optional launch-geometry overrides for the fused per-row kernels (0 = heuristic); used by the
- * tuning sweeps in bench.py, not by the product path */
+#ifdef BVB_TUNING_BUILD
+/* NOT part of the product library: `make -C brevitas_b200/csrc TUNING=1` builds libbrevitas_b200_tuning.so, the
+ * same kernels plus this process-wide launch-geometry override (0 = heuristic) for the sweeps under tools/.
+ * libbrevitas_b200.so itself keeps no mutable state. */
 void bvb_set_tuning(int rows_threads, int rows_stages, int rows_ctas_per_sm, int stream_threads, int stream_ctas_per_sm);
+#endif
 
 /* numerics self-test: the kernels divide by a row-/tensor-constant scale with nvcc's own div.rn.f32 instruction
  * sequence, its loop-invariant reciprocal refinement hoisted (csrc/common.cuh DivBy).  This entry point compares
@@ -172,6 +175,16 @@ int bvb_host_rows_fakequant_fwd_bwd(const void* h_x, const void* h_gy, void* h_y
                                     float int_threshold, float zero_point, float qmin, float qmax, int round_mode,
                                     int clamp_mode, int dtype, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t bvb_host_pipeline_workspace_bytes(int64_t rows, int64_t cols, int64_t chunk_rows, int want_y, int dtype);
+/* The call above creates and destroys its three streams and eleven events every time.  A caller that repeats it (an
+ * optimizer loop over host-resident master weights) creates the set once, passes it to the `_on` form and destroys it at
+ * the end; the handle belongs to the caller (one per device and per concurrent caller), the library keeps nothing. */
+int bvb_host_pipeline_create(void** handle);
+int bvb_host_pipeline_destroy(void* handle);
+int bvb_host_rows_fakequant_fwd_bwd_on(void* pipeline, const void* h_x, const void* h_gy, void* h_y, void* h_gx,
+                                       void* h_scale, int64_t rows, int64_t cols, int64_t chunk_rows,
+                                       float scaling_min_val, float int_threshold, float zero_point, float qmin, float qmax,
+                                       int round_mode, int clamp_mode, int dtype, void* workspace, int64_t workspace_bytes,
+                                       void* stream);
 /* Whole-tensor statistic (OverTensorView + AbsMax(None)): two-phase grid reduction, then quant pass.
  * workspace: >= bvb_workspace_bytes() bytes of device scratch.  absmax_out: 1 element of T; scale_out:
  * 1 element of scale_dtype (fp32 when a 0-dim T threshold is divided by a 0-dim fp32 int_threshold).      */

@@ -14,8 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     from brevitas_b200 import _lib
     header = open(os.path.join(ROOT, "include", "brevitas_b200.h")).read()
-    declared = set(re.findall(r"\b(bvb_\w+)\s*\(", header))
-    assert len(declared) >= 30
+    product = re.sub(r"#ifdef BVB_TUNING_BUILD.*?#endif", "", header, flags=re.S)     # sweep-build-only declarations
+    declared = set(re.findall(r"\b(bvb_\w+)\s*\(", product))
+    assert len(declared) >= 30 and "bvb_set_tuning" not in declared
+    exported = os.popen(f"nm -D {_lib.LIB_PATH}").read()
+    assert "bvb_set_tuning" not in exported, "the product library must not carry the mutable tuning state"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:

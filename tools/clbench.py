@@ -1,6 +1,17 @@
 #!/usr/bin/env python
-"""Device time of the channels-last per-channel-scale kernels (NHWC activation, [1,C,1,1] scale) for a sweep of CTAs
+"""Needs the sweep build: `make -C brevitas_b200/csrc TUNING=1` and BREVITAS_B200_LIB=brevitas_b200/libbrevitas_b200_tuning.so.
+Device time of the channels-last per-channel-scale kernels (NHWC activation, [1,C,1,1] scale) for a sweep of CTAs
 per SM (bvb_set_tuning stream_ctas_per_sm), CUDA-graph replay.   python tools/clbench.py [--per-sm 0,2,3,4,6,8]"""
+def _set_tuning(lib, *a):
+    import ctypes
+    fn = getattr(lib, "bvb_set_tuning", None)
+    if fn is None:
+        raise SystemExit("bvb_set_tuning is only in the sweep build: make -C brevitas_b200/csrc TUNING=1; "
+                         "BREVITAS_B200_LIB=brevitas_b200/libbrevitas_b200_tuning.so")
+    fn.restype, fn.argtypes = None, [ctypes.c_int] * 5
+    fn(*a)
+
+
 import argparse
 import os
 import sys
@@ -33,7 +44,7 @@ def main():
         }
         for name, (fn, passes) in cases.items():
             for per_sm in [int(v) for v in a.per_sm.split(",")]:
-                lib.bvb_set_tuning(0, 0, 0, 0, per_sm)
+                _set_tuning(lib, 0, 0, 0, 0, per_sm)
                 for i in range(3):
                     fn(i)
                 torch.cuda.synchronize()
@@ -52,7 +63,7 @@ def main():
                 print(f"{str(dt)[6:]:9s} {name:24s} ctas/sm={per_sm:<3d} {ms * 1e3:8.1f} us  "
                       f"{n * es * passes / ms / 1e6:7.0f} GB/s", flush=True)
                 del g, keep
-    lib.bvb_set_tuning(0, 0, 0, 0, 0)
+    _set_tuning(lib, 0, 0, 0, 0, 0)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Kernel micro-benchmark / tuning sweep for the per-row fused kernels (run on the GPU box).
+"""Needs the sweep build: `make -C brevitas_b200/csrc TUNING=1` and BREVITAS_B200_LIB=brevitas_b200/libbrevitas_b200_tuning.so.
+Kernel micro-benchmark / tuning sweep for the per-row fused kernels (run on the GPU box).
 
     python tools/kbench.py --kernel bwd --dtype f32 --rows 4096 --cols 11008 --sweep
 Prints one line per geometry: kernel time (CUDA events, inputs rotated over > L2 worth of buffers) and GB/s.
@@ -7,6 +8,16 @@ bvb_set_tuning(rows_threads, rows_stages, rows_ctas_per_sm, stream_threads, stre
   fwd: threads, stages, CTAs/SM            bwd: stream_threads = 32*consumer warps, rows_threads = vectors per
   thread per tile, rows_stages = ring depth, stream_ctas_per_sm = CTAs/SM
 """
+def _set_tuning(lib, *a):
+    import ctypes
+    fn = getattr(lib, "bvb_set_tuning", None)
+    if fn is None:
+        raise SystemExit("bvb_set_tuning is only in the sweep build: make -C brevitas_b200/csrc TUNING=1; "
+                         "BREVITAS_B200_LIB=brevitas_b200/libbrevitas_b200_tuning.so")
+    fn.restype, fn.argtypes = None, [ctypes.c_int] * 5
+    fn(*a)
+
+
 import argparse
 import itertools
 import os
@@ -96,7 +107,7 @@ def main():
                   itertools.product([2, 3, 4, 6, 8], [2, 4, 8], [2, 3], [2, 3, 4, 6, 8])]
     best = None
     for c in combos:
-        lib.bvb_set_tuning(*c)
+        _set_tuning(lib, *c)
         ms = timeit()
         if ms is None:
             print(c, "launch failed:", _lib.last_error())
@@ -108,7 +119,7 @@ def main():
             best = (ms, c)
     if best:
         print("BEST", best[1], f"{best[0] * 1e3:.1f} us", f"{bytes_ / (best[0] * 1e-3) / 1e9:.0f} GB/s")
-    lib.bvb_set_tuning(0, 0, 0, 0, 0)
+    _set_tuning(lib, 0, 0, 0, 0, 0)
 
 
 if __name__ == "__main__":
