@@ -397,15 +397,20 @@ def absmax_tensor(x):
     return out
 
 
-def abs_kth_value_rows(x, rows, cols, k, want_index=False):
+def abs_kth_value_rows(x, rows, cols, k, want_index=False, signed=False):
+    """k-th smallest of |x| (signed=False) or of x itself (signed=True) per row; optionally the smallest index attaining it"""
     dev = _check_cuda(x)
     x = _c(x)
     out = torch.empty(rows, dtype=x.dtype, device=dev)
     idx = torch.empty(rows, dtype=torch.int64, device=dev) if want_index else None
     ws = torch.empty(_lib.load().bvb_kth_workspace_bytes(rows), dtype=torch.uint8, device=dev)
-    _launch(dev, "bvb_abs_kth_value_rows", x.data_ptr(), out.data_ptr(), _ptr(idx), rows, cols, k, dtype_tag(x),
-            ws.data_ptr(), _stream(dev))
+    _launch(dev, "bvb_kth_value_rows" if signed else "bvb_abs_kth_value_rows", x.data_ptr(), out.data_ptr(), _ptr(idx),
+            rows, cols, k, dtype_tag(x), ws.data_ptr(), _stream(dev))
     return out, idx
+
+
+def kth_value_rows(x, rows, cols, k, want_index=False):
+    return abs_kth_value_rows(x, rows, cols, k, want_index, signed=True)
 
 
 def percentile_k(q: float, n: int) -> int:

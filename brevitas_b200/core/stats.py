@@ -79,8 +79,21 @@ class AbsPercentile(nn.Module):
 
 
 # ---- remaining statistics of stats_op.py.  Those built on the per-row abs-max reuse the
-# sm_100a reduction; min / mean / variance / signed k-th value are the same ATen reductions the reference issues
-# (they run once per tensor on statistics-sized outputs and are outside the measured hot path) -----------------
+# sm_100a reduction, the signed percentiles the exact radix select on order-preserving keys (``kth_value_rows``: the
+# reference's ``kthvalue`` is a sort-class ATen op, 1.7 s on a ResNet-18 activation); min / mean / variance are the
+# ATen reductions the reference issues on statistics-sized outputs -----------------
+def _kth_signed(x: Tensor, k: int, dim: Optional[int]) -> Tensor:
+    """``x.view(-1).kthvalue(k).values`` (dim None) or ``x.kthvalue(k, dim).values`` of a 2-D x"""
+    if dim is None:
+        val, _ = torch.ops.brevitas_b200.kth_value_rows(x.reshape(-1), 1, x.numel(), k)
+        return val.view(())
+    if dim % 2 == 0:
+        x = x.t()
+    rows, cols = x.shape
+    val, _ = torch.ops.brevitas_b200.kth_value_rows(x.contiguous(), rows, cols, k)
+    return val
+
+
 DEFAULT_STD_DEV_EPSILON = 1e-8
 
 
@@ -115,11 +128,10 @@ class NegativePercentileOrZero(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         if self.stats_reduce_dim is None:
             k = int(math.ceil(.01 * self.q * x.numel()))
-            result = x.view(-1).kthvalue(k).values
         else:
             assert len(x.size()) == 2, "Only 2-dim input is supported."
             k = int(math.ceil(.01 * self.q * x.shape[self.stats_reduce_dim]))
-            result = x.kthvalue(k, dim=self.stats_reduce_dim).values
+        result = _kth_signed(x, k, self.stats_reduce_dim)
         zero = self.zero().to(result.dtype)
         return torch.where(result <= zero, result, zero)
 
@@ -138,15 +150,15 @@ class PercentileInterval(nn.Module):
             n = x.numel()
             low_k = int(math.ceil(.01 * self.low_q * n))
             high_k = int(math.floor(.01 * self.high_q * n + 0.5))
-            low_result = x.view(-1).kthvalue(low_k).values
-            high_result = x.view(-1).kthvalue(high_k).values
+            low_result = _kth_signed(x, low_k, None)
+            high_result = _kth_signed(x, high_k, None)
         else:
             assert len(x.size()) == 2, "Only 2-dim input is supported."
             n = x.shape[self.stats_reduce_dim]
             low_k = int(math.ceil(.01 * self.low_q * n))
             high_k = int(math.floor(.01 * self.high_q * n + 0.5))
-            low_result = x.kthvalue(low_k, dim=self.stats_reduce_dim).values
-            high_result = x.kthvalue(high_k, dim=self.stats_reduce_dim).values
+            low_result = _kth_signed(x, low_k, self.stats_reduce_dim)
+            high_result = _kth_signed(x, high_k, self.stats_reduce_dim)
         return torch.abs(high_result - low_result)
 
 

@@ -31,25 +31,29 @@ constexpr int KTH_COMPACT_ROWS = 2;
 constexpr uint32_t KTH_COMPACT_CAP = 1u << 22;
 constexpr int KTH_NO_COMPACT = 99;
 
-template <typename T> struct KeyTraits;
+// KeyTraits<T, SIGNED>: SIGNED = false orders |x| (AbsPercentile); SIGNED = true orders x itself (the signed k-th value of
+// NegativePercentileOrZero / PercentileInterval, stats_op.py:69-126): the usual order-preserving map of IEEE bits to
+// unsigned integers (flip all bits of negatives, the sign bit of non-negatives), every NaN mapped above +inf, which is
+// where torch.kthvalue puts NaN.
+template <typename T, bool SIGNED = false> struct KeyTraits;
 // Digit layout, most significant first.  The FIRST digit is the whole 8-bit exponent, so that from the second pass on
 // only the elements in the answer's binade are candidates (with byte-aligned digits the first one holds just the top
 // 7 exponent bits -- two binades -- and the second pass still histograms a large part of the tensor).
-template <> struct KeyTraits<float> {
+template <> struct KeyTraits<float, false> {
     static constexpr int PASSES = 4;
     __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 23 : (pass == 1 ? 15 : (pass == 2 ? 7 : 0)); }
     __device__ __forceinline__ static int width(int pass) { return pass == 3 ? 7 : 8; }
     __device__ __forceinline__ static uint32_t key(float v) { return __float_as_uint(v) & 0x7fffffffu; }
     __device__ __forceinline__ static float value(uint32_t k) { return __uint_as_float(k); }
 };
-template <> struct KeyTraits<__nv_bfloat16> {
+template <> struct KeyTraits<__nv_bfloat16, false> {
     static constexpr int PASSES = 2;
     __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 7 : 0; }      // exponent | 7-bit mantissa
     __device__ __forceinline__ static int width(int pass) { return pass == 0 ? 8 : 7; }
     __device__ __forceinline__ static uint32_t key(float v) { return (__float_as_uint(v) >> 16) & 0x7fffu; }
     __device__ __forceinline__ static float value(uint32_t k) { return __uint_as_float(k << 16); }
 };
-template <> struct KeyTraits<__half> {
+template <> struct KeyTraits<__half, false> {
     static constexpr int PASSES = 2;
     __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 8 : 0; }      // 15-bit key: 7 | 8 bits
     __device__ __forceinline__ static int width(int pass) { return pass == 0 ? 7 : 8; }
@@ -58,12 +62,45 @@ template <> struct KeyTraits<__half> {
         __half_raw r; r.x = (unsigned short)k; return __half2float(__half(r));
     }
 };
+// signed keys: 32 (fp32) / 16 (bf16, fp16) bits in byte-aligned digits
+__device__ __forceinline__ uint32_t ordered32(uint32_t b) { return b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u); }
+__device__ __forceinline__ uint32_t unordered32(uint32_t k) { return k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu); }
+template <> struct KeyTraits<float, true> {
+    static constexpr int PASSES = 4;
+    __device__ __forceinline__ static int shift(int pass) { return 24 - 8 * pass; }
+    __device__ __forceinline__ static int width(int) { return 8; }
+    __device__ __forceinline__ static uint32_t key(float v) { return v != v ? 0xffffffffu : ordered32(__float_as_uint(v)); }
+    __device__ __forceinline__ static float value(uint32_t k) { return __uint_as_float(k == 0xffffffffu ? 0x7fc00000u : unordered32(k)); }
+};
+template <> struct KeyTraits<__nv_bfloat16, true> {
+    static constexpr int PASSES = 2;
+    __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 8 : 0; }
+    __device__ __forceinline__ static int width(int) { return 8; }
+    __device__ __forceinline__ static uint32_t key(float v) { return v != v ? 0xffffu : (ordered32(__float_as_uint(v)) >> 16); }
+    __device__ __forceinline__ static float value(uint32_t k) {
+        return __uint_as_float(k == 0xffffu ? 0x7fc00000u : unordered32(k << 16) & 0xffff0000u);
+    }
+};
+template <> struct KeyTraits<__half, true> {
+    static constexpr int PASSES = 2;
+    __device__ __forceinline__ static int shift(int pass) { return pass == 0 ? 8 : 0; }
+    __device__ __forceinline__ static int width(int) { return 8; }
+    __device__ __forceinline__ static uint32_t key(float v) {
+        if (v != v) return 0xffffu;
+        const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(v));
+        return (h ^ ((h & 0x8000u) ? 0xffffu : 0x8000u)) & 0xffffu;
+    }
+    __device__ __forceinline__ static float value(uint32_t k) {
+        if (k == 0xffffu) return __uint_as_float(0x7fc00000u);
+        __half_raw r; r.x = (unsigned short)((k ^ ((k & 0x8000u) ? 0x8000u : 0xffffu)) & 0xffffu); return __half2float(__half(r));
+    }
+};
 
 // Resolve the digits fixed by passes [0, upto) for one row.  Executed by warp 0 of a block; returns
 // (prefix, remaining k) to every lane.  hist counts are exact, so the walk is deterministic.
 // compact_at (optional): 1 + the first pass whose selected bin holds <= cap elements = the pass that copies the
 // candidates aside (KTH_NO_COMPACT if there is none among the resolved passes).
-template <typename T>
+template <typename T, bool SIGNED = false>
 __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, int64_t row, int upto, int64_t k,
                                             uint32_t& prefix, int64_t& krem, uint32_t cap = 0, int* compact_at = nullptr) {
     const int lane = threadIdx.x & 31;
@@ -108,34 +145,35 @@ __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, 
         before = __shfl_sync(0xffffffffu, before, src);
         pop = __shfl_sync(0xffffffffu, pop, src);
         if (cat == KTH_NO_COMPACT && pop <= cap) cat = q + 1;
-        prefix = (prefix << KeyTraits<T>::width(q)) | (uint32_t)bin;
+        prefix = (prefix << KeyTraits<T, SIGNED>::width(q)) | (uint32_t)bin;
         krem -= before;
     }
     if (compact_at) *compact_at = cat;
 }
 
 // one radix pass: histogram digit `pass` of the keys whose higher digits equal the resolved prefix
-template <typename T>
+template <typename T, bool SIGNED>
 __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                 int vec_ok, int pass, int64_t k, uint32_t* hist,
                                                                 unsigned long long* first_index, uint32_t cap,
                                                                 uint32_t* ccount, uint32_t* ckeys,
                                                                 unsigned long long* cidx) {
     constexpr int V = DT<T>::VEC;
-    constexpr int P = KeyTraits<T>::PASSES;
+    using KT = KeyTraits<T, SIGNED>;
+    constexpr int P = KT::PASSES;
     constexpr bool CAN_COMPACT = P >= 3;       // 2-digit keys: the copying pass would be the last one
     __shared__ uint32_t sh[KTH_THREADS / 32][KTH_BINS];
     __shared__ uint32_t s_prefix;
     __shared__ int s_mode;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int shift = KeyTraits<T>::shift(pass);
-    const uint32_t digit_mask = (1u << KeyTraits<T>::width(pass)) - 1u;
-    const int prefix_shift = shift + KeyTraits<T>::width(pass);      // the bits above this digit are the resolved prefix
+    const int shift = KT::shift(pass);
+    const uint32_t digit_mask = (1u << KT::width(pass)) - 1u;
+    const int prefix_shift = shift + KT::width(pass);      // the bits above this digit are the resolved prefix
     for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
         for (int i = threadIdx.x; i < (KTH_THREADS / 32) * KTH_BINS; i += KTH_THREADS) (&sh[0][0])[i] = 0;
         if (warp == 0) {
             uint32_t prefix; int64_t krem; int cat;
-            kth_resolve<T>(hist, rows, row, pass, k, prefix, krem, cap, &cat);
+            kth_resolve<T, SIGNED>(hist, rows, row, pass, k, prefix, krem, cap, &cat);
             if (lane == 0) {
                 s_prefix = prefix;
                 // 0: scan the tensor   1: scan it and copy the candidates aside   2: scan the copy made by pass `cat`
@@ -161,7 +199,7 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
             constexpr int NV = decltype(nv_tag)::value;
             uint32_t key[NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) key[i] = KeyTraits<T>::key(v[i]);
+            for (int i = 0; i < NV; ++i) key[i] = KT::key(v[i]);
             if (pass == 0) {
                 if (valid) {
 #pragma unroll
@@ -267,25 +305,26 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
 }
 
 // all digits resolved: write the value; optionally locate the smallest index attaining it
-template <typename T>
+template <typename T, bool SIGNED>
 __global__ void __launch_bounds__(KTH_THREADS) kth_final_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                  int64_t k, const uint32_t* hist, T* out,
                                                                  long long* index_out,
                                                                  const unsigned long long* first_index) {
-    constexpr int P = KeyTraits<T>::PASSES;
+    using KT = KeyTraits<T, SIGNED>;
+    constexpr int P = KT::PASSES;
     __shared__ uint32_t s_key;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
         if (warp == 0) {
             uint32_t prefix; int64_t krem;
-            kth_resolve<T>(hist, rows, row, P, k, prefix, krem);
+            kth_resolve<T, SIGNED>(hist, rows, row, P, k, prefix, krem);
             if (lane == 0) s_key = prefix;
         }
         __syncthreads();
         const uint32_t key = s_key;
-        if (blockIdx.x == 0 && threadIdx.x == 0) out[row] = DT<T>::from_f(KeyTraits<T>::value(key));
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[row] = DT<T>::from_f(KT::value(key));
         if (index_out && blockIdx.x == 0 && threadIdx.x == 0) {
-            const uint32_t last_bin = key & ((1u << KeyTraits<T>::width(P - 1)) - 1u);
+            const uint32_t last_bin = key & ((1u << KT::width(P - 1)) - 1u);
             index_out[row] = (long long)first_index[row * KTH_BINS + last_bin];
         }
         __syncthreads();
@@ -296,10 +335,10 @@ static inline int64_t kth_base_bytes(int64_t rows) {
     return (int64_t)sizeof(uint32_t) * 4 * rows * KTH_BINS + (int64_t)sizeof(unsigned long long) * rows * KTH_BINS;
 }
 
-template <typename T>
+template <typename T, bool SIGNED>
 static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
                       void* workspace, cudaStream_t st) {
-    constexpr int P = KeyTraits<T>::PASSES;
+    constexpr int P = KeyTraits<T, SIGNED>::PASSES;
     constexpr int V = DT<T>::VEC;
     uint32_t* hist = (uint32_t*)workspace;
     unsigned long long* first_index = (unsigned long long*)(hist + (size_t)4 * (size_t)rows * KTH_BINS);
@@ -326,11 +365,11 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     uint32_t* ckeys = (uint32_t*)(cbase + 256);
     unsigned long long* cidx = (unsigned long long*)(cbase + 256 + sizeof(uint32_t) * (size_t)rows * KTH_COMPACT_CAP);
     for (int pass = 0; pass < P; ++pass)
-        kth_hist_kernel<T><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist,
+        kth_hist_kernel<T, SIGNED><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist,
                                                          (index_out && pass == P - 1) ? first_index : nullptr, cap,
                                                          ccount, ckeys, cidx);
     const dim3 fgrid(1u, (unsigned)gy);                                  // one CTA per row resolves the last digit
-    kth_final_kernel<T><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out,
+    kth_final_kernel<T, SIGNED><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out,
                                                        first_index);
     return check_launch("bvb_abs_kth_value_rows");
 }
@@ -369,7 +408,19 @@ extern "C" int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_o
     if (k < 1 || k > cols)
         return fail(BVB_EINVAL, "bvb_abs_kth_value_rows: k = %lld out of range [1, %lld]", (long long)k, (long long)cols);
     if (!x || !out || !workspace) return fail(BVB_EINVAL, "bvb_abs_kth_value_rows: null pointer");
-    BVB_DISPATCH_DTYPE(dtype, return launch_kth<T>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream));
+    BVB_DISPATCH_DTYPE(dtype, return (launch_kth<T, false>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream)));
+    return BVB_OK;
+}
+
+// signed k-th smallest value: x.kthvalue(k) of NegativePercentileOrZero / PercentileInterval (stats_op.py:69-126)
+extern "C" int bvb_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols,
+                                  int64_t k, int dtype, void* workspace, void* stream) {
+    if (rows < 0 || cols < 0) return fail(BVB_EINVAL, "bvb_kth_value_rows: negative size");
+    if (rows == 0) return BVB_OK;
+    if (k < 1 || k > cols)
+        return fail(BVB_EINVAL, "bvb_kth_value_rows: k = %lld out of range [1, %lld]", (long long)k, (long long)cols);
+    if (!x || !out || !workspace) return fail(BVB_EINVAL, "bvb_kth_value_rows: null pointer");
+    BVB_DISPATCH_DTYPE(dtype, return (launch_kth<T, true>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream)));
     return BVB_OK;
 }
 

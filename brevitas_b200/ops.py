@@ -445,6 +445,7 @@ torch.library.register_autograd(f"{FQ_NS}::binary_quant", _binary_bwd, setup_con
 _FQ.define("absmax_rows(Tensor x, int rows, int cols) -> Tensor")
 _FQ.define("absmax_tensor(Tensor x) -> Tensor")
 _FQ.define("abs_kth_value_rows(Tensor x, int rows, int cols, int k) -> (Tensor, Tensor)")
+_FQ.define("kth_value_rows(Tensor x, int rows, int cols, int k) -> (Tensor, Tensor)")
 _FQ.define("running_stats_update_(Tensor(a!) running, Tensor stat, float momentum, bool first) -> ()")
 _FQ.impl("absmax_rows", lambda x, r, c: K.absmax_rows(x, r, c), "CUDA")
 _FQ.impl("absmax_rows", _no_cpu("absmax_rows"), "CPU")
@@ -452,11 +453,15 @@ _FQ.impl("absmax_tensor", lambda x: K.absmax_tensor(x), "CUDA")
 _FQ.impl("absmax_tensor", _no_cpu("absmax_tensor"), "CPU")
 _FQ.impl("abs_kth_value_rows", lambda x, r, c, k: K.abs_kth_value_rows(x, r, c, k, want_index=True), "CUDA")
 _FQ.impl("abs_kth_value_rows", _no_cpu("abs_kth_value_rows"), "CPU")
+_FQ.impl("kth_value_rows", lambda x, r, c, k: K.kth_value_rows(x, r, c, k, want_index=True), "CUDA")
+_FQ.impl("kth_value_rows", _no_cpu("kth_value_rows"), "CPU")
 _FQ.impl("running_stats_update_", lambda r, s, m, f: (K.running_stats_update(r, s, m, f), None)[1], "CUDA")
 _FQ.impl("running_stats_update_", _no_cpu("running_stats_update_"), "CPU")
 torch.library.register_fake(f"{FQ_NS}::absmax_rows", lambda x, r, c: x.new_empty(r), lib=_FQ)
 torch.library.register_fake(f"{FQ_NS}::absmax_tensor", lambda x: x.new_empty(()), lib=_FQ)
 torch.library.register_fake(f"{FQ_NS}::abs_kth_value_rows",
+                            lambda x, r, c, k: (x.new_empty(r), x.new_empty(r, dtype=torch.int64)), lib=_FQ)
+torch.library.register_fake(f"{FQ_NS}::kth_value_rows",
                             lambda x, r, c, k: (x.new_empty(r), x.new_empty(r, dtype=torch.int64)), lib=_FQ)
 
 
@@ -516,3 +521,15 @@ def _kth_bwd(ctx, gval, gidx):
 
 
 torch.library.register_autograd(f"{FQ_NS}::abs_kth_value_rows", _kth_bwd, setup_context=_kth_setup, lib=_FQ)
+
+
+def _kth_signed_bwd(ctx, gval, gidx):
+    # x.kthvalue(k): the gradient goes to the selected index
+    x, idx = ctx.saved_tensors
+    rows, cols = ctx.rc
+    gx = torch.zeros(rows, cols, dtype=x.dtype, device=x.device)
+    gx.scatter_(1, idx.view(rows, 1), gval.to(x.dtype).view(rows, 1))
+    return gx.view(x.shape), None, None, None
+
+
+torch.library.register_autograd(f"{FQ_NS}::kth_value_rows", _kth_signed_bwd, setup_context=_kth_setup, lib=_FQ)

@@ -223,6 +223,10 @@ int bvb_absmax_tensor(const void* x, void* out, int64_t n, int dtype, void* work
  * copied to once few enough are left, so that a high percentile of an fp32 tensor costs two reads instead of four). */
 int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
                            int dtype, void* workspace, void* stream);
+/* the SIGNED k-th smallest value, x.kthvalue(k) (NegativePercentileOrZero, PercentileInterval: stats_op.py:69-126),
+ * same select on order-preserving keys of x itself (every NaN sorts last, like torch.kthvalue); same workspace */
+int bvb_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
+                           int dtype, void* workspace, void* stream);
 int64_t bvb_kth_workspace_bytes(int64_t rows);
 /* _RuntimeStats EMA (stats_wrapper.py:56-65): first != 0: running *= stat; else
  * running = running * one_minus_momentum + (T)(momentum * stat).  The caller passes (float)(1.0 - m) computed

@@ -302,3 +302,34 @@ def test_layer_output_zero_point_follows_the_reference_bias_rule():
     shifted(x)
     with pytest.raises(RuntimeError, match="zero point of output accumulator"):
         lin(shifted(x - 3.0))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,cols", [(1, 1), (1, 1000), (1, 1 << 20), (6, 250), (3, 4099), (2, 300001)])
+def test_signed_kth_value_select(rows, cols, dtype):
+    """bvb_kth_value_rows (NegativePercentileOrZero / PercentileInterval, stats_op.py:69-126) against torch.kthvalue:
+    exact value for every regime of k, the smallest index attaining it, NaN sorted last, both zeros, infinities."""
+    from brevitas_b200 import _kernels as K
+    g = torch.Generator().manual_seed(rows * 7919 + cols)
+    x = (torch.randn(rows, cols, generator=g) * 3.0)
+    if cols >= 250:
+        x[:, 3], x[:, 5], x[:, 7], x[:, 11], x[:, 13] = 0.0, -0.0, float("inf"), float("-inf"), 2.5
+        x[:, 17] = 2.5                                   # a tie
+    xd = x.to(TDT[dtype]).cuda()
+    xf = xd.float().cpu()
+    for k in sorted({1, 2, max(1, cols // 100), max(1, cols // 2), max(1, cols - cols // 20), cols}):
+        val, idx = K.kth_value_rows(xd, rows, cols, k, want_index=True)
+        want = xf.kthvalue(k, dim=1).values
+        got = val.float().cpu()
+        assert torch.equal(got, want) or torch.equal(got.abs(), want.abs()) and bool(((got == 0) == (want == 0)).all()), (k, got, want)
+        picked = xf.gather(1, idx.cpu().view(rows, 1)).view(-1)
+        assert torch.equal(picked, got), (k, picked, got)
+        first = (xf == got.view(rows, 1)).float().argmax(dim=1)
+        assert torch.equal(first, idx.cpu()), (k, first, idx)
+    if cols >= 250:                                      # NaN is the largest element
+        xn = xd.clone()
+        xn[:, 19] = float("nan")
+        val, _ = K.kth_value_rows(xn, rows, cols, cols)
+        assert bool(torch.isnan(val).all())
+        val, _ = K.kth_value_rows(xn, rows, cols, cols - 1)
+        assert bool(torch.isinf(val).all() and (val > 0).all())
