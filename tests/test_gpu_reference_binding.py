@@ -60,7 +60,7 @@ def tol_of(key, dtype_tag):
     return eps
 
 
-def compare_group(group, out, dtypes):
+def compare_group(group, out, dtypes, grads_by_tolerance=False):
     gold = load(group)
     assert set(out) == set(gold), sorted(set(out) ^ set(gold))[:10]
     checked = exact = 0
@@ -72,7 +72,8 @@ def compare_group(group, out, dtypes):
         got, want = np.asarray(out[key], dtype=np.float64), np.asarray(gold[key], dtype=np.float64)
         leaf = parts[-1]
         is_sum = leaf.startswith(SUM_LEAVES) or any(s in parts for s in SUM_STATS) or \
-            (group == "param_from_stats" and leaf.startswith("gvalue"))
+            (group == "param_from_stats" and leaf.startswith("gvalue")) or \
+            (grads_by_tolerance and leaf.startswith("g") and leaf not in ("g", "gs"))
         checked += 1
         g32, w32 = np.asarray(out[key], np.float32), np.asarray(gold[key], np.float32)
         if not is_sum and leaf.startswith("gx") and g32.shape == w32.shape and g32.size > 64:

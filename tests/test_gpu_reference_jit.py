@@ -34,7 +34,9 @@ total = 0
 for group in ("ste", "int_quant", "weight_stats", "binary", "kat", "runtime_token"):
     before = _kernels.launch_count
     out = run_generator(group)
-    checked, exact = compare_group(group, out, ("f32",))
+    # forward values bit-exact; gradients by tolerance: a scripted module's backward is TorchScript's own symbolic
+    # autodiff (and fuser), whose op order differs from eager autograd's -- a property of the reference under the JIT
+    checked, exact = compare_group(group, out, ("f32",), grads_by_tolerance=True)
     n = _kernels.launch_count - before
     assert n > 0, group
     total += n

@@ -317,7 +317,7 @@ def test_signed_kth_value_select(rows, cols, dtype):
         x[:, 17] = 2.5                                   # a tie
     xd = x.to(TDT[dtype]).cuda()
     xf = xd.float().cpu()
-    for k in sorted({1, 2, max(1, cols // 100), max(1, cols // 2), max(1, cols - cols // 20), cols}):
+    for k in sorted({1, min(2, cols), max(1, cols // 100), max(1, cols // 2), max(1, cols - cols // 20), cols}):
         val, idx = K.kth_value_rows(xd, rows, cols, k, want_index=True)
         want = xf.kthvalue(k, dim=1).values
         got = val.float().cpu()
