@@ -1702,7 +1702,10 @@ static RowsGeom rows_geometry(int64_t cols, int elem_size) {
         if (threads < 64) threads = 64;
         if (ctas == 1 && 3 * stride <= 100 * 1024) stages = 3;
     } else {
-        threads = 128;
+        // r02 sweep with 32 / 64 / 128-thread CTAs (profiles/r02_fwd_bf16_small_cta_sweep.md): two warps per row beat four
+        // by 3 % on both north-star shapes (C2 bf16 35.3 -> 34.1 us, C3 bf16 48.3 -> 46.8 us); one warp per row (a
+        // quarter of the per-row instructions) gains nothing more -- these kernels are not issue-bound
+        threads = row_bytes >= 4096 ? 64 : 128;
         ctas = (int)((200 * 1024) / (2 * stride));
         if (ctas > 6) ctas = 6;
         if (ctas < 1) { ctas = 1; threads = 256; }

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--reps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--small", action="store_true", help="fwd sweep over 32/64/128-thread CTAs")
     ap.add_argument("--tuning", type=str, default="")
     a = ap.parse_args()
     tdt, tag, esz = DT[a.dtype]
@@ -100,6 +101,8 @@ def main():
         combos = [tuple(int(v) for v in a.tuning.split(","))]
     elif not a.sweep:
         combos = [(0, 0, 0, 0, 0)]
+    elif a.kernel == "fwd" and a.small:      # few warps per row: 1-2 warps own a row (less per-row overhead per element)
+        combos = [(t, s, c, 0, 0) for t, s, c in itertools.product([32, 64, 128], [2, 3], [4, 6, 8, 10, 12, 16])]
     elif a.kernel == "fwd":
         combos = [(t, s, c, 0, 0) for t, s, c in itertools.product([128, 256, 512, 1024], [2, 3, 4], [1, 2, 3, 4, 6])]
     else:
