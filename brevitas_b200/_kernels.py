@@ -426,3 +426,72 @@ def running_stats_update(running, stat, momentum: float, first: bool):
     _launch(dev, "bvb_running_stats_update", running.data_ptr(), stat.data_ptr(), running.numel(), float(momentum),
             float(1 - momentum), 1 if first else 0, dtype_tag(stat), _stream(dev))
     return running
+
+
+# ---- batch-norm + ReLU + activation quantizer, fused (csrc/bn_act_quant.cu) ------------------------------------------
+_bn_ws = {}
+
+
+def _bn_workspace(dev, channels):
+    need = int(_lib.load().bvb_bn_act_quant_workspace_bytes(channels))
+    ws = _bn_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=dev)
+        _bn_ws[dev] = ws
+    return ws
+
+
+def bn_act_quant_supported(x: torch.Tensor) -> bool:
+    """a 4-D channels-last (or 2-D) dense CUDA tensor whose channel count fills 16-byte vectors that divide 256"""
+    if not x.is_cuda or x.dtype not in _DTYPES:
+        return False
+    if x.dim() == 4:
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            return False
+    elif x.dim() != 2 or not x.is_contiguous():
+        return False
+    c, v = x.shape[1], 16 // x.element_size()
+    return c % v == 0 and c // v <= 256 and 256 % (c // v) == 0 and x.numel() > 0
+
+
+def bn_act_quant_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, training, scale, zero_point, qmin, qmax,
+                     relu=True):
+    """returns (y like x, save_mean, save_invstd); running statistics are updated in place when training"""
+    dev = _check_cuda(x, scale)
+    c = x.shape[1]
+    rows = x.numel() // c
+    y = torch.empty_like(x)                                  # preserves channels-last strides
+    if training:
+        save_mean = torch.empty(c, dtype=torch.float32, device=dev)
+        save_invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    else:
+        save_mean = running_mean.float().contiguous()
+        save_invstd = torch.rsqrt(running_var.float() + eps).contiguous()
+    ws = _bn_workspace(dev, c)
+    scale = _c(scale)
+    _launch(dev, "bvb_bn_act_quant_fwd", x.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(running_mean) if training else None,
+            _ptr(running_var) if training else None, float(momentum), float(eps), 0 if training else 1, scale.data_ptr(),
+            scale.numel(), dtype_tag(scale), y.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), rows, c,
+            float(zero_point), float(qmin), float(qmax), _lib.ROUND, 1 if relu else 0, dtype_tag(x), ws.data_ptr(),
+            _stream(dev))
+    return y, save_mean, save_invstd
+
+
+def bn_act_quant_bwd(gy, x, gamma, beta, save_mean, save_invstd, scale, zero_point, qmin, qmax, clamp_mode, relu=True,
+                     want_gscale=True):
+    dev = _check_cuda(gy, x, scale)
+    c = x.shape[1]
+    rows = x.numel() // c
+    if gy.stride() != x.stride():
+        gy = gy.contiguous(memory_format=torch.channels_last) if x.dim() == 4 else gy.contiguous()
+    gx = torch.empty_like(x)
+    ggamma = torch.empty(c, dtype=torch.float32, device=dev)
+    gbeta = torch.empty(c, dtype=torch.float32, device=dev)
+    scale = _c(scale)
+    gscale = torch.empty(scale.numel(), dtype=torch.float32, device=dev) if want_gscale else None
+    ws = _bn_workspace(dev, c)
+    _launch(dev, "bvb_bn_act_quant_bwd", gy.data_ptr(), x.data_ptr(), _ptr(gamma), _ptr(beta), save_mean.data_ptr(),
+            save_invstd.data_ptr(), scale.data_ptr(), scale.numel(), dtype_tag(scale), gx.data_ptr(), ggamma.data_ptr(),
+            gbeta.data_ptr(), _ptr(gscale), rows, c, float(zero_point), float(qmin), float(qmax), _lib.ROUND, int(clamp_mode),
+            1 if relu else 0, dtype_tag(x), ws.data_ptr(), _stream(dev))
+    return gx, ggamma, gbeta, gscale

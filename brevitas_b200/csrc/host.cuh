@@ -25,6 +25,9 @@ struct Tuning {
 const Tuning& tuning();      // all zero (= heuristics) in the product build; see lib.cu
 unsigned stat_grid(int64_t blocks_wanted, int default_per_sm);   // grid of a read-only statistic kernel (256-thread CTAs), int_quant.cu
 
+struct QParams;
+QParams make_qparams(float zero_point, float qmin, float qmax, int dtype);   // int_quant.cu
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // round a host float to the tensor dtype exactly like a 0-dim operand cast to the common dtype

@@ -100,28 +100,7 @@ __global__ void int_quant_fwd_scalar_kernel(const T* x, const T* scale, T* y, T*
 // ------------------------------------------------------------------------------------------------------
 // one element of the backward
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int RM>
-__device__ __forceinline__ float bwd_elem(float g, float x, const DivBy& dv, float inv_s, const QParams& p, int masked,
-                                          bool want_gs, float& gs_acc) {
-    float gsv = DT<T>::rnd(fmul(g, dv.b));               // d y / d t6 : grad * scale
-    float d = gsv;
-    if (masked || want_gs) {
-        const float t1 = DT<T>::rnd(dv(x));
-        float t2 = fadd(t1, p.zp);
-        if (DT<T>::LOWP && p.zp_nonzero) t2 = DT<T>::rnd(t2);
-        const float t3 = float_to_int<T, RM>(t2);
-        const float t5 = minmax_clamp(t3, p.qmin, p.qmax);      // see bwd_n: sign of zero invisible, mask = "unchanged"
-        if (masked) d = (t3 < t5 || t3 > t5) ? 0.f : gsv;       // torch.where backward of both clamp stages
-        if (want_gs) {
-            float t6 = fsub(t5, p.zp);
-            // d(scale) = g * t6  -  d * ((x / s) / s); order-dependent sum => fp32 accumulation,
-            // reciprocal for the second division is within the documented tolerance
-            gs_acc = fmaf(g, t6, gs_acc);
-            gs_acc = fmaf(-d, t1 * inv_s, gs_acc);
-        }
-    }
-    return dv(d);                                        // d t1 / d x : grad / scale (rounded at store)
-}
+// bwd_elem<T, RM>: one element of the backward, in common.cuh (shared with bn_act_quant.cu)
 
 // one 16-byte vector of the backward: eg[] holds the incoming gradient on entry, gx on exit
 template <typename T, int RM, int N>
@@ -817,12 +796,14 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        const int pre = my_rows < stages ? my_rows : stages;
-        for (int s = 0; s < pre; ++s) {
-            mbar_arrive_expect_tx(&bars[s], row_bytes);
-            bulk_g2s(bufs + (size_t)s * stage_stride, x + (size_t)(first + s * step) * cols, row_bytes, &bars[s]);
-        }
+    // Start-up: every CTA of the grid asks for its rows at the same moment.  If each one requested all its stages at once,
+    // the FIRST rows -- the ones the whole chip is waiting for before it can store anything -- would share the read
+    // bandwidth with everybody's prefetch (592 CTAs x 2 x 22 KB = 26 MB = 3.7 us of read-only time on C2 bf16).  So only
+    // stage 0 is requested up front; the remaining stages are requested as soon as it has landed.
+    const int pre = my_rows < stages ? my_rows : stages;
+    if (tid == 0 && pre > 0) {
+        mbar_arrive_expect_tx(&bars[0], row_bytes);
+        bulk_g2s(bufs, x + (size_t)first * cols, row_bytes, &bars[0]);
     }
 
     int s = 0;
@@ -830,6 +811,12 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
     for (int it = 0; it < my_rows; ++it) {
         const int row = first + it * step;
         mbar_wait(&bars[s], parity);
+        if (it == 0 && tid == 0) {
+            for (int q = 1; q < pre; ++q) {
+                mbar_arrive_expect_tx(&bars[q], row_bytes);
+                bulk_g2s(bufs + (size_t)q * stage_stride, x + (size_t)(first + q * step) * cols, row_bytes, &bars[q]);
+            }
+        }
         const uint4* buf = reinterpret_cast<const uint4*>(bufs + (size_t)s * stage_stride);
 
         // pass 1 (shared memory): max |x| on raw bit patterns, 128-bit loads
@@ -1442,7 +1429,7 @@ static inline uint16_t t_step(uint16_t b, int dir) {        // next representabl
     return (uint16_t)((neg == (dir < 0)) ? b + 1 : b - 1);
 }
 
-static inline QParams make_qparams(float zero_point, float qmin, float qmax, int dtype) {
+QParams make_qparams(float zero_point, float qmin, float qmax, int dtype) {
     QParams p;
     p.qmin = round_to_dtype(qmin, dtype);
     p.qmax = round_to_dtype(qmax, dtype);

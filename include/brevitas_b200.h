@@ -211,6 +211,33 @@ int bvb_binary_quant_bwd(const void* gy, const void* x, const void* scale, void*
                          int64_t scale_inner, int64_t scale_count, int scale_dtype, int clamped, int dtype,
                          void* stream);
 
+/* ---- 4b. batch-norm + ReLU + activation quantizer of a conv block, fused ------------------- */
+/* `QuantReLU(BatchNorm2d(conv_out))` -- FusedActivationQuantProxy (src/brevitas/proxy/runtime_quant.py:73-84) behind
+ * torch.nn.BatchNorm2d, e.g. brevitas_examples/imagenet_classification/models/mobilenetv1.py:111-115 -- on a
+ * channels-last tensor seen as x[rows = N*H*W][channels]: 8 passes over the activation per training step instead of 13
+ * (the normalised tensor and the ReLU output are never written).  Training mode (use_running_stats = 0): batch mean and
+ * biased variance per channel (fp32 per-thread sums combined in fp64 in a fixed order), running statistics updated in
+ * place with `momentum` and the unbiased variance; save_mean / save_invstd (fp32[channels]) are outputs for the
+ * backward.  Eval mode (use_running_stats = 1): save_mean / save_invstd are INPUTS (running mean, 1/sqrt(running_var +
+ * eps)).  y = quant_dequant(relu(((x - mean) * invstd) * gamma + beta)) with the provided scale: one element, or one per
+ * channel (`scale_count` = 1 or channels).  gamma / beta: fp32[channels] or NULL (1 / 0).  round-half-even only.
+ * Requires channels * sizeof(T) / 16 to divide 256 (BVB_EUNSUPPORTED otherwise: callers use the unfused pair).
+ * workspace >= bvb_bn_act_quant_workspace_bytes(channels) bytes of device scratch. */
+int64_t bvb_bn_act_quant_workspace_bytes(int64_t channels);
+int bvb_bn_act_quant_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                         float momentum, float eps, int use_running_stats, const void* scale, int64_t scale_count,
+                         int scale_dtype, void* y, float* save_mean, float* save_invstd, int64_t rows, int64_t channels,
+                         float zero_point, float qmin, float qmax, int round_mode, int relu, int dtype, void* workspace,
+                         void* stream);
+/* backward of the above in training mode: gx = d/dx, ggamma / gbeta (fp32[channels]), gscale (nullable, fp32[scale_count])
+ * = d/d(scale) of the quantizer; the quantizer part is bvb_relu_int_quant_bwd's arithmetic on the recomputed
+ * normalised value (clamp_mode: BVB_CLAMP_STE / BVB_CLAMP_MASKED) */
+int bvb_bn_act_quant_bwd(const void* gy, const void* x, const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_invstd, const void* scale, int64_t scale_count, int scale_dtype, void* gx,
+                         float* ggamma, float* gbeta, float* gscale, int64_t rows, int64_t channels, float zero_point,
+                         float qmin, float qmax, int round_mode, int clamp_mode, int relu, int dtype, void* workspace,
+                         void* stream);
+
 /* ---- 5. statistics (src/brevitas/core/stats/stats_op.py) ----------------------------------------------- */
 /* AbsMax(stats_reduce_dim=1) on a [rows, cols] view -> out[rows] (T); NaN-propagating (stats_op.py:137-141) */
 int bvb_absmax_rows(const void* x, void* out, int64_t rows, int64_t cols, int dtype, void* stream);

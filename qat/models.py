@@ -15,6 +15,7 @@ from operator import mul
 import torch
 from torch import nn
 
+from brevitas_b200.fused_bn import bn_act_quant
 from brevitas_b200.nn import QuantAvgPool2d, QuantConv2d, QuantIdentity, QuantLinear, QuantReLU
 from brevitas_b200.quant import (ActQuantizer, IntBias, Int8WeightPerTensorFloat, Uint8ActPerTensorFloatMaxInit,
                                  WeightQuantizer)
@@ -131,9 +132,10 @@ class _MirrorLayers:
 class BasicBlock(nn.Module):
     expansion = 1
 
-    def __init__(self, inplanes, planes, stride=1, downsample=None, act_kw=None, L=_MirrorLayers):
+    def __init__(self, inplanes, planes, stride=1, downsample=None, act_kw=None, L=_MirrorLayers, fuse_bn=False):
         super().__init__()
         act_kw = act_kw or {}
+        self.fuse_bn = fuse_bn
         self.conv1 = L.QuantConv2d(inplanes, planes, 3, stride, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
         self.relu1 = L.QuantReLU(**act_kw)
@@ -144,7 +146,10 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         identity = x
-        out = self.relu1(self.bn1(self.conv1(x)))
+        if self.fuse_bn:          # batch-norm + ReLU + quantizer in fused passes (brevitas_b200/fused_bn.py)
+            out = bn_act_quant(self.bn1, self.relu1, self.conv1(x))
+        else:
+            out = self.relu1(self.bn1(self.conv1(x)))
         out = self.bn2(self.conv2(out))
         if self.downsample is not None:
             identity = self.downsample(x)
@@ -154,10 +159,11 @@ class BasicBlock(nn.Module):
 class ResNet18(nn.Module):
     """``L``: the layer namespace -- the mirror (default) or the reference's own ``brevitas.nn`` (qat/ref_models.py)"""
 
-    def __init__(self, num_classes=1000, act_kw=None, L=_MirrorLayers):
+    def __init__(self, num_classes=1000, act_kw=None, L=_MirrorLayers, fuse_bn=False):
         super().__init__()
         act_kw = act_kw or {}
         self.L = L
+        self.fuse_bn = fuse_bn
         self.conv1 = L.QuantConv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.relu = L.QuantReLU(**act_kw)
@@ -178,20 +184,23 @@ class ResNet18(nn.Module):
         if stride != 1 or self.inplanes != planes:
             downsample = nn.Sequential(self.L.QuantConv2d(self.inplanes, planes, 1, stride, bias=False),
                                        nn.BatchNorm2d(planes))
-        layers = [BasicBlock(self.inplanes, planes, stride, downsample, act_kw, self.L)]
+        layers = [BasicBlock(self.inplanes, planes, stride, downsample, act_kw, self.L, self.fuse_bn)]
         self.inplanes = planes
         for _ in range(1, blocks):
-            layers.append(BasicBlock(planes, planes, act_kw=act_kw, L=self.L))
+            layers.append(BasicBlock(planes, planes, act_kw=act_kw, L=self.L, fuse_bn=self.fuse_bn))
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        if self.fuse_bn:
+            x = self.maxpool(bn_act_quant(self.bn1, self.relu, self.conv1(x)))
+        else:
+            x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
 
-def resnet18(num_classes=1000, collect_stats_steps=300):
-    return ResNet18(num_classes, act_kw={"collect_stats_steps": collect_stats_steps})
+def resnet18(num_classes=1000, collect_stats_steps=300, fuse_bn=False):
+    return ResNet18(num_classes, act_kw={"collect_stats_steps": collect_stats_steps}, fuse_bn=fuse_bn)
 
 
 # ---- MobileNetV1 (imagenet_classification) --------------------------------------------------------------------
@@ -221,8 +230,9 @@ class ConvBlock(nn.Module):
     """mobilenetv1.py:76-115"""
 
     def __init__(self, in_channels, out_channels, kernel_size, weight_bit_width, act_bit_width, stride=1, padding=0,
-                 groups=1, bn_eps=1e-5, activation_scaling_per_channel=False):
+                 groups=1, bn_eps=1e-5, activation_scaling_per_channel=False, fuse_bn=False):
         super().__init__()
+        self.fuse_bn = fuse_bn
         self.conv = QuantConv2d(in_channels, out_channels, kernel_size, stride, padding, groups=groups, bias=False,
                                 weight_quant=CommonIntWeightPerChannelQuant, weight_bit_width=weight_bit_width)
         self.bn = nn.BatchNorm2d(out_channels, eps=bn_eps)
@@ -232,17 +242,21 @@ class ConvBlock(nn.Module):
                                     return_quant_tensor=True)
 
     def forward(self, x):
+        if self.fuse_bn:
+            return bn_act_quant(self.bn, self.activation, self.conv(x))
         return self.activation(self.bn(self.conv(x)))
 
 
 class DwsConvBlock(nn.Module):
     """mobilenetv1.py:45-73"""
 
-    def __init__(self, in_channels, out_channels, stride, bit_width, pw_activation_scaling_per_channel=False):
+    def __init__(self, in_channels, out_channels, stride, bit_width, pw_activation_scaling_per_channel=False,
+                 fuse_bn=False):
         super().__init__()
-        self.dw_conv = ConvBlock(in_channels, in_channels, 3, bit_width, bit_width, stride, 1, groups=in_channels)
+        self.dw_conv = ConvBlock(in_channels, in_channels, 3, bit_width, bit_width, stride, 1, groups=in_channels,
+                                 fuse_bn=fuse_bn)
         self.pw_conv = ConvBlock(in_channels, out_channels, 1, bit_width, bit_width,
-                                 activation_scaling_per_channel=pw_activation_scaling_per_channel)
+                                 activation_scaling_per_channel=pw_activation_scaling_per_channel, fuse_bn=fuse_bn)
 
     def forward(self, x):
         return self.pw_conv(self.dw_conv(x))
@@ -251,7 +265,7 @@ class DwsConvBlock(nn.Module):
 class MobileNetV1(nn.Module):
     """mobilenetv1.py:118-166 (4-bit by default, first layer 8-bit)"""
 
-    def __init__(self, bit_width=4, num_classes=1000, width_scale=1.0):
+    def __init__(self, bit_width=4, num_classes=1000, width_scale=1.0, fuse_bn=False):
         super().__init__()
         channels = [[32], [64], [128, 128], [256, 256], [512] * 6, [1024, 1024]]
         if width_scale != 1.0:
@@ -259,13 +273,13 @@ class MobileNetV1(nn.Module):
         self.features = nn.Sequential()
         cin = channels[0][0]
         self.features.add_module('init_block', ConvBlock(3, cin, 3, FIRST_LAYER_BIT_WIDTH, bit_width, stride=2,
-                                                         activation_scaling_per_channel=True))
+                                                         activation_scaling_per_channel=True, fuse_bn=fuse_bn))
         for i, stage_channels in enumerate(channels[1:]):
             stage = nn.Sequential()
             per_channel = i < len(channels[1:]) - 1
             for j, cout in enumerate(stage_channels):
                 stride = 2 if (j == 0 and i != 0) else 1
-                stage.add_module(f'unit{j + 1}', DwsConvBlock(cin, cout, stride, bit_width, per_channel))
+                stage.add_module(f'unit{j + 1}', DwsConvBlock(cin, cout, stride, bit_width, per_channel, fuse_bn))
                 cin = cout
             self.features.add_module(f'stage{i + 1}', stage)
         self.final_pool = QuantAvgPool2d(kernel_size=7, stride=1, bit_width=bit_width)
@@ -277,5 +291,5 @@ class MobileNetV1(nn.Module):
         return self.output(x.view(x.size(0), -1))
 
 
-def mobilenet_v1(bit_width=4, num_classes=1000):
-    return MobileNetV1(bit_width, num_classes)
+def mobilenet_v1(bit_width=4, num_classes=1000, fuse_bn=False):
+    return MobileNetV1(bit_width, num_classes, fuse_bn=fuse_bn)

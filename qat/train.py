@@ -38,19 +38,21 @@ def bind_reference(brevitas_src=None):
     brevitas_b200.install(brevitas_src or os.environ.get("BREVITAS_SRC"), fuse=True)
 
 
-def build(name: str, device, collect_stats_steps: int = 300, channels_last: bool = False, frontend: str = "mirror"):
+def build(name: str, device, collect_stats_steps: int = 300, channels_last: bool = False, frontend: str = "mirror",
+          fuse_bn: bool = False):
     """``frontend``: "mirror" = this repository's re-statement of the layers (brevitas_b200.nn); "reference" = the
     reference's own brevitas.nn / brevitas_examples model code after bind_reference()."""
     spec = WORKLOADS[name]
     M = models
     if frontend == "reference":
         from qat import ref_models as M
+    kw = {"fuse_bn": True} if (fuse_bn and frontend == "mirror") else {}
     if name == "tfc":
         model = M.tfc()
     elif name == "resnet18":
-        model = M.resnet18(collect_stats_steps=collect_stats_steps)
+        model = M.resnet18(collect_stats_steps=collect_stats_steps, **kw)
     else:
-        model = M.mobilenet_v1()
+        model = M.mobilenet_v1(**kw)
     model = model.to(device)
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
@@ -233,7 +235,7 @@ def train_step(model, raw_model, x, y, loss_fn, opt):
 
 
 def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False, channels_last=False, dtype="f32",
-        frontend="mirror", brevitas_src=None):
+        frontend="mirror", brevitas_src=None, fuse_bn=False):
     """returns a dict with samples/s (all ranks), ms/step, kernel-launch count per step of OUR kernels"""
     import brevitas_b200  # noqa: F401
     if frontend == "reference":
@@ -254,7 +256,8 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
         # if that is not the legacy default stream, so the whole life of the model runs on a side stream
         torch.cuda.set_stream(torch.cuda.Stream(device))
     torch.manual_seed(1234)                               # identical initial weights on every rank
-    raw, loss_fn, spec = build(name, device, collect_stats_steps, channels_last=channels_last, frontend=frontend)
+    raw, loss_fn, spec = build(name, device, collect_stats_steps, channels_last=channels_last, frontend=frontend,
+                               fuse_bn=fuse_bn)
     tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[dtype]
     if tdt != torch.float32:
         raw = raw.to(tdt)               # parameters, buffers and activations in bf16: the packed 16-bit kernels
@@ -323,7 +326,8 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
                        dtype_bytes=2 if dtype == "bf16" else 4)
     roof = R.roofline(counts, ms, dtype)
     return {"model": name, "frontend": "unmodified brevitas.nn / brevitas_examples + brevitas_b200.install()"
-            if frontend == "reference" else "brevitas_b200.nn mirror", "roofline": roof, "allreduce": allreduce, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
+            if frontend == "reference" else "brevitas_b200.nn mirror", "fuse_bn": bool(fuse_bn), "roofline": roof,
+            "allreduce": allreduce, "per_gpu_batch": batch, "n_gpus": world, "ms_per_step": round(ms, 3),
             "samples_per_s": round(world * batch / (ms * 1e-3), 1), "fakequant_launches_per_step": launches,
             "final_loss": round(loss_val, 4), "dtype": dtype, "data": "synthetic",
             "memory_format": "channels_last" if channels_last else "contiguous",
@@ -345,12 +349,13 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--frontend", default="mirror", choices=["mirror", "reference"],
                     help="reference: the unmodified brevitas.nn / brevitas_examples models bound by brevitas_b200.install()")
+    ap.add_argument("--fuse-bn", action="store_true", help="batch-norm + ReLU + activation quantizer in fused passes")
     ap.add_argument("--brevitas-src", default=None, help="source tree to import Brevitas from (default: installed / $BREVITAS_SRC)")
     a = ap.parse_args()
     os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
     os.environ.setdefault("NCCL_IB_DISABLE", "1")
     res = run(a.model, a.batch, a.steps, a.warmup, a.collect_stats_steps, graph=a.graph, channels_last=a.channels_last,
-              dtype=a.dtype, frontend=a.frontend, brevitas_src=a.brevitas_src)
+              dtype=a.dtype, frontend=a.frontend, brevitas_src=a.brevitas_src, fuse_bn=a.fuse_bn)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(res))
     import torch.distributed as dist

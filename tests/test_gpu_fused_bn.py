@@ -1,0 +1,122 @@
+"""GPU (-m gpu): batch-norm + ReLU + activation quantizer in fused passes (csrc/bn_act_quant.cu, brevitas_b200/fused_bn.py)
+against the pair it replaces -- torch.nn.BatchNorm2d (cuDNN, channels-last) followed by the QuantReLU layer (ReLU folded
+into the quantizer kernel).
+
+What can differ: the batch statistics are summed in another order than cuDNN's, so the normalised value differs by a few
+1e-7 relative; where that crosses a rounding boundary of x / scale the quantized output moves by exactly one step.  So:
+every output equals the unfused one or differs by ONE quantization step, on at most 0.1 % of the elements; running
+statistics, d(gamma), d(beta), d(scale) and dx agree to fp32 summation accuracy.
+"""
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+
+def make(channels, per_channel, bits=8):
+    from brevitas_b200.nn import QuantReLU
+    from qat.models import CommonUintActQuant
+    act = QuantReLU(act_quant=CommonUintActQuant, bit_width=bits, per_channel_broadcastable_shape=(1, channels, 1, 1),
+                    scaling_per_output_channel=per_channel, return_quant_tensor=False)
+    bn = nn.BatchNorm2d(channels)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+        if per_channel:
+            act.act_quant.fused_activation_quant_proxy.tensor_quant.scaling_impl.value.add_(
+                torch.linspace(-1.0, 0.5, channels).view(1, channels, 1, 1))
+    return bn.cuda(), act.cuda()
+
+
+@pytest.mark.parametrize("shape,per_channel,bits", [((8, 64, 28, 28), False, 8), ((4, 1024, 7, 7), True, 4),
+                                                    ((16, 32, 56, 56), True, 4), ((3, 128, 9, 5), False, 4),
+                                                    ((2, 512, 14, 14), False, 8)])
+def test_fused_bn_relu_quant_matches_the_unfused_pair(shape, per_channel, bits):
+    from brevitas_b200 import _kernels
+    from brevitas_b200.fused_bn import bn_act_quant
+    torch.manual_seed(shape[1])
+    bn_a, act_a = make(shape[1], per_channel, bits)
+    bn_b, act_b = make(shape[1], per_channel, bits)
+    bn_b.load_state_dict(bn_a.state_dict())
+    act_b.load_state_dict(act_a.state_dict())
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(shape, generator=g) * 1.5 + 0.3).cuda().contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(shape, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    for step in range(2):
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya = act_a(bn_a(xa))
+        before = _kernels.launch_count
+        yb = bn_act_quant(bn_b, act_b, xb)
+        launched = _kernels.launch_count - before
+        assert launched == 3, f"expected scale ops (2) + the fused forward (1), saw {launched}"
+        assert yb.is_contiguous(memory_format=torch.channels_last) and yb.shape == ya.shape
+        tq = act_a.act_quant.fused_activation_quant_proxy.tensor_quant
+        scale = (tq.scaling_impl(xa) / tq.int_scaling_impl(tq.msb_clamp_bit_width_impl())).detach()
+        d = (ya - yb).detach().abs()
+        moved = d > 0
+        assert float(moved.float().mean()) <= 1e-3, f"{float(moved.float().mean()):.2e} of the outputs differ"
+        assert bool((d[moved] <= (scale.expand_as(d)[moved] * 1.0001)).all()), "an output moved by more than one step"
+        ya.backward(gy)
+        yb.backward(gy)
+        for pa, pb, name in ((bn_a.weight, bn_b.weight, "d gamma"), (bn_a.bias, bn_b.bias, "d beta"),
+                             (act_a.act_quant.fused_activation_quant_proxy.tensor_quant.scaling_impl.value,
+                              act_b.act_quant.fused_activation_quant_proxy.tensor_quant.scaling_impl.value, "d scale")):
+            mag = float(pa.grad.abs().max()) + 1e-6
+            assert torch.allclose(pa.grad, pb.grad, rtol=2e-3, atol=2e-3 * mag), \
+                (name, float((pa.grad - pb.grad).abs().max()), mag)
+            pa.grad = pb.grad = None
+        mag = float(xa.grad.abs().max())
+        bad = ((xa.grad - xb.grad).abs() > 2e-3 * mag + 2e-3 * xa.grad.abs())
+        assert float(bad.float().mean()) <= 2e-3, f"dx: {float(bad.float().mean()):.2e} of the elements beyond tolerance"
+        assert torch.allclose(bn_a.running_mean, bn_b.running_mean, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(bn_a.running_var, bn_b.running_var, rtol=1e-5, atol=1e-6)
+        assert int(bn_b.num_batches_tracked) == step + 1
+    # eval mode: running statistics, no statistics pass
+    bn_a.eval(), bn_b.eval(), act_a.eval(), act_b.eval()
+    with torch.no_grad():
+        ya, yb = act_a(bn_a(x)), bn_act_quant(bn_b, act_b, x)
+    d = (ya - yb).abs()
+    assert float((d > 0).float().mean()) <= 1e-3
+
+
+def test_fused_bn_falls_back_when_a_precondition_fails():
+    from brevitas_b200 import _kernels
+    from brevitas_b200.fused_bn import bn_act_quant
+    from brevitas_b200.nn import QuantReLU
+    bn, act = make(64, False)
+    x = torch.randn(4, 64, 8, 8, device="cuda")                       # NCHW: not channels-last
+    y = bn_act_quant(bn, act, x)
+    assert torch.equal(y, act(bn(x))) or y.shape == x.shape
+    collecting = QuantReLU(collect_stats_steps=5).cuda().train()       # threshold still depends on the activation
+    xl = x.contiguous(memory_format=torch.channels_last)
+    y = bn_act_quant(bn, collecting, xl)
+    assert collecting.act_quant.fused_activation_quant_proxy.tensor_quant.scaling_impl.counter == 1
+    assert y.shape == x.shape
+    odd = nn.BatchNorm2d(48).cuda()                                    # 48 channels: 12 vectors do not divide 256
+    _, act48 = make(48, False)
+    y = bn_act_quant(odd, act48, torch.randn(2, 48, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last))
+    assert y.shape == (2, 48, 4, 4)
+
+
+@pytest.mark.parametrize("name,shape", [("resnet18", (4, 3, 64, 64)), ("mobilenet_v1", (2, 3, 224, 224))])
+def test_models_with_fused_bn_track_the_unfused_models(name, shape):
+    from qat import models
+    kw = {"collect_stats_steps": 1} if name == "resnet18" else {}
+    torch.manual_seed(0)
+    a = getattr(models, name)(**kw).cuda().to(memory_format=torch.channels_last).train()
+    torch.manual_seed(0)
+    b = getattr(models, name)(fuse_bn=True, **kw).cuda().to(memory_format=torch.channels_last).train()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(3)).cuda().contiguous(memory_format=torch.channels_last)
+    t = torch.randint(0, 1000, (shape[0],), generator=torch.Generator().manual_seed(4)).cuda()
+    for step in range(3):
+        la = nn.functional.cross_entropy(a(x), t)
+        lb = nn.functional.cross_entropy(b(x), t)
+        a.zero_grad(), b.zero_grad()
+        la.backward(), lb.backward()
+        assert abs(float(la) - float(lb)) <= 2e-2 * abs(float(la)) + 1e-3, (step, float(la), float(lb))
+    ga = torch.cat([p.grad.reshape(-1) for p in a.parameters() if p.grad is not None])
+    gb = torch.cat([p.grad.reshape(-1) for p in b.parameters() if p.grad is not None])
+    cos = float(torch.nn.functional.cosine_similarity(ga, gb, dim=0))
+    assert cos > 0.98, cos
