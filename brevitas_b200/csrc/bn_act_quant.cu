@@ -78,7 +78,7 @@ __device__ __forceinline__ void cta_store_partials(const float (&acc)[NS][V], fl
 
 // ---- forward 1: per-channel sum and sum of squares ------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial,
+__global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial,
                                                              int64_t rows, int C, int cv_n, int rl_n) {
     constexpr int V = DT<T>::VEC;
     __shared__ float smem[2 * BN_THREADS * V];
@@ -158,21 +158,50 @@ struct BnThread {
     BnCh ch[V];
     DivBy dv[V];
     float inv_s[V];
+    // backward, fp32, zero zero-point: the clamp mask of the reference chain as two comparisons on the normalised value.
+    // t1 = y / s (correctly rounded, monotone in y for s > 0) and round() are monotone, so
+    //   round(y / s) > qmax  <=>  y >= y_hi,      round(y / s) < qmin  <=>  y <= y_lo
+    // for thresholds found once per scale with the exact division (a few probes around (qmax + 0.5) * s); exact, not an
+    // approximation (NaN compares false on both sides = gradient kept, like the reference's where-based clamp).
+    float y_hi[V], y_lo[V];
+    bool fast;              // thresholds valid for every scale of this thread
     __device__ __forceinline__ BnThread(int c0, const float* mean, const float* invstd, const float* gamma,
-                                        const float* beta, const void* scale, int scale_count, int scale_f32) {
+                                        const float* beta, const void* scale, int scale_count, int scale_f32,
+                                        const QParams* p = nullptr) {
+        fast = p != nullptr && !DT<T>::LOWP && !p->zp_nonzero;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             ch[i] = {mean[c0 + i], invstd[c0 + i], gamma ? gamma[c0 + i] : 1.f, beta ? beta[c0 + i] : 0.f};
             const float s = load_scale<T>(scale, scale_f32, scale_count == 1 ? 0 : c0 + i);
             dv[i] = DivBy(s, DT<T>::MUL_DIV_EXACT && !scale_f32);
             inv_s[i] = dv[i].approx_recip();
+            y_hi[i] = y_lo[i] = 0.f;
+            if (fast && (scale_count != 1 || i == 0)) {
+                if (!(s > 0.f) || !(s < 3.0e38f) || !dv[i].fast) { fast = false; continue; }
+                // smallest t with rintf(t) > qmax / largest t with rintf(t) < qmin (round-half-even)
+                float t_hi = p->qmax + 0.5f, t_lo = p->qmin - 0.5f;
+                if (!(rintf(t_hi) > p->qmax)) t_hi = nextafterf(t_hi, 3.0e38f);
+                if (!(rintf(t_lo) < p->qmin)) t_lo = nextafterf(t_lo, -3.0e38f);
+                float yh = fmul(t_hi, s), yl = fmul(t_lo, s);
+                int guard = 0;
+                while (__fdiv_rn(yh, s) >= t_hi && ++guard < 64) yh = nextafterf(yh, -3.0e38f);     // below the threshold
+                while (!(__fdiv_rn(yh, s) >= t_hi) && ++guard < 64) yh = nextafterf(yh, 3.0e38f);   // first value at / above
+                while (__fdiv_rn(yl, s) <= t_lo && ++guard < 64) yl = nextafterf(yl, 3.0e38f);
+                while (!(__fdiv_rn(yl, s) <= t_lo) && ++guard < 64) yl = nextafterf(yl, -3.0e38f);
+                if (guard >= 64) { fast = false; continue; }
+                y_hi[i] = yh;
+                y_lo[i] = yl;
+            } else if (fast) {
+                y_hi[i] = y_hi[0];
+                y_lo[i] = y_lo[0];
+            }
         }
     }
 };
 
 // ---- forward 3: normalise, ReLU, quantize ---------------------------------------------------------------------------
 template <typename T, int RM>
-__global__ void __launch_bounds__(BN_THREADS) bn_act_quant_apply_kernel(
+__global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_apply_kernel(
         const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
         const float* __restrict__ gamma, const float* __restrict__ beta, const void* __restrict__ scale, int scale_count,
         int scale_f32, int64_t rows, int cv_n, int rl_n, int relu, QParams p) {
@@ -214,6 +243,21 @@ __device__ __forceinline__ float bn_bwd_elem(float g, float x, const BnThread<T>
     xhat = fmul(fsub(x, th.ch[i].mean), th.ch[i].invstd);
     const float yb = DT<T>::rnd(fadd(fmul(xhat, th.ch[i].gamma), th.ch[i].beta));
     const float v = relu ? relu_f(yb) : yb;
+    if (th.fast) {
+        // same values as bwd_elem: d = (g * s) kept or zeroed by the clamp mask, gradient = d / s
+        float d = fmul(g, th.dv[i].b);
+        if (masked && (v >= th.y_hi[i] || v <= th.y_lo[i])) d = 0.f;
+        if (want_gs) {
+            // d(scale) = g * t5 - d * (t1 / s): an order-dependent sum, reciprocal-multiply within its tolerance (as bwd_elem)
+            const float t1 = v * th.inv_s[i];
+            const float t5 = fminf(fmaxf(rintf(t1), p.qmin), p.qmax);
+            gs_acc = fmaf(g, t5, gs_acc);
+            gs_acc = fmaf(-d, t1 * th.inv_s[i], gs_acc);
+        }
+        float r = th.dv[i](d);
+        if (relu && yb <= 0.f) r = 0.f;
+        return r;
+    }
     float r = bwd_elem<T, RM>(g, v, th.dv[i], th.inv_s[i], p, masked, want_gs, gs_acc);
     r = DT<T>::rnd(r);
     if (relu && yb <= 0.f) r = 0.f;          // ATen's threshold_backward: keeps the gradient unless y <= 0
@@ -222,7 +266,7 @@ __device__ __forceinline__ float bn_bwd_elem(float g, float x, const BnThread<T>
 
 // ---- backward 1: per-channel sum(gy), sum(gy * xhat), d(scale) -------------------------------------------------------
 template <typename T, int RM>
-__global__ void __launch_bounds__(BN_THREADS) bn_act_quant_bwd_reduce_kernel(
+__global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_reduce_kernel(
         const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
         const float* __restrict__ gamma, const float* __restrict__ beta, const void* __restrict__ scale, int scale_count,
         int scale_f32, float* __restrict__ partial, int64_t rows, int C, int cv_n, int rl_n, int relu, int masked,
@@ -230,7 +274,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_quant_bwd_reduce_kernel(
     constexpr int V = DT<T>::VEC;
     __shared__ float smem[3 * BN_THREADS * V];
     const int cv = threadIdx.x % cv_n, rlane = threadIdx.x / cv_n;
-    const BnThread<T> th(cv * V, mean, invstd, gamma, beta, scale, scale_count, scale_f32);
+    const BnThread<T> th(cv * V, mean, invstd, gamma, beta, scale, scale_count, scale_f32, &p);
     float acc[3][V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
@@ -300,7 +344,7 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_scalar_gscale_kernel(const flo
 
 // ---- backward 3: dx = gamma * invstd * (gy - mean(gy) - xhat * mean(gy * xhat)) --------------------------------------
 template <typename T, int RM>
-__global__ void __launch_bounds__(BN_THREADS) bn_act_quant_bwd_dx_kernel(
+__global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_dx_kernel(
         const T* __restrict__ g, const T* __restrict__ x, T* __restrict__ gx, const float* __restrict__ mean,
         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
         const void* __restrict__ scale, int scale_count, int scale_f32, const float* __restrict__ gbeta,
@@ -308,7 +352,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_quant_bwd_dx_kernel(
         QParams p) {
     constexpr int V = DT<T>::VEC;
     const int cv = threadIdx.x % cv_n, rlane = threadIdx.x / cv_n;
-    const BnThread<T> th(cv * V, mean, invstd, gamma, beta, scale, scale_count, scale_f32);
+    const BnThread<T> th(cv * V, mean, invstd, gamma, beta, scale, scale_count, scale_f32, &p);
     float a[V], mb[V], mg[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
