@@ -397,14 +397,17 @@ def absmax_tensor(x):
     return out
 
 
-def abs_kth_value_rows(x, rows, cols, k, want_index=False, signed=False):
-    """k-th smallest of |x| (signed=False) or of x itself (signed=True) per row; optionally the smallest index attaining it"""
+def abs_kth_value_rows(x, rows, cols, k, want_index=False, signed=False, pre_relu=False, dense_ok=False):
+    """k-th smallest of |x| (signed=False), of x itself (signed=True) or of relu(x) (pre_relu) per row; optionally the
+    smallest index attaining it.  dense_ok: x is a dense channels-last tensor read in MEMORY order (whole-tensor
+    statistics are permutation invariant); the index is then a storage offset."""
     dev = _check_cuda(x)
-    x = _c(x)
+    x = _dense(x) if dense_ok else _c(x)
     out = torch.empty(rows, dtype=x.dtype, device=dev)
     idx = torch.empty(rows, dtype=torch.int64, device=dev) if want_index else None
     ws = torch.empty(_lib.load().bvb_kth_workspace_bytes(rows), dtype=torch.uint8, device=dev)
-    _launch(dev, "bvb_kth_value_rows" if signed else "bvb_abs_kth_value_rows", x.data_ptr(), out.data_ptr(), _ptr(idx),
+    name = "bvb_kth_value_rows" if signed else ("bvb_relu_abs_kth_value_rows" if pre_relu else "bvb_abs_kth_value_rows")
+    _launch(dev, name, x.data_ptr(), out.data_ptr(), _ptr(idx),
             rows, cols, k, dtype_tag(x), ws.data_ptr(), _stream(dev))
     return out, idx
 

@@ -223,8 +223,16 @@ class RescalingIntQuant(nn.Module):
         if not x.is_cuda or type(self.int_quant.delay_wrapper.delay_impl) is not _NoDelay:
             return None
         independent = getattr(self.scaling_impl, 'input_independent', None)
-        if independent is None or not independent():
+        if independent is None:
             return None
+        collecting = False
+        if not independent():
+            # statistics-collection phase: the threshold is a percentile of relu(x).  The select kernel takes relu(x)'s
+            # statistic straight from x, so the ReLU still folds into the quantizer kernel
+            probe = getattr(self.scaling_impl, 'pre_relu_collecting', None)
+            if probe is None or not probe(x):
+                return None
+            collecting = True
         bit_width = self.msb_clamp_bit_width_impl()
         cfg = self._host_config(bit_width.dtype)
         if cfg is None:
@@ -232,7 +240,12 @@ class RescalingIntQuant(nn.Module):
         zp, qmin, qmax, rm, cm, _ = cfg
         if zp is None:
             return None
-        threshold = self.scaling_impl(x)                    # x is ignored (input independent)
+        if not collecting:
+            threshold = self.scaling_impl(x)                # x is ignored (input independent)
+        elif x.dtype != torch.float32 and x.dtype != self.scaling_impl.buffer.dtype:
+            return None                                     # mixed-dtype collection: the two-kernel path handles it
+        else:
+            threshold = self.scaling_impl(x, pre_relu=True)
         scale = threshold / self.int_scaling_impl(bit_width)
         if not (scale.dtype == x.dtype or (scale.numel() == 1 and scale.dtype == torch.float32)):
             return None

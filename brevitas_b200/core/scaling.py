@@ -145,10 +145,23 @@ class ParameterFromRuntimeStatsScaling(nn.Module):
             self.restrict_inplace_preprocess = Identity()
             self.restrict_preprocess = Identity()
 
-    def training_forward(self, stats_input: Tensor) -> Tensor:
+    def pre_relu_collecting(self, x: Tensor) -> bool:
+        """still collecting, and the statistic of relu(x) can be taken by the ReLU-folded select (whole-tensor
+        AbsPercentile over a dense tensor, scalar threshold): the caller may then skip the ReLU pass"""
+        from .function_wrapper import OverTensorView
+        from .stats import AbsPercentile
+        impl = self.stats.stats_impl
+        return (self.training and self.counter < self.collect_stats_steps and type(impl) is AbsPercentile
+                and type(self.stats_input_view_shape_impl) is OverTensorView and tuple(self.buffer.shape) == ()
+                and impl.relu_tensor_supported(x))
+
+    def training_forward(self, stats_input: Tensor, pre_relu: bool = False) -> Tensor:
         if self.counter < self.collect_stats_steps:
-            stats_input = self.stats_input_view_shape_impl(stats_input)
-            stats = self.stats(stats_input)
+            if pre_relu:                   # statistic of relu(stats_input), ReLU folded into the select kernel
+                stats = self.stats.stats_impl.forward_relu_tensor(stats_input).view(self.buffer.shape)
+            else:
+                stats_input = self.stats_input_view_shape_impl(stats_input)
+                stats = self.stats(stats_input)
             stats = stats + 0. * self.value      # keeps `value` in the graph (DDP, standalone.py:234-235)
             clamped_stats = self.clamp_scaling(stats)
             new_counter = self.counter + 1
@@ -168,9 +181,9 @@ class ParameterFromRuntimeStatsScaling(nn.Module):
         """true once the collection phase is over (or in eval mode): the statistics input is ignored"""
         return (not self.training) or self.counter >= self.collect_stats_steps
 
-    def forward(self, stats_input: Tensor) -> Tensor:
+    def forward(self, stats_input: Tensor, pre_relu: bool = False) -> Tensor:
         if self.training:
-            return self.training_forward(stats_input)
+            return self.training_forward(stats_input, pre_relu)
         if self.counter <= self.collect_stats_steps:
             out = self.restrict_preprocess(self.buffer)
         else:

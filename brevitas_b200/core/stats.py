@@ -77,6 +77,16 @@ class AbsPercentile(nn.Module):
         val, _ = torch.ops.brevitas_b200.abs_kth_value_rows(x.contiguous(), rows, cols, k)
         return val
 
+    def relu_tensor_supported(self, x: Tensor) -> bool:
+        dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))
+        return self.stats_reduce_dim is None and x.is_cuda and dense and x.numel() > 0
+
+    def forward_relu_tensor(self, x: Tensor) -> Tensor:
+        """``self(relu(x).reshape(-1))`` without materialising relu(x) and with a one-element (sparse) gradient"""
+        k = int(math.floor(.01 * self.q * x.numel() + 0.5))
+        val, _ = torch.ops.brevitas_b200.relu_abs_kth_value_tensor(x, k)
+        return val.view(())
+
 
 # ---- remaining statistics of stats_op.py (SURVEY.md §8f rank 3).  Those built on the per-row abs-max reuse the
 # sm_100a reduction, the signed percentiles the exact radix select on order-preserving keys (``kth_value_rows``: the

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
                                                                 int vec_ok, int pass, int64_t k, uint32_t* hist,
                                                                 unsigned long long* first_index, uint32_t cap,
                                                                 uint32_t* ccount, uint32_t* ckeys,
-                                                                unsigned long long* cidx) {
+                                                                unsigned long long* cidx, int pre_relu) {
     constexpr int V = DT<T>::VEC;
     using KT = KeyTraits<T, SIGNED>;
     constexpr int P = KT::PASSES;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
             constexpr int NV = decltype(nv_tag)::value;
             uint32_t key[NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) key[i] = KT::key(v[i]);
+            for (int i = 0; i < NV; ++i) key[i] = KT::key(pre_relu ? relu_f(v[i]) : v[i]);   // statistic of relu(x)
             if (pass == 0) {
                 if (valid) {
 #pragma unroll
@@ -337,7 +337,7 @@ static inline int64_t kth_base_bytes(int64_t rows) {
 
 template <typename T, bool SIGNED>
 static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
-                      void* workspace, cudaStream_t st) {
+                      void* workspace, cudaStream_t st, int pre_relu = 0) {
     constexpr int P = KeyTraits<T, SIGNED>::PASSES;
     constexpr int V = DT<T>::VEC;
     uint32_t* hist = (uint32_t*)workspace;
@@ -367,7 +367,7 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     for (int pass = 0; pass < P; ++pass)
         kth_hist_kernel<T, SIGNED><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist,
                                                          (index_out && pass == P - 1) ? first_index : nullptr, cap,
-                                                         ccount, ckeys, cidx);
+                                                         ccount, ckeys, cidx, pre_relu);
     const dim3 fgrid(1u, (unsigned)gy);                                  // one CTA per row resolves the last digit
     kth_final_kernel<T, SIGNED><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out,
                                                        first_index);
@@ -409,6 +409,20 @@ extern "C" int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_o
         return fail(BVB_EINVAL, "bvb_abs_kth_value_rows: k = %lld out of range [1, %lld]", (long long)k, (long long)cols);
     if (!x || !out || !workspace) return fail(BVB_EINVAL, "bvb_abs_kth_value_rows: null pointer");
     BVB_DISPATCH_DTYPE(dtype, return (launch_kth<T, false>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream)));
+    return BVB_OK;
+}
+
+// AbsPercentile of relu(x) without materialising relu(x): the statistic of a QuantReLU's quantizer while it still
+// collects (FusedActivationQuantProxy: activation_impl then tensor_quant, proxy/runtime_quant.py:81-84; scaling from
+// ParameterFromRuntimeStatsScaling, core/scaling/standalone.py:230-244).  |relu(x)| = relu(x): keys of max(x, +0).
+extern "C" int bvb_relu_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols,
+                                           int64_t k, int dtype, void* workspace, void* stream) {
+    if (rows < 0 || cols < 0) return fail(BVB_EINVAL, "bvb_relu_abs_kth_value_rows: negative size");
+    if (rows == 0) return BVB_OK;
+    if (k < 1 || k > cols)
+        return fail(BVB_EINVAL, "bvb_relu_abs_kth_value_rows: k = %lld out of range [1, %lld]", (long long)k, (long long)cols);
+    if (!x || !out || !workspace) return fail(BVB_EINVAL, "bvb_relu_abs_kth_value_rows: null pointer");
+    BVB_DISPATCH_DTYPE(dtype, return (launch_kth<T, false>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream, 1)));
     return BVB_OK;
 }
 

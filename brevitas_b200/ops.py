@@ -533,3 +533,37 @@ def _kth_signed_bwd(ctx, gval, gidx):
 
 
 torch.library.register_autograd(f"{FQ_NS}::kth_value_rows", _kth_signed_bwd, setup_context=_kth_setup, lib=_FQ)
+
+
+# k-th smallest of relu(x) over a WHOLE dense tensor (row-major or channels-last, read in memory order): the statistic of
+# a QuantReLU quantizer in its collection phase with the ReLU folded in.  Its gradient is ONE element; handing autograd
+# a sparse tensor lets the engine add it to the quantizer's dense gradient with a one-element scatter instead of the
+# dense zero-fill + dense add a one-hot gradient costs (0.47 + 0.6 ms per ResNet-18 step in round 1).
+_FQ.define("relu_abs_kth_value_tensor(Tensor x, int k) -> (Tensor, Tensor)")
+_FQ.impl("relu_abs_kth_value_tensor",
+         lambda x, k: K.abs_kth_value_rows(x, 1, x.numel(), k, want_index=True, pre_relu=True, dense_ok=True), "CUDA")
+_FQ.impl("relu_abs_kth_value_tensor", _no_cpu("relu_abs_kth_value_tensor"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::relu_abs_kth_value_tensor",
+                            lambda x, k: (x.new_empty(1), x.new_empty(1, dtype=torch.int64)), lib=_FQ)
+
+
+def _relu_kth_setup(ctx, inputs, output):
+    x, k = inputs
+    val, idx = output
+    ctx.save_for_backward(x, idx)
+    ctx.mark_non_differentiable(idx)
+
+
+def _relu_kth_bwd(ctx, gval, gidx):
+    x, idx = ctx.saved_tensors
+    off = idx.view(())                                       # storage offset of the selected element
+    # dense tensor: a dimension's coordinate is (offset // stride) % size
+    coords = torch.stack([(off // st) % sz if sz > 1 else torch.zeros_like(off) for sz, st in zip(x.shape, x.stride())])
+    sel = x[tuple(coords.unbind(0))] if x.dim() > 0 else x
+    # d relu(x) / dx: ATen's threshold_backward keeps the gradient unless x <= 0; |.| of a non-negative value: sign +1
+    g = torch.where(sel <= 0, torch.zeros_like(gval.reshape(())), gval.reshape(()).to(x.dtype))
+    return torch.sparse_coo_tensor(coords.view(x.dim(), 1), g.reshape(1), x.shape), None
+
+
+torch.library.register_autograd(f"{FQ_NS}::relu_abs_kth_value_tensor", _relu_kth_bwd, setup_context=_relu_kth_setup,
+                                lib=_FQ)

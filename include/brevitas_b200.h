@@ -250,6 +250,11 @@ int bvb_absmax_tensor(const void* x, void* out, int64_t n, int dtype, void* work
  * copied to once few enough are left, so that a high percentile of an fp32 tensor costs two reads instead of four). */
 int bvb_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
                            int dtype, void* workspace, void* stream);
+/* AbsPercentile of relu(x) -- the statistic of a QuantReLU whose quantizer still collects (nn.ReLU then tensor_quant,
+ * src/brevitas/proxy/runtime_quant.py:81-84; core/scaling/standalone.py:230-244) -- without a ReLU pass: keys of
+ * max(x, +0).  Same contract and workspace as bvb_abs_kth_value_rows. */
+int bvb_relu_abs_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
+                                int dtype, void* workspace, void* stream);
 /* the SIGNED k-th smallest value, x.kthvalue(k) (NegativePercentileOrZero, PercentileInterval: stats_op.py:69-126),
  * same select on order-preserving keys of x itself (every NaN sorts last, like torch.kthvalue); same workspace */
 int bvb_kth_value_rows(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,

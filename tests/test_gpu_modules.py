@@ -348,3 +348,50 @@ def test_sigmoid_tanh_and_conv_transpose1d_layers(B):
     torch.testing.assert_close(t(xin), torch.nn.functional.conv_transpose1d(xin, ref_w, t.bias, 2), rtol=1e-4, atol=1e-5)
     eight = torch.tensor(8.0, device="cuda")
     assert int(t.max_acc_bit_width(eight, eight)) == 21      # ceil(log2(255*255*2*10))
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_relu_folds_into_the_quantizer_while_collecting_statistics(B, channels_last):
+    """QuantReLU with the default Uint8ActPerTensorFloat quantizer during its first `collect_stats_steps` steps: the
+    threshold is the 99.999th percentile of relu(x) (core/scaling/standalone.py:230-244).  The ReLU-folded select +
+    relu_int_quant pair must give what nn.ReLU followed by the quantizer gives: same outputs, scale, buffer, and the
+    same input gradient -- including the ONE element the statistic's gradient reaches (handed to autograd sparse)."""
+    from brevitas_b200 import _kernels
+    from brevitas_b200.nn import QuantReLU
+    torch.manual_seed(3)
+    folded = QuantReLU(collect_stats_steps=3).cuda().train()
+    plain = QuantReLU(collect_stats_steps=3).cuda().train()
+    fq = plain.act_quant.fused_activation_quant_proxy
+    for step in range(5):                                    # 3 collection steps, the switch-over, one learned step
+        x = torch.randn(6, 16, 10, 10, generator=torch.Generator().manual_seed(step)).cuda() * (1 + step)
+        if channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        g = torch.randn(6, 16, 10, 10, generator=torch.Generator().manual_seed(50 + step)).cuda()
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        relu_calls = []
+        h = folded.act_quant.fused_activation_quant_proxy.activation_impl.register_forward_hook(lambda *a: relu_calls.append(1))
+        before = _kernels.launch_count
+        ya = folded(xa)
+        launches = _kernels.launch_count - before
+        h.remove()
+        assert not relu_calls, f"step {step}: the ReLU ran as a separate pass"
+        yb_in = torch.relu(xb)                               # the unfolded composition, on the same modules' twin
+        out = fq.tensor_quant(yb_in)
+        yb = out[0]
+        assert torch.equal(ya, yb), f"step {step}: outputs differ"
+        sa = folded.quant_act_scale() if hasattr(folded, "quant_act_scale") else None
+        ta, tb = folded.act_quant.fused_activation_quant_proxy.tensor_quant.scaling_impl, fq.tensor_quant.scaling_impl
+        assert torch.equal(ta.buffer, tb.buffer) and ta.counter == tb.counter, f"step {step}: statistics differ"
+        (ya * g).sum().backward()
+        (yb * g).sum().backward()
+        assert not xa.grad.is_sparse and xa.grad.shape == x.shape
+        assert torch.allclose(xa.grad, xb.grad, rtol=1e-5, atol=1e-6), \
+            f"step {step}: max |d grad| {float((xa.grad - xb.grad).abs().max())}"
+        same = (xa.grad.view(torch.int32) == xb.grad.contiguous().view(torch.int32) if not channels_last else
+                xa.grad.contiguous().view(torch.int32) == xb.grad.contiguous().view(torch.int32))
+        assert float(same.float().mean()) > 0.999
+        va, vb = ta.value.grad, tb.value.grad
+        assert (va is None) == (vb is None)
+        if va is not None:
+            assert torch.allclose(va, vb, rtol=1e-4, atol=1e-5)
+            ta.value.grad = tb.value.grad = None
