@@ -245,12 +245,16 @@ class RescalingIntQuant(nn.Module):
         elif x.dtype != torch.float32 and x.dtype != self.scaling_impl.buffer.dtype:
             return None                                     # mixed-dtype collection: the two-kernel path handles it
         else:
-            threshold = self.scaling_impl(x, pre_relu=True)
+            holder = {}                                     # pairs the statistic with the quantizer call below
+            threshold = self.scaling_impl(x, pre_relu=holder)
         scale = threshold / self.int_scaling_impl(bit_width)
         if not (scale.dtype == x.dtype or (scale.numel() == 1 and scale.dtype == torch.float32)):
             return None
         zero_point = self.zero_point_impl(x, scale, bit_width)
-        y = torch.ops.brevitas_b200.relu_int_quant(x, scale, zp, qmin, qmax, rm, cm)
+        if collecting:
+            y = _ops.CollectingReluQuant.apply(x, scale, zp, qmin, qmax, rm, cm, holder)
+        else:
+            y = torch.ops.brevitas_b200.relu_int_quant(x, scale, zp, qmin, qmax, rm, cm)
         return y, scale, zero_point, bit_width
 
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:

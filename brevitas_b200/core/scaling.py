@@ -155,10 +155,10 @@ class ParameterFromRuntimeStatsScaling(nn.Module):
                 and type(self.stats_input_view_shape_impl) is OverTensorView and tuple(self.buffer.shape) == ()
                 and impl.relu_tensor_supported(x))
 
-    def training_forward(self, stats_input: Tensor, pre_relu: bool = False) -> Tensor:
+    def training_forward(self, stats_input: Tensor, pre_relu: Optional[dict] = None) -> Tensor:
         if self.counter < self.collect_stats_steps:
-            if pre_relu:                   # statistic of relu(stats_input), ReLU folded into the select kernel
-                stats = self.stats.stats_impl.forward_relu_tensor(stats_input).view(self.buffer.shape)
+            if pre_relu is not None:       # statistic of relu(stats_input), ReLU folded into the select kernel
+                stats = self.stats.stats_impl.forward_relu_tensor(stats_input, pre_relu).view(self.buffer.shape)
             else:
                 stats_input = self.stats_input_view_shape_impl(stats_input)
                 stats = self.stats(stats_input)
@@ -181,7 +181,7 @@ class ParameterFromRuntimeStatsScaling(nn.Module):
         """true once the collection phase is over (or in eval mode): the statistics input is ignored"""
         return (not self.training) or self.counter >= self.collect_stats_steps
 
-    def forward(self, stats_input: Tensor, pre_relu: bool = False) -> Tensor:
+    def forward(self, stats_input: Tensor, pre_relu: Optional[dict] = None) -> Tensor:
         if self.training:
             return self.training_forward(stats_input, pre_relu)
         if self.counter <= self.collect_stats_steps:

@@ -81,11 +81,12 @@ class AbsPercentile(nn.Module):
         dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))
         return self.stats_reduce_dim is None and x.is_cuda and dense and x.numel() > 0
 
-    def forward_relu_tensor(self, x: Tensor) -> Tensor:
-        """``self(relu(x).reshape(-1))`` without materialising relu(x) and with a one-element (sparse) gradient"""
+    def forward_relu_tensor(self, x: Tensor, holder: dict) -> Tensor:
+        """``self(relu(x).reshape(-1))`` without materialising relu(x); ``holder`` pairs this call with the quantizer call
+        of the same forward so that the statistic's one-element gradient is folded into the quantizer's (ops.py)"""
+        from ..ops import CollectingStat
         k = int(math.floor(.01 * self.q * x.numel() + 0.5))
-        val, _ = torch.ops.brevitas_b200.relu_abs_kth_value_tensor(x, k)
-        return val.view(())
+        return CollectingStat.apply(x, k, holder)
 
 
 # ---- remaining statistics of stats_op.py (SURVEY.md §8f rank 3).  Those built on the per-row abs-max reuse the

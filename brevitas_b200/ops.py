@@ -535,35 +535,55 @@ def _kth_signed_bwd(ctx, gval, gidx):
 torch.library.register_autograd(f"{FQ_NS}::kth_value_rows", _kth_signed_bwd, setup_context=_kth_setup, lib=_FQ)
 
 
-# k-th smallest of relu(x) over a WHOLE dense tensor (row-major or channels-last, read in memory order): the statistic of
-# a QuantReLU quantizer in its collection phase with the ReLU folded in.  Its gradient is ONE element; handing autograd
-# a sparse tensor lets the engine add it to the quantizer's dense gradient with a one-element scatter instead of the
-# dense zero-fill + dense add a one-hot gradient costs (0.47 + 0.6 ms per ResNet-18 step in round 1).
-_FQ.define("relu_abs_kth_value_tensor(Tensor x, int k) -> (Tensor, Tensor)")
-_FQ.impl("relu_abs_kth_value_tensor",
-         lambda x, k: K.abs_kth_value_rows(x, 1, x.numel(), k, want_index=True, pre_relu=True, dense_ok=True), "CUDA")
-_FQ.impl("relu_abs_kth_value_tensor", _no_cpu("relu_abs_kth_value_tensor"), "CPU")
-torch.library.register_fake(f"{FQ_NS}::relu_abs_kth_value_tensor",
-                            lambda x, k: (x.new_empty(1), x.new_empty(1, dtype=torch.int64)), lib=_FQ)
+# ---- QuantReLU in its statistics-collection phase, ReLU folded --------------
+# The threshold is the k-th smallest of relu(x) (AbsPercentile, core/scaling/standalone.py:230-244) and the quantizer then
+# runs on relu(x) with a scale derived from it.  Two autograd functions share a `holder` dict for one forward call:
+#   CollectingStat        stat = k-th smallest of relu(x), taken from x by the ReLU-folded select (no ReLU pass)
+#   CollectingReluQuant   y = relu_int_quant(x, scale)
+# In the backward CollectingReluQuant runs first (the statistic sits upstream of its scale) and leaves its dense input
+# gradient in the holder; CollectingStat then adds its ONE-element gradient to that tensor in place and returns nothing.
+# A one-hot dense gradient (zero-fill + dense add: 0.47 + 0.6 ms per ResNet-18 step in round 1) never exists; a sparse
+# gradient was measured too and is worse (ATen's dense + sparse add copies the dense side to NCHW order: +7 ms per step).
+def _storage_order(t: Tensor) -> Tensor:
+    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
 
 
-def _relu_kth_setup(ctx, inputs, output):
-    x, k = inputs
-    val, idx = output
-    ctx.save_for_backward(x, idx)
-    ctx.mark_non_differentiable(idx)
+class CollectingStat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, holder):
+        val, idx = K.abs_kth_value_rows(x, 1, x.numel(), k, want_index=True, pre_relu=True, dense_ok=True)
+        ctx.save_for_backward(x, idx)
+        ctx.holder = holder
+        return val.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, idx = ctx.saved_tensors
+        sel = _storage_order(x)[idx]                                   # the selected element (a device read, no sync)
+        # d relu / dx keeps the gradient unless x <= 0 (ATen's threshold_backward); |relu(x)| = relu(x): sign +1
+        val = torch.where(sel <= 0, torch.zeros_like(sel), g.to(x.dtype).reshape(1))
+        gx = ctx.holder.pop("gx", None)
+        if gx is not None and gx.stride() == x.stride():
+            _storage_order(gx).index_add_(0, idx, val)                 # folded into the quantizer's gradient, in place
+            return None, None, None
+        gx = torch.zeros_like(x)                                       # quantizer output unused this step: one-hot
+        _storage_order(gx).index_add_(0, idx, val)
+        return gx, None, None
 
 
-def _relu_kth_bwd(ctx, gval, gidx):
-    x, idx = ctx.saved_tensors
-    off = idx.view(())                                       # storage offset of the selected element
-    # dense tensor: a dimension's coordinate is (offset // stride) % size
-    coords = torch.stack([(off // st) % sz if sz > 1 else torch.zeros_like(off) for sz, st in zip(x.shape, x.stride())])
-    sel = x[tuple(coords.unbind(0))] if x.dim() > 0 else x
-    # d relu(x) / dx: ATen's threshold_backward keeps the gradient unless x <= 0; |.| of a non-negative value: sign +1
-    g = torch.where(sel <= 0, torch.zeros_like(gval.reshape(())), gval.reshape(()).to(x.dtype))
-    return torch.sparse_coo_tensor(coords.view(x.dim(), 1), g.reshape(1), x.shape), None
+class CollectingReluQuant(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, zp, qmin, qmax, rm, cm, holder):
+        ctx.save_for_backward(x, scale)
+        ctx.q = (zp, qmin, qmax, rm, cm)
+        ctx.holder = holder
+        return K.int_quant_fwd(x, scale, zp, qmin, qmax, rm, pre_relu=True)
 
-
-torch.library.register_autograd(f"{FQ_NS}::relu_abs_kth_value_tensor", _relu_kth_bwd, setup_context=_relu_kth_setup,
-                                lib=_FQ)
+    @staticmethod
+    def backward(ctx, gy):
+        x, scale = ctx.saved_tensors
+        zp, qmin, qmax, rm, cm = ctx.q
+        want_gs = ctx.needs_input_grad[1]
+        gx, gs = K.int_quant_bwd(gy.to(x.dtype), x, scale, zp, qmin, qmax, rm, cm, want_gs, pre_relu=True)
+        ctx.holder["gx"] = gx
+        return gx, (_reduce_gscale(gs, scale) if want_gs else None), None, None, None, None, None, None
