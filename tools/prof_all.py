@@ -53,7 +53,20 @@ def main():
         # AbsPercentile (99.999 %) over a whole activation tensor: 4 (fp32) / 2 (bf16) reads by construction
         "abs_percentile_f32": (lambda i: K.abs_kth_value_rows(W[i % NS].reshape(-1), 1, R * C, int(0.99999 * R * C + 0.5)), R * C * 16),
         "abs_percentile_bf16": (lambda i: K.abs_kth_value_rows(X[i % NS].reshape(-1), 1, T * D, int(0.99999 * T * D + 0.5)), T * D * 4),
+        # r02: signed k-th value (NegativePercentileOrZero / PercentileInterval), ReLU-folded select (collection phase)
+        "kth_signed_f32_q5": (lambda i: K.kth_value_rows(W[i % NS].reshape(-1), 1, R * C, int(0.05 * R * C + 0.5)), R * C * 16),
+        "relu_abs_percentile_f32": (lambda i: K.abs_kth_value_rows(W[i % NS].reshape(-1), 1, R * C, int(0.99999 * R * C + 0.5), pre_relu=True), R * C * 16),
     }
+    # r02: batch-norm + ReLU + activation quantizer in fused passes, ResNet-18 stem shape [256,64,112,112] NHWC fp32
+    BN, BC = 256 * 112 * 112, 64
+    XB = [torch.randn(256, BC, 112, 112, device=dev, generator=gen).contiguous(memory_format=torch.channels_last) for _ in range(2)]
+    GB = torch.randn(256, BC, 112, 112, device=dev, generator=gen).contiguous(memory_format=torch.channels_last)
+    gam, bet = torch.ones(BC, device=dev), torch.zeros(BC, device=dev)
+    rm_, rv_ = torch.zeros(BC, device=dev), torch.ones(BC, device=dev)
+    sbn = torch.tensor(0.02, device=dev)
+    _, sm_, si_ = K.bn_act_quant_fwd(XB[0], gam, bet, rm_, rv_, 0.1, 1e-5, True, sbn, 0.0, 0.0, 255.0)
+    cases["bn_relu_quant_f32_fwd"] = (lambda i: K.bn_act_quant_fwd(XB[i % 2], gam, bet, rm_, rv_, 0.1, 1e-5, True, sbn, 0.0, 0.0, 255.0), BN * BC * 12)
+    cases["bn_relu_quant_f32_bwd"] = (lambda i: K.bn_act_quant_bwd(GB, XB[i % 2], gam, bet, sm_, si_, sbn, 0.0, 0.0, 255.0, 1), BN * BC * 20)
     only = [s for s in a.only.split(",") if s]
     period = 6                                    # lcm of the input rotations above
     for name, (fn, nbytes) in cases.items():
