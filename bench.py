@@ -520,6 +520,11 @@ def main():
         qat["mobilenet_v1_4b"] = qat_run("mobilenet_v1", 128, 20, 3, channels_last=True, graph=True)
         if world > 1 or args.qat_all:
             qat["mobilenet_v1_4b_eager_ddp"] = qat_run("mobilenet_v1", 128, 10, 3, channels_last=True)
+        # batch-norm + ReLU + activation quantizer in fused passes (csrc/bn_act_quant.cu): 8 instead of 13 passes over an
+        # activation per step.  Quantizer arithmetic unchanged; the batch statistics are summed in another order than
+        # cuDNN's, so results track the unfused step to fp32 summation accuracy, not bit for bit (tests/test_gpu_fused_bn.py)
+        qat["resnet18_int8_fused_bn"] = qat_run("resnet18", args.qat_batch, 20, 3, channels_last=True, graph=True, fuse_bn=True)
+        qat["mobilenet_v1_4b_fused_bn"] = qat_run("mobilenet_v1", 128, 20, 3, channels_last=True, graph=True, fuse_bn=True)
         # the same three workloads built by the REFERENCE's own, unmodified model code (brevitas.nn layers, injector,
         # proxies, brevitas_examples models) after brevitas_b200.install(): the drop-in a Brevitas user gets.  The host
         # framework is imported from the copy that travelled with the repository (a user has it pip-installed).
@@ -609,6 +614,10 @@ def main():
             r = qat.get(k + "_reference_frontend")
             if r is not None:
                 line["qat_scaling"][k]["unmodified_brevitas_nn_samples_per_s"] = r["samples_per_s"]
+            r = qat.get(k + "_fused_bn")
+            if r is not None:
+                line["qat_scaling"][k]["fused_bn_samples_per_s"] = r["samples_per_s"]
+                line["qat_scaling"][k]["fused_bn_ms_per_step"] = r["ms_per_step"]
     args.emit(line)
     if dist is not None:
         dist.destroy_process_group()
