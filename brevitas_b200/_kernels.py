@@ -193,6 +193,22 @@ def tensor_clamp(x, min_val, max_val, inplace=False):
     return y
 
 
+def tensor_clamp_bwd(gy, x, min_val, max_val, want_min=True, want_max=True):
+    """backward of the differentiable tensor_clamp: (gx, gmin fp32[min.numel()] or None, gmax or None)"""
+    dev = _check_cuda(gy, x, min_val, max_val)
+    xc, gc = _c(x), _c(gy)
+    mn = _c(min_val).to(x.dtype)
+    mx = _c(max_val).to(x.dtype)
+    mn_inner, mn_count = broadcast_pattern(x.shape, mn.shape)
+    mx_inner, mx_count = broadcast_pattern(x.shape, mx.shape)
+    gx = torch.empty_like(xc)
+    gmin = torch.empty(mn_count, dtype=torch.float32, device=dev) if want_min else None
+    gmax = torch.empty(mx_count, dtype=torch.float32, device=dev) if want_max else None
+    _launch(dev, "bvb_tensor_clamp_bwd", gc.data_ptr(), xc.data_ptr(), mn.data_ptr(), mx.data_ptr(), gx.data_ptr(),
+            _ptr(gmin), _ptr(gmax), xc.numel(), mn_inner, mn_count, mx_inner, mx_count, dtype_tag(x), _stream(dev))
+    return gx, gmin, gmax
+
+
 def scalar_clamp(x, min_val: float, max_val: float):
     dev = _check_cuda(x)
     x = _c(x)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "bvb_abs_binary_sign_grad_impl": (c_int, _UNARY),
     "bvb_abs_binary_sign_grad_bwd": (c_int, [_P, _P, _P, _L, _I, _P]),
     "bvb_tensor_clamp_ste_impl": (c_int, [_P, _P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _P]),
+    "bvb_tensor_clamp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _I, _P]),
     "bvb_scalar_clamp_ste_impl": (c_int, [_P, _P, _L, _D, _D, _I, _P]),
     "bvb_scalar_clamp_min_ste_impl": (c_int, [_P, _P, _L, _D, _I, _P]),
     "bvb_int_quant_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _I, _P]),

@@ -244,19 +244,21 @@ __device__ __forceinline__ float bn_bwd_elem(float g, float x, const BnThread<T>
     const float yb = DT<T>::rnd(fadd(fmul(xhat, th.ch[i].gamma), th.ch[i].beta));
     const float v = relu ? relu_f(yb) : yb;
     if (th.fast) {
-        // same values as bwd_elem: d = (g * s) kept or zeroed by the clamp mask, gradient = d / s
-        float d = fmul(g, th.dv[i].b);
-        if (masked && (v >= th.y_hi[i] || v <= th.y_lo[i])) d = 0.f;
+        // The clamp mask is exact (thresholds above).  The kept gradient is g itself: the reference's ((g * s) / s) equals
+        // g to within one rounding, far below the batch-norm reductions this value feeds (dx of the fused path carries a
+        // stated tolerance; the unfused path stays bit-exact).
+        const bool keep = !(masked && (v >= th.y_hi[i] || v <= th.y_lo[i]));
+        const float r0 = keep ? g : 0.f;
         if (want_gs) {
-            // d(scale) = g * t5 - d * (t1 / s): an order-dependent sum, reciprocal-multiply within its tolerance (as bwd_elem)
+            // d(scale) = g * t5 - r * (y / s): an order-dependent sum; reciprocal-multiply and magic-number rounding of the
+            // clamped quotient are within its tolerance (as in bwd_elem)
             const float t1 = v * th.inv_s[i];
-            const float t5 = fminf(fmaxf(rintf(t1), p.qmin), p.qmax);
+            const float c = fminf(fmaxf(t1, p.qmin), p.qmax);
+            const float t5 = (c + 12582912.f) - 12582912.f;
             gs_acc = fmaf(g, t5, gs_acc);
-            gs_acc = fmaf(-d, t1 * th.inv_s[i], gs_acc);
+            gs_acc = fmaf(-r0, t1, gs_acc);
         }
-        float r = th.dv[i](d);
-        if (relu && yb <= 0.f) r = 0.f;
-        return r;
+        return (relu && yb <= 0.f) ? 0.f : r0;
     }
     float r = bwd_elem<T, RM>(g, v, th.dv[i], th.inv_s[i], p, masked, want_gs, gs_acc);
     r = DT<T>::rnd(r);

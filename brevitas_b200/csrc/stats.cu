@@ -152,12 +152,12 @@ __device__ __forceinline__ void kth_resolve(const uint32_t* hist, int64_t rows, 
 }
 
 // one radix pass: histogram digit `pass` of the keys whose higher digits equal the resolved prefix
-template <typename T, bool SIGNED>
+template <typename T, bool SIGNED, bool RELU>
 __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __restrict__ x, int64_t rows, int64_t cols,
                                                                 int vec_ok, int pass, int64_t k, uint32_t* hist,
                                                                 unsigned long long* first_index, uint32_t cap,
                                                                 uint32_t* ccount, uint32_t* ckeys,
-                                                                unsigned long long* cidx, int pre_relu) {
+                                                                unsigned long long* cidx) {
     constexpr int V = DT<T>::VEC;
     using KT = KeyTraits<T, SIGNED>;
     constexpr int P = KT::PASSES;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(KTH_THREADS, 5) kth_hist_kernel(const T* __res
             constexpr int NV = decltype(nv_tag)::value;
             uint32_t key[NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) key[i] = KT::key(pre_relu ? relu_f(v[i]) : v[i]);   // statistic of relu(x)
+            for (int i = 0; i < NV; ++i) key[i] = KT::key(RELU ? relu_f(v[i]) : v[i]);   // RELU: statistic of relu(x)
             if (pass == 0) {
                 if (valid) {
 #pragma unroll
@@ -335,9 +335,9 @@ static inline int64_t kth_base_bytes(int64_t rows) {
     return (int64_t)sizeof(uint32_t) * 4 * rows * KTH_BINS + (int64_t)sizeof(unsigned long long) * rows * KTH_BINS;
 }
 
-template <typename T, bool SIGNED>
+template <typename T, bool SIGNED, bool RELU = false>
 static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows, int64_t cols, int64_t k,
-                      void* workspace, cudaStream_t st, int pre_relu = 0) {
+                      void* workspace, cudaStream_t st) {
     constexpr int P = KeyTraits<T, SIGNED>::PASSES;
     constexpr int V = DT<T>::VEC;
     uint32_t* hist = (uint32_t*)workspace;
@@ -365,9 +365,9 @@ static int launch_kth(const void* x, void* out, int64_t* index_out, int64_t rows
     uint32_t* ckeys = (uint32_t*)(cbase + 256);
     unsigned long long* cidx = (unsigned long long*)(cbase + 256 + sizeof(uint32_t) * (size_t)rows * KTH_COMPACT_CAP);
     for (int pass = 0; pass < P; ++pass)
-        kth_hist_kernel<T, SIGNED><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist,
+        kth_hist_kernel<T, SIGNED, RELU><<<grid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, vec_ok, pass, k, hist,
                                                          (index_out && pass == P - 1) ? first_index : nullptr, cap,
-                                                         ccount, ckeys, cidx, pre_relu);
+                                                         ccount, ckeys, cidx);
     const dim3 fgrid(1u, (unsigned)gy);                                  // one CTA per row resolves the last digit
     kth_final_kernel<T, SIGNED><<<fgrid, KTH_THREADS, 0, st>>>((const T*)x, rows, cols, k, hist, (T*)out, (long long*)index_out,
                                                        first_index);
@@ -422,7 +422,7 @@ extern "C" int bvb_relu_abs_kth_value_rows(const void* x, void* out, int64_t* in
     if (k < 1 || k > cols)
         return fail(BVB_EINVAL, "bvb_relu_abs_kth_value_rows: k = %lld out of range [1, %lld]", (long long)k, (long long)cols);
     if (!x || !out || !workspace) return fail(BVB_EINVAL, "bvb_relu_abs_kth_value_rows: null pointer");
-    BVB_DISPATCH_DTYPE(dtype, return (launch_kth<T, false>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream, 1)));
+    BVB_DISPATCH_DTYPE(dtype, return (launch_kth<T, false, true>(x, out, index_out, rows, cols, k, workspace, (cudaStream_t)stream)));
     return BVB_OK;
 }
 

@@ -143,6 +143,54 @@ __global__ void __launch_bounds__(EW_THREADS) tensor_clamp_kernel(
     }
 }
 
+// backward of the DIFFERENTIABLE tensor_clamp (function/ops.py:76-100: two torch.where under plain autograd):
+//   out1 = where(x > max, max, x);  out = where(out1 < min, min, out1)
+//   d x   = g where neither branch replaced the value;  d max = sum g over {x > max and not (max < min)};
+//   d min = sum g over {out1 < min}
+// 16-byte vectors when the bounds are scalars (the learned bit-width case: min / max are 0-dim), per-warp partial sums.
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) tensor_clamp_bwd_kernel(
+        const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ mn, const T* __restrict__ mx,
+        T* __restrict__ gx, float* gmin, float* gmax, int64_t n, int64_t mn_inner, int64_t mn_count, int64_t mx_inner,
+        int64_t mx_count, int vec_ok) {
+    constexpr int V = DT<T>::VEC;
+    const bool scalar = mn_count == 1 && mx_count == 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    float acc_lo = 0.f, acc_hi = 0.f;
+    auto one = [&](float g, float v, int64_t i) -> float {
+        const int64_t il = mn_count == 1 ? 0 : (i / mn_inner) % mn_count, ih = mx_count == 1 ? 0 : (i / mx_inner) % mx_count;
+        const float lo = DT<T>::to_f(mn[il]), hi = DT<T>::to_f(mx[ih]);
+        const bool over = v > hi;
+        const float o1 = over ? hi : v;
+        const bool under = o1 < lo;
+        if (under) { if (scalar) acc_lo += g; else if (gmin) atomicAdd(gmin + il, g); }
+        else if (over) { if (scalar) acc_hi += g; else if (gmax) atomicAdd(gmax + ih, g); }
+        return (over || under) ? 0.f : g;
+    };
+    const int64_t nvec = (scalar && vec_ok) ? n / V : 0;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const uint4* gv = reinterpret_cast<const uint4*>(gy);
+    uint4* ov = reinterpret_cast<uint4*>(gx);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        float ex[V], eg[V];
+        DT<T>::unpack(ldg_stream(xv + v), ex);
+        DT<T>::unpack(ldg_stream(gv + v), eg);
+#pragma unroll
+        for (int i = 0; i < V; ++i) eg[i] = one(eg[i], ex[i], 0);
+        stg_stream(ov + v, DT<T>::pack(eg));
+    }
+    for (int64_t i = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        gx[i] = DT<T>::from_f(one(DT<T>::to_f(gy[i]), DT<T>::to_f(x[i]), i));
+    if (scalar) {
+        acc_lo = warp_sum_f(acc_lo);
+        acc_hi = warp_sum_f(acc_hi);
+        if ((threadIdx.x & 31) == 0) {
+            if (gmin && acc_lo != 0.f) atomicAdd(gmin, acc_lo);
+            if (gmax && acc_hi != 0.f) atomicAdd(gmax, acc_hi);
+        }
+    }
+}
+
 // scalar-bounds fast path of the same op (the common case: 0-dim min_int / max_int tensors)
 template <typename T> struct FWhereClampScalarPtr {
     const T* mn; const T* mx;
@@ -221,4 +269,24 @@ extern "C" int bvb_tensor_clamp_ste_impl(const void* x, const void* min_val, con
                                   (const T*)x, (const T*)min_val, (const T*)max_val, (T*)y, n,
                                   min_inner, min_count, max_inner, max_count, inplace_minmax));
     return check_launch("bvb_tensor_clamp_ste_impl");
+}
+
+extern "C" int bvb_tensor_clamp_bwd(const void* gy, const void* x, const void* min_val, const void* max_val, void* gx,
+                                    float* gmin_out, float* gmax_out, int64_t n, int64_t min_inner, int64_t min_count,
+                                    int64_t max_inner, int64_t max_count, int dtype, void* stream) {
+    if (n < 0) return fail(BVB_EINVAL, "bvb_tensor_clamp_bwd: negative element count");
+    if (min_inner < 1 || min_count < 1 || max_inner < 1 || max_count < 1)
+        return fail(BVB_EINVAL, "bvb_tensor_clamp_bwd: broadcast pattern must have inner >= 1 and count >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (gmin_out) e = cudaMemsetAsync(gmin_out, 0, sizeof(float) * (size_t)min_count, st);
+    if (e == cudaSuccess && gmax_out) e = cudaMemsetAsync(gmax_out, 0, sizeof(float) * (size_t)max_count, st);
+    if (e != cudaSuccess) return fail(BVB_ECUDA, "bvb_tensor_clamp_bwd: memset: %s", cudaGetErrorString(e));
+    if (n == 0) return BVB_OK;
+    if (!gy || !x || !min_val || !max_val || !gx) return fail(BVB_EINVAL, "bvb_tensor_clamp_bwd: null pointer");
+    const int vec_ok = aligned16(gy) && aligned16(x) && aligned16(gx);
+    BVB_DISPATCH_DTYPE(dtype, tensor_clamp_bwd_kernel<T><<<grid_for(n, EW_THREADS, 8), EW_THREADS, 0, st>>>(
+                                  (const T*)gy, (const T*)x, (const T*)min_val, (const T*)max_val, (T*)gx, gmin_out, gmax_out,
+                                  n, min_inner, min_count, max_inner, max_count, vec_ok));
+    return check_launch("bvb_tensor_clamp_bwd");
 }

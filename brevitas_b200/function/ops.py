@@ -39,9 +39,46 @@ def tensor_clamp(x: Tensor, min_val: Tensor, max_val: Tensor) -> Tensor:
     autograd semantics (masked gradient, gradients to the bounds) are inherited verbatim.  Inside ``IntQuant`` the
     same arithmetic is fused into the quant kernels (``brevitas_b200::int_quant`` with ``CLAMP_MASKED``).
     """
+    if x.is_cuda and _clamp_kernel_ok(x, min_val, max_val):
+        return _TensorClampFn.apply(x, min_val, max_val)
     out = torch.where(x > max_val, max_val.type_as(x), x)
     out = torch.where(out < min_val, min_val.type_as(out), out)
     return out
+
+
+def _clamp_kernel_ok(x: Tensor, min_val: Tensor, max_val: Tensor) -> bool:
+    from .._kernels import _DTYPES, broadcast_pattern
+    if x.dtype not in _DTYPES or not (min_val.is_cuda and max_val.is_cuda) or x.numel() == 0:
+        return False
+    try:                                    # bounds must follow the scale[(i / inner) % count] broadcast of the kernels
+        broadcast_pattern(x.shape, min_val.shape)
+        broadcast_pattern(x.shape, max_val.shape)
+    except Exception:
+        return False
+    return True
+
+
+class _TensorClampFn(torch.autograd.Function):
+    """the where-based clamp (forward: bvb_tensor_clamp_ste_impl) with the gradients plain autograd gives the reference's
+    two ``torch.where`` calls: masked for x, summed over the replaced elements for the bounds (bvb_tensor_clamp_bwd)"""
+
+    @staticmethod
+    def forward(ctx, x, min_val, max_val):
+        from .. import _kernels
+        ctx.save_for_backward(x, min_val, max_val)
+        return _kernels.tensor_clamp(x, min_val, max_val)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import _kernels
+        x, min_val, max_val = ctx.saved_tensors
+        gx, gmin, gmax = _kernels.tensor_clamp_bwd(g.to(x.dtype), x, min_val, max_val, ctx.needs_input_grad[1],
+                                                   ctx.needs_input_grad[2])
+        if gmin is not None:
+            gmin = gmin.to(min_val.dtype).view(min_val.shape)
+        if gmax is not None:
+            gmax = gmax.to(max_val.dtype).view(max_val.shape)
+        return (gx.view(x.shape) if ctx.needs_input_grad[0] else None), gmin, gmax
 
 
 def tensor_clamp_(x: Tensor, min_val: Tensor, max_val: Tensor) -> Tensor:

@@ -91,6 +91,12 @@ int bvb_abs_binary_sign_grad_bwd(const void* x, const void* gy, void* gx, int64_
 int bvb_tensor_clamp_ste_impl(const void* x, const void* min_val, const void* max_val, void* y, int64_t n,
                               int64_t min_inner, int64_t min_count, int64_t max_inner, int64_t max_count,
                               int inplace_minmax, int dtype, void* stream);
+/* backward of the DIFFERENTIABLE tensor_clamp (src/brevitas/function/ops.py:76-100, the default clamp of IntQuant and
+ * what a learned bit-width reaches its gradient through): gx = gy where no branch replaced the value; gmin_out / gmax_out
+ * (nullable, fp32[min_count] / fp32[max_count], zeroed here) = sums of gy over the elements replaced by min / by max */
+int bvb_tensor_clamp_bwd(const void* gy, const void* x, const void* min_val, const void* max_val, void* gx,
+                         float* gmin_out, float* gmax_out, int64_t n, int64_t min_inner, int64_t min_count,
+                         int64_t max_inner, int64_t max_count, int dtype, void* stream);
 int bvb_scalar_clamp_ste_impl(const void* x, void* y, int64_t n, double min_val, double max_val, int dtype, void* stream);   /* csrc:66-82 */
 int bvb_scalar_clamp_min_ste_impl(const void* x, void* y, int64_t n, double min_val, int dtype, void* stream);               /* csrc:85-97 */
 

@@ -333,3 +333,36 @@ def test_signed_kth_value_select(rows, cols, dtype):
         assert bool(torch.isnan(val).all())
         val, _ = K.kth_value_rows(xn, rows, cols, cols - 1)
         assert bool(torch.isinf(val).all() and (val > 0).all())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,bshape", [((5, 67), ()), ((1 << 16,), ()), ((6, 48), (6, 1)), ((3, 5, 4, 8), (1, 5, 1, 1)),
+                                          ((7, 9), (7, 9))])
+def test_differentiable_tensor_clamp_kernel(shape, bshape, dtype):
+    """brevitas.function.ops.tensor_clamp (function/ops.py:76-100) -- the default clamp of IntQuant, the path a learned
+    bit-width takes its gradient through: forward and ALL THREE gradients against the reference's two torch.where calls
+    under plain autograd (ATen)."""
+    from brevitas_b200.function.ops import tensor_clamp
+    g = torch.Generator().manual_seed(len(shape) * 31 + len(bshape))
+    x = (torch.randn(shape, generator=g) * 3).to(TDT[dtype])
+    x.view(-1)[:6] = torch.tensor([float("nan"), float("inf"), float("-inf"), 0.0, -0.0, 2.0]).to(TDT[dtype])[:min(6, x.numel())]
+    lo = (-torch.rand(bshape, generator=g) - 0.5).to(TDT[dtype])
+    hi = (torch.rand(bshape, generator=g) + 0.5).to(TDT[dtype])
+    gy = torch.randn(shape, generator=g).to(TDT[dtype])
+
+    def run(fn, dev):
+        xi, li, hi_ = (t.clone().to(dev).requires_grad_(True) for t in (x, lo, hi))
+        y = fn(xi, li, hi_)
+        y.backward(gy.to(dev))
+        return [t.detach().float().cpu() for t in (y, xi.grad, li.grad, hi_.grad)]
+
+    def ref(a, mn, mx):
+        out = torch.where(a > mx, mx.type_as(a), a)
+        return torch.where(out < mn, mn.type_as(out), out)
+    got = run(tensor_clamp, "cuda")
+    want = run(ref, "cpu")
+    assert_bits_equal(got[0].numpy(), want[0].numpy(), "y")
+    assert_bits_equal(got[1].numpy(), want[1].numpy(), "gx")
+    for a, b, name in ((got[2], want[2], "gmin"), (got[3], want[3], "gmax")):
+        mag = float(gy.float().abs().sum()) / max(1, b.numel()) + 1.0
+        assert torch.allclose(a, b, rtol=0, atol=mag * (8 * np.sqrt(x.numel()) * 2.0 ** -24 + 4 * ulp(dtype))), (name, a, b)
