@@ -95,6 +95,12 @@ class AbsPercentile(nn.Module):
 # ATen reductions the reference issues on statistics-sized outputs -----------------
 def _kth_signed(x: Tensor, k: int, dim: Optional[int]) -> Tensor:
     """``x.view(-1).kthvalue(k).values`` (dim None) or ``x.kthvalue(k, dim).values`` of a 2-D x"""
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        # integer / fp64 statistics inputs (the reference's own tests feed integer tensors, tests/brevitas/core/
+        # test_stats.py:44-72): ATen's kthvalue, as the reference
+        if dim is None:
+            return x.view(-1).kthvalue(k).values
+        return x.kthvalue(k, dim=dim).values
     if dim is None:
         val, _ = torch.ops.brevitas_b200.kth_value_rows(x.reshape(-1), 1, x.numel(), k)
         return val.view(())
