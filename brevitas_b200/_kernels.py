@@ -474,7 +474,7 @@ def bn_act_quant_supported(x: torch.Tensor) -> bool:
 
 
 def bn_act_quant_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, training, scale, zero_point, qmin, qmax,
-                     relu=True):
+                     relu=True, residual=None):
     """returns (y like x, save_mean, save_invstd); running statistics are updated in place when training"""
     dev = _check_cuda(x, scale)
     c = x.shape[1]
@@ -488,7 +488,9 @@ def bn_act_quant_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, t
         save_invstd = torch.rsqrt(running_var.float() + eps).contiguous()
     ws = _bn_workspace(dev, c)
     scale = _c(scale)
-    _launch(dev, "bvb_bn_act_quant_fwd", x.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(running_mean) if training else None,
+    if residual is not None and (residual.shape != x.shape or residual.stride() != x.stride() or residual.dtype != x.dtype):
+        raise RuntimeError("bn_act_quant: the residual must have the shape, strides and dtype of x")
+    _launch(dev, "bvb_bn_act_quant_fwd", x.data_ptr(), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(running_mean) if training else None,
             _ptr(running_var) if training else None, float(momentum), float(eps), 0 if training else 1, scale.data_ptr(),
             scale.numel(), dtype_tag(scale), y.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), rows, c,
             float(zero_point), float(qmin), float(qmax), _lib.ROUND, 1 if relu else 0, dtype_tag(x), ws.data_ptr(),
@@ -497,7 +499,7 @@ def bn_act_quant_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, t
 
 
 def bn_act_quant_bwd(gy, x, gamma, beta, save_mean, save_invstd, scale, zero_point, qmin, qmax, clamp_mode, relu=True,
-                     want_gscale=True):
+                     want_gscale=True, residual=None, want_gresidual=False):
     dev = _check_cuda(gy, x, scale)
     c = x.shape[1]
     rows = x.numel() // c
@@ -509,8 +511,9 @@ def bn_act_quant_bwd(gy, x, gamma, beta, save_mean, save_invstd, scale, zero_poi
     scale = _c(scale)
     gscale = torch.empty(scale.numel(), dtype=torch.float32, device=dev) if want_gscale else None
     ws = _bn_workspace(dev, c)
-    _launch(dev, "bvb_bn_act_quant_bwd", gy.data_ptr(), x.data_ptr(), _ptr(gamma), _ptr(beta), save_mean.data_ptr(),
+    gres = torch.empty_like(x) if (residual is not None and want_gresidual) else None
+    _launch(dev, "bvb_bn_act_quant_bwd", gy.data_ptr(), x.data_ptr(), _ptr(residual), _ptr(gres), _ptr(gamma), _ptr(beta), save_mean.data_ptr(),
             save_invstd.data_ptr(), scale.data_ptr(), scale.numel(), dtype_tag(scale), gx.data_ptr(), ggamma.data_ptr(),
             gbeta.data_ptr(), _ptr(gscale), rows, c, float(zero_point), float(qmin), float(qmax), _lib.ROUND, int(clamp_mode),
             1 if relu else 0, dtype_tag(x), ws.data_ptr(), _stream(dev))
-    return gx, ggamma, gbeta, gscale
+    return gx, ggamma, gbeta, gscale, gres

@@ -63,8 +63,8 @@ SIGNATURES = {
     "bvb_tensor_absmax_int_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P]),
     "bvb_workspace_bytes": (c_int64, []),
     "bvb_bn_act_quant_workspace_bytes": (c_int64, [_L]),
-    "bvb_bn_act_quant_fwd": (c_int, [_P, _P, _P, _P, _P, _F, _F, _I, _P, _L, _I, _P, _P, _P, _L, _L, _F, _F, _F, _I, _I, _I, _P, _P]),
-    "bvb_bn_act_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _L, _L, _F, _F, _F, _I, _I, _I, _I, _P, _P]),
+    "bvb_bn_act_quant_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _F, _F, _I, _P, _L, _I, _P, _P, _P, _L, _L, _F, _F, _F, _I, _I, _I, _P, _P]),
+    "bvb_bn_act_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _L, _L, _F, _F, _F, _I, _I, _I, _I, _P, _P]),
     "bvb_binary_quant_fwd": (c_int, [_P, _P, _P, _L, _L, _L, _I, _I, _I, _P]),
     "bvb_binary_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _P]),
     "bvb_absmax_rows": (c_int, [_P, _P, _L, _L, _I, _P]),

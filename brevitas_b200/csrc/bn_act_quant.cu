@@ -202,32 +202,39 @@ struct BnThread {
 // ---- forward 3: normalise, ReLU, quantize ---------------------------------------------------------------------------
 template <typename T, int RM>
 __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_apply_kernel(
-        const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
-        const float* __restrict__ gamma, const float* __restrict__ beta, const void* __restrict__ scale, int scale_count,
-        int scale_f32, int64_t rows, int cv_n, int rl_n, int relu, QParams p) {
+        const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, const float* __restrict__ mean,
+        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+        const void* __restrict__ scale, int scale_count, int scale_f32, int64_t rows, int cv_n, int rl_n, int relu,
+        QParams p) {
     constexpr int V = DT<T>::VEC;
     const int cv = threadIdx.x % cv_n, rlane = threadIdx.x / cv_n;
     const BnThread<T> th(cv * V, mean, invstd, gamma, beta, scale, scale_count, scale_f32);
     const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const uint4* rv = reinterpret_cast<const uint4*>(res);       // nullable: y = quant(relu(bn(x) + res))
     uint4* yv = reinterpret_cast<uint4*>(y);
     const int64_t rstride = (int64_t)gridDim.x * rl_n;
     for (int64_t r0 = (int64_t)blockIdx.x * rl_n + rlane; r0 < rows; r0 += rstride * BN_UNROLL) {
-        uint4 q[BN_UNROLL];
+        uint4 q[BN_UNROLL], qr[BN_UNROLL];
         bool ok[BN_UNROLL];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL; ++u) {
             const int64_t r = r0 + (int64_t)u * rstride;
             ok[u] = r < rows;
-            if (ok[u]) q[u] = ldg_stream(xv + r * cv_n + cv);
+            if (ok[u]) {
+                q[u] = ldg_stream(xv + r * cv_n + cv);
+                if (rv) qr[u] = ldg_stream(rv + r * cv_n + cv);
+            }
         }
 #pragma unroll
         for (int u = 0; u < BN_UNROLL; ++u) {
             if (!ok[u]) continue;
-            float e[V];
+            float e[V], er[V];
             DT<T>::unpack(q[u], e);
+            if (rv) DT<T>::unpack(qr[u], er);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float v = DT<T>::rnd(bn_apply(e[i], th.ch[i]));
+                if (rv) v = DT<T>::rnd(fadd(v, er[i]));
                 if (relu) v = relu_f(v);
                 e[i] = quant_dequant<T, RM>(v, th.dv[i], p);
             }
@@ -239,9 +246,11 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_apply
 // one element of the backward up to the batch-norm output: returns d(loss)/d(bn output); accumulates d(scale)
 template <typename T, int RM>
 __device__ __forceinline__ float bn_bwd_elem(float g, float x, const BnThread<T>& th, int i, const QParams& p, int masked,
-                                             int relu, bool want_gs, float& gs_acc, float& xhat) {
+                                             int relu, bool want_gs, float& gs_acc, float& xhat, bool has_res = false,
+                                             float res = 0.f) {
     xhat = fmul(fsub(x, th.ch[i].mean), th.ch[i].invstd);
-    const float yb = DT<T>::rnd(fadd(fmul(xhat, th.ch[i].gamma), th.ch[i].beta));
+    float yb = DT<T>::rnd(fadd(fmul(xhat, th.ch[i].gamma), th.ch[i].beta));
+    if (has_res) yb = DT<T>::rnd(fadd(yb, res));
     const float v = relu ? relu_f(yb) : yb;
     if (th.fast) {
         // The clamp mask is exact (thresholds above).  The kept gradient is g itself: the reference's ((g * s) / s) equals
@@ -269,10 +278,10 @@ __device__ __forceinline__ float bn_bwd_elem(float g, float x, const BnThread<T>
 // ---- backward 1: per-channel sum(gy), sum(gy * xhat), d(scale) -------------------------------------------------------
 template <typename T, int RM>
 __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_reduce_kernel(
-        const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-        const float* __restrict__ gamma, const float* __restrict__ beta, const void* __restrict__ scale, int scale_count,
-        int scale_f32, float* __restrict__ partial, int64_t rows, int C, int cv_n, int rl_n, int relu, int masked,
-        int want_gs, QParams p) {
+        const T* __restrict__ g, const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
+        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+        const void* __restrict__ scale, int scale_count, int scale_f32, float* __restrict__ partial, int64_t rows, int C,
+        int cv_n, int rl_n, int relu, int masked, int want_gs, QParams p) {
     constexpr int V = DT<T>::VEC;
     __shared__ float smem[3 * BN_THREADS * V];
     const int cv = threadIdx.x % cv_n, rlane = threadIdx.x / cv_n;
@@ -282,9 +291,10 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_r
     for (int i = 0; i < V; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     const uint4* gv = reinterpret_cast<const uint4*>(g);
+    const uint4* rv = reinterpret_cast<const uint4*>(res);
     const int64_t rstride = (int64_t)gridDim.x * rl_n;
     for (int64_t r0 = (int64_t)blockIdx.x * rl_n + rlane; r0 < rows; r0 += rstride * (BN_UNROLL / 2)) {
-        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2];
+        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2], qr[BN_UNROLL / 2];
         bool ok[BN_UNROLL / 2];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
@@ -293,18 +303,21 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_r
             if (ok[u]) {
                 qx[u] = ldg_stream(xv + r * cv_n + cv);
                 qg[u] = ldg_stream(gv + r * cv_n + cv);
+                if (rv) qr[u] = ldg_stream(rv + r * cv_n + cv);
             }
         }
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
             if (!ok[u]) continue;
-            float ex[V], eg[V];
+            float ex[V], eg[V], er[V];
             DT<T>::unpack(qx[u], ex);
             DT<T>::unpack(qg[u], eg);
+            if (rv) DT<T>::unpack(qr[u], er);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float xhat;
-                const float r = bn_bwd_elem<T, RM>(eg[i], ex[i], th, i, p, masked, relu, want_gs != 0, acc[2][i], xhat);
+                const float r = bn_bwd_elem<T, RM>(eg[i], ex[i], th, i, p, masked, relu, want_gs != 0, acc[2][i], xhat,
+                                                   rv != nullptr, rv ? er[i] : 0.f);
                 acc[0][i] += r;
                 acc[1][i] = fmaf(r, xhat, acc[1][i]);
             }
@@ -347,7 +360,8 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_scalar_gscale_kernel(const flo
 // ---- backward 3: dx = gamma * invstd * (gy - mean(gy) - xhat * mean(gy * xhat)) --------------------------------------
 template <typename T, int RM>
 __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_dx_kernel(
-        const T* __restrict__ g, const T* __restrict__ x, T* __restrict__ gx, const float* __restrict__ mean,
+        const T* __restrict__ g, const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ gx,
+        T* __restrict__ gres, const float* __restrict__ mean,
         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
         const void* __restrict__ scale, int scale_count, int scale_f32, const float* __restrict__ gbeta,
         const float* __restrict__ ggamma, float inv_count, int64_t rows, int cv_n, int rl_n, int relu, int masked,
@@ -364,10 +378,12 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_d
     }
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     const uint4* gv = reinterpret_cast<const uint4*>(g);
+    const uint4* rv = reinterpret_cast<const uint4*>(res);
     uint4* ov = reinterpret_cast<uint4*>(gx);
+    uint4* orv = reinterpret_cast<uint4*>(gres);                 // nullable: gradient of the residual input
     const int64_t rstride = (int64_t)gridDim.x * rl_n;
     for (int64_t r0 = (int64_t)blockIdx.x * rl_n + rlane; r0 < rows; r0 += rstride * (BN_UNROLL / 2)) {
-        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2];
+        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2], qr[BN_UNROLL / 2];
         bool ok[BN_UNROLL / 2];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
@@ -376,27 +392,33 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_d
             if (ok[u]) {
                 qx[u] = ldg_stream(xv + r * cv_n + cv);
                 qg[u] = ldg_stream(gv + r * cv_n + cv);
+                if (rv) qr[u] = ldg_stream(rv + r * cv_n + cv);
             }
         }
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
             if (!ok[u]) continue;
-            float ex[V], eg[V];
+            float ex[V], eg[V], er[V];
             DT<T>::unpack(qx[u], ex);
             DT<T>::unpack(qg[u], eg);
+            if (rv) DT<T>::unpack(qr[u], er);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float xhat, unused = 0.f;
-                const float r = bn_bwd_elem<T, RM>(eg[i], ex[i], th, i, p, masked, relu, false, unused, xhat);
+                const float r = bn_bwd_elem<T, RM>(eg[i], ex[i], th, i, p, masked, relu, false, unused, xhat,
+                                                   rv != nullptr, rv ? er[i] : 0.f);
+                er[i] = r;                                      // d(loss) / d(residual) = d(loss) / d(bn output)
                 eg[i] = fmul(a[i], fsub(fsub(r, mb[i]), fmul(xhat, mg[i])));
             }
-            stg_stream(ov + (r0 + (int64_t)u * rstride) * cv_n + cv, DT<T>::pack(eg));
+            const int64_t o = (r0 + (int64_t)u * rstride) * cv_n + cv;
+            stg_stream(ov + o, DT<T>::pack(eg));
+            if (orv) stg_stream(orv + o, DT<T>::pack(er));
         }
     }
 }
 
 template <typename T>
-static int launch_bn_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+static int launch_bn_fwd(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
                          float momentum, float eps, int use_running, const void* scale, int64_t scale_count,
                          int scale_f32, void* y, float* save_mean, float* save_invstd, int64_t rows, int64_t channels,
                          const QParams& p, int relu, float* workspace, cudaStream_t st) {
@@ -412,13 +434,14 @@ static int launch_bn_fwd(const void* x, const float* gamma, const float* beta, f
         bn_fwd_finalize_kernel<<<(C + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, st>>>(
             workspace, (int)g.grid, C, inv_count, unbias, eps, momentum, save_mean, save_invstd, running_mean, running_var);
     }
+    if (res && !aligned16(res)) return fail(BVB_EUNSUPPORTED, "bvb_bn_act_quant_fwd: residual not 16-byte aligned");
     bn_act_quant_apply_kernel<T, RM_ROUND><<<g.grid, BN_THREADS, 0, st>>>(
-        (const T*)x, (T*)y, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, rows, g.cv, g.rl, relu, p);
+        (const T*)x, (const T*)res, (T*)y, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, rows, g.cv, g.rl, relu, p);
     return check_launch("bvb_bn_act_quant_fwd");
 }
 
 template <typename T>
-static int launch_bn_bwd(const void* gy, const void* x, const float* gamma, const float* beta, const float* save_mean,
+static int launch_bn_bwd(const void* gy, const void* x, const void* res, void* gres, const float* gamma, const float* beta, const float* save_mean,
                          const float* save_invstd, const void* scale, int64_t scale_count, int scale_f32, void* gx,
                          float* ggamma, float* gbeta, float* gscale, int64_t rows, int64_t channels, const QParams& p,
                          int relu, int masked, float* workspace, cudaStream_t st) {
@@ -426,8 +449,10 @@ static int launch_bn_bwd(const void* gy, const void* x, const float* gamma, cons
     if (!g.ok || !aligned16(x) || !aligned16(gy) || !aligned16(gx))
         return fail(BVB_EUNSUPPORTED, "bvb_bn_act_quant_bwd: unsupported channel count %lld or alignment", (long long)channels);
     const int C = (int)channels;
+    if ((res && !aligned16(res)) || (gres && !aligned16(gres)))
+        return fail(BVB_EUNSUPPORTED, "bvb_bn_act_quant_bwd: residual tensors not 16-byte aligned");
     bn_act_quant_bwd_reduce_kernel<T, RM_ROUND><<<g.grid, BN_THREADS, 0, st>>>(
-        (const T*)gy, (const T*)x, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, workspace, rows,
+        (const T*)gy, (const T*)x, (const T*)res, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, workspace, rows,
         C, g.cv, g.rl, relu, masked, gscale != nullptr, p);
     // d(scale): per channel straight into gscale, or (one scale) into scratch behind the partials and then summed
     float* gs_channel = !gscale ? nullptr : (scale_count > 1 ? gscale : workspace + (size_t)g.grid * BN_SLOTS * C);
@@ -435,7 +460,7 @@ static int launch_bn_bwd(const void* gy, const void* x, const float* gamma, cons
         workspace, (int)g.grid, C, gbeta, ggamma, gs_channel);
     if (gscale && scale_count == 1) bn_scalar_gscale_kernel<<<1, FIN_THREADS, 0, st>>>(gs_channel, C, gscale);
     bn_act_quant_bwd_dx_kernel<T, RM_ROUND><<<g.grid, BN_THREADS, 0, st>>>(
-        (const T*)gy, (const T*)x, (T*)gx, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, gbeta,
+        (const T*)gy, (const T*)x, (const T*)res, (T*)gx, (T*)gres, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, gbeta,
         ggamma, (float)(1.0 / (double)rows), rows, g.cv, g.rl, relu, masked, p);
     return check_launch("bvb_bn_act_quant_bwd");
 }
@@ -449,7 +474,7 @@ extern "C" int64_t bvb_bn_act_quant_workspace_bytes(int64_t channels) {
     return (int64_t)sizeof(float) * channels * (BN_SLOTS * (int64_t)sm_count() * BN_CTAS_PER_SM + 1);
 }
 
-extern "C" int bvb_bn_act_quant_fwd(const void* x, const float* gamma, const float* beta, float* running_mean,
+extern "C" int bvb_bn_act_quant_fwd(const void* x, const void* residual, const float* gamma, const float* beta, float* running_mean,
                                     float* running_var, float momentum, float eps, int use_running_stats,
                                     const void* scale, int64_t scale_count, int scale_dtype, void* y, float* save_mean,
                                     float* save_invstd, int64_t rows, int64_t channels, float zero_point, float qmin,
@@ -465,14 +490,15 @@ extern "C" int bvb_bn_act_quant_fwd(const void* x, const float* gamma, const flo
         return fail(BVB_EINVAL, "bvb_bn_act_quant_fwd: scale dtype must match (a one-element scale may be fp32)");
     const QParams p = make_qparams(zero_point, qmin, qmax, dtype);
     const int scale_f32 = (scale_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;
-    BVB_DISPATCH_DTYPE(dtype, return launch_bn_fwd<T>(x, gamma, beta, running_mean, running_var, momentum, eps,
+    BVB_DISPATCH_DTYPE(dtype, return launch_bn_fwd<T>(x, residual, gamma, beta, running_mean, running_var, momentum, eps,
                                                       use_running_stats, scale, scale_count, scale_f32, y, save_mean,
                                                       save_invstd, rows, channels, p, relu, (float*)workspace,
                                                       (cudaStream_t)stream));
     return BVB_OK;
 }
 
-extern "C" int bvb_bn_act_quant_bwd(const void* gy, const void* x, const float* gamma, const float* beta,
+extern "C" int bvb_bn_act_quant_bwd(const void* gy, const void* x, const void* residual, void* gresidual,
+                                    const float* gamma, const float* beta,
                                     const float* save_mean, const float* save_invstd, const void* scale,
                                     int64_t scale_count, int scale_dtype, void* gx, float* ggamma, float* gbeta,
                                     float* gscale, int64_t rows, int64_t channels, float zero_point, float qmin, float qmax,
@@ -486,7 +512,7 @@ extern "C" int bvb_bn_act_quant_bwd(const void* gy, const void* x, const float* 
         return fail(BVB_EINVAL, "bvb_bn_act_quant_bwd: one scale or one per channel");
     const QParams p = make_qparams(zero_point, qmin, qmax, dtype);
     const int scale_f32 = (scale_dtype == BVB_F32 && dtype != BVB_F32) ? 1 : 0;
-    BVB_DISPATCH_DTYPE(dtype, return launch_bn_bwd<T>(gy, x, gamma, beta, save_mean, save_invstd, scale, scale_count,
+    BVB_DISPATCH_DTYPE(dtype, return launch_bn_bwd<T>(gy, x, residual, gresidual, gamma, beta, save_mean, save_invstd, scale, scale_count,
                                                       scale_f32, gx, ggamma, gbeta, gscale, rows, channels, p, relu,
                                                       clamp_mode == BVB_CLAMP_MASKED, (float*)workspace,
                                                       (cudaStream_t)stream));

@@ -25,26 +25,27 @@ from . import _lib
 
 class _BnActQuantFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, running_mean, running_var, momentum, eps, training, zero_point, qmin, qmax,
-                clamp_mode, relu):
+    def forward(ctx, x, gamma, beta, scale, residual, running_mean, running_var, momentum, eps, training, zero_point, qmin,
+                qmax, clamp_mode, relu):
         y, save_mean, save_invstd = K.bn_act_quant_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, training,
-                                                       scale, zero_point, qmin, qmax, relu)
-        ctx.save_for_backward(x, gamma, beta, scale, save_mean, save_invstd)
+                                                       scale, zero_point, qmin, qmax, relu, residual)
+        ctx.save_for_backward(x, gamma, beta, scale, save_mean, save_invstd, residual)
         ctx.cfg = (zero_point, qmin, qmax, clamp_mode, relu, training)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, gamma, beta, scale, save_mean, save_invstd = ctx.saved_tensors
+        x, gamma, beta, scale, save_mean, save_invstd, residual = ctx.saved_tensors
         zero_point, qmin, qmax, clamp_mode, relu, training = ctx.cfg
         if not training:
             raise RuntimeError("bn_act_quant: backward through eval-mode batch-norm is not fused; call act(bn(x))")
         want_gs = ctx.needs_input_grad[3]
-        gx, ggamma, gbeta, gscale = K.bn_act_quant_bwd(gy, x, gamma, beta, save_mean, save_invstd, scale, zero_point, qmin,
-                                                       qmax, clamp_mode, relu, want_gs)
+        gx, ggamma, gbeta, gscale, gres = K.bn_act_quant_bwd(
+            gy, x, gamma, beta, save_mean, save_invstd, scale, zero_point, qmin, qmax, clamp_mode, relu, want_gs, residual,
+            residual is not None and ctx.needs_input_grad[4])
         if gscale is not None:
             gscale = gscale.to(scale.dtype).view(scale.shape)
-        return (gx, ggamma if gamma is not None else None, gbeta if beta is not None else None, gscale,
+        return (gx, ggamma if gamma is not None else None, gbeta if beta is not None else None, gscale, gres,
                 None, None, None, None, None, None, None, None, None, None)
 
 
@@ -56,8 +57,9 @@ def _tensor_quant_of(act: nn.Module):
     return proxy, fq, getattr(fq, "tensor_quant", None)
 
 
-def bn_act_quant(bn: nn.Module, act: nn.Module, x: torch.Tensor):
-    """``act(bn(x))`` -- fused when possible (see the module docstring), the unfused pair otherwise"""
+def bn_act_quant(bn: nn.Module, act: nn.Module, x: torch.Tensor, residual: Optional[torch.Tensor] = None):
+    """``act(bn(x))`` -- or ``act(bn(x) + residual)``, the closing block of a ResNet BasicBlock -- fused when possible
+    (see the module docstring), the unfused modules otherwise"""
     from .core.quant import RescalingIntQuant, _NoDelay
     proxy, fq, tq = _tensor_quant_of(act)
     ok = (isinstance(x, torch.Tensor) and type(bn) is nn.BatchNorm2d and tq is not None and type(tq) is RescalingIntQuant
@@ -77,14 +79,15 @@ def bn_act_quant(bn: nn.Module, act: nn.Module, x: torch.Tensor):
         zp, qmin, qmax, rm, cm, _ = cfg
         scale = tq.scaling_impl(x) / tq.int_scaling_impl(bit_width)
         ok = scale.dtype == x.dtype and scale.numel() in (1, x.shape[1])
-    if not ok:
-        return act(bn(x))
-    if bn.training and bn.momentum is None:
-        return act(bn(x))                                  # cumulative moving average: left to torch
+    if ok and residual is not None:
+        ok = (isinstance(residual, torch.Tensor) and residual.shape == x.shape and residual.dtype == x.dtype
+              and residual.stride() == x.stride())
+    if not ok or (bn.training and bn.momentum is None):    # (cumulative moving average: left to torch)
+        return act(bn(x)) if residual is None else act(bn(x) + residual)
     if bn.training:
         bn.num_batches_tracked.add_(1)
     relu = type(fq.activation_impl) is nn.ReLU
-    y = _BnActQuantFn.apply(x, bn.weight, bn.bias, scale, bn.running_mean, bn.running_var,
+    y = _BnActQuantFn.apply(x, bn.weight, bn.bias, scale, residual, bn.running_mean, bn.running_var,
                             bn.momentum if bn.momentum is not None else 0.0, bn.eps, bn.training, zp, qmin, qmax, cm, relu)
     if not getattr(act, "return_quant_tensor", False):
         return y

@@ -227,10 +227,13 @@ int bvb_binary_quant_bwd(const void* gy, const void* x, const void* scale, void*
  * backward.  Eval mode (use_running_stats = 1): save_mean / save_invstd are INPUTS (running mean, 1/sqrt(running_var +
  * eps)).  y = quant_dequant(relu(((x - mean) * invstd) * gamma + beta)) with the provided scale: one element, or one per
  * channel (`scale_count` = 1 or channels).  gamma / beta: fp32[channels] or NULL (1 / 0).  round-half-even only.
+ * `residual` (nullable, same shape and dtype as x): y = quant_dequant(relu(bn(x) + residual)), the closing block of a
+ * ResNet BasicBlock (`relu(bn2(conv2(.)) + identity)`); the backward then also returns `gresidual` (nullable) = the
+ * gradient of that input, which equals the gradient of the batch-norm output.
  * Requires channels * sizeof(T) / 16 to divide 256 (BVB_EUNSUPPORTED otherwise: callers use the unfused pair).
  * workspace >= bvb_bn_act_quant_workspace_bytes(channels) bytes of device scratch. */
 int64_t bvb_bn_act_quant_workspace_bytes(int64_t channels);
-int bvb_bn_act_quant_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+int bvb_bn_act_quant_fwd(const void* x, const void* residual, const float* gamma, const float* beta, float* running_mean, float* running_var,
                          float momentum, float eps, int use_running_stats, const void* scale, int64_t scale_count,
                          int scale_dtype, void* y, float* save_mean, float* save_invstd, int64_t rows, int64_t channels,
                          float zero_point, float qmin, float qmax, int round_mode, int relu, int dtype, void* workspace,
@@ -238,7 +241,7 @@ int bvb_bn_act_quant_fwd(const void* x, const float* gamma, const float* beta, f
 /* backward of the above in training mode: gx = d/dx, ggamma / gbeta (fp32[channels]), gscale (nullable, fp32[scale_count])
  * = d/d(scale) of the quantizer; the quantizer part is bvb_relu_int_quant_bwd's arithmetic on the recomputed
  * normalised value (clamp_mode: BVB_CLAMP_STE / BVB_CLAMP_MASKED) */
-int bvb_bn_act_quant_bwd(const void* gy, const void* x, const float* gamma, const float* beta, const float* save_mean,
+int bvb_bn_act_quant_bwd(const void* gy, const void* x, const void* residual, void* gresidual, const float* gamma, const float* beta, const float* save_mean,
                          const float* save_invstd, const void* scale, int64_t scale_count, int scale_dtype, void* gx,
                          float* ggamma, float* gbeta, float* gscale, int64_t rows, int64_t channels, float zero_point,
                          float qmin, float qmax, int round_mode, int clamp_mode, int relu, int dtype, void* workspace,

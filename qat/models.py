@@ -150,9 +150,11 @@ class BasicBlock(nn.Module):
             out = bn_act_quant(self.bn1, self.relu1, self.conv1(x))
         else:
             out = self.relu1(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
         if self.downsample is not None:
             identity = self.downsample(x)
+        if self.fuse_bn:          # relu(bn(.) + identity) with its quantizer: the residual variant of the fused passes
+            return bn_act_quant(self.bn2, self.relu2, self.conv2(out), residual=identity)
+        out = self.bn2(self.conv2(out))
         return self.relu2(out + identity)
 
 

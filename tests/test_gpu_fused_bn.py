@@ -120,3 +120,36 @@ def test_models_with_fused_bn_track_the_unfused_models(name, shape):
     gb = torch.cat([p.grad.reshape(-1) for p in b.parameters() if p.grad is not None])
     cos = float(torch.nn.functional.cosine_similarity(ga, gb, dim=0))
     assert cos > 0.98, cos
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 28, 28), (4, 256, 14, 14)])
+def test_fused_bn_residual_variant(shape):
+    """relu(bn(x) + identity) followed by its quantizer -- the closing block of a ResNet BasicBlock -- in fused passes;
+    the residual input gets the gradient of the batch-norm output"""
+    from brevitas_b200.fused_bn import bn_act_quant
+    torch.manual_seed(7)
+    bn_a, act_a = make(shape[1], False)
+    bn_b, act_b = make(shape[1], False)
+    bn_b.load_state_dict(bn_a.state_dict())
+    act_b.load_state_dict(act_a.state_dict())
+    g = torch.Generator().manual_seed(2)
+    mk = lambda s=1.0: (torch.randn(shape, generator=g) * s).cuda().contiguous(memory_format=torch.channels_last)
+    x, r, gy = mk(1.5), mk(0.7), mk()
+    xa, ra, xb, rb = (t.clone().requires_grad_(True) for t in (x, r, x, r))
+    ya = act_a(bn_a(xa) + ra)
+    yb = bn_act_quant(bn_b, act_b, xb, residual=rb)
+    tq = act_a.act_quant.fused_activation_quant_proxy.tensor_quant
+    scale = (tq.scaling_impl(xa) / tq.int_scaling_impl(tq.msb_clamp_bit_width_impl())).detach()
+    d = (ya - yb).detach().abs()
+    assert float((d > 0).float().mean()) <= 1e-3 and float(d.max()) <= float(scale) * 1.0001
+    ya.backward(gy)
+    yb.backward(gy)
+    for a, b, name in ((xa.grad, xb.grad, "dx"), (ra.grad, rb.grad, "d residual")):
+        mag = float(a.abs().max())
+        bad = (a - b).abs() > 2e-3 * mag + 2e-3 * a.abs()
+        assert float(bad.float().mean()) <= 2e-3, (name, float(bad.float().mean()))
+    assert torch.allclose(bn_a.weight.grad, bn_b.weight.grad, rtol=2e-3, atol=2e-3 * float(bn_a.weight.grad.abs().max()))
+    assert torch.allclose(bn_a.bias.grad, bn_b.bias.grad, rtol=2e-3, atol=2e-3 * float(bn_a.bias.grad.abs().max()))
+    # a mismatching residual (other layout) takes the unfused modules
+    y = bn_act_quant(bn_b, act_b, x, residual=r.contiguous())
+    assert y.shape == x.shape
