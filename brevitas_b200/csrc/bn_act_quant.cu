@@ -264,8 +264,9 @@ __device__ __forceinline__ float bn_bwd_elem(float g, float x, const BnThread<T>
             const float t1 = v * th.inv_s[i];
             const float c = fminf(fmaxf(t1, p.qmin), p.qmax);
             const float t5 = (c + 12582912.f) - 12582912.f;
-            gs_acc = fmaf(g, t5, gs_acc);
-            gs_acc = fmaf(-r0, t1, gs_acc);
+            // one term per element: g * (t5 - t1) where the gradient is kept (the rounding residual, |.| <= 0.5: the two
+            // large sums sum g*t5 and sum g*t1 never meet in an fp32 accumulator), g * t5 where it is clamped
+            gs_acc = fmaf(g, keep ? (t5 - t1) : t5, gs_acc);
         }
         return (relu && yb <= 0.f) ? 0.f : r0;
     }
