@@ -163,13 +163,28 @@ class IntQuant(nn.Module):
         y = torch.ops.brevitas_b200.int_quant_zpt(x, scale, zero_point, qmin, qmax, modes[0], modes[1])
         return self.delay_wrapper(x, y)
 
+    def _host_scalars(self, zero_point: Tensor, bit_width: Tensor):
+        """(zero_point, qmin, qmax) as host floats for a DIRECT call with 0-dim tensor arguments.  The reference never
+        synchronises here; neither does this after the first call with the same (unmodified) tensors: the values are
+        cached per (storage, version) of the two tensors, so a training loop that passes its quantizer's constant buffers
+        reads them back once, not every step."""
+        key = (zero_point.data_ptr(), zero_point._version, bit_width.data_ptr(), bit_width._version,
+               zero_point.device, bit_width.device)
+        cache = self.__dict__.setdefault("_scalar_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) > 8:
+                cache.clear()
+            hit = (float(zero_point), float(self.min_int(bit_width)), float(self.max_int(bit_width)))
+            cache[key] = hit
+        return hit
+
     def forward(self, scale: Tensor, zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
         if (x.is_cuda and zero_point.numel() == 1 and bit_width.numel() == 1 and not zero_point.requires_grad
                 and not bit_width.requires_grad and not torch.cuda.is_current_stream_capturing()):
-            # direct call with tensor arguments: one read-back of the two 0-dim tensors, then the fused kernel
-            qmin = float(self.min_int(bit_width))
-            qmax = float(self.max_int(bit_width))
-            y = self.forward_fused(scale, float(zero_point), qmin, qmax, x)
+            # direct call with tensor arguments: the two 0-dim tensors are read back once (cached), then the fused kernel
+            zp, qmin, qmax = self._host_scalars(zero_point, bit_width)
+            y = self.forward_fused(scale, zp, qmin, qmax, x)
             if y is not None:
                 return y
         y_int = self.to_int(scale, zero_point, bit_width, x)

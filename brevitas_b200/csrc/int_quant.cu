@@ -133,8 +133,7 @@ __device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], cons
             if (masked) d[i] = (t3 < t5 || t3 > t5) ? 0.f : d[i];
             if (want_gs) {
                 const float t6 = (RM & RM_ZP0) ? t5 : fsub(t5, p.zp);
-                gs_acc = fmaf(eg[i], t6, gs_acc);
-                gs_acc = fmaf(-d[i], t1r * inv_s, gs_acc);
+                gs_acc += fmaf(eg[i], t6, -(d[i] * (t1r * inv_s)));      // per-element difference first (see bwd_elem)
             }
         }
     }
