@@ -12,6 +12,7 @@ injected sub-modules (rounding mode, clamp-gradient mode, statistic, view).  Con
 not cover (tensor-valued zero-point, learned bit-width, exotic injected modules) run the literal reference
 sequence on the STE kernels (op-level drop-in).
 """
+import weakref
 from functools import lru_cache
 from typing import Optional, Tuple
 
@@ -102,6 +103,9 @@ def _int_threshold(kind: str, signed: bool, narrow_range: bool, bit_width: int, 
     return float(impl(bw))
 
 
+_SCALAR_CACHE = weakref.WeakKeyDictionary()     # IntQuant module -> [(zero-point ref, version, bit-width ref, version, values)]
+
+
 class IntQuant(nn.Module):
     """Scaled, shifted, uniform integer quantization, output in dequantized format (int_base.py:15-97).
 
@@ -166,18 +170,19 @@ class IntQuant(nn.Module):
     def _host_scalars(self, zero_point: Tensor, bit_width: Tensor):
         """(zero_point, qmin, qmax) as host floats for a DIRECT call with 0-dim tensor arguments.  The reference never
         synchronises here; neither does this after the first call with the same (unmodified) tensors: the values are
-        cached per (storage, version) of the two tensors, so a training loop that passes its quantizer's constant buffers
+        cached per (tensor object, version) of the two tensors, so a training loop that passes its quantizer's constant buffers
         reads them back once, not every step."""
-        key = (zero_point.data_ptr(), zero_point._version, bit_width.data_ptr(), bit_width._version,
-               zero_point.device, bit_width.device)
-        cache = self.__dict__.setdefault("_scalar_cache", {})
-        hit = cache.get(key)
-        if hit is None:
-            if len(cache) > 8:
-                cache.clear()
-            hit = (float(zero_point), float(self.min_int(bit_width)), float(self.max_int(bit_width)))
-            cache[key] = hit
-        return hit
+        cache = _SCALAR_CACHE.setdefault(self, [])          # kept outside the module: it must stay picklable
+        for zr, zv, br, bv, vals in cache:
+            # the very same tensor OBJECTS, unmodified since (weak references: a freed tensor never matches, and a new tensor
+            # that happens to reuse its memory is another object)
+            if zr() is zero_point and br() is bit_width and zv == zero_point._version and bv == bit_width._version:
+                return vals
+        vals = (float(zero_point), float(self.min_int(bit_width)), float(self.max_int(bit_width)))
+        if len(cache) >= 4:
+            cache.pop(0)
+        cache.append((weakref.ref(zero_point), zero_point._version, weakref.ref(bit_width), bit_width._version, vals))
+        return vals
 
     def forward(self, scale: Tensor, zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Tensor:
         if (x.is_cuda and zero_point.numel() == 1 and bit_width.numel() == 1 and not zero_point.requires_grad
