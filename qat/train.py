@@ -70,7 +70,10 @@ def make_optimizer(model, spec, capturable=False):
     if spec["opt"] == "adam":
         return torch.optim.Adam(model.parameters(), lr=spec["lr"], capturable=capturable)
     # graph mode: the fused multi-tensor SGD (one launch set per step instead of ~4 foreach launches per chunk)
-    return torch.optim.SGD(model.parameters(), lr=spec["lr"], momentum=0.9, weight_decay=1e-4, fused=bool(capturable))
+    # (eager mode: fused=None lets torch pick its multi-tensor "foreach" path; an explicit False would select the
+    # single-tensor loop -- 3 element-wise launches per parameter and step)
+    return torch.optim.SGD(model.parameters(), lr=spec["lr"], momentum=0.9, weight_decay=1e-4,
+                           fused=True if capturable else None)
 
 
 class FlatGrads:
