@@ -33,7 +33,7 @@ constexpr int BN_SLOTS = 4;            // per-channel partial sums per CTA: fwd 
 struct BnGeom { int cv, rl; unsigned grid; bool ok; };
 
 template <typename T>
-static BnGeom bn_geometry(int64_t rows, int64_t channels) {
+static BnGeom bn_geometry(int64_t rows, int64_t channels, int ctas_per_sm = BN_CTAS_PER_SM) {
     constexpr int V = DT<T>::VEC;
     BnGeom g = {0, 0, 0, false};
     if (channels < V || channels % V != 0) return g;
@@ -42,7 +42,7 @@ static BnGeom bn_geometry(int64_t rows, int64_t channels) {
     g.cv = (int)cv;
     g.rl = BN_THREADS / (int)cv;
     int64_t want = (rows + g.rl - 1) / g.rl;
-    const int64_t cap = (int64_t)sm_count() * BN_CTAS_PER_SM;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     g.grid = (unsigned)want;
@@ -200,8 +200,12 @@ struct BnThread {
 };
 
 // ---- forward 3: normalise, ReLU, quantize ---------------------------------------------------------------------------
-template <typename T, int RM>
-__global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_apply_kernel(
+// RES: a residual input is added before the ReLU (compile-time: its loads and registers exist only in that variant, which
+// runs two resident CTAs per SM instead of three)
+constexpr int BN_CTAS_RES = 2;
+
+template <typename T, int RM, bool RES>
+__global__ void __launch_bounds__(BN_THREADS, RES ? BN_CTAS_RES : BN_CTAS_PER_SM) bn_act_quant_apply_kernel(
         const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, const float* __restrict__ mean,
         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
         const void* __restrict__ scale, int scale_count, int scale_f32, int64_t rows, int cv_n, int rl_n, int relu,
@@ -210,11 +214,11 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_apply
     const int cv = threadIdx.x % cv_n, rlane = threadIdx.x / cv_n;
     const BnThread<T> th(cv * V, mean, invstd, gamma, beta, scale, scale_count, scale_f32);
     const uint4* xv = reinterpret_cast<const uint4*>(x);
-    const uint4* rv = reinterpret_cast<const uint4*>(res);       // nullable: y = quant(relu(bn(x) + res))
+    const uint4* rv = reinterpret_cast<const uint4*>(res);       // RES: y = quant(relu(bn(x) + res))
     uint4* yv = reinterpret_cast<uint4*>(y);
     const int64_t rstride = (int64_t)gridDim.x * rl_n;
     for (int64_t r0 = (int64_t)blockIdx.x * rl_n + rlane; r0 < rows; r0 += rstride * BN_UNROLL) {
-        uint4 q[BN_UNROLL], qr[BN_UNROLL];
+        uint4 q[BN_UNROLL], qr[RES ? BN_UNROLL : 1];
         bool ok[BN_UNROLL];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL; ++u) {
@@ -222,21 +226,27 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_apply
             ok[u] = r < rows;
             if (ok[u]) {
                 q[u] = ldg_stream(xv + r * cv_n + cv);
-                if (rv) qr[u] = ldg_stream(rv + r * cv_n + cv);
+                if constexpr (RES) qr[u] = ldg_stream(rv + r * cv_n + cv);
             }
         }
 #pragma unroll
         for (int u = 0; u < BN_UNROLL; ++u) {
             if (!ok[u]) continue;
-            float e[V], er[V];
+            float e[V], er[RES ? V : 1];
             DT<T>::unpack(q[u], e);
-            if (rv) DT<T>::unpack(qr[u], er);
+            if constexpr (RES) DT<T>::unpack(qr[u], er);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float v = DT<T>::rnd(bn_apply(e[i], th.ch[i]));
-                if (rv) v = DT<T>::rnd(fadd(v, er[i]));
+                if constexpr (RES) v = DT<T>::rnd(fadd(v, er[i]));
                 if (relu) v = relu_f(v);
-                e[i] = quant_dequant<T, RM>(v, th.dv[i], p);
+                e[i] = v;
+            }
+            if (scale_count == 1) {          // one divisor for the vector: ONE slow-path test for all V quotients
+                quant_dequant_n<T, RM, V>(e, th.dv[0], p);
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) e[i] = quant_dequant<T, RM>(e[i], th.dv[i], p);
             }
             stg_stream(yv + (r0 + (int64_t)u * rstride) * cv_n + cv, DT<T>::pack(e));
         }
@@ -277,8 +287,8 @@ __device__ __forceinline__ float bn_bwd_elem(float g, float x, const BnThread<T>
 }
 
 // ---- backward 1: per-channel sum(gy), sum(gy * xhat), d(scale) -------------------------------------------------------
-template <typename T, int RM>
-__global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_reduce_kernel(
+template <typename T, int RM, bool RES>
+__global__ void __launch_bounds__(BN_THREADS, RES ? BN_CTAS_RES : BN_CTAS_PER_SM) bn_act_quant_bwd_reduce_kernel(
         const T* __restrict__ g, const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
         const void* __restrict__ scale, int scale_count, int scale_f32, float* __restrict__ partial, int64_t rows, int C,
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_r
     const uint4* rv = reinterpret_cast<const uint4*>(res);
     const int64_t rstride = (int64_t)gridDim.x * rl_n;
     for (int64_t r0 = (int64_t)blockIdx.x * rl_n + rlane; r0 < rows; r0 += rstride * (BN_UNROLL / 2)) {
-        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2], qr[BN_UNROLL / 2];
+        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2], qr[RES ? BN_UNROLL / 2 : 1];
         bool ok[BN_UNROLL / 2];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
@@ -304,21 +314,21 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_r
             if (ok[u]) {
                 qx[u] = ldg_stream(xv + r * cv_n + cv);
                 qg[u] = ldg_stream(gv + r * cv_n + cv);
-                if (rv) qr[u] = ldg_stream(rv + r * cv_n + cv);
+                if constexpr (RES) qr[u] = ldg_stream(rv + r * cv_n + cv);
             }
         }
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
             if (!ok[u]) continue;
-            float ex[V], eg[V], er[V];
+            float ex[V], eg[V], er[RES ? V : 1];
             DT<T>::unpack(qx[u], ex);
             DT<T>::unpack(qg[u], eg);
-            if (rv) DT<T>::unpack(qr[u], er);
+            if constexpr (RES) DT<T>::unpack(qr[u], er);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float xhat;
                 const float r = bn_bwd_elem<T, RM>(eg[i], ex[i], th, i, p, masked, relu, want_gs != 0, acc[2][i], xhat,
-                                                   rv != nullptr, rv ? er[i] : 0.f);
+                                                   RES, RES ? er[i] : 0.f);
                 acc[0][i] += r;
                 acc[1][i] = fmaf(r, xhat, acc[1][i]);
             }
@@ -359,8 +369,8 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_scalar_gscale_kernel(const flo
 }
 
 // ---- backward 3: dx = gamma * invstd * (gy - mean(gy) - xhat * mean(gy * xhat)) --------------------------------------
-template <typename T, int RM>
-__global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_dx_kernel(
+template <typename T, int RM, bool RES>
+__global__ void __launch_bounds__(BN_THREADS, RES ? BN_CTAS_RES : BN_CTAS_PER_SM) bn_act_quant_bwd_dx_kernel(
         const T* __restrict__ g, const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ gx,
         T* __restrict__ gres, const float* __restrict__ mean,
         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -384,7 +394,7 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_d
     uint4* orv = reinterpret_cast<uint4*>(gres);                 // nullable: gradient of the residual input
     const int64_t rstride = (int64_t)gridDim.x * rl_n;
     for (int64_t r0 = (int64_t)blockIdx.x * rl_n + rlane; r0 < rows; r0 += rstride * (BN_UNROLL / 2)) {
-        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2], qr[BN_UNROLL / 2];
+        uint4 qx[BN_UNROLL / 2], qg[BN_UNROLL / 2], qr[RES ? BN_UNROLL / 2 : 1];
         bool ok[BN_UNROLL / 2];
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
@@ -393,27 +403,29 @@ __global__ void __launch_bounds__(BN_THREADS, BN_CTAS_PER_SM) bn_act_quant_bwd_d
             if (ok[u]) {
                 qx[u] = ldg_stream(xv + r * cv_n + cv);
                 qg[u] = ldg_stream(gv + r * cv_n + cv);
-                if (rv) qr[u] = ldg_stream(rv + r * cv_n + cv);
+                if constexpr (RES) qr[u] = ldg_stream(rv + r * cv_n + cv);
             }
         }
 #pragma unroll
         for (int u = 0; u < BN_UNROLL / 2; ++u) {
             if (!ok[u]) continue;
-            float ex[V], eg[V], er[V];
+            float ex[V], eg[V], er[RES ? V : 1];
             DT<T>::unpack(qx[u], ex);
             DT<T>::unpack(qg[u], eg);
-            if (rv) DT<T>::unpack(qr[u], er);
+            if constexpr (RES) DT<T>::unpack(qr[u], er);
+            const int64_t o = (r0 + (int64_t)u * rstride) * cv_n + cv;
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float xhat, unused = 0.f;
                 const float r = bn_bwd_elem<T, RM>(eg[i], ex[i], th, i, p, masked, relu, false, unused, xhat,
-                                                   rv != nullptr, rv ? er[i] : 0.f);
-                er[i] = r;                                      // d(loss) / d(residual) = d(loss) / d(bn output)
+                                                   RES, RES ? er[i] : 0.f);
+                if constexpr (RES) er[i] = r;                   // d(loss) / d(residual) = d(loss) / d(bn output)
                 eg[i] = fmul(a[i], fsub(fsub(r, mb[i]), fmul(xhat, mg[i])));
             }
-            const int64_t o = (r0 + (int64_t)u * rstride) * cv_n + cv;
             stg_stream(ov + o, DT<T>::pack(eg));
-            if (orv) stg_stream(orv + o, DT<T>::pack(er));
+            if constexpr (RES) {
+                if (orv) stg_stream(orv + o, DT<T>::pack(er));
+            }
         }
     }
 }
@@ -423,7 +435,7 @@ static int launch_bn_fwd(const void* x, const void* res, const float* gamma, con
                          float momentum, float eps, int use_running, const void* scale, int64_t scale_count,
                          int scale_f32, void* y, float* save_mean, float* save_invstd, int64_t rows, int64_t channels,
                          const QParams& p, int relu, float* workspace, cudaStream_t st) {
-    const BnGeom g = bn_geometry<T>(rows, channels);
+    const BnGeom g = bn_geometry<T>(rows, channels, res ? BN_CTAS_RES : BN_CTAS_PER_SM);
     if (!g.ok || !aligned16(x) || !aligned16(y))
         return fail(BVB_EUNSUPPORTED, "bvb_bn_act_quant_fwd: channels = %lld must divide or be divided by %d vectors of "
                     "16 bytes, tensors 16-byte aligned", (long long)channels, BN_THREADS);
@@ -436,8 +448,14 @@ static int launch_bn_fwd(const void* x, const void* res, const float* gamma, con
             workspace, (int)g.grid, C, inv_count, unbias, eps, momentum, save_mean, save_invstd, running_mean, running_var);
     }
     if (res && !aligned16(res)) return fail(BVB_EUNSUPPORTED, "bvb_bn_act_quant_fwd: residual not 16-byte aligned");
-    bn_act_quant_apply_kernel<T, RM_ROUND><<<g.grid, BN_THREADS, 0, st>>>(
-        (const T*)x, (const T*)res, (T*)y, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, rows, g.cv, g.rl, relu, p);
+    if (res)
+        bn_act_quant_apply_kernel<T, RM_ROUND, true><<<g.grid, BN_THREADS, 0, st>>>(
+            (const T*)x, (const T*)res, (T*)y, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, rows,
+            g.cv, g.rl, relu, p);
+    else
+        bn_act_quant_apply_kernel<T, RM_ROUND, false><<<g.grid, BN_THREADS, 0, st>>>(
+            (const T*)x, nullptr, (T*)y, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, rows,
+            g.cv, g.rl, relu, p);
     return check_launch("bvb_bn_act_quant_fwd");
 }
 
@@ -446,23 +464,34 @@ static int launch_bn_bwd(const void* gy, const void* x, const void* res, void* g
                          const float* save_invstd, const void* scale, int64_t scale_count, int scale_f32, void* gx,
                          float* ggamma, float* gbeta, float* gscale, int64_t rows, int64_t channels, const QParams& p,
                          int relu, int masked, float* workspace, cudaStream_t st) {
-    const BnGeom g = bn_geometry<T>(rows, channels);
+    const BnGeom g = bn_geometry<T>(rows, channels, res ? BN_CTAS_RES : BN_CTAS_PER_SM);
     if (!g.ok || !aligned16(x) || !aligned16(gy) || !aligned16(gx))
         return fail(BVB_EUNSUPPORTED, "bvb_bn_act_quant_bwd: unsupported channel count %lld or alignment", (long long)channels);
     const int C = (int)channels;
     if ((res && !aligned16(res)) || (gres && !aligned16(gres)))
         return fail(BVB_EUNSUPPORTED, "bvb_bn_act_quant_bwd: residual tensors not 16-byte aligned");
-    bn_act_quant_bwd_reduce_kernel<T, RM_ROUND><<<g.grid, BN_THREADS, 0, st>>>(
-        (const T*)gy, (const T*)x, (const T*)res, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, workspace, rows,
-        C, g.cv, g.rl, relu, masked, gscale != nullptr, p);
+    if (res)
+        bn_act_quant_bwd_reduce_kernel<T, RM_ROUND, true><<<g.grid, BN_THREADS, 0, st>>>(
+            (const T*)gy, (const T*)x, (const T*)res, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32,
+            workspace, rows, C, g.cv, g.rl, relu, masked, gscale != nullptr, p);
+    else
+        bn_act_quant_bwd_reduce_kernel<T, RM_ROUND, false><<<g.grid, BN_THREADS, 0, st>>>(
+            (const T*)gy, (const T*)x, nullptr, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32,
+            workspace, rows, C, g.cv, g.rl, relu, masked, gscale != nullptr, p);
     // d(scale): per channel straight into gscale, or (one scale) into scratch behind the partials and then summed
     float* gs_channel = !gscale ? nullptr : (scale_count > 1 ? gscale : workspace + (size_t)g.grid * BN_SLOTS * C);
     bn_bwd_finalize_kernel<<<(C + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, st>>>(
         workspace, (int)g.grid, C, gbeta, ggamma, gs_channel);
     if (gscale && scale_count == 1) bn_scalar_gscale_kernel<<<1, FIN_THREADS, 0, st>>>(gs_channel, C, gscale);
-    bn_act_quant_bwd_dx_kernel<T, RM_ROUND><<<g.grid, BN_THREADS, 0, st>>>(
-        (const T*)gy, (const T*)x, (const T*)res, (T*)gx, (T*)gres, save_mean, save_invstd, gamma, beta, scale, (int)scale_count, scale_f32, gbeta,
-        ggamma, (float)(1.0 / (double)rows), rows, g.cv, g.rl, relu, masked, p);
+    const float inv_count = (float)(1.0 / (double)rows);
+    if (res)
+        bn_act_quant_bwd_dx_kernel<T, RM_ROUND, true><<<g.grid, BN_THREADS, 0, st>>>(
+            (const T*)gy, (const T*)x, (const T*)res, (T*)gx, (T*)gres, save_mean, save_invstd, gamma, beta, scale,
+            (int)scale_count, scale_f32, gbeta, ggamma, inv_count, rows, g.cv, g.rl, relu, masked, p);
+    else
+        bn_act_quant_bwd_dx_kernel<T, RM_ROUND, false><<<g.grid, BN_THREADS, 0, st>>>(
+            (const T*)gy, (const T*)x, nullptr, (T*)gx, nullptr, save_mean, save_invstd, gamma, beta, scale,
+            (int)scale_count, scale_f32, gbeta, ggamma, inv_count, rows, g.cv, g.rl, relu, masked, p);
     return check_launch("bvb_bn_act_quant_bwd");
 }
 
