@@ -240,13 +240,7 @@ __global__ void __launch_bounds__(BN_THREADS, RES ? BN_CTAS_RES : BN_CTAS_PER_SM
                 float v = DT<T>::rnd(bn_apply(e[i], th.ch[i]));
                 if constexpr (RES) v = DT<T>::rnd(fadd(v, er[i]));
                 if (relu) v = relu_f(v);
-                e[i] = v;
-            }
-            if (scale_count == 1) {          // one divisor for the vector: ONE slow-path test for all V quotients
-                quant_dequant_n<T, RM, V>(e, th.dv[0], p);
-            } else {
-#pragma unroll
-                for (int i = 0; i < V; ++i) e[i] = quant_dequant<T, RM>(e[i], th.dv[i], p);
+                e[i] = quant_dequant<T, RM>(v, th.dv[i], p);     // (the vector form quant_dequant_n measured 6 % slower here)
             }
             stg_stream(yv + (r0 + (int64_t)u * rstride) * cv_n + cv, DT<T>::pack(e));
         }
