@@ -12,6 +12,8 @@ would build, out of ``brevitas_b200.core`` modules.
 """
 from typing import Optional, Tuple
 
+import math
+
 import torch
 from torch import nn
 
@@ -126,14 +128,41 @@ class WeightQuantizer(Quantizer):
             scaling = ParameterScaling(float(cls.scaling_const), shape if shape else None, cls._restrict(),
                                        cls.scaling_min_val)
         elif st == "PARAMETER_FROM_STATS":
-            # learned scale initialised from the weight statistics (parameter.py:37-61): a one-off, construction-time
-            # reduction of a (still host-resident or device) parameter -- not part of the training hot path
+            # learned scale initialised from the weight statistics, the way the reference does it (solver/parameter.py:
+            # 39-45, 88-92: ParameterFromStatsScalingInit calls a StatsFromParameterScaling built from the CONFIGURED
+            # scaling_stats_op, restriction and scaling_min_val once, at construction).  The tracked weight may
+            # still live on the host at that point, so the one-off statistic runs on plain ATen (construction time, not the
+            # hot path): the reference's literal op sequence of _ParameterListStats + _StatsScaling.
             with torch.no_grad():
-                w2 = weight.detach().movedim(output_channel_dim, 0).reshape(weight.shape[output_channel_dim], -1) \
-                    if cls.scaling_per_output_channel else weight.detach().reshape(1, -1)
-                init = w2.abs().max(dim=1)[0].view(shape).clone()
+                restrict = cls._restrict()
+                stats_in = view(weight.detach())
+                op, q = cls.scaling_stats_op, float(getattr(cls, "high_percentile_q", 99.999))
+                a = stats_in.abs()
+                if op == "MAX":
+                    stat = a.max(dim=reduce_dim)[0] if reduce_dim is not None else a.max()
+                elif op == "PERCENTILE":
+                    if reduce_dim is None:
+                        stat = a.view(-1).kthvalue(int(math.floor(.01 * q * a.numel() + 0.5))).values
+                    else:
+                        stat = a.kthvalue(int(math.floor(.01 * q * a.shape[reduce_dim] + 0.5)), dim=reduce_dim).values
+                elif op == "AVE":
+                    stat = a.mean(dim=reduce_dim) if reduce_dim is not None else a.mean()
+                elif op == "MAX_AVE":
+                    stat = a.max(dim=1)[0].mean()
+                else:
+                    raise NotImplementedError(f"PARAMETER_FROM_STATS initialisation with scaling_stats_op={op}")
+                stat = stat.view(shape)
+                stat = restrict.restrict_init_tensor(stat)                      # pre-restriction (log2 for LOG_FP / PoT)
+                if cls.restrict_scaling_type == "POWER_OF_TWO" and not stat.is_cuda:
+                    # the restriction's float_to_int_impl is an STE kernel (CUDA only); same values with ATen on the host
+                    f2i = type(getattr(restrict, "float_to_int_impl", None)).__name__
+                    rnd = {"CeilSte": torch.ceil, "FloorSte": torch.floor}.get(f2i, torch.round)
+                    stat = 2.0 ** rnd(stat)
+                else:
+                    stat = restrict(stat)                                       # post-restriction (2 ** ., rounding for PoT)
                 if cls.scaling_min_val:
-                    init = init.clamp_min(cls.scaling_min_val)
+                    stat = stat.clamp_min(cls.scaling_min_val)
+                init = stat.clone()
             scaling = ParameterScaling(init, shape if shape else None, cls._restrict(), cls.scaling_min_val)
         else:
             raise NotImplementedError(f"scaling_impl_type={st}")
