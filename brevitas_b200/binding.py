@@ -171,6 +171,23 @@ def _swap_everywhere(table: Dict[type, type]):
                 _set(deps, name, _make_init_spec(new), "item")
 
 
+def _scope_parameter_init():
+    """``ParameterFromStatsScalingInit.__call__`` (quant/solver/parameter.py:39-45) evaluates a statistic of the layer's
+    weight while the layer is being constructed, i.e. on the host: run exactly that call inside
+    ``ops.parameter_init_on_host`` (the one scope in which the ops accept host tensors)."""
+    from brevitas.quant.solver import parameter as solver_parameter
+    from .ops import parameter_init_on_host
+    cls = solver_parameter.ParameterFromStatsScalingInit
+    original = cls.__call__
+
+    def __call__(self):
+        with parameter_init_on_host():
+            return original(self)
+
+    __call__.__wrapped__ = original
+    _set(cls, "__call__", __call__)
+
+
 def install(reference_path: Optional[str] = None, fuse: bool = True):
     """Bind Brevitas (already importable, or found under ``reference_path``) to the B200 kernels.  Idempotent.
     Returns the ``brevitas`` package."""
@@ -188,6 +205,7 @@ def install(reference_path: Optional[str] = None, fuse: bool = True):
         _set(ops_ste, "fn_prefix", torch)
         _set(brevitas, "NATIVE_STE_BACKEND_LOADED", True)       # a native STE backend IS loaded: this library
         config.bind(ref_config)
+        _scope_parameter_init()
         _state["installed"] = True
     if fuse and not _state["fused"]:
         # everything that holds references to the core classes must be loaded before the sweep

@@ -10,6 +10,8 @@ Two dispatcher namespaces are defined:
 Every op has a CUDA implementation only (ctypes -> C-ABI -> sm_100a kernels), an autograd formula and a
 fake/meta implementation.  Calling any of them with CPU tensors raises: there is no CPU fallback.
 """
+import contextlib
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -27,12 +29,42 @@ STE_NS = "autograd_ste_ops"
 FQ_NS = "brevitas_b200"
 
 
-def _no_cpu(name):
+class _HostInit(threading.local):
+    depth = 0
+
+
+_HOST_INIT = _HostInit()
+
+
+@contextlib.contextmanager
+def parameter_init_on_host():
+    """Scope of a ONE-OFF parameter initialisation that the reference evaluates at layer construction, before the
+    user had a chance to move the layer to the GPU: ``ParameterFromStatsScalingInit.__call__`` (quant/solver/
+    parameter.py:39-45) runs a ``StatsFromParameterScaling`` over the still host-resident weight to produce the initial
+    value of a learned scale.  Inside this scope -- and nowhere else -- the handful of ops such an initialiser is made of
+    accept host tensors and evaluate the reference's literal ATen expression; ``binding.install()`` enters it around
+    exactly that call.  Outside it every op raises on host tensors: no forward / backward ever runs on the CPU."""
+    _HOST_INIT.depth += 1
+    try:
+        yield
+    finally:
+        _HOST_INIT.depth -= 1
+
+
+def _no_cpu(name, init_expr=None):
     def _raise(*args, **kwargs):
+        if init_expr is not None and _HOST_INIT.depth > 0:
+            return init_expr(*args, **kwargs)
         raise RuntimeError(
             f"{name}: CPU tensors are not supported -- brevitas_b200 is a CUDA (sm_100a) implementation with no "
             "CPU fallback. Move the module and its inputs to a B200.")
     return _raise
+
+
+def _host_kth(x, rows, cols, k, absolute):
+    v = x.reshape(rows, cols)
+    r = (v.abs() if absolute else v).kthvalue(k, dim=1)
+    return r.values, r.indices
 
 
 # ============================================================================================================
@@ -55,10 +87,14 @@ _UNARY_STE = {
 }
 
 
+# float_to_int of a power-of-two restriction inside a construction-time scale initialiser (see parameter_init_on_host)
+_UNARY_INIT_EXPR = {"round_ste_impl": torch.round, "ceil_ste_impl": torch.ceil, "floor_ste_impl": torch.floor}
+
+
 def _def_unary(op_name, c_name):
     _STE.define(f"{op_name}(Tensor x) -> Tensor")
     _STE.impl(op_name, lambda x, _c=c_name: K.unary(_c, x), "CUDA")
-    _STE.impl(op_name, _no_cpu(op_name), "CPU")
+    _STE.impl(op_name, _no_cpu(op_name, _UNARY_INIT_EXPR.get(op_name)), "CPU")
     torch.library.register_fake(f"{STE_NS}::{op_name}", lambda x: torch.empty_like(x), lib=_STE)
     torch.library.register_autograd(f"{STE_NS}::{op_name}", _identity_backward, lib=_STE)
 
@@ -69,7 +105,7 @@ for _op, _c in _UNARY_STE.items():
 # abs_binary_sign_grad_impl: forward abs, backward binary_sign(x) * g   (csrc:182-194)
 _STE.define("abs_binary_sign_grad_impl(Tensor x) -> Tensor")
 _STE.impl("abs_binary_sign_grad_impl", lambda x: K.unary("bvb_abs_binary_sign_grad_impl", x), "CUDA")
-_STE.impl("abs_binary_sign_grad_impl", _no_cpu("abs_binary_sign_grad_impl"), "CPU")
+_STE.impl("abs_binary_sign_grad_impl", _no_cpu("abs_binary_sign_grad_impl", torch.abs), "CPU")
 torch.library.register_fake(f"{STE_NS}::abs_binary_sign_grad_impl", lambda x: torch.empty_like(x), lib=_STE)
 
 _FQ.define("abs_binary_sign_grad_backward(Tensor x, Tensor gy) -> Tensor")
@@ -108,7 +144,8 @@ _STE.impl("tensor_clamp_ste_impl_", _no_cpu("tensor_clamp_ste_impl_"), "CPU")
 class _InplaceTensorClampSte(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, min_val, max_val):
-        ctx.mark_dirty(x)
+        # no ctx.mark_dirty: like the reference's Python backend (ops/autograd_ste_ops.py:146-148) this mutates its
+        # input behind autograd's back, which is what lets BinaryQuant-style callers clamp a leaf weight in place
         with torch._C._AutoDispatchBelowAutograd():
             torch.ops.autograd_ste_ops.tensor_clamp_ste_impl_(x, min_val, max_val)
         return x
@@ -129,7 +166,7 @@ torch.library.register_autograd(f"{STE_NS}::scalar_clamp_ste_impl", lambda ctx, 
 
 _STE.define("scalar_clamp_min_ste_impl(Tensor x, float min_val) -> Tensor")
 _STE.impl("scalar_clamp_min_ste_impl", lambda x, lo: K.scalar_clamp_min(x, lo), "CUDA")
-_STE.impl("scalar_clamp_min_ste_impl", _no_cpu("scalar_clamp_min_ste_impl"), "CPU")
+_STE.impl("scalar_clamp_min_ste_impl", _no_cpu("scalar_clamp_min_ste_impl", torch.clamp_min), "CPU")
 torch.library.register_fake(f"{STE_NS}::scalar_clamp_min_ste_impl", lambda x, lo: torch.empty_like(x), lib=_STE)
 torch.library.register_autograd(f"{STE_NS}::scalar_clamp_min_ste_impl", lambda ctx, g: (g, None), lib=_STE)
 
@@ -448,13 +485,13 @@ _FQ.define("abs_kth_value_rows(Tensor x, int rows, int cols, int k) -> (Tensor, 
 _FQ.define("kth_value_rows(Tensor x, int rows, int cols, int k) -> (Tensor, Tensor)")
 _FQ.define("running_stats_update_(Tensor(a!) running, Tensor stat, float momentum, bool first) -> ()")
 _FQ.impl("absmax_rows", lambda x, r, c: K.absmax_rows(x, r, c), "CUDA")
-_FQ.impl("absmax_rows", _no_cpu("absmax_rows"), "CPU")
+_FQ.impl("absmax_rows", _no_cpu("absmax_rows", lambda x, rows, cols: x.reshape(rows, cols).abs().max(dim=1)[0]), "CPU")
 _FQ.impl("absmax_tensor", lambda x: K.absmax_tensor(x), "CUDA")
-_FQ.impl("absmax_tensor", _no_cpu("absmax_tensor"), "CPU")
+_FQ.impl("absmax_tensor", _no_cpu("absmax_tensor", lambda x: x.abs().max()), "CPU")
 _FQ.impl("abs_kth_value_rows", lambda x, r, c, k: K.abs_kth_value_rows(x, r, c, k, want_index=True), "CUDA")
-_FQ.impl("abs_kth_value_rows", _no_cpu("abs_kth_value_rows"), "CPU")
+_FQ.impl("abs_kth_value_rows", _no_cpu("abs_kth_value_rows", lambda x, r, c, k: _host_kth(x, r, c, k, True)), "CPU")
 _FQ.impl("kth_value_rows", lambda x, r, c, k: K.kth_value_rows(x, r, c, k, want_index=True), "CUDA")
-_FQ.impl("kth_value_rows", _no_cpu("kth_value_rows"), "CPU")
+_FQ.impl("kth_value_rows", _no_cpu("kth_value_rows", lambda x, r, c, k: _host_kth(x, r, c, k, False)), "CPU")
 _FQ.impl("running_stats_update_", lambda r, s, m, f: (K.running_stats_update(r, s, m, f), None)[1], "CUDA")
 _FQ.impl("running_stats_update_", _no_cpu("running_stats_update_"), "CPU")
 torch.library.register_fake(f"{FQ_NS}::absmax_rows", lambda x, r, c: x.new_empty(r), lib=_FQ)

@@ -254,3 +254,33 @@ def test_config_flags_follow_the_reference_after_install():
         ref_config.IGNORE_MISSING_KEYS = old
         uninstall()
     assert config.IGNORE_MISSING_KEYS is False
+
+
+@needs_ref
+@pytest.mark.parametrize("fuse", [False, True])
+def test_construction_time_scale_init_runs_on_the_host_and_nothing_else_does(fuse):
+    """quant/solver/parameter.py:39-45: a learned scale initialised from the weight statistic is evaluated while the layer
+    is constructed (weights still on the host).  That one call is scoped (ops.parameter_init_on_host) and gives the
+    reference's values bit for bit; a forward on host tensors still raises -- no CPU fallback for the path itself."""
+    import brevitas_b200
+    from brevitas_b200.binding import uninstall
+    uninstall()
+    try:
+        for name in ("Int4WeightPerTensorFloatDecoupled", "Int8WeightPerChannelFloatDecoupled"):
+            brevitas_b200.install(reference_src(), fuse=fuse)
+            import brevitas.nn as qnn
+            import brevitas.quant as Q
+            torch.manual_seed(0)
+            ours = qnn.QuantLinear(16, 8, False, weight_quant=getattr(Q, name))
+            with pytest.raises(RuntimeError, match="CPU tensors are not supported"):
+                ours(torch.randn(2, 16))
+            with pytest.raises(RuntimeError, match="CPU tensors are not supported"):
+                torch.ops.brevitas_b200.absmax_tensor(torch.randn(4))           # outside the scope: raises
+            uninstall()
+            torch.manual_seed(0)
+            ref = qnn.QuantLinear(16, 8, False, weight_quant=getattr(Q, name))
+            assert set(ours.state_dict()) == set(ref.state_dict())
+            for k, v in ref.state_dict().items():
+                assert torch.equal(v, ours.state_dict()[k]), (name, k)
+    finally:
+        uninstall()
