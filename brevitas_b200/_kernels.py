@@ -393,6 +393,86 @@ def binary_quant_bwd(gy, x, scale, clamped: bool, want_gscale: bool):
     return gx, gs
 
 
+# ---- general integer quantizer (decoupled / device-resident range) and ternary ---------------------------------------
+
+def _general_args(x, pre_scale, scale):
+    pi, pc = broadcast_pattern(x.shape, pre_scale.shape)
+    si, sc = broadcast_pattern(x.shape, scale.shape)
+    if pre_scale.dtype != x.dtype or scale.dtype != x.dtype:
+        raise RuntimeError("brevitas_b200: general_int_quant needs both scales in the dtype of the input")
+    if pc != 1 and sc != 1 and (pc != sc or pi != si):
+        raise RuntimeError("brevitas_b200: general_int_quant needs one broadcast pattern for both scales")
+    inner = pi if pc != 1 else si
+    return inner, pc, sc
+
+
+def _f32_scalar(t):
+    if t.numel() != 1:
+        raise RuntimeError("brevitas_b200: general_int_quant takes one-element zero-points and integer bounds")
+    return t.detach().to(torch.float32).reshape(1)
+
+
+def general_int_quant_supported(x, pre_scale, scale, *scalars) -> bool:
+    if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        return False
+    if pre_scale.dtype != x.dtype or scale.dtype != x.dtype or any(t.numel() != 1 for t in scalars):
+        return False
+    try:
+        _general_args(x, pre_scale, scale)
+    except RuntimeError:
+        return False
+    return True
+
+
+def general_int_quant_fwd(x, pre_scale, scale, pre_zp, zp, lo, hi, round_mode):
+    dev = _check_cuda(x, pre_scale, scale, pre_zp, zp, lo, hi)
+    x = _dense(x) if pre_scale.numel() == 1 and scale.numel() == 1 else _c(x)
+    pre_scale, scale = _c(pre_scale), _c(scale)
+    inner, pc, sc = _general_args(x, pre_scale, scale)
+    pre_zp, zp, lo, hi = (_f32_scalar(t) for t in (pre_zp, zp, lo, hi))
+    y = torch.empty_like(x)
+    _launch(dev, "bvb_general_int_quant_fwd", x.data_ptr(), pre_scale.data_ptr(), scale.data_ptr(), pre_zp.data_ptr(),
+            zp.data_ptr(), lo.data_ptr(), hi.data_ptr(), y.data_ptr(), x.numel(), inner, pc, sc, round_mode, dtype_tag(x),
+            _stream(dev))
+    return y
+
+
+def general_int_quant_bwd(gy, x, pre_scale, scale, pre_zp, zp, lo, hi, round_mode, clamp_mode, same_scale, want_sums):
+    """returns (gx, sums fp64 [d pre_scale | d scale | d min_int | d max_int] or None)"""
+    dev = _check_cuda(gy, x, pre_scale, scale, pre_zp, zp, lo, hi)
+    x = _dense(x) if pre_scale.numel() == 1 and scale.numel() == 1 else _c(x)
+    pre_scale, scale = _c(pre_scale), _c(scale)
+    gy = _like(gy, x)
+    inner, pc, sc = _general_args(x, pre_scale, scale)
+    pre_zp, zp, lo, hi = (_f32_scalar(t) for t in (pre_zp, zp, lo, hi))
+    gx = torch.empty_like(x)
+    sums = torch.empty(pc + sc + 2, dtype=torch.float64, device=dev) if want_sums else None
+    _launch(dev, "bvb_general_int_quant_bwd", gy.data_ptr(), x.data_ptr(), pre_scale.data_ptr(), scale.data_ptr(),
+            pre_zp.data_ptr(), zp.data_ptr(), lo.data_ptr(), hi.data_ptr(), gx.data_ptr(), _ptr(sums), x.numel(), inner, pc, sc,
+            round_mode, clamp_mode, 1 if same_scale else 0, dtype_tag(x), _stream(dev))
+    return gx, sums
+
+
+def ternary_quant_fwd(x, scale, threshold: float):
+    dev = _check_cuda(x, scale)
+    x, scale = _dense(x), _c(scale)
+    y = torch.empty_like(x)
+    _launch(dev, "bvb_ternary_quant_fwd", x.data_ptr(), scale.data_ptr(), y.data_ptr(), x.numel(), threshold, dtype_tag(x),
+            _stream(dev))
+    return y
+
+
+def ternary_quant_bwd(gy, x, scale, threshold: float, want_gscale: bool):
+    dev = _check_cuda(gy, x, scale)
+    x, scale = _dense(x), _c(scale)
+    gy = _like(gy, x)
+    gx = torch.empty_like(x)
+    gs = torch.empty(1, dtype=torch.float64, device=dev) if want_gscale else None
+    _launch(dev, "bvb_ternary_quant_bwd", gy.data_ptr(), x.data_ptr(), scale.data_ptr(), gx.data_ptr(), _ptr(gs), x.numel(),
+            threshold, dtype_tag(x), _stream(dev))
+    return gx, gs
+
+
 # ---- statistics --------------------------------------------------------------------------------------------
 
 def absmax_rows(x, rows, cols):

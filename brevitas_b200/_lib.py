@@ -67,6 +67,11 @@ SIGNATURES = {
     "bvb_bn_act_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _L, _L, _F, _F, _F, _I, _I, _I, _I, _P, _P]),
     "bvb_binary_quant_fwd": (c_int, [_P, _P, _P, _L, _L, _L, _I, _I, _I, _P]),
     "bvb_binary_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _P]),
+    "bvb_general_int_quant_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P]),
+    "bvb_general_int_quant_sums": (c_int64, [_L, _L]),
+    "bvb_general_int_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _I, _I, _P]),
+    "bvb_ternary_quant_fwd": (c_int, [_P, _P, _P, _L, _F, _I, _P]),
+    "bvb_ternary_quant_bwd": (c_int, [_P, _P, _P, _P, _P, _L, _F, _I, _P]),
     "bvb_absmax_rows": (c_int, [_P, _P, _L, _L, _I, _P]),
     "bvb_absmax_tensor": (c_int, [_P, _P, _L, _I, _P, _P]),
     "bvb_abs_kth_value_rows": (c_int, [_P, _P, _P, _L, _L, _L, _I, _P, _P]),

@@ -9,8 +9,9 @@ Same constructor arguments, same sub-module names (``int_quant``, ``scaling_impl
 ``forward`` executes: where the reference issues ~9-20 ATen kernels, these modules launch ONE kernel
 (statistic + scale + quant-dequant) or one kernel after a few tiny scale ops, selected from the types of the
 injected sub-modules (rounding mode, clamp-gradient mode, statistic, view).  Configurations the fused kernels do
-not cover (tensor-valued zero-point, learned bit-width, exotic injected modules) run the literal reference
-sequence on the STE kernels (op-level drop-in).
+not cover (exotic injected modules, mixed dtypes) run the literal reference sequence on the STE kernels (op-level
+drop-in); a learned bit-width and the decoupled quantizers take ``general_int_quant``, whose range inputs
+stay on the device.
 """
 import weakref
 from functools import lru_cache
@@ -19,6 +20,7 @@ from typing import Optional, Tuple
 import torch
 from torch import Tensor, nn
 
+from .. import _kernels as _K
 from .. import _lib
 from .. import ops as _ops  # noqa: F401
 from ..function.ops import max_int, min_int
@@ -192,9 +194,27 @@ class IntQuant(nn.Module):
             y = self.forward_fused(scale, zp, qmin, qmax, x)
             if y is not None:
                 return y
+        y = self.forward_device_range(scale, zero_point, bit_width, x)
+        if y is not None:
+            return y
         y_int = self.to_int(scale, zero_point, bit_width, x)
         y = y_int - zero_point
         y = scalar_mul(y, scale)
+        return self.delay_wrapper(x, y)
+
+    def forward_device_range(self, scale: Tensor, zero_point: Tensor, bit_width: Tensor, x: Tensor) -> Optional[Tensor]:
+        """One kernel whose zero-point and integer range stay ON THE DEVICE (``general_int_quant``): the learned bit-width
+        path (core/bit_width/parameter.py:23-98 -- the masked clamp's backward returns d(min_int) and d(max_int), which is
+        what trains the bit-width), and direct calls that must not read anything back (CUDA-graph capture).  None if not
+        applicable."""
+        modes = self.kernel_modes()
+        if modes is None or zero_point.requires_grad:
+            return None
+        if not _K.general_int_quant_supported(x, scale, scale, zero_point, bit_width):
+            return None
+        lo, hi = self.min_int(bit_width), self.max_int(bit_width)          # 0-dim ATen ops, differentiable in bit_width
+        y = torch.ops.brevitas_b200.general_int_quant(x, scale, scale, zero_point, zero_point, lo, hi, modes[0], modes[1],
+                                                      True)
         return self.delay_wrapper(x, y)
 
 
@@ -472,6 +492,15 @@ class DecoupledIntQuant(nn.Module):
 
     def forward(self, pre_scale: Tensor, pre_zero_point: Tensor, scale: Tensor, zero_point: Tensor, bit_width: Tensor,
                 x: Tensor) -> Tensor:
+        rm = ROUND_MODE_OF.get(type(self.float_to_int_impl))
+        cm = CLAMP_MODE_OF.get(type(self.tensor_clamp_impl))
+        if (rm is not None and cm is not None and not pre_zero_point.requires_grad and not zero_point.requires_grad
+                and _K.general_int_quant_supported(x, pre_scale, scale, pre_zero_point, zero_point, bit_width)):
+            # one kernel: rounding with (pre_scale, pre_zero_point), dequantization with (scale, zero_point); its backward
+            # returns d(pre_scale) and d(scale) separately (and the bounds' gradients under a masked clamp)
+            y = torch.ops.brevitas_b200.general_int_quant(x, pre_scale, scale, pre_zero_point, zero_point,
+                                                          self.min_int(bit_width), self.max_int(bit_width), rm, cm, False)
+            return self.delay_wrapper(x, y)
         y_int = self.to_int(pre_scale, pre_zero_point, bit_width, x)
         y = y_int - zero_point
         y = scalar_mul(y, scale)
@@ -519,6 +548,9 @@ class TernaryQuant(nn.Module):
 
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         scale = self.scaling_impl(x)
+        if x.is_cuda and x.dtype == torch.float32 and scale.dtype == torch.float32 and scale.numel() == 1:
+            y = torch.ops.brevitas_b200.ternary_quant(x, scale, float(self.threshold))
+            return self.delay_wrapper(x, y), scale, self.zero_point(), self.bit_width()
         mask = x.abs().gt(self.threshold * scale)
         y = mask.float() * ternary_sign_ste(x)
         y = y * scale

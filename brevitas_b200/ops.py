@@ -478,6 +478,104 @@ def _binary_bwd(ctx, gy):
 torch.library.register_autograd(f"{FQ_NS}::binary_quant", _binary_bwd, setup_context=_binary_setup, lib=_FQ)
 
 
+# ---- general integer quantizer: DecoupledIntQuant, and IntQuant with a device-resident range (learned bit-width) -------
+_FQ.define("general_int_quant(Tensor x, Tensor pre_scale, Tensor scale, Tensor pre_zero_point, Tensor zero_point, "
+           "Tensor min_int, Tensor max_int, int round_mode, int clamp_mode, bool same_scale) -> Tensor")
+_FQ.define("general_int_quant_backward(Tensor gy, Tensor x, Tensor pre_scale, Tensor scale, Tensor pre_zero_point, "
+           "Tensor zero_point, Tensor min_int, Tensor max_int, int round_mode, int clamp_mode, bool same_scale, "
+           "bool want_sums) -> (Tensor, Tensor)")
+
+
+def _general_bwd_cuda(gy, x, ps, s, pzp, zp, lo, hi, rm, cm, same, want):
+    gx, sums = K.general_int_quant_bwd(gy, x, ps, s, pzp, zp, lo, hi, rm, cm, same, want)
+    if sums is None:
+        sums = torch.empty(0, dtype=torch.float64, device=x.device)
+    return gx, sums
+
+
+_FQ.impl("general_int_quant", lambda x, ps, s, pzp, zp, lo, hi, rm, cm, same: K.general_int_quant_fwd(
+    x, ps, s, pzp, zp, lo, hi, rm), "CUDA")
+_FQ.impl("general_int_quant", _no_cpu("general_int_quant"), "CPU")
+_FQ.impl("general_int_quant_backward", _general_bwd_cuda, "CUDA")
+_FQ.impl("general_int_quant_backward", _no_cpu("general_int_quant_backward"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::general_int_quant",
+                            lambda x, ps, s, pzp, zp, lo, hi, rm, cm, same: torch.empty_like(x), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::general_int_quant_backward",
+    lambda gy, x, ps, s, pzp, zp, lo, hi, rm, cm, same, want: (
+        torch.empty_like(x), x.new_empty(ps.numel() + s.numel() + 2 if want else 0, dtype=torch.float64)), lib=_FQ)
+
+
+def _general_setup(ctx, inputs, output):
+    x, ps, s, pzp, zp, lo, hi, rm, cm, same = inputs
+    ctx.save_for_backward(x, ps, s, pzp, zp, lo, hi)
+    ctx.q = (rm, cm, same)
+
+
+def _general_bwd(ctx, gy):
+    x, ps, s, pzp, zp, lo, hi = ctx.saved_tensors
+    rm, cm, same = ctx.q
+    need = ctx.needs_input_grad
+    if need[3] or need[4]:
+        raise RuntimeError("brevitas_b200::general_int_quant has no gradient for its zero-points (callers with a learned "
+                           "zero-point take the int_quant_zpt kernel or the literal sequence)")
+    want = need[1] or need[2] or need[5] or need[6]
+    gx, sums = torch.ops.brevitas_b200.general_int_quant_backward(gy.to(x.dtype), x, ps, s, pzp, zp, lo, hi, rm, cm, same, want)
+    pc, sc = ps.numel(), s.numel()
+    g_ps = g_s = g_lo = g_hi = None
+    if need[1] and not same:
+        g_ps = sums[:pc].to(ps.dtype).view(ps.shape)
+    if need[2] or (same and need[1]):
+        g_s = sums[pc:pc + sc].to(s.dtype).view(s.shape)          # same_scale: the whole d(scale), handed to one input
+    if cm == 1:                                                  # masked clamp: torch.where routes the clipped gradient to
+        if need[5]:                                              # the bounds (function/ops.py:98-99)
+            g_lo = sums[pc + sc].to(lo.dtype).view(lo.shape)
+        if need[6]:
+            g_hi = sums[pc + sc + 1].to(hi.dtype).view(hi.shape)
+    return (gx if need[0] else None, g_ps, g_s, None, None, g_lo, g_hi, None, None, None)
+
+
+torch.library.register_autograd(f"{FQ_NS}::general_int_quant", _general_bwd, setup_context=_general_setup, lib=_FQ)
+
+
+# ---- TernaryQuant (fp32) ---------------------------------------------------------------------------------------------
+_FQ.define("ternary_quant(Tensor x, Tensor scale, float threshold) -> Tensor")
+_FQ.define("ternary_quant_backward(Tensor gy, Tensor x, Tensor scale, float threshold, bool want_gscale) -> (Tensor, Tensor)")
+
+
+def _ternary_bwd_cuda(gy, x, scale, threshold, want):
+    gx, gs = K.ternary_quant_bwd(gy, x, scale, threshold, want)
+    if gs is None:
+        gs = torch.empty(0, dtype=torch.float64, device=x.device)
+    return gx, gs
+
+
+_FQ.impl("ternary_quant", lambda x, s, t: K.ternary_quant_fwd(x, s, t), "CUDA")
+_FQ.impl("ternary_quant", _no_cpu("ternary_quant"), "CPU")
+_FQ.impl("ternary_quant_backward", _ternary_bwd_cuda, "CUDA")
+_FQ.impl("ternary_quant_backward", _no_cpu("ternary_quant_backward"), "CPU")
+torch.library.register_fake(f"{FQ_NS}::ternary_quant", lambda x, s, t: torch.empty_like(x), lib=_FQ)
+torch.library.register_fake(
+    f"{FQ_NS}::ternary_quant_backward",
+    lambda gy, x, s, t, w: (torch.empty_like(x), x.new_empty(1 if w else 0, dtype=torch.float64)), lib=_FQ)
+
+
+def _ternary_setup(ctx, inputs, output):
+    x, scale, threshold = inputs
+    ctx.save_for_backward(x, scale)
+    ctx.threshold = threshold
+
+
+def _ternary_bwd(ctx, gy):
+    x, scale = ctx.saved_tensors
+    want = ctx.needs_input_grad[1]
+    gx, gs = torch.ops.brevitas_b200.ternary_quant_backward(gy.to(x.dtype), x, scale, ctx.threshold, want)
+    return (gx if ctx.needs_input_grad[0] else None, gs.to(scale.dtype).view(scale.shape) if want else None, None)
+
+
+torch.library.register_autograd(f"{FQ_NS}::ternary_quant", _ternary_bwd, setup_context=_ternary_setup, lib=_FQ)
+
+
 # ---- statistics (forward values; see brevitas_b200.core.stats for the module wrappers) ------------------------
 _FQ.define("absmax_rows(Tensor x, int rows, int cols) -> Tensor")
 _FQ.define("absmax_tensor(Tensor x) -> Tensor")

@@ -217,6 +217,37 @@ int bvb_binary_quant_bwd(const void* gy, const void* x, const void* scale, void*
                          int64_t scale_inner, int64_t scale_count, int scale_dtype, int clamped, int dtype,
                          void* stream);
 
+/* ---- 4a. the remaining quantizer flavours, one kernel per direction ------------------------- */
+/* General integer quantizer: DecoupledIntQuant.forward (src/brevitas/core/quant/int_base.py:132-182) and
+ * IntQuant.forward (int_base.py:64-97) when the range must stay on the device -- a learned bit-width
+ * (src/brevitas/core/bit_width/parameter.py:23-98), or a call that may not read anything back (CUDA-graph capture):
+ *   c = where-clamp(float_to_int(x / pre_scale + pre_zero_point), min_int, max_int);  y = (c - zero_point) * scale
+ * pre_scale / scale: dtype of x, pre_scale_count / scale_count elements each (1, or one shared broadcast pattern
+ * scale[(i / scale_inner) % count]).  pre_zero_point, zero_point, min_int, max_int: ONE fp32 element each, in device
+ * memory; the bounds are rounded to the tensor dtype like the reference's `.type_as(x)`.                           */
+int bvb_general_int_quant_fwd(const void* x, const void* pre_scale, const void* scale, const float* pre_zero_point,
+                              const float* zero_point, const float* min_int, const float* max_int, void* y, int64_t n,
+                              int64_t scale_inner, int64_t pre_scale_count, int64_t scale_count, int round_mode,
+                              int dtype, void* stream);
+/* gx = ((gy * scale) * m) / pre_scale  (m = 1 for BVB_CLAMP_STE, else the where-clamp mask).  sums (nullable, fp64,
+ * bvb_general_int_quant_sums() elements, zeroed here) = [ d pre_scale (pre_scale_count) | d scale (scale_count) |
+ * d min_int | d max_int ]: d scale = sum gy * (c - zero_point), d pre_scale = - sum gx' * ((x / pre_scale) / pre_scale),
+ * d min_int / d max_int = the gradient of the lanes clipped low / high (BVB_CLAMP_MASKED only).  same_scale != 0
+ * (pre_scale IS scale, IntQuant.forward): the two scale sums are taken as one difference per element and the whole
+ * d scale is returned in the second block.                                                                         */
+int64_t bvb_general_int_quant_sums(int64_t pre_scale_count, int64_t scale_count);
+int bvb_general_int_quant_bwd(const void* gy, const void* x, const void* pre_scale, const void* scale,
+                              const float* pre_zero_point, const float* zero_point, const float* min_int,
+                              const float* max_int, void* gx, double* sums, int64_t n, int64_t scale_inner,
+                              int64_t pre_scale_count, int64_t scale_count, int round_mode, int clamp_mode,
+                              int same_scale, int dtype, void* stream);
+/* TernaryQuant.forward (src/brevitas/core/quant/ternary.py:58-72): y = float(|x| > threshold * s) * sign(x) * s with ONE
+ * scale; fp32 only (the reference's result is fp32 whatever the input, BVB_EUNSUPPORTED otherwise).
+ * Backward: gx = (gy * s) * mask; gscale (nullable, one fp64, zeroed here) = sum gy * mask * sign(x).              */
+int bvb_ternary_quant_fwd(const void* x, const void* scale, void* y, int64_t n, float threshold, int dtype, void* stream);
+int bvb_ternary_quant_bwd(const void* gy, const void* x, const void* scale, void* gx, double* gscale, int64_t n,
+                          float threshold, int dtype, void* stream);
+
 /* ---- 4b. batch-norm + ReLU + activation quantizer of a conv block, fused ------------------- */
 /* `QuantReLU(BatchNorm2d(conv_out))` -- FusedActivationQuantProxy (src/brevitas/proxy/runtime_quant.py:73-84) behind
  * torch.nn.BatchNorm2d, e.g. brevitas_examples/imagenet_classification/models/mobilenetv1.py:111-115 -- on a
