@@ -239,3 +239,29 @@ def test_learned_bit_width_through_the_reference_layers(ref, kind):
     assert torch.allclose(gf, gr, rtol=1e-4, atol=1e-5 * float(gr.abs().max()))
     assert float(br) != 0.0
     assert abs(float(bf) - float(br)) <= 1e-4 * gsum, (float(bf), float(br))
+
+
+def test_module_paths_launch_one_kernel_each():
+    """DecoupledIntQuant, IntQuant with a learned bit-width and TernaryQuant: ONE library launch per forward, one per backward"""
+    import brevitas_b200  # noqa: F401
+    from brevitas_b200 import _kernels
+    from brevitas_b200.core import function_wrapper as fw
+    from brevitas_b200.core.quant import DecoupledIntQuant, IntQuant, TernaryQuant
+    from brevitas_b200.core.scaling import ParameterScaling
+    x = torch.randn(32, 64, device="cuda", requires_grad=True)
+    s = torch.tensor(0.05, device="cuda", requires_grad=True)
+    ps = torch.tensor(0.04, device="cuda", requires_grad=True)
+    z = torch.tensor(0.0, device="cuda")
+    bw = torch.tensor(4.0, device="cuda", requires_grad=True)
+    dq = DecoupledIntQuant(True, True, fw.RoundSte(), fw.TensorClampSte()).cuda()
+    iq = IntQuant(True, True, fw.RoundSte(), fw.TensorClamp()).cuda()
+    tq = TernaryQuant(ParameterScaling(0.7), 0.5).cuda()
+    for name, call in (("decoupled", lambda: dq(ps, z, s, z, bw.detach(), x)),
+                       ("learned bit-width", lambda: iq(s, z, bw, x)),
+                       ("ternary", lambda: tq(x)[0])):
+        before = _kernels.launch_count
+        y = call()
+        fwd = _kernels.launch_count - before
+        y.sum().backward()
+        bwd = _kernels.launch_count - before - fwd
+        assert (fwd, bwd) == (1, 1), (name, fwd, bwd)
