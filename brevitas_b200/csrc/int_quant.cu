@@ -852,6 +852,94 @@ __global__ void rows_fwd_tma_kernel(const T* __restrict__ x, T* __restrict__ y, 
     }
 }
 
+// Same contract, output through the TMA engine as well: the row is quantized IN PLACE in its shared-memory stage and
+// leaves with ONE bulk copy (cp.async.bulk.global.shared::cta) instead of a 128-bit store per thread and vector.  While
+// row r is computed, row r-1 is still being read out of its stage; that stage is refilled (row r+stages-1) in the middle
+// of row r, after the abs-max pass.  stages = 2 therefore prefetches only during the quantization pass of the row before,
+// stages = 3 a whole row ahead.
+template <typename T, int RM>
+__global__ void rows_fwd_tma_store_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ scale_out,
+                                          T* __restrict__ absmax_out, int rows, int cols, int stages, uint32_t stage_stride,
+                                          float min_val, int has_min, float int_thr, QParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint32_t* red = reinterpret_cast<uint32_t*>(smem + 64);
+    unsigned char* bufs = smem + ROWS_SMEM_HEADER;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t)cols * (uint32_t)sizeof(T);
+    const int nvec = (int)(row_bytes >> 4);
+    const int first = blockIdx.x, step = gridDim.x;
+    const int my_rows = (rows - first + step - 1) / step;
+    const int ahead = stages - 1;                     // loads in flight, the row being computed included
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int pre = my_rows < ahead ? my_rows : ahead;
+    if (tid == 0 && pre > 0) {                        // staggered start-up, see rows_fwd_tma_kernel
+        mbar_arrive_expect_tx(&bars[0], row_bytes);
+        bulk_g2s(bufs, x + (size_t)first * cols, row_bytes, &bars[0]);
+    }
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (int it = 0; it < my_rows; ++it) {
+        const int row = first + it * step;
+        mbar_wait(&bars[s], parity);
+        if (it == 0 && tid == 0) {
+            for (int q = 1; q < pre; ++q) {
+                mbar_arrive_expect_tx(&bars[q], row_bytes);
+                bulk_g2s(bufs + (size_t)q * stage_stride, x + (size_t)(first + q * step) * cols, row_bytes, &bars[q]);
+            }
+        }
+        unsigned char* stage = bufs + (size_t)s * stage_stride;
+        const uint4* buf = reinterpret_cast<const uint4*>(stage);
+
+        AbsMaxAcc<T> am;
+#pragma unroll 4
+        for (int v = tid; v < nvec; v += blockDim.x) am.add(lds128(buf + v));
+        uint32_t m = warp_max_u32(am.result());
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        m = warp_max_u32(lane < nw ? red[lane] : 0u);
+
+        // refill the stage whose row left one iteration ago (its read-out has had the whole abs-max pass to finish;
+        // the only bulk group that can still be pending is that one store)
+        if (tid == 0 && it + ahead < my_rows) {
+            bulk_wait_read<0>();
+            const int sn = (s == 0) ? stages - 1 : s - 1;
+            mbar_arrive_expect_tx(&bars[sn], row_bytes);
+            bulk_g2s(bufs + (size_t)sn * stage_stride, x + (size_t)(first + (it + ahead) * step) * cols, row_bytes, &bars[sn]);
+        }
+
+        const float amax = DT<T>::bits_to_f(m);
+        const float sc = finalize_scale<T>(amax, min_val, has_min, int_thr);
+        const ScaleCtx<T> cx(sc, true, p, PackedPath<T, RM>::value);
+        if (tid == 0) {
+            scale_out[row] = DT<T>::from_f(sc);
+            if (absmax_out) absmax_out[row] = DT<T>::from_f(amax);
+        }
+
+        with_mode<T, RM, true>(cx.mode, [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+#pragma unroll 2
+            for (int v = tid; v < nvec; v += blockDim.x)
+                sts128(stage + (size_t)v * 16, qdq_vec<T, RM, MODE>(lds128(buf + v), cx, p));
+        });
+        fence_proxy_async_smem();                     // the generic-proxy writes above -> visible to the bulk copy
+        __syncthreads();                              // everyone is done with stage s and red[]
+        if (tid == 0) {
+            bulk_s2g(y + (size_t)row * cols, stage, row_bytes);
+            bulk_commit();
+        }
+        if (++s == stages) { s = 0; parity ^= 1u; }
+    }
+    if (tid == 0) bulk_wait_all<0>();                 // the stores must have left shared memory before the CTA exits
+}
+
 // generic rows forward: one CTA per row, element loads, any cols / alignment (second read hits L1/L2)
 template <typename T, int RM>
 __global__ void rows_fwd_generic_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ scale_out,
@@ -1664,10 +1752,10 @@ static int launch_int_quant_bwd(const void* gy, const void* x, const void* scale
 }
 
 // geometry of the TMA rows kernel
-struct RowsGeom { int threads, stages, ctas_per_sm; uint32_t stage_stride; size_t smem; bool ok; };
+struct RowsGeom { int threads, stages, ctas_per_sm; uint32_t stage_stride; size_t smem; bool ok; bool tma_store; };
 
 static RowsGeom rows_geometry(int64_t cols, int elem_size) {
-    RowsGeom g = {0, 0, 0, 0, 0, false};
+    RowsGeom g = {0, 0, 0, 0, 0, false, false};
     const int64_t row_bytes = cols * elem_size;
     if (row_bytes < 16 || (row_bytes & 15) != 0) return g;
     g.stage_stride = (uint32_t)((row_bytes + 127) & ~(int64_t)127);
@@ -1695,10 +1783,19 @@ static RowsGeom rows_geometry(int64_t cols, int elem_size) {
         ctas = (int)((200 * 1024) / (2 * stride));
         if (ctas > 6) ctas = 6;
         if (ctas < 1) { ctas = 1; threads = 256; }
+        // long 16-bit rows (C2: 22 KB): quantize in place and let the TMA engine write the row back
+        // (rows_fwd_tma_store_kernel; 3 stages x 3 CTAs x 128 threads).  r02 sweep, profiles/r02_fwd_tma_store_sweep.md:
+        // C2 bf16 33.8 -> 32.9 us, fp16 34.6 -> 33.0 us; 8 KB rows (C3) and fp32 rows gain nothing (<= 1 %) and keep
+        // the per-thread stores
+        if (row_bytes >= 16384 && 3 * (ROWS_SMEM_HEADER + 3 * stride + 1024) <= 227 * 1024) {
+            g.tma_store = true;
+            threads = 128; stages = 3; ctas = 3;
+        }
     }
     const Tuning& t = tuning();
     if (t.rows_threads > 0) threads = t.rows_threads;
-    if (t.rows_stages > 0) stages = t.rows_stages;
+    if (t.rows_stages >= 100) { g.tma_store = true; stages = t.rows_stages - 100; }     // sweep build: 100 + stages
+    else if (t.rows_stages > 0) { g.tma_store = false; stages = t.rows_stages; }
     if (t.rows_ctas_per_sm > 0) ctas = t.rows_ctas_per_sm;
     if (stages > ROWS_MAX_STAGES) stages = ROWS_MAX_STAGES;
     int max_ctas = 2048 / threads;
@@ -1730,6 +1827,21 @@ static int launch_rows_fwd(const void* x, void* y, void* scale_out, void* absmax
                                                  227 * 1024);
             if (e != cudaSuccess) return fail(BVB_ECUDA, "rows_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        if (g.tma_store) {
+            static bool attr_set_store[64] = {false};
+            if (dev < 0 || dev >= 64 || !attr_set_store[dev]) {
+                cudaError_t e = cudaFuncSetAttribute(rows_fwd_tma_store_kernel<T, RM>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (e != cudaSuccess) return fail(BVB_ECUDA, "rows_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                if (dev >= 0 && dev < 64) attr_set_store[dev] = true;
+            }
+            int64_t grid = (int64_t)resident_ctas(rows_fwd_tma_store_kernel<T, RM>, g.threads, g.smem, g.ctas_per_sm) * sm_count();
+            if (grid > rows) grid = rows;
+            rows_fwd_tma_store_kernel<T, RM><<<(unsigned)grid, g.threads, g.smem, st>>>(
+                (const T*)x, (T*)y, (T*)scale_out, (T*)absmax_out, (int)rows, (int)cols, g.stages, g.stage_stride,
+                min_val, has_min, int_thr, p);
+            return check_launch("bvb_rows_absmax_int_quant_fwd");
         }
         int64_t grid = (int64_t)resident_ctas(rows_fwd_tma_kernel<T, RM>, g.threads, g.smem, g.ctas_per_sm) * sm_count();
         if (grid > rows) grid = rows;

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--small", action="store_true", help="fwd sweep over 32/64/128-thread CTAs")
+    ap.add_argument("--store", action="store_true", help="fwd sweep of the TMA-store variant (rows_stages = 100 + stages)")
     ap.add_argument("--tuning", type=str, default="")
     a = ap.parse_args()
     tdt, tag, esz = DT[a.dtype]
@@ -101,6 +102,24 @@ def main():
         combos = [tuple(int(v) for v in a.tuning.split(","))]
     elif not a.sweep:
         combos = [(0, 0, 0, 0, 0)]
+    elif a.kernel == "fwd" and a.store:
+        combos = [(0, 0, 0, 0, 0)] + [(t, 100 + s, c, 0, 0) for t, s, c in
+                                      itertools.product(*(([256, 512, 1024], [2, 3, 4], [1, 2]) if a.dtype == "f32" else
+                                                          ([64, 128, 256], [2, 3], [3, 4, 5, 6, 8, 10])))]
+        # the variant must produce the same bits as the default kernel
+        _set_tuning(lib, 0, 0, 0, 0, 0)
+        run(0)
+        torch.cuda.synchronize()
+        y0, s0 = Y.clone(), S.clone()
+        for c in combos[1:]:
+            _set_tuning(lib, *c)
+            Y.zero_()
+            if run(0):
+                continue
+            torch.cuda.synchronize()
+            assert torch.equal(Y.view(torch.int16 if esz == 2 else torch.int32), y0.view(torch.int16 if esz == 2 else torch.int32)), c
+            assert torch.equal(S, s0), c
+        print("store variant bit-identical to the default kernel for", len(combos) - 1, "geometries")
     elif a.kernel == "fwd" and a.small:      # few warps per row: 1-2 warps own a row (less per-row overhead per element)
         combos = [(t, s, c, 0, 0) for t, s, c in itertools.product([32, 64, 128], [2, 3], [4, 6, 8, 10, 12, 16])]
     elif a.kernel == "fwd":
