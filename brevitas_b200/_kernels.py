@@ -512,6 +512,27 @@ def kth_value_rows(x, rows, cols, k, want_index=False):
     return abs_kth_value_rows(x, rows, cols, k, want_index, signed=True)
 
 
+_mm_ws = {}
+
+
+def minmax_rows(x, rows, cols):
+    """(min, max, argmin, argmax) of every row of x[rows][cols] in one read (csrc/stats.cu)"""
+    dev = _check_cuda(x)
+    x = _c(x)
+    need = int(_lib.load().bvb_minmax_workspace_bytes(rows))
+    ws = _mm_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+        _mm_ws[dev] = ws
+    mn = torch.empty(rows, dtype=x.dtype, device=dev)
+    mx = torch.empty(rows, dtype=x.dtype, device=dev)
+    imn = torch.empty(rows, dtype=torch.int64, device=dev)
+    imx = torch.empty(rows, dtype=torch.int64, device=dev)
+    _launch(dev, "bvb_minmax_rows", x.data_ptr(), mn.data_ptr(), mx.data_ptr(), imn.data_ptr(), imx.data_ptr(), rows, cols,
+            dtype_tag(x), ws.data_ptr(), _stream(dev))
+    return mn, mx, imn, imx
+
+
 def percentile_k(q: float, n: int) -> int:
     """k of AbsPercentile (src/brevitas/core/stats/stats_op.py:55, 61): floor(.01 * q * n + 0.5), 1-indexed."""
     return int(math.floor(.01 * q * n + 0.5))

@@ -78,6 +78,8 @@ SIGNATURES = {
     "bvb_kth_value_rows": (c_int, [_P, _P, _P, _L, _L, _L, _I, _P, _P]),
     "bvb_relu_abs_kth_value_rows": (c_int, [_P, _P, _P, _L, _L, _L, _I, _P, _P]),
     "bvb_kth_workspace_bytes": (c_int64, [_L]),
+    "bvb_minmax_rows": (c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P]),
+    "bvb_minmax_workspace_bytes": (c_int64, [_L]),
     "bvb_running_stats_update": (c_int, [_P, _P, _L, _F, _F, _I, _I, _P]),
 }
 

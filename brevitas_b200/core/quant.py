@@ -28,6 +28,7 @@ from ..function.ops_ste import binary_sign_ste, round_ste, ternary_sign_ste
 from .bit_width import BitWidthConst
 from .function_wrapper import CLAMP_MODE_OF, ROUND_MODE_OF, RoundSte, TensorClamp
 from .scaling import IntScaling, PowerOfTwoIntScaling
+from .stats import shared_minmax
 from .utils import StatelessBuffer
 from .zero_point import ZeroZeroPoint
 
@@ -313,9 +314,10 @@ class RescalingIntQuant(nn.Module):
         if zp is None:
             # asymmetric: scale and zero-point from their (statistics-sized) implementations, the tensor itself through
             # ONE kernel with the zero-point as a device operand; its backward returns d(scale) and d(zero_point)
-            threshold = self.scaling_impl(x)
-            scale = threshold / self.int_scaling_impl(bit_width)
-            zero_point = self.zero_point_impl(x, scale, bit_width)
+            with shared_minmax():           # AbsMinMax (scale) and NegativeMinOrZero (zero-point) share one read of x
+                threshold = self.scaling_impl(x)
+                scale = threshold / self.int_scaling_impl(bit_width)
+                zero_point = self.zero_point_impl(x, scale, bit_width)
             y = self.int_quant.forward_fused_zpt(scale, zero_point, qmin, qmax, x)
             if y is None:
                 y = self.int_quant(scale, zero_point, bit_width, x)

@@ -6,7 +6,9 @@ The reductions run on the sm_100a kernels (``brevitas_b200::absmax_rows`` / ``ab
 ``abs_kth_value_rows``); when a quantizer can fuse the statistic with the quant-dequant pass it asks the
 wrapper for an :class:`AbsMaxPlan` instead of calling it (see ``RescalingIntQuant``).
 """
+import contextlib
 import math
+import threading
 from typing import List, NamedTuple, Optional, Tuple
 
 import torch
@@ -114,6 +116,49 @@ def _kth_signed(x: Tensor, k: int, dim: Optional[int]) -> Tensor:
 DEFAULT_STD_DEV_EPSILON = 1e-8
 
 
+# ---- minimum and maximum from ONE read, shared between the statistics of one quantizer call ------------------------------
+# The asymmetric weight quantizers take torch.max + torch.min (AbsMinMax -> scale) and torch.min again (NegativeMinOrZero ->
+# zero-point) over the same view of the same weight.  `minmax_rows` returns both extrema from one pass; inside
+# `shared_minmax()` (entered by RescalingIntQuant around its scale and zero-point computation) the second statistic reuses
+# the result of the first instead of reading the tensor again.
+class _MinMaxMemo(threading.local):
+    table = None
+
+
+_MEMO = _MinMaxMemo()
+
+
+@contextlib.contextmanager
+def shared_minmax():
+    prev, _MEMO.table = _MEMO.table, {}
+    try:
+        yield
+    finally:
+        _MEMO.table = prev
+
+
+def _minmax(x: Tensor, dim: Optional[int]):
+    """(min, max) of the whole tensor (dim None) or along one dim of a 2-D tensor; None if the kernel does not apply"""
+    if not (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and x.numel() > 0
+            and x.numel() < 2 ** 31 and (dim is None or x.dim() == 2)):
+        return None
+    table = _MEMO.table
+    key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, x._version, dim)
+    if table is not None and key in table:
+        return table[key]
+    if dim is None:
+        mn, mx, _, _ = torch.ops.brevitas_b200.minmax_rows(x.reshape(-1), 1, x.numel(), True)
+        res = (mn.view(()), mx.view(()))
+    else:
+        xx = x.t() if dim % 2 == 0 else x
+        rows, cols = xx.shape
+        mn, mx, _, _ = torch.ops.brevitas_b200.minmax_rows(xx.contiguous(), rows, cols, False)
+        res = (mn, mx)
+    if table is not None:
+        table[key] = res
+    return res
+
+
 class NegativeMinOrZero(nn.Module):
     """``min(x)`` (whole tensor or along a dim) if it is <= 0 else 0 (stats_op.py:22-39)."""
 
@@ -124,7 +169,10 @@ class NegativeMinOrZero(nn.Module):
         self.zero = StatelessBuffer(torch.tensor(0.0))
 
     def forward(self, x: Tensor) -> Tensor:
-        if self.stats_reduce_dim is None:
+        both = _minmax(x, self.stats_reduce_dim)
+        if both is not None:
+            min_val = both[0]
+        elif self.stats_reduce_dim is None:
             min_val = torch.min(x)
         else:
             min_val = torch.min(x, dim=self.stats_reduce_dim)[0]
@@ -187,6 +235,9 @@ class AbsMinMax(nn.Module):
         self.stats_reduce_dim = stats_reduce_dim
 
     def forward(self, x: Tensor):
+        both = _minmax(x, self.stats_reduce_dim)
+        if both is not None:
+            return torch.abs(both[1] - both[0])
         if self.stats_reduce_dim is None:
             return torch.abs(torch.max(x) - torch.min(x))
         max_val = torch.max(x, dim=self.stats_reduce_dim)[0]

@@ -438,6 +438,131 @@ extern "C" int bvb_kth_value_rows(const void* x, void* out, int64_t* index_out, 
     return BVB_OK;
 }
 
+// ---- minimum AND maximum of every row with their positions, ONE read ------------------------------------------------
+// The asymmetric weight quantizers (ShiftedUint8Weight*: scale from AbsMinMax, stats_op.py:144-158; zero-point from
+// NegativeMinOrZero, stats_op.py:22-39) take torch.max once and torch.min twice over the same tensor; this is the three
+// reductions in one pass.  Selection semantics of ATen's CUDA reductions: NaN wins, then the value, then the LOWEST index
+// (-0.0 and +0.0 compare equal); the outputs are the selected ELEMENTS (read back by position), so their bits are exact.
+namespace bvb {
+constexpr int MM_THREADS = 256;
+
+struct MinMaxAcc {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    __device__ __forceinline__ void add(float v, uint32_t idx) {
+        uint32_t b = __float_as_uint(v);
+        if (b == 0x80000000u) b = 0u;
+        const bool nan = v != v;
+        const uint32_t k = ordered32(b);
+        const unsigned long long a = ((unsigned long long)(nan ? 0u : k) << 32) | idx;
+        const unsigned long long c = ((unsigned long long)(nan ? 0xffffffffu : k) << 32) | (uint32_t)~idx;
+        lo = a < lo ? a : lo;
+        hi = c > hi ? c : hi;
+    }
+    __device__ __forceinline__ void merge(unsigned long long l, unsigned long long h) {
+        lo = l < lo ? l : lo;
+        hi = h > hi ? h : hi;
+    }
+    __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) merge(__shfl_xor_sync(0xffffffffu, lo, o), __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(MM_THREADS) minmax_rows_kernel(const T* __restrict__ x, unsigned long long* partial,
+                                                                 int64_t cols, int splits, int64_t per_split, int vec_ok) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ unsigned long long red[2][MM_THREADS / 32];
+    const int64_t row = blockIdx.x / splits;
+    const int split = blockIdx.x % splits;
+    const int64_t begin = (int64_t)split * per_split;
+    int64_t end = begin + per_split;
+    if (end > cols) end = cols;
+    const T* xr = x + row * cols;
+    MinMaxAcc acc;
+    if (vec_ok) {                                       // per_split and cols are multiples of V, rows 16-byte aligned
+        const uint4* xv = reinterpret_cast<const uint4*>(xr);
+        for (int64_t v = begin / V + threadIdx.x; v < end / V; v += MM_THREADS) {
+            float e[V];
+            DT<T>::unpack(ldg_stream(xv + v), e);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc.add(e[i], (uint32_t)(v * V + i));
+        }
+    } else {
+        for (int64_t i = begin + threadIdx.x; i < end; i += MM_THREADS) acc.add(DT<T>::to_f(xr[i]), (uint32_t)i);
+    }
+    acc.warp_reduce();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = acc.lo; red[1][warp] = acc.hi; }
+    __syncthreads();
+    if (warp == 0) {
+        MinMaxAcc t;
+        if (lane < MM_THREADS / 32) t.merge(red[0][lane], red[1][lane]);
+        t.warp_reduce();
+        if (lane == 0) {
+            partial[2 * (size_t)blockIdx.x] = t.lo;
+            partial[2 * (size_t)blockIdx.x + 1] = t.hi;
+        }
+    }
+}
+
+template <typename T>
+__global__ void minmax_finalize_kernel(const T* __restrict__ x, const unsigned long long* partial, T* mn, T* mx,
+                                       int64_t* imn, int64_t* imx, int64_t rows, int64_t cols, int splits) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    MinMaxAcc t;
+    for (int sidx = lane; sidx < splits; sidx += 32)
+        t.merge(partial[2 * ((size_t)row * splits + sidx)], partial[2 * ((size_t)row * splits + sidx) + 1]);
+    t.warp_reduce();
+    if (lane == 0) {
+        const uint32_t il = (uint32_t)t.lo, ih = ~(uint32_t)t.hi;
+        mn[row] = x[row * cols + il];
+        mx[row] = x[row * cols + ih];
+        if (imn) imn[row] = (int64_t)il;
+        if (imx) imx[row] = (int64_t)ih;
+    }
+}
+
+constexpr int64_t MM_MIN_CTAS = 512;            // few rows: split them until about this many CTAs read (3-4 per SM)
+static int minmax_splits(int64_t rows, int64_t cols, int vec) {
+    int64_t want = (MM_MIN_CTAS + rows - 1) / rows;
+    const int64_t most = (cols + (int64_t)MM_THREADS * vec * 4 - 1) / ((int64_t)MM_THREADS * vec * 4);
+    if (want > most) want = most;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+}  // namespace bvb
+
+extern "C" int64_t bvb_minmax_workspace_bytes(int64_t rows) {           // one (min, max) pair of 64-bit words per CTA
+    if (rows < 1) rows = 1;
+    return 16 * rows * ((MM_MIN_CTAS + rows - 1) / rows);
+}
+
+extern "C" int bvb_minmax_rows(const void* x, void* min_out, void* max_out, int64_t* argmin_out, int64_t* argmax_out,
+                               int64_t rows, int64_t cols, int dtype, void* workspace, void* stream) {
+    if (rows < 0 || cols < 0) return fail(BVB_EINVAL, "bvb_minmax_rows: negative size");
+    if (rows == 0) return BVB_OK;
+    if (cols < 1 || cols >= ((int64_t)1 << 32)) return fail(BVB_EINVAL, "bvb_minmax_rows: 1 <= cols < 2^32 required");
+    if (!x || !min_out || !max_out || !workspace) return fail(BVB_EINVAL, "bvb_minmax_rows: null pointer");
+    const int vec = 16 / dtype_size(dtype);
+    const int splits = minmax_splits(rows, cols, vec);
+    if ((int64_t)rows * splits >= ((int64_t)1 << 31)) return fail(BVB_EUNSUPPORTED, "bvb_minmax_rows: too many rows");
+    int64_t per = (cols + splits - 1) / splits;
+    per = (per + vec - 1) / vec * vec;
+    const int vec_ok = aligned16(x) && (cols % vec) == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    BVB_DISPATCH_DTYPE(dtype, {
+        minmax_rows_kernel<T><<<(unsigned)(rows * splits), MM_THREADS, 0, st>>>(
+            (const T*)x, (unsigned long long*)workspace, cols, splits, per, vec_ok);
+        minmax_finalize_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+            (const T*)x, (const unsigned long long*)workspace, (T*)min_out, (T*)max_out, argmin_out, argmax_out, rows, cols,
+            splits);
+    });
+    return check_launch("bvb_minmax_rows");
+}
+
 extern "C" int bvb_running_stats_update(float* running, const void* stat, int64_t count, float momentum,
                                         float one_minus_momentum, int first, int dtype, void* stream) {
     if (count < 0) return fail(BVB_EINVAL, "bvb_running_stats_update: negative size");

@@ -670,6 +670,51 @@ def _kth_signed_bwd(ctx, gval, gidx):
 torch.library.register_autograd(f"{FQ_NS}::kth_value_rows", _kth_signed_bwd, setup_context=_kth_setup, lib=_FQ)
 
 
+# ---- min AND max of every row in one read (AbsMinMax + NegativeMinOrZero of the asymmetric weight quantizers) -----------
+_FQ.define("minmax_rows(Tensor x, int rows, int cols, bool whole) -> (Tensor, Tensor, Tensor, Tensor)")
+_FQ.impl("minmax_rows", lambda x, r, c, whole: K.minmax_rows(x, r, c), "CUDA")
+_FQ.impl("minmax_rows", _no_cpu("minmax_rows"), "CPU")
+torch.library.register_fake(
+    f"{FQ_NS}::minmax_rows",
+    lambda x, r, c, whole: (x.new_empty(r), x.new_empty(r), x.new_empty(r, dtype=torch.int64),
+                            x.new_empty(r, dtype=torch.int64)), lib=_FQ)
+
+
+def _minmax_setup(ctx, inputs, output):
+    x, rows, cols, whole = inputs
+    mn, mx, imn, imx = output
+    ctx.save_for_backward(x, mn, mx, imn, imx)
+    ctx.rcw = (rows, cols, whole)
+    ctx.mark_non_differentiable(imn, imx)
+    ctx.set_materialize_grads(False)
+
+
+def _minmax_bwd(ctx, gmn, gmx, _gimn, _gimx):
+    x, mn, mx, imn, imx = ctx.saved_tensors
+    rows, cols, whole = ctx.rcw
+    if whole:
+        # torch.min(x) / torch.max(x) over the whole tensor: the gradient is split evenly over tied extrema
+        # (ATen's evenly_distribute_backward), the reference's own dense expression
+        gx = None
+        for g, ext in ((gmn, mn), (gmx, mx)):
+            if g is None:
+                continue
+            mask = x == ext.view(())
+            part = mask * (g.to(x.dtype).view(()) / mask.sum())
+            gx = part if gx is None else gx + part
+        return gx, None, None, None
+    # torch.min(x, dim) / torch.max(x, dim): the gradient goes to the selected position
+    gx = torch.zeros(rows, cols, dtype=x.dtype, device=x.device)
+    if gmn is not None:
+        gx.scatter_add_(1, imn.view(rows, 1), gmn.to(x.dtype).view(rows, 1))
+    if gmx is not None:
+        gx.scatter_add_(1, imx.view(rows, 1), gmx.to(x.dtype).view(rows, 1))
+    return gx.view(x.shape), None, None, None
+
+
+torch.library.register_autograd(f"{FQ_NS}::minmax_rows", _minmax_bwd, setup_context=_minmax_setup, lib=_FQ)
+
+
 # ---- QuantReLU in its statistics-collection phase, ReLU folded --------------
 # The threshold is the k-th smallest of relu(x) (AbsPercentile, core/scaling/standalone.py:230-244) and the quantizer then
 # runs on relu(x) with a scale derived from it.  Two autograd functions share a `holder` dict for one forward call:

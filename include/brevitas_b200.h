@@ -217,6 +217,15 @@ int bvb_binary_quant_bwd(const void* gy, const void* x, const void* scale, void*
                          int64_t scale_inner, int64_t scale_count, int scale_dtype, int clamped, int dtype,
                          void* stream);
 
+/* Minimum AND maximum of every row with their positions in ONE read: torch.max(x, dim) + torch.min(x, dim) of AbsMinMax
+ * (src/brevitas/core/stats/stats_op.py:144-158) and the torch.min of NegativeMinOrZero (stats_op.py:22-39) that the
+ * asymmetric weight quantizers run over the same tensor.  Selection as ATen's CUDA reductions: NaN wins, then the value,
+ * then the lowest index; the outputs are the selected elements themselves.  argmin_out / argmax_out (nullable): int64
+ * positions inside the row.  workspace: bvb_minmax_workspace_bytes(rows) bytes of device memory.                  */
+int64_t bvb_minmax_workspace_bytes(int64_t rows);
+int bvb_minmax_rows(const void* x, void* min_out, void* max_out, int64_t* argmin_out, int64_t* argmax_out, int64_t rows,
+                    int64_t cols, int dtype, void* workspace, void* stream);
+
 /* ---- 4a. the remaining quantizer flavours, one kernel per direction ------------------------- */
 /* General integer quantizer: DecoupledIntQuant.forward (src/brevitas/core/quant/int_base.py:132-182) and
  * IntQuant.forward (int_base.py:64-97) when the range must stay on the device -- a learned bit-width

@@ -265,3 +265,71 @@ def test_module_paths_launch_one_kernel_each():
         y.sum().backward()
         bwd = _kernels.launch_count - before - fwd
         assert (fwd, bwd) == (1, 1), (name, fwd, bwd)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (5, 33), (64, 1024), (3, 100003), (1, 3 * 1024 * 1024 + 5), (700, 96)])
+def test_minmax_rows_vs_aten(rows, cols, dtype):
+    """one read for min AND max (+ positions): ATen's selection rules -- NaN wins, then the value, then the lowest index"""
+    import brevitas_b200  # noqa: F401
+    gen = torch.Generator().manual_seed(rows * 31 + cols)
+    x = torch.randn(rows, cols, generator=gen).to(dtype).cuda()
+    if cols >= 7:
+        x[0, 1] = x[0].max()              # tie for the maximum: lowest index wins
+        x[0, 5] = x[0, 1]
+        x[-1, 3] = float("inf")
+        x[-1, 4] = float("-inf")
+    if rows >= 5 and cols >= 33:
+        x[2, 9] = float("nan")
+        x[2, 20] = float("nan")
+        x[3] = 0.0
+        x[3, 7] = -0.0                     # -0.0 == +0.0: position 0 is selected for both
+    mn, mx, imn, imx = torch.ops.brevitas_b200.minmax_rows(x, rows, cols, False)
+    rmin, rmax = torch.min(x, dim=1), torch.max(x, dim=1)
+    same_bits(mn, rmin.values, "min")
+    same_bits(mx, rmax.values, "max")
+    finite_rows = ~torch.isnan(rmin.values)
+    assert torch.equal(imn[finite_rows], rmin.indices[finite_rows]) and torch.equal(imx[finite_rows], rmax.indices[finite_rows])
+    if rows >= 5 and cols >= 33:
+        assert int(imn[2]) == 9 and int(imx[2]) == 9 and int(imn[3]) == 0 and int(imx[3]) == 0
+    # gradients: along a dim the selected position takes it all; over the whole tensor tied extrema share it
+    for whole in (False, True):
+        xa = x.clone()
+        if whole:
+            xa = torch.nan_to_num(xa.reshape(1, -1), 0.0, 5.0, -5.0)
+            if xa.numel() > 3:
+                xa[0, 2] = xa.max()
+        r_, c_ = xa.shape
+        a = xa.clone().requires_grad_(True)
+        b = xa.clone().requires_grad_(True)
+        mn, mx, _, _ = torch.ops.brevitas_b200.minmax_rows(a.reshape(-1) if whole else a, r_, c_, whole)
+        if whole:
+            ref_mn, ref_mx = torch.min(b.reshape(-1)).view(1), torch.max(b.reshape(-1)).view(1)
+        else:
+            ref_mn, ref_mx = torch.min(b, dim=1)[0], torch.max(b, dim=1)[0]
+        w1 = torch.randn(r_, generator=gen).to(dtype).cuda()
+        w2 = torch.randn(r_, generator=gen).to(dtype).cuda()
+        keep = ~torch.isnan(ref_mn.detach())
+        ((mn * w1)[keep].sum() + (mx * w2)[keep].sum()).backward()
+        ((ref_mn * w1)[keep].sum() + (ref_mx * w2)[keep].sum()).backward()
+        same_bits(a.grad, b.grad, f"d x (whole={whole})")
+
+
+@pytest.mark.parametrize("name", ["ShiftedUint8WeightPerTensorFloat", "ShiftedUint8WeightPerChannelFloat"])
+def test_asymmetric_weight_quantizer_reads_the_weight_twice(name):
+    """statistics (min and max, shared by scale and zero-point) + the quantizer: TWO library launches, no ATen reduction"""
+    import brevitas_b200  # noqa: F401
+    from brevitas_b200 import _kernels
+    import brevitas_b200.nn as qnn
+    import brevitas_b200.quant as Q
+    layer = qnn.QuantConv2d(16, 32, 3, bias=False, weight_quant=getattr(Q, name)).cuda()
+    layer.quant_weight()
+    before = _kernels.launch_count
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        qw = layer.quant_weight()
+        torch.cuda.synchronize()
+    assert _kernels.launch_count - before == 2
+    names = [e.key for e in prof.key_averages()]
+    assert any("minmax_rows_kernel" in n for n in names), names
+    assert not any("reduce_kernel" in n for n in names), names          # no torch.min / torch.max pass is left
+    assert qw.zero_point is not None
