@@ -1,7 +1,7 @@
 #!/bin/bash
 # Final evidence set of a round (run on the GPU box): TAG=r01w bash tools/capture_round.sh; copy the files from
 # gpurun_out/ into profiles/ (raw csv under profiles/raw/) and run tools/make_profile_summary.py $TAG
-TAG=${TAG:-r02a}
+TAG=${TAG:-r02c}
 set -x
 python bench.py --qat-all > gpurun_out/${TAG}_bench_plain.json 2> gpurun_out/${TAG}_bench_plain.err; echo bench rc=$?
 (python tools/prof_all.py; python tools/prof_misc.py) > gpurun_out/${TAG}_kernel_timings_graph_replay.log 2>&1

@@ -67,6 +67,17 @@ def main():
     _, sm_, si_ = K.bn_act_quant_fwd(XB[0], gam, bet, rm_, rv_, 0.1, 1e-5, True, sbn, 0.0, 0.0, 255.0)
     cases["bn_relu_quant_f32_fwd"] = (lambda i: K.bn_act_quant_fwd(XB[i % 2], gam, bet, rm_, rv_, 0.1, 1e-5, True, sbn, 0.0, 0.0, 255.0), BN * BC * 12)
     cases["bn_relu_quant_f32_bwd"] = (lambda i: K.bn_act_quant_bwd(GB, XB[i % 2], gam, bet, sm_, si_, sbn, 0.0, 0.0, 255.0, 1), BN * BC * 20)
+    # r02: the remaining quantizer flavours (csrc/quant_variants.cu) and the one-read min + max statistic, C2 weight size
+    z0, lo8, hi8 = torch.tensor(0.0, device=dev), torch.tensor(-127.0, device=dev), torch.tensor(127.0, device=dev)
+    pre_ch, post_ch = sch.view(R, 1), (sch * 0.9).view(R, 1)
+    cases["decoupled_f32_rows_fwd"] = (lambda i: K.general_int_quant_fwd(W[i % NS], pre_ch, post_ch, z0, z0, lo8, hi8, 0), R * C * 8)
+    cases["decoupled_f32_rows_bwd_sums"] = (lambda i: K.general_int_quant_bwd(G[i % 2], W[i % NS], pre_ch, post_ch, z0, z0, lo8, hi8, 0, 0, False, True), R * C * 12)
+    cases["learned_bw_f32_scalar_fwd"] = (lambda i: K.general_int_quant_fwd(W[i % NS], s0f, s0f, z0, z0, lo8, hi8, 0), R * C * 8)
+    cases["learned_bw_f32_scalar_bwd_sums"] = (lambda i: K.general_int_quant_bwd(G[i % 2], W[i % NS], s0f, s0f, z0, z0, lo8, hi8, 0, 1, True, True), R * C * 12)
+    cases["ternary_f32_fwd"] = (lambda i: K.ternary_quant_fwd(W[i % NS], s0f, 0.5), R * C * 8)
+    cases["ternary_f32_bwd_gs"] = (lambda i: K.ternary_quant_bwd(G[i % 2], W[i % NS], s0f, 0.5, True), R * C * 12)
+    cases["minmax_rows_f32"] = (lambda i: K.minmax_rows(W[i % NS], R, C), R * C * 4)
+    cases["minmax_tensor_f32"] = (lambda i: K.minmax_rows(W[i % NS].reshape(-1), 1, R * C), R * C * 4)
     only = [s for s in a.only.split(",") if s]
     period = 6                                    # lcm of the input rotations above
     for name, (fn, nbytes) in cases.items():
