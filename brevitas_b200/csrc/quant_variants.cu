@@ -61,17 +61,17 @@ struct GenRange {
 };
 
 template <typename T>
-__device__ __forceinline__ void gen_codes(float x, float ps, const GenRange<T>& r, int rm, float& t1, float& t3, float& t5) {
-    t1 = DT<T>::rnd(__fdiv_rn(x, ps));
+__device__ __forceinline__ void gen_codes(float x, const DivBy& dv, const GenRange<T>& r, int rm, float& t1, float& t3, float& t5) {
+    t1 = DT<T>::rnd(dv(x));
     const float t2 = DT<T>::rnd(fadd(t1, r.pre_zp));        // -0.0 + 0.0 = +0.0 like the reference
     t3 = f2i_runtime<T>(t2, rm);
     t5 = where_clamp(t3, r.lo, r.hi);
 }
 
 template <typename T>
-__device__ __forceinline__ float gen_fwd_elem(float x, float ps, float s, const GenRange<T>& r, int rm) {
+__device__ __forceinline__ float gen_fwd_elem(float x, const DivBy& dv, float s, const GenRange<T>& r, int rm) {
     float t1, t3, t5;
-    gen_codes<T>(x, ps, r, rm, t1, t3, t5);
+    gen_codes<T>(x, dv, r, rm, t1, t3, t5);
     const float t6 = DT<T>::rnd(fsub(t5, r.zp));
     return fmul(t6, s);
 }
@@ -81,13 +81,13 @@ struct GenAcc {
 };
 
 template <typename T>
-__device__ __forceinline__ float gen_bwd_elem(float g, float x, float ps, float s, const GenRange<T>& r, const GenQ& q,
+__device__ __forceinline__ float gen_bwd_elem(float g, float x, const DivBy& dv, float s, const GenRange<T>& r, const GenQ& q,
                                               GenAcc& a) {
     const float gc = DT<T>::rnd(fmul(g, s));                  // MulBackward: d(c - zp)
     float d = gc;
     if (q.masked || q.want_sums) {
         float t1, t3, t5;
-        gen_codes<T>(x, ps, r, q.round_mode, t1, t3, t5);
+        gen_codes<T>(x, dv, r, q.round_mode, t1, t3, t5);
         if (q.masked) {
             // where(c1 < min, min, c1) with c1 = where(t3 > max, max, t3), walked backwards
             const bool over = t3 > r.hi;
@@ -98,12 +98,12 @@ __device__ __forceinline__ float gen_bwd_elem(float g, float x, float ps, float 
         }
         if (q.want_sums) {
             const float t6 = DT<T>::rnd(fsub(t5, r.zp));
-            const float back = d * DT<T>::rnd(__fdiv_rn(t1, ps));           // DivBackward wrt the divisor: -d * ((x / s) / s)
+            const float back = d * DT<T>::rnd(dv(t1));                      // DivBackward wrt the divisor: -d * ((x / s) / s)
             if (q.same_scale) a.post += fmaf(g, t6, -back);                  // the two nearly cancel: difference per element
             else { a.post = fmaf(g, t6, a.post); a.pre -= back; }
         }
     }
-    return __fdiv_rn(d, ps);
+    return dv(d);
 }
 
 template <typename T>
@@ -154,23 +154,24 @@ __global__ void __launch_bounds__(QV_THREADS) general_int_quant_kernel(GenQ q) {
                 if (q.post_count > 1) s = DT<T>::to_f(s_p[idx]);
                 if (BWD && idx != acc_idx) { gen_flush<T>(q, acc, acc_idx); acc_idx = idx; }
             }
+            const DivBy dv(ps, DT<T>::MUL_DIV_EXACT);
             if constexpr (VECTOR) {
                 float ex[V], eg[V];
                 DT<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(q.x) + v), ex);
                 if constexpr (BWD) {
                     DT<T>::unpack(ldg_stream(reinterpret_cast<const uint4*>(q.gy) + v), eg);
 #pragma unroll
-                    for (int i = 0; i < V; ++i) ex[i] = gen_bwd_elem<T>(eg[i], ex[i], ps, s, r, q, acc);
+                    for (int i = 0; i < V; ++i) ex[i] = gen_bwd_elem<T>(eg[i], ex[i], dv, s, r, q, acc);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < V; ++i) ex[i] = gen_fwd_elem<T>(ex[i], ps, s, r, q.round_mode);
+                    for (int i = 0; i < V; ++i) ex[i] = gen_fwd_elem<T>(ex[i], dv, s, r, q.round_mode);
                 }
                 stg_stream(reinterpret_cast<uint4*>(q.out) + v, DT<T>::pack(ex));
             } else {
                 const float xv = DT<T>::to_f(reinterpret_cast<const T*>(q.x)[v]);
                 float o;
-                if constexpr (BWD) o = gen_bwd_elem<T>(DT<T>::to_f(reinterpret_cast<const T*>(q.gy)[v]), xv, ps, s, r, q, acc);
-                else o = gen_fwd_elem<T>(xv, ps, s, r, q.round_mode);
+                if constexpr (BWD) o = gen_bwd_elem<T>(DT<T>::to_f(reinterpret_cast<const T*>(q.gy)[v]), xv, dv, s, r, q, acc);
+                else o = gen_fwd_elem<T>(xv, dv, s, r, q.round_mode);
                 reinterpret_cast<T*>(q.out)[v] = DT<T>::from_f(o);
             }
         }
@@ -197,6 +198,92 @@ __global__ void __launch_bounds__(QV_THREADS) general_int_quant_kernel(GenQ q) {
     }
 }
 
+// Tiled flavour for long runs of one scale (one scale for the tensor, or a scale per row / plane with at least a tile of
+// 16-byte vectors per run): a CTA owns a CONTIGUOUS range of tiles that never straddle a run, so the scale index, the
+// divisor set-up and the scale loads are per tile instead of per vector, 4 independent vectors are in flight per thread,
+// and the per-scale sums are reduced by the CTA once per run (two fp64 atomics per run and CTA instead of per thread).
+constexpr int QT_UNROLL = 4;
+constexpr int QT_TILE = QV_THREADS * QT_UNROLL;
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(QV_THREADS) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
+                                                                             int64_t total_tiles) {
+    constexpr int V = DT<T>::VEC;
+    __shared__ double red[32];
+    const GenRange<T> r(q);
+    const T* ps_p = reinterpret_cast<const T*>(q.pre_scale);
+    const T* s_p = reinterpret_cast<const T*>(q.scale);
+    const int64_t count = q.pre_count > q.post_count ? q.pre_count : q.post_count;
+    const uint4* xv = reinterpret_cast<const uint4*>(q.x);
+    const uint4* gv = reinterpret_cast<const uint4*>(q.gy);
+    uint4* ov = reinterpret_cast<uint4*>(q.out);
+    const int64_t t0 = total_tiles * blockIdx.x / gridDim.x, t1 = total_tiles * (blockIdx.x + 1) / gridDim.x;
+    GenAcc acc;
+    int64_t cur = -1;
+    float ps = 1.f, s = 1.f;
+    DivBy dv;
+    auto flush = [&]() {              // uniform over the CTA
+        if (!BWD || !q.want_sums || cur < 0) return;
+        const double pre = q.same_scale ? 0.0 : block_sum_d((double)acc.pre, red);
+        const double post = block_sum_d((double)acc.post, red);
+        if (threadIdx.x == 0) {
+            if (!q.same_scale && pre != 0.0) atomicAdd(q.sums + (q.pre_count == 1 ? 0 : cur), pre);
+            if (post != 0.0) atomicAdd(q.sums + q.pre_count + (q.post_count == 1 ? 0 : cur), post);
+        }
+        acc.pre = acc.post = 0.f;
+    };
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t run = t / tiles_per_run;
+        const int64_t off = (t - run * tiles_per_run) * QT_TILE;
+        const int64_t idx = count > 1 ? run % count : 0;
+        if (idx != cur) {
+            flush();
+            cur = idx;
+            ps = DT<T>::to_f(ps_p[q.pre_count > 1 ? idx : 0]);
+            s = DT<T>::to_f(s_p[q.post_count > 1 ? idx : 0]);
+            dv = DivBy(ps, DT<T>::MUL_DIV_EXACT);
+        }
+        const int64_t base = run * inner_u + off;
+        const int64_t len = inner_u - off;                       // vectors left in this run (the tile takes up to QT_TILE)
+        uint4 qx[QT_UNROLL], qg[QT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < QT_UNROLL; ++u) {
+            const int64_t o = threadIdx.x + (int64_t)u * QV_THREADS;
+            if (o < len) {
+                qx[u] = ldg_stream(xv + base + o);
+                if constexpr (BWD) qg[u] = ldg_stream(gv + base + o);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < QT_UNROLL; ++u) {
+            const int64_t o = threadIdx.x + (int64_t)u * QV_THREADS;
+            if (o < len) {
+                float ex[V], eg[V];
+                DT<T>::unpack(qx[u], ex);
+                if constexpr (BWD) {
+                    DT<T>::unpack(qg[u], eg);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) ex[i] = gen_bwd_elem<T>(eg[i], ex[i], dv, s, r, q, acc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) ex[i] = gen_fwd_elem<T>(ex[i], dv, s, r, q.round_mode);
+                }
+                stg_stream(ov + base + o, DT<T>::pack(ex));
+            }
+        }
+    }
+    if constexpr (BWD) {
+        flush();
+        if (q.want_sums && q.masked) {
+            const double lo = block_sum_d((double)acc.lo, red), hi = block_sum_d((double)acc.hi, red);
+            if (threadIdx.x == 0) {
+                if (lo != 0.0) atomicAdd(q.sums + q.pre_count + q.post_count, lo);
+                if (hi != 0.0) atomicAdd(q.sums + q.pre_count + q.post_count + 1, hi);
+            }
+        }
+    }
+}
+
 static inline unsigned qv_grid(int64_t units) {
     int64_t b = (units + (int64_t)QV_THREADS * QV_UNROLL - 1) / ((int64_t)QV_THREADS * QV_UNROLL);
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -211,7 +298,31 @@ static int launch_general(const GenQ& q, cudaStream_t st, const char* what) {
     const int64_t count = q.pre_count > q.post_count ? q.pre_count : q.post_count;
     bool vec = aligned16(q.x) && aligned16(q.out) && (!BWD || aligned16(q.gy)) && q.n % V == 0;
     if (count > 1 && q.inner % V != 0) vec = false;
-    if (vec) general_int_quant_kernel<T, BWD, true><<<qv_grid(q.n / V), QV_THREADS, 0, st>>>(q);
+    if (count == 1 && q.n % V != 0 && q.n >= (int64_t)V * QT_TILE && aligned16(q.x) && aligned16(q.out) &&
+        (!BWD || aligned16(q.gy))) {
+        // one scale, ragged length: 16-byte vectors for the bulk, the last < V elements element-wise (the sums meet in
+        // the same fp64 words)
+        GenQ main = q, tail = q;
+        main.n = q.n / V * V;
+        const size_t skip = (size_t)main.n * sizeof(T);
+        tail.n = q.n - main.n;
+        tail.x = (const char*)q.x + skip;
+        tail.out = (char*)q.out + skip;
+        if (BWD) tail.gy = (const char*)q.gy + skip;
+        const int rc = launch_general<T, BWD>(main, st, what);
+        if (rc != BVB_OK) return rc;
+        general_int_quant_kernel<T, BWD, false><<<1, QV_THREADS, 0, st>>>(tail);
+        return check_launch(what);
+    }
+    const int64_t inner_u = count > 1 ? q.inner / V : q.n / V;
+    if (vec && inner_u >= QT_TILE / 2) {
+        const int64_t runs = (q.n / V) / inner_u;
+        const int64_t tiles_per_run = (inner_u + QT_TILE - 1) / QT_TILE;
+        const int64_t total = runs * tiles_per_run;
+        int64_t grid = (int64_t)sm_count() * 8;
+        if (grid > total) grid = total;
+        general_int_quant_tiled_kernel<T, BWD><<<(unsigned)grid, QV_THREADS, 0, st>>>(q, inner_u, tiles_per_run, total);
+    } else if (vec) general_int_quant_kernel<T, BWD, true><<<qv_grid(q.n / V), QV_THREADS, 0, st>>>(q);
     else general_int_quant_kernel<T, BWD, false><<<qv_grid(q.n), QV_THREADS, 0, st>>>(q);
     return check_launch(what);
 }

@@ -482,7 +482,21 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_rows_kernel(const T* __rest
     MinMaxAcc acc;
     if (vec_ok) {                                       // per_split and cols are multiples of V, rows 16-byte aligned
         const uint4* xv = reinterpret_cast<const uint4*>(xr);
-        for (int64_t v = begin / V + threadIdx.x; v < end / V; v += MM_THREADS) {
+        const int64_t v1 = end / V;
+        int64_t v = begin / V + threadIdx.x;
+        for (; v + 3 * MM_THREADS < v1; v += 4 * MM_THREADS) {          // four independent 16-byte loads in flight
+            uint4 q4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q4[u] = ldg_stream(xv + v + u * MM_THREADS);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float e[V];
+                DT<T>::unpack(q4[u], e);
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc.add(e[i], (uint32_t)((v + u * MM_THREADS) * V + i));
+            }
+        }
+        for (; v < v1; v += MM_THREADS) {
             float e[V];
             DT<T>::unpack(ldg_stream(xv + v), e);
 #pragma unroll
