@@ -106,6 +106,62 @@ __device__ __forceinline__ float gen_bwd_elem(float g, float x, const DivBy& dv,
     return dv(d);
 }
 
+// one 16-byte vector at a time: the divisions of a vector share ONE slow-path test (DivBy::div_n), the d(pre_scale) term
+// (a tolerance-bound sum) multiplies by the reciprocal instead of dividing again, and RMC >= 0 fixes the rounding mode at
+// compile time (round-half-even, the default of every named quantizer)
+template <typename T, int RMC>
+__device__ __forceinline__ float f2i_sel(float v, int rm) {
+    if constexpr (RMC == RM_ROUND) return rintf(v);
+    else return f2i_runtime<T>(v, rm);
+}
+
+template <typename T, int RMC, int N>
+__device__ __forceinline__ void gen_fwd_n(float (&e)[N], const DivBy& dv, float s, const GenRange<T>& r, int rm) {
+    float t1[N];
+    dv.div_n<N>(e, t1);
+    DT<T>::template rnd_n<N>(t1);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const float t2 = DT<T>::rnd(fadd(t1[i], r.pre_zp));
+        const float t5 = where_clamp(f2i_sel<T, RMC>(t2, rm), r.lo, r.hi);
+        e[i] = fmul(DT<T>::rnd(fsub(t5, r.zp)), s);
+    }
+}
+
+template <typename T, int RMC, int N>
+__device__ __forceinline__ void gen_bwd_n(float (&eg)[N], const float (&ex)[N], const DivBy& dv, float inv_ps, float s,
+                                          const GenRange<T>& r, const GenQ& q, GenAcc& a) {
+    float d[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) d[i] = fmul(eg[i], s);
+    DT<T>::template rnd_n<N>(d);
+    if (q.masked || q.want_sums) {
+        float t1[N];
+        dv.div_n<N>(ex, t1);
+        DT<T>::template rnd_n<N>(t1);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float t2 = DT<T>::rnd(fadd(t1[i], r.pre_zp));
+            const float t3 = f2i_sel<T, RMC>(t2, q.round_mode);
+            const bool over = t3 > r.hi;
+            const float c1 = over ? r.hi : t3;
+            const bool under = c1 < r.lo;
+            const float t5 = under ? r.lo : c1;
+            if (q.masked) {
+                if (under) { a.lo += d[i]; d[i] = 0.f; }
+                else if (over) { a.hi += d[i]; d[i] = 0.f; }
+            }
+            if (q.want_sums) {
+                const float t6 = DT<T>::rnd(fsub(t5, r.zp));
+                const float back = d[i] * (t1[i] * inv_ps);
+                if (q.same_scale) a.post += fmaf(eg[i], t6, -back);
+                else { a.post = fmaf(eg[i], t6, a.post); a.pre -= back; }
+            }
+        }
+    }
+    dv.div_n<N>(d, eg);
+}
+
 template <typename T>
 __device__ __forceinline__ void gen_flush(const GenQ& q, GenAcc& a, int64_t idx) {
     if (!q.want_sums || idx < 0) return;
@@ -205,7 +261,7 @@ __global__ void __launch_bounds__(QV_THREADS) general_int_quant_kernel(GenQ q) {
 constexpr int QT_UNROLL = 4;
 constexpr int QT_TILE = QV_THREADS * QT_UNROLL;
 
-template <typename T, bool BWD>
+template <typename T, bool BWD, int RMC>
 __global__ void __launch_bounds__(QV_THREADS) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
                                                                              int64_t total_tiles) {
     constexpr int V = DT<T>::VEC;
@@ -220,7 +276,7 @@ __global__ void __launch_bounds__(QV_THREADS) general_int_quant_tiled_kernel(Gen
     const int64_t t0 = total_tiles * blockIdx.x / gridDim.x, t1 = total_tiles * (blockIdx.x + 1) / gridDim.x;
     GenAcc acc;
     int64_t cur = -1;
-    float ps = 1.f, s = 1.f;
+    float ps = 1.f, s = 1.f, inv_ps = 1.f;
     DivBy dv;
     auto flush = [&]() {              // uniform over the CTA
         if (!BWD || !q.want_sums || cur < 0) return;
@@ -242,6 +298,7 @@ __global__ void __launch_bounds__(QV_THREADS) general_int_quant_tiled_kernel(Gen
             ps = DT<T>::to_f(ps_p[q.pre_count > 1 ? idx : 0]);
             s = DT<T>::to_f(s_p[q.post_count > 1 ? idx : 0]);
             dv = DivBy(ps, DT<T>::MUL_DIV_EXACT);
+            inv_ps = dv.approx_recip();
         }
         const int64_t base = run * inner_u + off;
         const int64_t len = inner_u - off;                       // vectors left in this run (the tile takes up to QT_TILE)
@@ -262,13 +319,12 @@ __global__ void __launch_bounds__(QV_THREADS) general_int_quant_tiled_kernel(Gen
                 DT<T>::unpack(qx[u], ex);
                 if constexpr (BWD) {
                     DT<T>::unpack(qg[u], eg);
-#pragma unroll
-                    for (int i = 0; i < V; ++i) ex[i] = gen_bwd_elem<T>(eg[i], ex[i], dv, s, r, q, acc);
+                    gen_bwd_n<T, RMC, V>(eg, ex, dv, inv_ps, s, r, q, acc);
+                    stg_stream(ov + base + o, DT<T>::pack(eg));
                 } else {
-#pragma unroll
-                    for (int i = 0; i < V; ++i) ex[i] = gen_fwd_elem<T>(ex[i], dv, s, r, q.round_mode);
+                    gen_fwd_n<T, RMC, V>(ex, dv, s, r, q.round_mode);
+                    stg_stream(ov + base + o, DT<T>::pack(ex));
                 }
-                stg_stream(ov + base + o, DT<T>::pack(ex));
             }
         }
     }
@@ -321,7 +377,10 @@ static int launch_general(const GenQ& q, cudaStream_t st, const char* what) {
         const int64_t total = runs * tiles_per_run;
         int64_t grid = (int64_t)sm_count() * 8;
         if (grid > total) grid = total;
-        general_int_quant_tiled_kernel<T, BWD><<<(unsigned)grid, QV_THREADS, 0, st>>>(q, inner_u, tiles_per_run, total);
+        if (q.round_mode == RM_ROUND)
+            general_int_quant_tiled_kernel<T, BWD, RM_ROUND><<<(unsigned)grid, QV_THREADS, 0, st>>>(q, inner_u, tiles_per_run, total);
+        else
+            general_int_quant_tiled_kernel<T, BWD, -1><<<(unsigned)grid, QV_THREADS, 0, st>>>(q, inner_u, tiles_per_run, total);
     } else if (vec) general_int_quant_kernel<T, BWD, true><<<qv_grid(q.n / V), QV_THREADS, 0, st>>>(q);
     else general_int_quant_kernel<T, BWD, false><<<qv_grid(q.n), QV_THREADS, 0, st>>>(q);
     return check_launch(what);

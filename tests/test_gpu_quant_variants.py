@@ -49,7 +49,8 @@ def literal(x, ps, s, pzp, zp, lo, hi, round_impl, clamp_impl):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("pattern", ["scalar", "per_out_channel", "per_dim1", "pre_scalar_post_channel"])
+@pytest.mark.parametrize("pattern", ["scalar", "per_out_channel", "per_dim1", "pre_scalar_post_channel", "per_row_long",
+                                     "scalar_ragged_long"])
 @pytest.mark.parametrize("clamp", ["TensorClamp", "TensorClampSte"])
 @pytest.mark.parametrize("rounding", ["RoundSte", "FloorSte", "CeilSte", "RoundToZeroSte", "DPURoundSte"])
 def test_general_int_quant_vs_literal(dtype, pattern, clamp, rounding):
@@ -58,10 +59,11 @@ def test_general_int_quant_vs_literal(dtype, pattern, clamp, rounding):
     from brevitas_b200.core.function_wrapper import CLAMP_MODE_OF, ROUND_MODE_OF
     gen = torch.Generator().manual_seed(sum(map(ord, pattern + clamp + rounding)))
     # scalar: unaligned tail -> element-wise flavour; per_out_channel: inner 96 -> 16-byte vectors; per_dim1: inner 25
+    # per_row_long (>= 512 vectors per row) and scalar_ragged_long (bulk + element-wise tail): the tiled kernel
     shape = {"scalar": (7, 333), "per_out_channel": (8, 6, 4, 4), "per_dim1": (8, 6, 5, 5),
-             "pre_scalar_post_channel": (8, 6, 4, 4)}[pattern]
+             "pre_scalar_post_channel": (8, 6, 4, 4), "per_row_long": (6, 4104), "scalar_ragged_long": (3, 11001)}[pattern]
     sshape = {"scalar": (), "per_out_channel": (8, 1, 1, 1), "per_dim1": (1, 6, 1, 1),
-              "pre_scalar_post_channel": (8, 1, 1, 1)}[pattern]
+              "pre_scalar_post_channel": (8, 1, 1, 1), "per_row_long": (6, 1), "scalar_ragged_long": ()}[pattern]
     pshape = () if pattern == "pre_scalar_post_channel" else sshape
     x0 = (torch.randn(shape, generator=gen) * 3).to(dtype).cuda()
     g = torch.randn(shape, generator=gen).to(dtype).cuda()
