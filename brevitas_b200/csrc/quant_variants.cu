@@ -147,9 +147,10 @@ __device__ __forceinline__ void gen_bwd_n(float (&eg)[N], const float (&ex)[N], 
             const float c1 = over ? r.hi : t3;
             const bool under = c1 < r.lo;
             const float t5 = under ? r.lo : c1;
-            if (q.masked) {
-                if (under) { a.lo += d[i]; d[i] = 0.f; }
-                else if (over) { a.hi += d[i]; d[i] = 0.f; }
+            if (q.masked) {                                   // branch-free: selects, no divergence inside a vector
+                a.lo += under ? d[i] : 0.f;
+                a.hi += (over && !under) ? d[i] : 0.f;
+                d[i] = (over || under) ? 0.f : d[i];
             }
             if (q.want_sums) {
                 const float t6 = DT<T>::rnd(fsub(t5, r.zp));
@@ -262,7 +263,7 @@ constexpr int QT_UNROLL = 4;
 constexpr int QT_TILE = QV_THREADS * QT_UNROLL;
 
 template <typename T, bool BWD, int RMC>
-__global__ void __launch_bounds__(QV_THREADS) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
+__global__ void __launch_bounds__(QV_THREADS, 3) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
                                                                              int64_t total_tiles) {
     constexpr int V = DT<T>::VEC;
     __shared__ double red[32];
