@@ -263,7 +263,7 @@ constexpr int QT_UNROLL = 4;
 constexpr int QT_TILE = QV_THREADS * QT_UNROLL;
 
 template <typename T, bool BWD, int RMC>
-__global__ void __launch_bounds__(QV_THREADS, 3) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
+__global__ void __launch_bounds__(QV_THREADS, BWD ? 3 : 1) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
                                                                              int64_t total_tiles) {
     constexpr int V = DT<T>::VEC;
     __shared__ double red[32];
@@ -376,12 +376,17 @@ static int launch_general(const GenQ& q, cudaStream_t st, const char* what) {
         const int64_t runs = (q.n / V) / inner_u;
         const int64_t tiles_per_run = (inner_u + QT_TILE - 1) / QT_TILE;
         const int64_t total = runs * tiles_per_run;
-        int64_t grid = (int64_t)sm_count() * 8;
-        if (grid > total) grid = total;
-        if (q.round_mode == RM_ROUND)
-            general_int_quant_tiled_kernel<T, BWD, RM_ROUND><<<(unsigned)grid, QV_THREADS, 0, st>>>(q, inner_u, tiles_per_run, total);
-        else
-            general_int_quant_tiled_kernel<T, BWD, -1><<<(unsigned)grid, QV_THREADS, 0, st>>>(q, inner_u, tiles_per_run, total);
+        // ONE resident wave: the tiles are dealt out in equal contiguous ranges, so a second wave would only add a tail
+        auto launch = [&](auto kernel) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QV_THREADS, 0) != cudaSuccess || per_sm < 1)
+                per_sm = 2;
+            int64_t grid = (int64_t)sm_count() * per_sm;
+            if (grid > total) grid = total;
+            kernel<<<(unsigned)grid, QV_THREADS, 0, st>>>(q, inner_u, tiles_per_run, total);
+        };
+        if (q.round_mode == RM_ROUND) launch(general_int_quant_tiled_kernel<T, BWD, RM_ROUND>);
+        else launch(general_int_quant_tiled_kernel<T, BWD, -1>);
     } else if (vec) general_int_quant_kernel<T, BWD, true><<<qv_grid(q.n / V), QV_THREADS, 0, st>>>(q);
     else general_int_quant_kernel<T, BWD, false><<<qv_grid(q.n), QV_THREADS, 0, st>>>(q);
     return check_launch(what);
