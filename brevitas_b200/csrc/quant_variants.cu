@@ -263,7 +263,7 @@ constexpr int QT_UNROLL = 4;
 constexpr int QT_TILE = QV_THREADS * QT_UNROLL;
 
 template <typename T, bool BWD, int RMC>
-__global__ void __launch_bounds__(QV_THREADS, BWD ? 3 : 1) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
+__global__ void __launch_bounds__(QV_THREADS, BWD ? 3 : 4) general_int_quant_tiled_kernel(GenQ q, int64_t inner_u, int64_t tiles_per_run,
                                                                              int64_t total_tiles) {
     constexpr int V = DT<T>::VEC;
     __shared__ double red[32];
