@@ -446,6 +446,19 @@ extern "C" int bvb_kth_value_rows(const void* x, void* out, int64_t* index_out, 
 namespace bvb {
 constexpr int MM_THREADS = 256;
 
+// per-thread running extrema: a thread meets its elements in increasing index order, so plain float compares keep the
+// FIRST position of a tie (-0.0 == +0.0 included) and NaN is tracked on the side; folded into the packed form once
+struct MinMaxThread {
+    float lo_v = __int_as_float(0x7f800000), hi_v = __int_as_float(0xff800000);
+    uint32_t lo_i = 0xffffffffu, hi_i = 0xffffffffu, nan_i = 0xffffffffu, first_i = 0xffffffffu;
+    __device__ __forceinline__ void start(uint32_t idx) { first_i = idx; }
+    __device__ __forceinline__ void add(float v, uint32_t idx) {
+        nan_i = min(nan_i, (v != v) ? idx : 0xffffffffu);
+        if (v < lo_v) { lo_v = v; lo_i = idx; }
+        if (v > hi_v) { hi_v = v; hi_i = idx; }
+    }
+};
+
 struct MinMaxAcc {
     unsigned long long lo = ~0ull, hi = 0ull;
     __device__ __forceinline__ void add(float v, uint32_t idx) {
@@ -457,6 +470,13 @@ struct MinMaxAcc {
         const unsigned long long c = ((unsigned long long)(nan ? 0xffffffffu : k) << 32) | (uint32_t)~idx;
         lo = a < lo ? a : lo;
         hi = c > hi ? c : hi;
+    }
+    __device__ __forceinline__ void fold(const MinMaxThread& t) {
+        if (t.first_i == 0xffffffffu) return;                        // the thread met no element
+        if (t.nan_i != 0xffffffffu) { add(__int_as_float(0x7fc00000), t.nan_i); return; }
+        // nothing below +inf (above -inf) was met: every element was +inf (-inf), the first one is selected
+        add(t.lo_v, t.lo_i != 0xffffffffu ? t.lo_i : t.first_i);
+        add(t.hi_v, t.hi_i != 0xffffffffu ? t.hi_i : t.first_i);
     }
     __device__ __forceinline__ void merge(unsigned long long l, unsigned long long h) {
         lo = l < lo ? l : lo;
@@ -479,11 +499,12 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_rows_kernel(const T* __rest
     int64_t end = begin + per_split;
     if (end > cols) end = cols;
     const T* xr = x + row * cols;
-    MinMaxAcc acc;
+    MinMaxThread acc;
     if (vec_ok) {                                       // per_split and cols are multiples of V, rows 16-byte aligned
         const uint4* xv = reinterpret_cast<const uint4*>(xr);
         const int64_t v1 = end / V;
         int64_t v = begin / V + threadIdx.x;
+        if (v < v1) acc.start((uint32_t)(v * V));
         for (; v + 3 * MM_THREADS < v1; v += 4 * MM_THREADS) {          // four independent 16-byte loads in flight
             uint4 q4[4];
 #pragma unroll
@@ -503,11 +524,14 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_rows_kernel(const T* __rest
             for (int i = 0; i < V; ++i) acc.add(e[i], (uint32_t)(v * V + i));
         }
     } else {
+        if (begin + threadIdx.x < end) acc.start((uint32_t)(begin + threadIdx.x));
         for (int64_t i = begin + threadIdx.x; i < end; i += MM_THREADS) acc.add(DT<T>::to_f(xr[i]), (uint32_t)i);
     }
-    acc.warp_reduce();
+    MinMaxAcc packed;
+    packed.fold(acc);
+    packed.warp_reduce();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[0][warp] = acc.lo; red[1][warp] = acc.hi; }
+    if (lane == 0) { red[0][warp] = packed.lo; red[1][warp] = packed.hi; }
     __syncthreads();
     if (warp == 0) {
         MinMaxAcc t;
