@@ -449,8 +449,11 @@ constexpr int MM_THREADS = 256;
 // per-thread running extrema: a thread meets its elements in increasing index order, so plain float compares keep the
 // FIRST position of a tie (-0.0 == +0.0 included) and NaN is tracked on the side; folded into the packed form once
 struct MinMaxThread {
-    float lo_v = __int_as_float(0x7f800000), hi_v = __int_as_float(0xff800000);
-    uint32_t lo_i = 0xffffffffu, hi_i = 0xffffffffu, nan_i = 0xffffffffu, first_i = 0xffffffffu;
+    float lo_v, hi_v;
+    uint32_t lo_i, hi_i, nan_i, first_i;
+    __device__ __forceinline__ MinMaxThread()
+        : lo_v(__int_as_float(0x7f800000)), hi_v(__int_as_float(0xff800000)), lo_i(0xffffffffu), hi_i(0xffffffffu),
+          nan_i(0xffffffffu), first_i(0xffffffffu) {}
     __device__ __forceinline__ void start(uint32_t idx) { first_i = idx; }
     __device__ __forceinline__ void add(float v, uint32_t idx) {
         nan_i = min(nan_i, (v != v) ? idx : 0xffffffffu);
