@@ -452,7 +452,7 @@ struct MinMaxThread {
     float lo_v, hi_v;
     uint32_t lo_i, hi_i, nan_i, first_i;
     __device__ __forceinline__ MinMaxThread()
-        : lo_v(__int_as_float(0x7f800000)), hi_v(__int_as_float(0xff800000)), lo_i(0xffffffffu), hi_i(0xffffffffu),
+        : lo_v(INFINITY), hi_v(-INFINITY), lo_i(0xffffffffu), hi_i(0xffffffffu),
           nan_i(0xffffffffu), first_i(0xffffffffu) {}
     __device__ __forceinline__ void start(uint32_t idx) { first_i = idx; }
     __device__ __forceinline__ void add(float v, uint32_t idx) {
