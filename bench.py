@@ -514,6 +514,10 @@ def main():
         # activation tensor (AbsPercentile, radix select): step time while collecting (SURVEY.md §8d C4 "warm-up")
         qat["resnet18_int8_collecting_stats"] = qat_run("resnet18", args.qat_batch, 6, 3, collect_stats_steps=10 ** 6,
                                                         channels_last=True)
+        # the same phase as ONE CUDA graph (identical device work from its second to its last-but-one step; the host-side
+        # step counters are advanced at every replay, qat/train.py::GraphedStep)
+        qat["resnet18_int8_collecting_stats_cuda_graph"] = qat_run("resnet18", args.qat_batch, 10, 3,
+                                                                   collect_stats_steps=10 ** 6, channels_last=True, graph=True)
         qat["tfc_2w2a"] = qat_run("tfc", 256, 30, 5)                                # configs[0] shape, on the GPU
         qat["tfc_2w2a_cuda_graph"] = qat_run("tfc", 256, 200, 5, graph=True)        # same step as one CUDA graph
         # BASELINE.json configs[4]: ~1100 small launches per step, host-bound when launched eagerly

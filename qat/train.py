@@ -159,14 +159,28 @@ class FlatGrads:
                 self.flat.div_(self.world)
 
 
-def assert_capturable(model):
+def collecting_modules(model):
+    """the scaling modules that are still in their statistics-collection phase (core/scaling/standalone.py:230-244)"""
+    return [(name, m) for name, m in model.named_modules()
+            if getattr(m, "collect_stats_steps", None) is not None and hasattr(m, "counter") and m.training
+            and int(m.counter) <= int(m.collect_stats_steps)]
+
+
+def assert_capturable(model, collecting=False):
     """A CUDA graph replays device work only: host-side state that a step is supposed to advance would freeze at its
-    capture-time value.  Refuse to capture while any quantizer still counts steps on the host."""
-    for name, m in model.named_modules():
-        steps = getattr(m, "collect_stats_steps", None)
-        if steps is not None and hasattr(m, "counter") and m.training and int(m.counter) <= int(steps):
+    capture-time value.  Refuse to capture while any quantizer still counts steps on the host -- unless the
+    caller captures the COLLECTION phase itself (``collecting``): between its first and its last step every collecting step
+    issues the same device work (statistic, momentum update of the buffer, quantization with the batch statistic) as long as
+    the running average uses a fixed momentum, and the caller advances the host counters at every replay."""
+    for name, m in collecting_modules(model):
+        steps = int(m.collect_stats_steps)
+        if not collecting:
             raise RuntimeError(f"{name}: still collecting statistics ({int(m.counter)} of {steps} steps); run the "
                                "collection phase eagerly before capturing the step in a CUDA graph")
+        if int(m.counter) < 1 or int(m.counter) >= steps or getattr(m, "momentum", None) is None:
+            raise RuntimeError(f"{name}: the collection phase is capturable between its first and last step and with a fixed "
+                               f"momentum only (counter {int(m.counter)} of {steps}, momentum {getattr(m, 'momentum', None)})")
+    for name, m in model.named_modules():
         if getattr(m, "first_batch", False) and m.training:
             raise RuntimeError(f"{name}: running statistics not initialised yet (first_batch); run one eager step first")
         if int(getattr(m, "quant_delay_steps", 0) or 0) > 0:
@@ -179,11 +193,15 @@ class GraphedStep:
     microseconds per step), and the C-ABI is capture-safe by construction (no allocation outside torch's caching
     allocator, no sync, current stream)."""
 
-    def __init__(self, raw_model, loss_fn, opt, x, y, world=1, dist=None, bucket_bytes=64 << 20):
+    def __init__(self, raw_model, loss_fn, opt, x, y, world=1, dist=None, bucket_bytes=64 << 20, collecting=False):
         bucket_bytes = int(float(os.environ.get("QAT_BUCKET_MB", bucket_bytes / (1 << 20))) * (1 << 20))
         self.raw, self.loss_fn, self.opt, self.world, self.dist = raw_model, loss_fn, opt, world, dist
         self.x, self.y = x.clone(), y.clone()
-        assert_capturable(raw_model)
+        assert_capturable(raw_model, collecting)
+        # a graph of the collection phase: the host-side step counters are advanced here at every replay, and the graph
+        # refuses to run the step that ends the phase (that one re-initialises the learned scale: run it eagerly, then
+        # capture the steady-state graph)
+        self.collectors = [m for _n, m in collecting_modules(raw_model)] if collecting else []
         self.grads = FlatGrads(raw_model.parameters(), world, dist, bucket_bytes)
         from brevitas_b200 import _kernels as K
         for _ in range(3):                       # warm-up on the (non-default) current stream, see run()
@@ -209,6 +227,11 @@ class GraphedStep:
         if x is not None:
             self.x.copy_(x)
             self.y.copy_(y)
+        for m in self.collectors:
+            if int(m.counter) + 1 >= int(m.collect_stats_steps):
+                raise RuntimeError("the statistics-collection phase ends with this step: run it (and the next one) eagerly, "
+                                   "then capture the steady-state step")
+            m.counter = m.counter + 1
         self.graph.replay()
         return self.loss
 
@@ -281,7 +304,7 @@ def run(name, batch, steps, warmup, collect_stats_steps=2, log=None, graph=False
         loss = train_step(model, raw, *batches[i % 2], loss_fn, opt)
     torch.cuda.synchronize()
     if graph:
-        gstep = GraphedStep(raw, loss_fn, opt, *batches[0], world=world, dist=dist)
+        gstep = GraphedStep(raw, loss_fn, opt, *batches[0], world=world, dist=dist, collecting=collecting)
         step_fn = lambda i: gstep(*batches[i % 2])
     else:
         step_fn = lambda i: train_step(model, raw, *batches[i % 2], loss_fn, opt)

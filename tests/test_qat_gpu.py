@@ -161,3 +161,45 @@ def test_per_token_dynamic_quantizer_full_size():
     assert float(codes.abs().max()) <= 128.5
     y.backward(torch.ones_like(y))
     assert x.grad.shape == x.shape and torch.isfinite(x.grad.float()).all()
+
+
+def test_collection_phase_as_a_cuda_graph_matches_eager_steps():
+    """The statistics-collection phase captured as ONE CUDA graph (qat/train.py::GraphedStep(collecting=True)): host-side
+    step counters advance at every replay, the running statistics follow the eagerly launched twin, and the graph refuses
+    to run the step that ends the phase."""
+    from qat import models
+    from qat.train import WORKLOADS, GraphedStep, collecting_modules, make_batch, make_optimizer, train_step
+    spec = dict(WORKLOADS["resnet18"], classes=100)
+    dev = torch.device("cuda")
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):               # the whole life of a captured model runs on a side stream (see run())
+        twins = []
+        for _ in range(2):
+            torch.manual_seed(0)
+            m = models.resnet18(num_classes=100, collect_stats_steps=9).cuda().train().to(memory_format=torch.channels_last)
+            twins.append((m, make_optimizer(m, WORKLOADS["resnet18"], capturable=True)))
+        x, y = make_batch(spec, 8, dev, 0)
+        x = x.contiguous(memory_format=torch.channels_last)
+        loss_fn = nn.CrossEntropyLoss()
+        (eager, eopt), (graphed, gopt) = twins
+        for _ in range(2):
+            train_step(eager, eager, x, y, loss_fn, eopt)
+            train_step(graphed, graphed, x, y, loss_fn, gopt)
+        with pytest.raises(RuntimeError, match="still collecting"):
+            GraphedStep(graphed, loss_fn, gopt, x, y)                       # steady-state capture refuses
+        g = GraphedStep(graphed, loss_fn, gopt, x, y, collecting=True)      # 3 eager steps + the captured one: counter 6
+        assert len(g.collectors) == len(collecting_modules(graphed)) > 10
+        for _ in range(4):
+            train_step(eager, eager, x, y, loss_fn, eopt)
+        for _ in range(2):
+            g()                                                             # counters 7, 8
+            train_step(eager, eager, x, y, loss_fn, eopt)
+        torch.cuda.synchronize()
+        with pytest.raises(RuntimeError, match="collection phase ends"):
+            g()
+        for (n1, a), (_n2, b) in zip(collecting_modules(eager), collecting_modules(graphed)):
+            assert int(a.counter) == int(b.counter) == 8, (n1, a.counter, b.counter)
+            # same kernels in the same order; the scale-gradient sums use atomics, so the weights differ in the last bits
+            assert torch.allclose(a.buffer, b.buffer, rtol=2e-3, atol=0), (n1, float(a.buffer), float(b.buffer))
+    torch.cuda.current_stream().wait_stream(side)
