@@ -212,6 +212,8 @@ class GraphedStep:
         with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream()):
             self.loss = self._eager_step()
         self.captured_launches = K.launch_count - before
+        for m in self.collectors:                # the capture pass ran the host code of a step but no device work
+            m.counter = m.counter - 1
 
     def _eager_step(self):
         self.grads.zero()

@@ -188,12 +188,12 @@ def test_collection_phase_as_a_cuda_graph_matches_eager_steps():
             train_step(graphed, graphed, x, y, loss_fn, gopt)
         with pytest.raises(RuntimeError, match="still collecting"):
             GraphedStep(graphed, loss_fn, gopt, x, y)                       # steady-state capture refuses
-        g = GraphedStep(graphed, loss_fn, gopt, x, y, collecting=True)      # 3 eager steps + the captured one: counter 6
+        g = GraphedStep(graphed, loss_fn, gopt, x, y, collecting=True)      # 3 eager warm-up steps inside: counter 5
         assert len(g.collectors) == len(collecting_modules(graphed)) > 10
-        for _ in range(4):
+        for _ in range(3):
             train_step(eager, eager, x, y, loss_fn, eopt)
-        for _ in range(2):
-            g()                                                             # counters 7, 8
+        for _ in range(3):
+            g()                                                             # counters 6, 7, 8
             train_step(eager, eager, x, y, loss_fn, eopt)
         torch.cuda.synchronize()
         with pytest.raises(RuntimeError, match="collection phase ends"):
