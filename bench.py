@@ -537,6 +537,11 @@ def main():
             fe = dict(frontend="reference", brevitas_src=ref_src)
             qat["resnet18_int8_reference_frontend"] = qat_run("resnet18", args.qat_batch, 20, 3, channels_last=True, graph=True, **fe)
             qat["mobilenet_v1_4b_reference_frontend"] = qat_run("mobilenet_v1", 128, 20, 3, channels_last=True, graph=True, **fe)
+            # ... and with brevitas_b200.fuse_batch_norm(model): the modules are prepared, the model code is not touched
+            qat["resnet18_int8_reference_frontend_fused_bn"] = qat_run("resnet18", args.qat_batch, 20, 3, channels_last=True,
+                                                                       graph=True, fuse_bn=True, **fe)
+            qat["mobilenet_v1_4b_reference_frontend_fused_bn"] = qat_run("mobilenet_v1", 128, 20, 3, channels_last=True,
+                                                                         graph=True, fuse_bn=True, **fe)
             # the reference's FC.forward builds a tensor from a Python list every call (FC.py:66: a host-to-device copy),
             # so its step cannot be captured in a CUDA graph: launched eagerly
             qat["tfc_2w2a_reference_frontend"] = qat_run("tfc", 256, 30, 5, **fe)
@@ -618,6 +623,9 @@ def main():
             r = qat.get(k + "_reference_frontend")
             if r is not None:
                 line["qat_scaling"][k]["unmodified_brevitas_nn_samples_per_s"] = r["samples_per_s"]
+            r = qat.get(k + "_reference_frontend_fused_bn")
+            if r is not None:
+                line["qat_scaling"][k]["unmodified_brevitas_nn_fused_bn_samples_per_s"] = r["samples_per_s"]
             r = qat.get(k + "_fused_bn")
             if r is not None:
                 line["qat_scaling"][k]["fused_bn_samples_per_s"] = r["samples_per_s"]

@@ -15,3 +15,4 @@ from . import ops  # noqa: E402,F401  (registers torch.ops.autograd_ste_ops.* an
 from . import function  # noqa: E402,F401
 from . import core  # noqa: E402,F401
 from .binding import install, uninstall  # noqa: E402,F401  (binds an unmodified Brevitas installation to the kernels)
+from .fused_bn import bn_act_quant, fuse_batch_norm, unfuse_batch_norm  # noqa: E402,F401

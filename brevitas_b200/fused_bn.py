@@ -83,7 +83,9 @@ def bn_act_quant(bn: nn.Module, act: nn.Module, x: torch.Tensor, residual: Optio
         ok = (isinstance(residual, torch.Tensor) and residual.shape == x.shape and residual.dtype == x.dtype
               and residual.stride() == x.stride())
     if not ok or (bn.training and bn.momentum is None):    # (cumulative moving average: left to torch)
-        return act(bn(x)) if residual is None else act(bn(x) + residual)
+        bn_f = getattr(bn, "_b200_unfused_forward", bn)   # modules prepared by fuse_batch_norm(): their own forwards
+        act_f = getattr(act, "_b200_unfused_forward", act)
+        return act_f(bn_f(x)) if residual is None else act_f(bn_f(x) + residual)
     if bn.training:
         bn.num_batches_tracked.add_(1)
     relu = type(fq.activation_impl) is nn.ReLU
@@ -103,3 +105,88 @@ def _make_quant_tensor(act, value, scale, zero_point, bit_width, signed):
         return QuantTensor(value, scale, zero_point, bit_width, signed, act.training)
     from .nn import QuantTensor
     return QuantTensor(value, scale, zero_point, bit_width, signed, act.training)
+
+
+# ---- the same fusion for model code that calls the two modules itself (the reference's brevitas_examples models) -------
+class _PendingBatchNorm:
+    """What ``bn(x)`` -- or ``bn(x) + residual`` -- WILL be, handed from a fusing batch-norm to whatever consumes it.
+
+    A quantized activation layer prepared by :func:`fuse_batch_norm` takes it apart and runs the fused operator.  Anything
+    else gets the real tensor: torch functions through ``__torch_function__``, attribute access and arithmetic through the
+    methods below (the batch-norm then runs once, unfused, exactly as the model code asked)."""
+    __slots__ = ("bn", "x", "residual", "_value")
+
+    def __init__(self, bn, x, residual=None):
+        self.bn, self.x, self.residual, self._value = bn, x, residual, None
+
+    def materialize(self) -> torch.Tensor:
+        if self._value is None:
+            v = self.bn._b200_unfused_forward(self.x)
+            self._value = v if self.residual is None else v + self.residual
+        return self._value
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        from torch.utils._pytree import tree_map
+        real = lambda a: a.materialize() if isinstance(a, _PendingBatchNorm) else a      # noqa: E731
+        return func(*tree_map(real, args), **tree_map(real, kwargs or {}))
+
+    def _plus(self, other):
+        if (self._value is None and self.residual is None and isinstance(other, torch.Tensor)
+                and other.shape == self.x.shape):
+            return _PendingBatchNorm(self.bn, self.x, other)         # relu(bn(x) + identity): the residual flavour
+        return self.materialize() + other
+
+    __add__ = __radd__ = __iadd__ = _plus
+
+    def __sub__(self, other): return self.materialize() - other
+    def __rsub__(self, other): return other - self.materialize()
+    def __mul__(self, other): return self.materialize() * other
+    __rmul__ = __mul__
+    def __truediv__(self, other): return self.materialize() / other
+    def __neg__(self): return -self.materialize()
+    def __getitem__(self, item): return self.materialize()[item]
+    def __len__(self): return self.x.shape[0]
+
+    def __getattr__(self, name):            # .shape, .view(...), .mean(...): the tensor's
+        return getattr(self.materialize(), name)
+
+
+def fuse_batch_norm(model: nn.Module) -> int:
+    """Prepare ``model`` -- any model code on ``brevitas.nn`` / ``brevitas_b200.nn`` layers -- so that every
+    ``BatchNorm2d`` whose output goes straight (or through one ``+ identity``) into a quantized ReLU / identity layer runs as
+    the fused operator above, without touching the model's ``forward``.  Returns the number of batch-norms prepared; undo
+    with :func:`unfuse_batch_norm`.  State dict, parameters, hooks on other modules and the results of every unfused path
+    are unchanged."""
+    import types
+    count = 0
+    for m in model.modules():
+        if hasattr(m, "_b200_unfused_forward"):
+            continue
+        if type(m) is nn.BatchNorm2d:
+            m._b200_unfused_forward = m.forward
+
+            def bn_forward(self, x):
+                if isinstance(x, torch.Tensor) and K.bn_act_quant_supported(x):
+                    return _PendingBatchNorm(self, x)
+                return self._b200_unfused_forward(x)
+            m.forward = types.MethodType(bn_forward, m)
+            count += 1
+        elif _tensor_quant_of(m)[2] is not None:
+            m._b200_unfused_forward = m.forward
+
+            def act_forward(self, inp):
+                if isinstance(inp, _PendingBatchNorm):
+                    if inp._value is None:
+                        return bn_act_quant(inp.bn, self, inp.x, inp.residual)
+                    inp = inp.materialize()
+                return self._b200_unfused_forward(inp)
+            m.forward = types.MethodType(act_forward, m)
+    return count
+
+
+def unfuse_batch_norm(model: nn.Module) -> None:
+    for m in model.modules():
+        if "_b200_unfused_forward" in m.__dict__:
+            del m.__dict__["forward"]
+            del m.__dict__["_b200_unfused_forward"]

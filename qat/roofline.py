@@ -44,6 +44,8 @@ def account(model: nn.Module, x: torch.Tensor, optimizer_words: int = 5, world: 
     handles = []
 
     def numel(t):
+        if hasattr(type(t), "materialize"):          # a batch-norm output still waiting to be fused (fused_bn.py)
+            t = t.x
         t = getattr(t, "value", t)
         return t.numel() if isinstance(t, torch.Tensor) else 0
 

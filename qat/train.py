@@ -59,6 +59,10 @@ def build(name: str, device, collect_stats_steps: int = 300, channels_last: bool
         for prm in model.parameters():          # [1,C,1,1] scales are not images: keep the default strides DDP buckets expect
             if prm.dim() == 4 and prm.shape[0] == 1 and prm.shape[2:] == (1, 1):
                 prm.data = prm.data.reshape(-1).clone().view(prm.shape)      # default strides ([C,1,1,1], not [C,1,C,C])
+    if fuse_bn and frontend == "reference":
+        # the reference's model code calls batch-norm and activation itself: prepare the modules instead of the model
+        import brevitas_b200
+        brevitas_b200.fuse_batch_norm(model)
     if spec["loss"] == "ce":
         loss_fn = nn.CrossEntropyLoss()
     else:

@@ -146,3 +146,58 @@ def test_models_with_fused_bn_track_the_unfused_models(name, shape):
     print(f"{name}: loss {la:.5f} / control {lc:.5f} / fused {lf:.5f}; gradient cosine control {c_control:.5f}, fused {c_fused:.5f}")
     assert abs(lf - la) <= 2.0 * abs(lc - la) + 1e-3 * abs(la)
     assert c_fused >= c_control - 0.02 and c_fused > 0.9
+
+
+@pytest.mark.parametrize("name,shape", [("resnet18", (8, 3, 128, 128)), ("mobilenet_v1", (2, 3, 224, 224))])
+def test_fuse_batch_norm_prepares_unmodified_model_code(name, shape):
+    """brevitas_b200.fuse_batch_norm(model): the batch-norm hands a pending result to the activation layer, which runs
+    the fused operator -- the model's forward() is not touched.  Same launches and same numbers as the model that calls
+    bn_act_quant() explicitly; everything that is not a quantized activation gets the real batch-norm output."""
+    import brevitas_b200
+    from brevitas_b200 import _kernels
+    from qat import models
+    kw = {"collect_stats_steps": 1} if name == "resnet18" else {}
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(3)).cuda().contiguous(memory_format=torch.channels_last)
+    t = torch.randint(0, 1000, (shape[0],), generator=torch.Generator().manual_seed(4)).cuda()
+
+    def build(**extra):
+        torch.manual_seed(0)
+        return getattr(models, name)(**kw, **extra).cuda().to(memory_format=torch.channels_last).train()
+
+    def run(model):
+        names = []
+        real_call = _kernels.call
+        _kernels.call = lambda n, *a: (names.append(n), real_call(n, *a))[1]
+        try:
+            for step in range(3):
+                out = model(x)
+                loss = nn.functional.cross_entropy(out, t)
+                model.zero_grad()
+                loss.backward()
+        finally:
+            _kernels.call = real_call
+        grads = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+        return float(loss), grads, names.count("bvb_bn_act_quant_fwd"), names.count("bvb_bn_act_quant_bwd")
+
+    explicit = build(fuse_bn=True)
+    state = {k: v.clone() for k, v in explicit.state_dict().items()}
+    le, ge, fe, be = run(explicit)
+    prepared = build()
+    prepared.load_state_dict(state, strict=False)
+    n_bn = brevitas_b200.fuse_batch_norm(prepared)
+    assert n_bn == sum(type(m) is nn.BatchNorm2d for m in prepared.modules()) > 0
+    lp, gp, fp, bp = run(prepared)
+    assert (fp, bp) == (fe, be) and fp > 0, (fp, bp, fe, be)
+    assert abs(lp - le) <= 1e-5 * abs(le), (lp, le)
+    assert float(torch.nn.functional.cosine_similarity(gp, ge, dim=0)) > 0.99999
+    # a consumer that is not a quantized activation sees the plain batch-norm output
+    bn = next(m for m in prepared.modules() if type(m) is nn.BatchNorm2d)
+    xin = torch.randn(4, bn.num_features, 8, 8, device="cuda").contiguous(memory_format=torch.channels_last)
+    pending = bn(xin)
+    assert type(pending).__name__ == "_PendingBatchNorm"
+    ref = bn._b200_unfused_forward(xin)
+    assert torch.equal(torch.relu(pending), torch.relu(ref)) and torch.equal(pending * 2.0, ref * 2.0)
+    assert pending.shape == ref.shape and torch.equal(bn(xin) + 1.0, ref + 1.0)
+    brevitas_b200.unfuse_batch_norm(prepared)
+    assert isinstance(bn(xin), torch.Tensor)
+    assert prepared.state_dict().keys() == explicit.state_dict().keys()
