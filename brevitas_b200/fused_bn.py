@@ -132,6 +132,8 @@ class _PendingBatchNorm:
         return func(*tree_map(real, args), **tree_map(real, kwargs or {}))
 
     def _plus(self, other):
+        if isinstance(other, _PendingBatchNorm):         # e.g. the batch-norm that closes a ResNet downsample path
+            other = other.materialize()
         if (self._value is None and self.residual is None and isinstance(other, torch.Tensor)
                 and other.shape == self.x.shape):
             return _PendingBatchNorm(self.bn, self.x, other)         # relu(bn(x) + identity): the residual flavour
