@@ -282,9 +282,10 @@ def rand_np(shape, seed, scale=1.0):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("rows,cols", [(1, 8), (3, 1), (5, 17), (7, 1000), (64, 4096), (33, 11008), (2, 60000),
-                                       (300, 264), (2, 131072)])
+                                       (300, 264), (2, 131072), (1500, 8200), (445, 12288), (900, 9000)])
 def test_rows_fused_vs_oracle(K, rows, cols, dtype):
-    """TMA path (16-byte aligned rows), generic path (ragged rows) and oversized rows"""
+    """TMA path (16-byte aligned rows), generic path (ragged rows) and oversized rows; the last three shapes: 16-bit rows of
+    16 KB and more with 1-4 rows per CTA (the in-place + TMA-store forward, ring wrap-around and short tails)"""
     x = O.rnd(rand_np((rows, cols), rows * 1000 + cols, 0.7), dtype)
     g = O.rnd(rand_np((rows, cols), 7, 1.0), dtype)
     if rows > 2 and cols > 4:
