@@ -106,6 +106,7 @@ def _int_threshold(kind: str, signed: bool, narrow_range: bool, bit_width: int, 
     return float(impl(bw))
 
 
+_INT_THRESHOLD_CACHE = weakref.WeakKeyDictionary()     # RescalingIntQuant module -> {(device, dtype, bits): 0-dim tensor}
 _SCALAR_CACHE = weakref.WeakKeyDictionary()     # IntQuant module -> [(zero-point ref, version, bit-width ref, version, values)]
 
 
@@ -256,6 +257,25 @@ class RescalingIntQuant(nn.Module):
         zp = 0.0 if type(self.zero_point_impl) is ZeroZeroPoint else None
         return zp, qmin, qmax, modes[0], modes[1], thr
 
+    def int_threshold(self, bit_width: Tensor) -> Tensor:
+        """``int_scaling_impl(bit_width)``.  With a CONSTANT bit-width it is a constant too, yet the reference recomputes it
+        (a pow and one or two subtractions on a 0-dim tensor: three launches) in every forward of every quantizer -- 55
+        quantizers of a MobileNetV1 make 165 one-element launches per step.  Here it is computed once per device and dtype,
+        by the very same ops, and reused (not a buffer: nothing is added to the state dict)."""
+        if type(self.msb_clamp_bit_width_impl) is not BitWidthConst or type(self.int_scaling_impl) not in (
+                IntScaling, PowerOfTwoIntScaling) or bit_width.requires_grad:
+            return self.int_scaling_impl(bit_width)
+        key = (bit_width.device, bit_width.dtype, self.msb_clamp_bit_width_impl.bit_width_value)
+        cache = _INT_THRESHOLD_CACHE.setdefault(self, {})
+        thr = cache.get(key)
+        if thr is None:
+            if bit_width.is_cuda and torch.cuda.is_current_stream_capturing():
+                return self.int_scaling_impl(bit_width)       # (a tensor born inside a capture belongs to that graph)
+            with torch.no_grad():
+                thr = self.int_scaling_impl(bit_width)
+            cache[key] = thr
+        return thr
+
     def forward_pre_relu(self, x: Tensor) -> Optional[Tuple[Tensor, Tensor, Tensor, Tensor]]:
         """``self(torch.relu(x))`` in ONE kernel (``relu_int_quant``: the ReLU's own read + write pass and its
         backward pass disappear), or None when the configuration does not allow it: the threshold must not depend on
@@ -288,7 +308,7 @@ class RescalingIntQuant(nn.Module):
         else:
             holder = {}                                     # pairs the statistic with the quantizer call below
             threshold = self.scaling_impl(x, pre_relu=holder)
-        scale = threshold / self.int_scaling_impl(bit_width)
+        scale = threshold / self.int_threshold(bit_width)
         if not (scale.dtype == x.dtype or (scale.numel() == 1 and scale.dtype == torch.float32)):
             return None
         zero_point = self.zero_point_impl(x, scale, bit_width)
@@ -316,7 +336,7 @@ class RescalingIntQuant(nn.Module):
             # ONE kernel with the zero-point as a device operand; its backward returns d(scale) and d(zero_point)
             with shared_minmax():           # AbsMinMax (scale) and NegativeMinOrZero (zero-point) share one read of x
                 threshold = self.scaling_impl(x)
-                scale = threshold / self.int_scaling_impl(bit_width)
+                scale = threshold / self.int_threshold(bit_width)
                 zero_point = self.zero_point_impl(x, scale, bit_width)
             y = self.int_quant.forward_fused_zpt(scale, zero_point, qmin, qmax, x)
             if y is None:
@@ -339,7 +359,7 @@ class RescalingIntQuant(nn.Module):
             zero_point = self.zero_point_impl(x, scale, bit_width)
             return self.int_quant.delay_wrapper(x, y), scale, zero_point, bit_width
         threshold = self.scaling_impl(x)
-        int_threshold = self.int_scaling_impl(bit_width)
+        int_threshold = self.int_threshold(bit_width)
         scale = threshold / int_threshold
         zero_point = self.zero_point_impl(x, scale, bit_width)
         if scale.dtype != x.dtype and scale.numel() != 1:

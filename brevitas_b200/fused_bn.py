@@ -77,7 +77,7 @@ def bn_act_quant(bn: nn.Module, act: nn.Module, x: torch.Tensor, residual: Optio
         ok = cfg is not None and cfg[0] is not None and cfg[3] == _lib.ROUND
     if ok:
         zp, qmin, qmax, rm, cm, _ = cfg
-        scale = tq.scaling_impl(x) / tq.int_scaling_impl(bit_width)
+        scale = tq.scaling_impl(x) / tq.int_threshold(bit_width)
         ok = scale.dtype == x.dtype and scale.numel() in (1, x.shape[1])
     if ok and residual is not None:
         ok = (isinstance(residual, torch.Tensor) and residual.shape == x.shape and residual.dtype == x.dtype
