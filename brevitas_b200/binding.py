@@ -188,6 +188,32 @@ def _scope_parameter_init():
     _set(cls, "__call__", __call__)
 
 
+def _bind_integer_export():
+    """``QuantTensor.int()`` (quant_tensor/__init__.py:174-187): after the reference's own validity check, the codes are
+    written by ONE export kernel (1 read, 1 or 4 bytes written per element) instead of div, add, round and cast."""
+    from brevitas.quant_tensor import QuantTensor
+    original = QuantTensor.int
+
+    def int_(self, float_datatype=False):
+        value = self.value
+        if (float_datatype or not isinstance(value, torch.Tensor) or not value.is_cuda or self.scale is None
+                or self.zero_point is None or self.zero_point.numel() != 1
+                or value.dtype not in (torch.float32, torch.bfloat16, torch.float16) or self.scale.dtype != value.dtype):
+            return original(self, float_datatype)
+        if not self.is_valid:
+            raise RuntimeError("QuantTensor not valid.")
+        narrow = bool(self.bit_width <= 8.)
+        dtype = (torch.int8 if self.signed_t.item() else torch.uint8) if narrow else torch.int32
+        try:
+            return torch.ops.brevitas_b200.int_quant_to_int(value.detach(), self.scale.detach(), float(self.zero_point),
+                                                            None, None, 0, dtype)
+        except RuntimeError:                     # a scale layout the export kernel does not index
+            return original(self, float_datatype)
+
+    int_.__wrapped__ = original
+    _set(QuantTensor, "int", int_)
+
+
 def install(reference_path: Optional[str] = None, fuse: bool = True):
     """Bind Brevitas (already importable, or found under ``reference_path``) to the B200 kernels.  Idempotent.
     Returns the ``brevitas`` package."""
@@ -206,6 +232,7 @@ def install(reference_path: Optional[str] = None, fuse: bool = True):
         _set(brevitas, "NATIVE_STE_BACKEND_LOADED", True)       # a native STE backend IS loaded: this library
         config.bind(ref_config)
         _scope_parameter_init()
+        _bind_integer_export()
         _state["installed"] = True
     if fuse and not _state["fused"]:
         # everything that holds references to the core classes must be loaded before the sweep

@@ -147,3 +147,31 @@ def test_trunc_quantizer(ref):
         results.append(qt_fields(pool(act(x))))
     for f, a, b in zip(("value", "scale", "zero_point", "bit_width"), results[1], results[0]):
         same(a, b, f"TruncTo8bit {f}")
+
+
+@pytest.mark.parametrize("kind", ["weight_per_channel_int8", "act_uint4", "bias_int32"])
+def test_quant_tensor_integer_export(ref, kind):
+    """QuantTensor.int() of the reference after install(): same integers and dtype as the pure reference"""
+    results = []
+    for fused in (False, True):
+        qnn, Q = bound(ref, fused)
+        torch.manual_seed(0)
+        x = torch.randn(4, 12, generator=torch.Generator().manual_seed(2)).cuda()
+        if kind == "weight_per_channel_int8":
+            qt = qnn.QuantLinear(12, 8, False, weight_quant=Q.Int8WeightPerChannelFloat).cuda().quant_weight()
+        elif kind == "act_uint4":
+            act = qnn.QuantReLU(act_quant=Q.Uint8ActPerTensorFloatMaxInit, max_val=3.0, bit_width=4,
+                                return_quant_tensor=True).cuda()
+            qt = act(x)
+        else:
+            lin = qnn.QuantLinear(12, 8, True, bias_quant=Q.Int32Bias, input_quant=Q.Int8ActPerTensorFloat,
+                                  return_quant_tensor=True).cuda()
+            lin(x)
+            lin.eval()
+            lin.cache_inference_quant_bias = True
+            lin(x)
+            qt = lin.quant_bias()
+        results.append((qt.int(), qt.int(float_datatype=True)))
+    (ir, fr), (if_, ff) = results
+    assert ir.dtype == if_.dtype and torch.equal(ir, if_), (ir.dtype, if_.dtype)
+    assert torch.equal(fr, ff)
