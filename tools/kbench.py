@@ -11,6 +11,8 @@ bvb_set_tuning(rows_threads, rows_stages, rows_ctas_per_sm, stream_threads, stre
 def _set_tuning(lib, *a):
     import ctypes
     fn = getattr(lib, "bvb_set_tuning", None)
+    if fn is None and not any(a):
+        return                                   # product library, default geometry: nothing to set
     if fn is None:
         raise SystemExit("bvb_set_tuning is only in the sweep build: make -C brevitas_b200/csrc TUNING=1; "
                          "BREVITAS_B200_LIB=brevitas_b200/libbrevitas_b200_tuning.so")
