@@ -97,7 +97,9 @@ def main():
             shape = (int(rng.choice([1, 7, 1000, 4099, 65536 * 4 + 3, (1 << 20) + 5])),)
             sshape = ()
         elif kind == "rows" or kind == "fused_rows":
-            shape = (int(rng.choice([1, 3, 37, 300])), int(rng.choice([1, 8, 17, 264, 1000, 2048, 4096, 11008])))
+            shape = (int(rng.choice([1, 3, 37, 300, 1300])), int(rng.choice([1, 8, 17, 264, 1000, 2048, 4096, 8200, 11008])))
+            if shape[0] * shape[1] > 12_000_000:          # 1300 x 8200: several rows per CTA of the TMA-store forward
+                shape = (1300, 8200)
             sshape = (shape[0], 1)
         elif kind in ("nchw", "nhwc"):
             shape = (int(rng.integers(1, 5)), int(rng.choice([3, 16, 24, 64, 256])), int(rng.choice([1, 5, 14])), int(rng.choice([1, 7, 14])))
