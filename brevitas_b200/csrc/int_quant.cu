@@ -1828,7 +1828,7 @@ static int launch_rows_fwd(const void* x, void* y, void* scale_out, void* absmax
             if (e != cudaSuccess) return fail(BVB_ECUDA, "rows_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
-        if (g.tma_store) {
+        if constexpr (sizeof(T) == 2) if (g.tma_store) {      // 16-bit rows only (fp32 gains nothing: not instantiated)
             static bool attr_set_store[64] = {false};
             if (dev < 0 || dev >= 64 || !attr_set_store[dev]) {
                 cudaError_t e = cudaFuncSetAttribute(rows_fwd_tma_store_kernel<T, RM>,
