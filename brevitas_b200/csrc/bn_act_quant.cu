@@ -240,7 +240,15 @@ __global__ void __launch_bounds__(BN_THREADS, RES ? BN_CTAS_RES : BN_CTAS_PER_SM
                 float v = DT<T>::rnd(bn_apply(e[i], th.ch[i]));
                 if constexpr (RES) v = DT<T>::rnd(fadd(v, er[i]));
                 if (relu) v = relu_f(v);
-                e[i] = quant_dequant<T, RM>(v, th.dv[i], p);     // (the vector form quant_dequant_n measured 6 % slower here)
+                // the reference chain on v (quant_dequant in common.cuh), with the division that does not single zeros
+                // out: after a ReLU half of the values are +0
+                const float t1 = DT<T>::rnd(th.dv[i].div_zero_unsigned(v));
+                float t2 = fadd(t1, p.zp);
+                if (DT<T>::LOWP && p.zp_nonzero) t2 = DT<T>::rnd(t2);
+                const float t5 = where_clamp(float_to_int<T, RM>(t2), p.qmin, p.qmax);
+                float t6 = fsub(t5, p.zp);
+                if (DT<T>::LOWP && p.zp_nonzero) t6 = DT<T>::rnd(t6);
+                e[i] = fmul(t6, th.dv[i].b);
             }
             stg_stream(yv + (r0 + (int64_t)u * rstride) * cv_n + cv, DT<T>::pack(e));
         }

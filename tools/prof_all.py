@@ -78,6 +78,9 @@ def main():
     cases["ternary_f32_bwd_gs"] = (lambda i: K.ternary_quant_bwd(G[i % 2], W[i % NS], s0f, 0.5, True), R * C * 12)
     cases["minmax_rows_f32"] = (lambda i: K.minmax_rows(W[i % NS], R, C), R * C * 4)
     cases["minmax_tensor_f32"] = (lambda i: K.minmax_rows(W[i % NS].reshape(-1), 1, R * C), R * C * 4)
+    # post-ReLU activations are half zeros: the ReLU-folded quantizer on N(0,1) input
+    cases["act_f32_relu_scalar_fwd"] = (lambda i: K.int_quant_fwd(W[i % NS], s0f, 0.0, 0.0, 255.0, 0, pre_relu=True), R * C * 8)
+    cases["act_f32_relu_scalar_bwd_gs"] = (lambda i: K.int_quant_bwd(G[i % 2], W[i % NS], s0f, 0.0, 0.0, 255.0, 0, 1, True, pre_relu=True), R * C * 12)
     only = [s for s in a.only.split(",") if s]
     period = 6                                    # lcm of the input rotations above
     for name, (fn, nbytes) in cases.items():
