@@ -67,10 +67,11 @@ __global__ void __launch_bounds__(ST_THREADS) int_quant_fwd_kernel(
                     if (p.pre_relu) q[u] = relu_vec<T>(q[u]);
                     if (smode != 0) {      // scale index constant within a vector (literal formulation)
                         const ScaleCtx<T> cxv(DT<T>::to_f(scale[(v / inner_v) % count]), true, p, false);
-                        yq = qdq_vec<T, RM, VM_LITERAL, true>(q[u], cxv, p, codes ? &kq : nullptr);
+                        yq = qdq_vec<T, RM, VM_LITERAL, !DT<T>::LOWP>(q[u], cxv, p, codes ? &kq : nullptr);
                     } else {
-                        // (activations: zeros -- half of a post-ReLU tensor -- stay on the fast division path)
-                        yq = qdq_vec<T, RM, MODE, true>(q[u], cx0, p, codes ? &kq : nullptr);
+                        // (fp32 activations: zeros -- half of a post-ReLU tensor -- stay on the fast division path;
+                        // the 16-bit formulations multiply by an exact reciprocal and have no slow path to avoid)
+                        yq = qdq_vec<T, RM, MODE, !DT<T>::LOWP>(q[u], cx0, p, codes ? &kq : nullptr);
                     }
                     stg_stream(yv + v, yq);
                     if (codes) stg_stream(cv + v, kq);
@@ -114,8 +115,9 @@ __device__ __forceinline__ void bwd_n(float (&eg)[N], const float (&ex)[N], cons
     DT<T>::template rnd_n<N>(d);
     if (masked || want_gs) {
         float t1[N];
-        // t1 only feeds "+ zero_point" (masks, codes) and the tolerance-bound d(scale) sum: zeros stay on the fast path
-        dv.div_n<N, true>(ex, t1, ((RM & RM_ZP0) != 0) || zero_sign_invisible(p));
+        // (the zero-tolerant division of the forward was tried here too: the extra select per element costs more than the
+        // slow path it avoids -- ReLU-folded learned-scale backward 91.3 -> 99.0 us)
+        dv.div_n<N>(ex, t1);
         DT<T>::template rnd_n<N>(t1);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(PL_THREADS, BWD ? 2 : 4) int_quant_planes_kern
                             } else {
                                 uint4 kq;
                                 if (p.pre_relu) qx[u] = relu_vec<T>(qx[u]);
-                                const uint4 yq = qdq_vec<T, RM, MODE, true>(qx[u], cx, p, cv ? &kq : nullptr);
+                                const uint4 yq = qdq_vec<T, RM, MODE, !DT<T>::LOWP>(qx[u], cx, p, cv ? &kq : nullptr);
                                 stg_stream(ov + v, yq);
                                 if (cv) stg_stream(cv + v, kq);
                             }
