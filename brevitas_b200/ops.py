@@ -8,7 +8,8 @@ Two dispatcher namespaces are defined:
 * ``brevitas_b200`` -- the fused quantizer ops used by the module layer (``brevitas_b200.core``).
 
 Every op has a CUDA implementation only (ctypes -> C-ABI -> sm_100a kernels), an autograd formula and a
-fake/meta implementation.  Calling any of them with CPU tensors raises: there is no CPU fallback.
+fake/meta implementation.  Calling any of them with CPU tensors raises: there is no CPU fallback (the one scoped exception,
+``parameter_init_on_host`` below, serves the construction-time initialisation of a learned scale, never a forward).
 """
 import contextlib
 import threading
