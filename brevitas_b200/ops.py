@@ -8,8 +8,8 @@ Two dispatcher namespaces are defined:
 * ``brevitas_b200`` -- the fused quantizer ops used by the module layer (``brevitas_b200.core``).
 
 Every op has a CUDA implementation only (ctypes -> C-ABI -> sm_100a kernels), an autograd formula and a
-fake/meta implementation.  Calling any of them with CPU tensors raises: there is no CPU fallback (the one scoped exception,
-``parameter_init_on_host`` below, serves the construction-time initialisation of a learned scale, never a forward).
+fake/meta implementation.  Calling any of them with CPU tensors raises: there is no CPU fallback (inside the one scoped
+exception, ``parameter_init_on_host`` below, host tensors are staged to the GPU for a construction-time initialisation).
 """
 import contextlib
 import threading
@@ -43,8 +43,10 @@ def parameter_init_on_host():
     user had a chance to move the layer to the GPU: ``ParameterFromStatsScalingInit.__call__`` (quant/solver/
     parameter.py:39-45) runs a ``StatsFromParameterScaling`` over the still host-resident weight to produce the initial
     value of a learned scale.  Inside this scope -- and nowhere else -- the handful of ops such an initialiser is made of
-    accept host tensors and evaluate the reference's literal ATen expression; ``binding.install()`` enters it around
-    exactly that call.  Outside it every op raises on host tensors: no forward / backward ever runs on the CPU."""
+    accept host tensors: they are STAGED to the current CUDA device, the sm_100a kernel runs there, and the (statistics-
+    sized) result is copied back, so the value is computed by the same kernels as everything else and a machine without
+    a GPU fails loudly here as well.  ``binding.install()`` enters the scope around exactly that call.  Outside it every op
+    raises on host tensors: there is no CPU arithmetic in this package's ops."""
     _HOST_INIT.depth += 1
     try:
         yield
@@ -52,20 +54,24 @@ def parameter_init_on_host():
         _HOST_INIT.depth -= 1
 
 
-def _no_cpu(name, init_expr=None):
+def _no_cpu(name, staged=None):
+    """the CPU dispatch entry of an op: raises -- except for the ops a construction-time initialiser uses (``staged`` =
+    (namespace, op name)), which inside ``parameter_init_on_host`` run their CUDA kernel on a staged copy"""
     def _raise(*args, **kwargs):
-        if init_expr is not None and _HOST_INIT.depth > 0:
-            return init_expr(*args, **kwargs)
+        if staged is not None and _HOST_INIT.depth > 0:
+            if not torch.cuda.is_available():
+                raise RuntimeError(f"{name}: initialising a learned scale from the weight statistics runs the sm_100a "
+                                   "kernels and needs a CUDA device (brevitas_b200 has no CPU implementation)")
+            dev = torch.device("cuda", torch.cuda.current_device())
+            moved = [a.to(dev) if isinstance(a, Tensor) else a for a in args]
+            out = getattr(getattr(torch.ops, staged[0]), staged[1])(*moved, **kwargs)
+            if isinstance(out, Tensor):
+                return out.cpu()
+            return tuple(o.cpu() if isinstance(o, Tensor) else o for o in out)
         raise RuntimeError(
             f"{name}: CPU tensors are not supported -- brevitas_b200 is a CUDA (sm_100a) implementation with no "
             "CPU fallback. Move the module and its inputs to a B200.")
     return _raise
-
-
-def _host_kth(x, rows, cols, k, absolute):
-    v = x.reshape(rows, cols)
-    r = (v.abs() if absolute else v).kthvalue(k, dim=1)
-    return r.values, r.indices
 
 
 # ============================================================================================================
@@ -89,13 +95,13 @@ _UNARY_STE = {
 
 
 # float_to_int of a power-of-two restriction inside a construction-time scale initialiser (see parameter_init_on_host)
-_UNARY_INIT_EXPR = {"round_ste_impl": torch.round, "ceil_ste_impl": torch.ceil, "floor_ste_impl": torch.floor}
+_UNARY_INIT_OPS = ("round_ste_impl", "ceil_ste_impl", "floor_ste_impl")
 
 
 def _def_unary(op_name, c_name):
     _STE.define(f"{op_name}(Tensor x) -> Tensor")
     _STE.impl(op_name, lambda x, _c=c_name: K.unary(_c, x), "CUDA")
-    _STE.impl(op_name, _no_cpu(op_name, _UNARY_INIT_EXPR.get(op_name)), "CPU")
+    _STE.impl(op_name, _no_cpu(op_name, (STE_NS, op_name) if op_name in _UNARY_INIT_OPS else None), "CPU")
     torch.library.register_fake(f"{STE_NS}::{op_name}", lambda x: torch.empty_like(x), lib=_STE)
     torch.library.register_autograd(f"{STE_NS}::{op_name}", _identity_backward, lib=_STE)
 
@@ -106,7 +112,7 @@ for _op, _c in _UNARY_STE.items():
 # abs_binary_sign_grad_impl: forward abs, backward binary_sign(x) * g   (csrc:182-194)
 _STE.define("abs_binary_sign_grad_impl(Tensor x) -> Tensor")
 _STE.impl("abs_binary_sign_grad_impl", lambda x: K.unary("bvb_abs_binary_sign_grad_impl", x), "CUDA")
-_STE.impl("abs_binary_sign_grad_impl", _no_cpu("abs_binary_sign_grad_impl", torch.abs), "CPU")
+_STE.impl("abs_binary_sign_grad_impl", _no_cpu("abs_binary_sign_grad_impl", (STE_NS, "abs_binary_sign_grad_impl")), "CPU")
 torch.library.register_fake(f"{STE_NS}::abs_binary_sign_grad_impl", lambda x: torch.empty_like(x), lib=_STE)
 
 _FQ.define("abs_binary_sign_grad_backward(Tensor x, Tensor gy) -> Tensor")
@@ -167,7 +173,7 @@ torch.library.register_autograd(f"{STE_NS}::scalar_clamp_ste_impl", lambda ctx, 
 
 _STE.define("scalar_clamp_min_ste_impl(Tensor x, float min_val) -> Tensor")
 _STE.impl("scalar_clamp_min_ste_impl", lambda x, lo: K.scalar_clamp_min(x, lo), "CUDA")
-_STE.impl("scalar_clamp_min_ste_impl", _no_cpu("scalar_clamp_min_ste_impl", torch.clamp_min), "CPU")
+_STE.impl("scalar_clamp_min_ste_impl", _no_cpu("scalar_clamp_min_ste_impl", (STE_NS, "scalar_clamp_min_ste_impl")), "CPU")
 torch.library.register_fake(f"{STE_NS}::scalar_clamp_min_ste_impl", lambda x, lo: torch.empty_like(x), lib=_STE)
 torch.library.register_autograd(f"{STE_NS}::scalar_clamp_min_ste_impl", lambda ctx, g: (g, None), lib=_STE)
 
@@ -584,13 +590,13 @@ _FQ.define("abs_kth_value_rows(Tensor x, int rows, int cols, int k) -> (Tensor, 
 _FQ.define("kth_value_rows(Tensor x, int rows, int cols, int k) -> (Tensor, Tensor)")
 _FQ.define("running_stats_update_(Tensor(a!) running, Tensor stat, float momentum, bool first) -> ()")
 _FQ.impl("absmax_rows", lambda x, r, c: K.absmax_rows(x, r, c), "CUDA")
-_FQ.impl("absmax_rows", _no_cpu("absmax_rows", lambda x, rows, cols: x.reshape(rows, cols).abs().max(dim=1)[0]), "CPU")
+_FQ.impl("absmax_rows", _no_cpu("absmax_rows", (FQ_NS, "absmax_rows")), "CPU")
 _FQ.impl("absmax_tensor", lambda x: K.absmax_tensor(x), "CUDA")
-_FQ.impl("absmax_tensor", _no_cpu("absmax_tensor", lambda x: x.abs().max()), "CPU")
+_FQ.impl("absmax_tensor", _no_cpu("absmax_tensor", (FQ_NS, "absmax_tensor")), "CPU")
 _FQ.impl("abs_kth_value_rows", lambda x, r, c, k: K.abs_kth_value_rows(x, r, c, k, want_index=True), "CUDA")
-_FQ.impl("abs_kth_value_rows", _no_cpu("abs_kth_value_rows", lambda x, r, c, k: _host_kth(x, r, c, k, True)), "CPU")
+_FQ.impl("abs_kth_value_rows", _no_cpu("abs_kth_value_rows", (FQ_NS, "abs_kth_value_rows")), "CPU")
 _FQ.impl("kth_value_rows", lambda x, r, c, k: K.kth_value_rows(x, r, c, k, want_index=True), "CUDA")
-_FQ.impl("kth_value_rows", _no_cpu("kth_value_rows", lambda x, r, c, k: _host_kth(x, r, c, k, False)), "CPU")
+_FQ.impl("kth_value_rows", _no_cpu("kth_value_rows", (FQ_NS, "kth_value_rows")), "CPU")
 _FQ.impl("running_stats_update_", lambda r, s, m, f: (K.running_stats_update(r, s, m, f), None)[1], "CUDA")
 _FQ.impl("running_stats_update_", _no_cpu("running_stats_update_"), "CPU")
 torch.library.register_fake(f"{FQ_NS}::absmax_rows", lambda x, r, c: x.new_empty(r), lib=_FQ)

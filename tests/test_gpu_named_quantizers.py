@@ -175,3 +175,30 @@ def test_quant_tensor_integer_export(ref, kind):
     (ir, fr), (if_, ff) = results
     assert ir.dtype == if_.dtype and torch.equal(ir, if_), (ir.dtype, if_.dtype)
     assert torch.equal(fr, ff)
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+@pytest.mark.parametrize("name", ["Int4WeightPerTensorFloatDecoupled", "Int8WeightPerChannelFloatDecoupled"])
+def test_construction_time_scale_init_from_host_weights(ref, name, fuse):
+    """quant/solver/parameter.py:39-45: the learned scale is initialised from the weight statistic while the layer is
+    CONSTRUCTED, weights still on the host.  ops.parameter_init_on_host stages them to the GPU for that one call: the state
+    dict equals the pure reference's (computed by ATen on the CPU) bit for bit; a forward on host tensors still raises."""
+    import brevitas_b200
+    from brevitas_b200.binding import uninstall
+    uninstall()
+    brevitas_b200.install(ref, fuse=fuse)
+    import brevitas.nn as qnn
+    import brevitas.quant as Q
+    torch.manual_seed(0)
+    ours = qnn.QuantLinear(16, 8, False, weight_quant=getattr(Q, name))
+    assert all(not v.is_cuda for v in ours.state_dict().values())
+    with pytest.raises(RuntimeError, match="CPU tensors are not supported"):
+        ours(torch.randn(2, 16))
+    with pytest.raises(RuntimeError, match="CPU tensors are not supported"):
+        torch.ops.brevitas_b200.absmax_tensor(torch.randn(4))                   # outside the scope: raises
+    uninstall()
+    torch.manual_seed(0)
+    pure = qnn.QuantLinear(16, 8, False, weight_quant=getattr(Q, name))
+    assert set(ours.state_dict()) == set(pure.state_dict())
+    for k, v in pure.state_dict().items():
+        assert torch.equal(v, ours.state_dict()[k]), (name, k)
